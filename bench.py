@@ -1,0 +1,265 @@
+#!/usr/bin/env python
+"""bench.py — pose-graph windows/sec (10 keyframes x 2000 correspondences, 640x480 synthetic RGB-D) on N B200s.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` (torchrun for N>1) prints ONE JSON
+line on rank 0.  One "step" = one pass of the hot path over one batch of `--windows` independent tracking windows per GPU
+(BASELINE.json configs[1] replicated; configs[3] is 32 windows/GPU x 8 GPUs), i.e. weak scaling.
+
+  value     windows/s, whole job, inputs (frame maps, correspondences, poses, tables) already resident in HBM:
+            the three kernels of bt_solve_run timed with CUDA events on the launching stream.
+  e2e       the same metric through the reference-facing call (OptimizerGpu.optimizeWindows -> bt_solve_windows):
+            per step the host correspondences + poses + window tables go host->device and the poses come back, exactly
+            the arguments OptimizerGpu::optimizeFrames takes from the host; depth/normal maps are device-resident
+            Frame members in the reference API (Frame::_depth_gpu/_normal_gpu) and are passed as device pointers.
+  roofline  dominant kernel = k_solve; achieved = algorithmic bytes (iters*(N*npix*32 + C*32) + 2*N*64
+            per window) / CUDA-event duration of that kernel; peak = MEASURED_PEAKS.json hbm_gbs (fallback 6650).
+  cpu_baseline  oracle/ (CPU restatement, "port": the reference has no CPU optimizer) on the host cores, bounded sample.
+  --impl reference   the reference's OWN CUDA kernels + host-glue allocation pattern (oracle/_ref, built verbatim from
+            /root/reference) called once per window like Bundler::optimizeGPU does; plus the CPU port beside it.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--windows", type=int, default=32, help="windows per GPU per step (BASELINE configs[3]: 256 over 8 GPUs)")
+    ap.add_argument("--frames", type=int, default=10)
+    ap.add_argument("--corr", type=int, default=2000)
+    ap.add_argument("--scenes", type=int, default=4, help="distinct rendered scenes per GPU; windows cycle through them with their own pose noise and their own copy of the frame maps")
+    ap.add_argument("--cpu-windows", type=int, default=0, help="cpu_baseline sample size (0 = 2 per core)")
+    ap.add_argument("--ref-windows", type=int, default=8, help="windows per step for --impl reference")
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self.proc = None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self._stop.is_set():
+                    break
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop.set()
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def make_batch(args, rank, dev):
+    """`windows` windows per GPU: `scenes` rendered scenes, every window gets its OWN device copy of the frame maps (so
+    the batch footprint, windows*frames*6.1 MB, is far larger than the 126 MB L2) and its own initial-pose noise."""
+    import torch
+    from bundletrack_b200 import synth
+    from bundletrack_b200.optimizer import SolveWindow
+    scenes = [synth.make_window(1000 * rank + s, n_frames=args.frames, n_corr=args.corr) for s in range(min(args.scenes, args.windows))]
+    wins, host = [], []
+    for k in range(args.windows):
+        sc = scenes[k % len(scenes)]
+        rng = np.random.default_rng(77 + 1000 * rank + k)
+        poses = sc.poses_gt.copy()
+        for f in range(1, sc.n_frames):
+            poses[f] = sc.poses_gt[f] @ synth.se3(synth.so3_exp(rng.normal(0, np.deg2rad(1.0), 3)), rng.normal(0, 0.003, 3))
+        depth = [torch.from_numpy(sc.depth[f]).to(dev) for f in range(sc.n_frames)]
+        normal = [torch.from_numpy(sc.normal[f]).to(dev) for f in range(sc.n_frames)]
+        wins.append(SolveWindow(sc.corr, sc.H, sc.W, depth, normal, poses.astype(np.float32), sc.K))
+        host.append((sc, poses.astype(np.float32)))
+    return wins, host
+
+
+def cpu_baseline(host, n_windows):
+    """Oracle A (float build) on the host cores: threads over windows (the C call releases the GIL)."""
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    cores = os.cpu_count() or 1
+    n = n_windows or 2 * cores
+    oracle.build()
+    jobs = [host[k % len(host)] for k in range(n)]
+    def run(j):
+        sc, poses = j
+        return oracle.solve_window(sc.depth, sc.normal, sc.K, sc.corr, poses)
+    run(jobs[0])
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        list(ex.map(run, jobs))
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "windows/s", "cores": cores, "kind": "port",
+            "sample": f"{n} windows of the bench workload, oracle/solver_oracle.c (fp32), {cores} threads, {dt:.1f} s"}
+
+
+def main():
+    args = parse()
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.impl == "reference" and rank != 0:
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
+    wins, host = make_batch(args, rank, dev)
+    N, C = args.frames, args.corr
+    npix = (640 // 4) * (480 // 4)
+    workload = f"{args.windows} windows/GPU x ({N} keyframes, {C} corr, 640x480 -> 160x120 cache, 7 GN x 5 PCG), BASELINE configs[1] batched as configs[3]"
+    base = {"metric": "pose-graph windows/sec (10 KF x 2k corr)", "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "windows_per_gpu": args.windows, "frames": N, "corr": C, "gn_iters": 7, "pcg_iters": 5,
+                       "l2": f"inputs larger than L2: {args.windows * N * 6.1:.0f} MB of frame maps per GPU, each window its own copy", "parallelism": f"windows sharded, {world} rank(s), no data-path collective"}}
+
+    if args.impl == "reference":
+        import oracle
+        n = min(args.ref_windows, len(wins))
+        def step():
+            for k in range(n):
+                w = wins[k]
+                oracle.ref_optimize_frames(w.depths, w.normals, w.H, w.W, w.K, w.corr, w.poses)
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local); sampler.start()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        clocks = sampler.stop()
+        val = n * args.steps / dt
+        cb = cpu_baseline(host, args.cpu_windows)
+        out = dict(base, impl="reference", value=val, ms_per_step=dt / args.steps * 1e3, gpu_launches=0,
+                   e2e={"value": val, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                   cpu_baseline=dict(cb, note="the reference has no CPU optimizer (SURVEY.md D5); value above is its OWN CUDA path (oracle/_ref) on this GPU, one optimizeFrames-equivalent call per window; this entry is the CPU port"),
+                   clocks=clocks)
+        out["config"] = dict(base["config"], reference_sample=f"{n} windows per step through the reference's kernels + allocation pattern")
+        print(json.dumps(out))
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
+
+    from bundletrack_b200.optimizer import OptimizerGpu
+    stream = torch.cuda.current_stream().cuda_stream
+    opt = OptimizerGpu(None, device=local, max_windows=args.windows, max_frames=max(N, 2), max_corr=max(C, 1), stream=stream)
+    opt.enable_timing(True)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- value: resident inputs, kernels only
+    opt.stage(wins)
+    for _ in range(args.warmup):
+        opt.run()
+    sync_all()
+    sampler = ClockSampler(local); sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k_ms = []
+    ev0.record()
+    for _ in range(args.steps):
+        opt.run()
+        k_ms.append(None)
+    ev1.record()
+    sync_all()
+    clocks = sampler.stop()
+    elapsed = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    tm = opt.timing_ms()                      # per-kernel device time of the last step
+    stats = opt.stats()
+    poses = opt.fetch()
+    if world > 1:
+        dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
+        gathered = [torch.zeros(args.windows * N * 16, device=dev) for _ in range(world)]   # NCCL only to gather results
+        dist.all_gather(gathered, torch.from_numpy(np.concatenate([p.reshape(-1) for p in poses])).to(dev))
+    ms_step = float(elapsed.item()) / args.steps
+    value = world * args.windows / (ms_step * 1e-3)
+
+    # ---- e2e: host buffers in, host poses out, every step
+    for _ in range(args.warmup):
+        opt.optimizeWindows(wins)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out_poses = opt.optimizeWindows(wins)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_val = world * args.windows * args.steps / float(dt.item())
+    h2d = sum(len(w.corr) * 32 + w.n_frames * 64 + w.n_frames * 20 + 120 + 45 * 8 + 46 * 12 for w in wins)
+    d2h = sum(w.n_frames * 64 for w in wins)
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        alg_bytes = args.windows * (7 * (N * npix * 32 + C * 32) + 2 * N * 64)
+        ach = alg_bytes / (tm["solve"] * 1e-3) / 1e9
+        cb = cpu_baseline(host, args.cpu_windows)
+        from bundletrack_b200 import synth
+        import oracle
+        sc, p0 = host[0]
+        chk = synth.pose_errors(out_poses[0], oracle.solve_window(sc.depth, sc.normal, sc.K, sc.corr, p0))
+        out = dict(base, value=value, ms_per_step=ms_step, gpu_launches=3 * args.steps,
+                   e2e={"value": e2e_val, "unit": "windows/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                   roofline={"bound": "hbm", "kernel": "k_solve", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                             "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": tm},
+                   cpu_baseline=cb, clocks=clocks,
+                   parity={"window0_vs_oracle_rot_rad": chk[0], "window0_vs_oracle_trans_m": chk[1]},
+                   solver_stats=stats)
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+    opt.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,119 @@
+"""ctypes binding of the C-ABI (include/bundletrack_b200.h).  The shared library is built in-tree by
+__graft_entry__.build() / `make -C bundletrack_b200/csrc`; if it is missing, or the machine has no sm_100 GPU,
+every entry point fails loudly — there is no CPU or PyTorch fallback anywhere in this package."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libbundletrack_b200.so")
+
+BT_OK = 0
+
+
+class BtError(RuntimeError):
+    pass
+
+
+class SolverParams(ctypes.Structure):
+    _fields_ = [
+        ("num_iter_outer", ctypes.c_int),
+        ("num_iter_inner", ctypes.c_int),
+        ("robust_delta", ctypes.c_float),
+        ("image_downscale", ctypes.c_float),
+        ("dense_dist_thresh", ctypes.c_float),
+        ("dense_cos_normal_thresh", ctypes.c_float),
+        ("depth_min", ctypes.c_float),
+        ("depth_max", ctypes.c_float),
+        ("w_sparse", ctypes.c_float),
+        ("w_dense", ctypes.c_float),
+    ]
+
+
+class Window(ctypes.Structure):
+    _fields_ = [
+        ("n_frames", ctypes.c_int),
+        ("H", ctypes.c_int),
+        ("W", ctypes.c_int),
+        ("n_corr", ctypes.c_int),
+        ("corr", ctypes.c_void_p),
+        ("depth_dev", ctypes.POINTER(ctypes.c_void_p)),
+        ("normal_dev", ctypes.POINTER(ctypes.c_void_p)),
+        ("fx", ctypes.c_float),
+        ("fy", ctypes.c_float),
+        ("cx", ctypes.c_float),
+        ("cy", ctypes.c_float),
+        ("dense_pairs", ctypes.c_void_p),
+        ("n_dense_pairs", ctypes.c_int),
+        ("compat_flip", ctypes.c_int),
+    ]
+
+
+class SolverLimits(ctypes.Structure):
+    _fields_ = [
+        ("max_windows", ctypes.c_int),
+        ("max_frames", ctypes.c_int),
+        ("max_corr", ctypes.c_int),
+        ("H", ctypes.c_int),
+        ("W", ctypes.c_int),
+        ("image_downscale", ctypes.c_float),
+    ]
+
+
+class SolveStats(ctypes.Structure):
+    _fields_ = [
+        ("n_windows", ctypes.c_int),
+        ("n_tiles_total", ctypes.c_int),
+        ("n_kernel_launches", ctypes.c_int),
+        ("n_src_pixels", ctypes.c_longlong),
+    ]
+
+
+class DescView(ctypes.Structure):
+    _fields_ = [
+        ("dev", ctypes.c_void_p),
+        ("n", ctypes.c_int),
+        ("dim", ctypes.c_int),
+        ("pitch_bytes", ctypes.c_size_t),
+    ]
+
+
+# every symbol include/bundletrack_b200.h declares (tests/test_abi.py checks the .so exports all of them)
+EXPORTS = [
+    "bt_last_error", "bt_version", "bt_ctx_create", "bt_ctx_destroy", "bt_solver_reserve",
+    "bt_solve_windows", "bt_solve_stage", "bt_solve_run", "bt_solve_fetch", "bt_solve_get_stats",
+    "bt_solve_enable_debug", "bt_solve_debug_dense", "bt_solve_debug_counts", "bt_solve_enable_timing", "bt_solve_get_timing",
+    "bt_matcher_reserve", "bt_knn_match_pairs", "bt_ransac_reserve", "bt_ransac_pairs",
+    "bt_dev_alloc", "bt_dev_free", "bt_memcpy_h2d", "bt_memcpy_d2h", "bt_host_alloc_pinned", "bt_host_free_pinned",
+    "bt_stream_sync",
+]
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the in-tree shared library; raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BtError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). bundletrack_b200 has no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.bt_last_error.restype = ctypes.c_char_p
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ("bt_last_error", "bt_ctx_destroy"):
+            fn.restype = ctypes.c_int
+    lib.bt_ctx_destroy.restype = None
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != BT_OK:
+        msg = load().bt_last_error().decode("utf-8", "replace")
+        raise BtError(f"{what} failed with status {rc}: {msg}")

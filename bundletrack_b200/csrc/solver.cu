@@ -1,0 +1,1165 @@
+// solver.cu — B200-native Gauss-Newton x PCG pose-graph solve for a BATCH of independent tracking windows.
+//
+// Replaces (behind the C-ABI in include/bundletrack_b200.h) the reference's OptimizerGpu::optimizeFrames
+// (/root/reference/src/cuda/LossGPU.cu:53-139) -> CUDACache::storeFrame (CUDACache.cpp:76-88) -> SBA::align
+// (SBA.cpp:81-139) -> CUDASolverBundling::solve (Solver/CUDASolverBundling.cpp:190-288) -> solveBundlingStub
+// (Solver/SolverBundling.cu:931-1003): ~260 kernel launches, ~75 memsets, 7 blocking copies and ~110 cudaMalloc per
+// window there; THREE launches per BATCH here, none of them allocating:
+//
+//   k_prep_frames  one CTA per (window, frame): quarter-res cache (camera-space point + normal interleaved in one
+//                  32-byte texel so a bilinear tap is a single sector) + an order-preserving COMPACTED list of the
+//                  valid source pixels (the object mask leaves ~10 % of the image valid), + se(3) of the input pose.
+//   k_plan         one CTA: per-window tile counts -> exclusive scan -> flat tile list.
+//   k_solve        persistent, dynamically scheduled: tiles are (GN iteration, window, pair, pixel chunk); a tile
+//                  evaluates point-to-plane residuals/Jacobians for its chunk and reduces a 6x6 system in the TARGET
+//                  camera frame; the CTA that retires a window's last tile of an iteration runs that window's "tail":
+//                  assembles the (6(N-1))^2 normal equations in shared memory (dense blocks + explicit sparse
+//                  blocks from per-pair moment sums), runs the PCG steps, updates the poses and releases the
+//                  window's next iteration.  Tiles of iteration k+1 wait on a per-window flag, so all GN iterations
+//                  of all windows flow through ONE launch with no host round trip.
+//
+// Maths restated from the reference (see oracle/solver_oracle.c for the statement-by-statement CPU version):
+//   * dense residual/gates: findDenseCorr (Solver/SolverBundlingDenseUtil.h:78-110), bilinear taps
+//     (Solver/ICPUtil.h:83-110, zeros blended - SURVEY.md Q6), Huber weight (Solver/SolverBundlingUtil.h:24-39).
+//   * Jacobian rows: computeJacobianBlockRow_i/j (Solver/SolverBundlingEquationsLie.h:214-230) reduce analytically to
+//     J_i = [N, q x N], J_j = -J_i with N = R_i n_tgt and q the source point in the model frame (derivation in
+//     DESIGN.md), so one symmetric 6x6 + one 6-vector per pair carries all four blocks addToLocalSystem writes
+//     (SolverBundlingDenseUtil.h:217-285).  FlipJtJ (SolverBundling.cu:49-58) erases cross blocks with
+//     target > source; `compat_flip` reproduces that.
+//   * sparse term: evalMinusJTFDevice / applyJDevice / applyJTDevice (SolverBundlingEquationsLie.h:60-211) with the
+//     Huber weight on the gradient and the Jacobi preconditioner only; J^T J is formed explicitly
+//     from per-pair moment sums instead of matrix-free, which changes summation order only.
+//   * PCG recurrences and the 1e-6 guards: SolverBundling.cu:575-818; update x <- log(exp(delta) exp(x)):
+//     Solver/LieDerivUtil.h:126-194,276-282.
+#include <algorithm>
+#include <math.h>
+#include "bt_common.cuh"
+
+namespace bt {
+
+static constexpr int kThreads = 256;          // CTA size of k_solve
+static constexpr int kWarps = kThreads / 32;
+static constexpr int kTileVals = 28;          // 21 (sym 6x6) + 6 (rhs) + 1 (#correspondences found)
+static constexpr int kGrpVals = 44;           // sparse moment sums per pair group
+static constexpr int kMaxFrames = 32;
+static constexpr float kEps = 0.000001f;      // FLOAT_EPSILON, /root/reference/src/cuda/SolverUtil.h:10
+
+struct WinDesc {
+	int n_frames, n_corr, n_groups, n_pairs;
+	int corr_off, grp_off, pair_off, frame_off;
+	int tile_off, n_tiles;            // per GN iteration; written by k_plan
+	int H, W, w, h;                   // full / quarter resolution
+	float fx, fy, cx, cy;             // quarter-res intrinsics (CUDACache.cpp:20-24)
+	float ifx, ify, icx, icy;         // inverse full-res intrinsics (m_inputIntrinsicsInv)
+	float scaleW, scaleH;             // (W-1)/(w-1), (H-1)/(h-1)  (CUDAImageUtil.cu:57-58)
+	int compat_flip;
+	int pad;
+};
+
+struct Tile { int win; int pair; int start; int count; };  // pair < 0 => dummy tile (window without dense work)
+
+struct SolveArgs {
+	const WinDesc* wins;
+	int n_windows;
+	// frame slots
+	const float* const* depth_ptr;
+	const float4* const* normal_ptr;
+	const int* frame_win;
+	float4* texel;        // [F][2*npix_max]
+	float4* src;          // [F][2*npix_max]
+	int* nsrc;            // [F]
+	const float* pose_in; // [F][16]
+	float* x;             // [F][6]  rot, trans
+	float* T;             // [F][12] row-major 3x4 cam->model
+	float* pose_out;      // [F][16]
+	int npix_max;
+	// correspondences, grouped by (i,j)
+	const bt_entryj* corr;
+	const int* grp_i; const int* grp_j; const int* grp_start;   // grp_start has n_groups+1 entries per window
+	const uint2* pairs;   // (target, source)
+	// schedule
+	Tile* tiles; int* n_tiles_total; int max_tiles;
+	int* pair_tile0; int* pair_ntile;   // per (window, pair): first tile (relative to the window's tile_off) and tile count
+	float* partial;       // [max_tiles][kTileVals]
+	int* tiles_done;      // [n_windows]
+	int* iter_done;       // [n_windows]
+	int* queue;           // [1]
+	long long* n_src_px;  // [1] stats
+	int chunk;
+	bt_solver_params prm;
+	float* dbg_JtJ; float* dbg_Jtr; int dbg_stride;   // optional dense-system dump (last GN iteration)
+	float* dbg_cnt; int dbg_cnt_stride;               // optional per-pair #correspondences found (last GN iteration)
+};
+
+// ------------------------------------------------------------------------------------------------ device math
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 mk(float x, float y, float z) { V3 v; v.x = x; v.y = y; v.z = z; return v; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+
+// Rodrigues coefficients with the reference's Taylor branches (LieDerivUtil.h:46-70,150-194).
+__device__ void so3_coeffs(float theta_sq, float& A, float& B, float& C) {
+	if (theta_sq < 1e-8f) { A = 1.0f - 0.16666667f * theta_sq; B = 0.5f; C = 0.16666667f; }
+	else if (theta_sq < 1e-6f) {
+		C = 0.16666667f * (1.0f - 0.05f * theta_sq);
+		A = 1.0f - theta_sq * C;
+		B = 0.5f - 0.25f * 0.16666667f * theta_sq;
+	} else {
+		const float theta = sqrtf(theta_sq), inv = 1.0f / theta;
+		A = sinf(theta) * inv;
+		B = (1.0f - cosf(theta)) * (inv * inv);
+		C = (1.0f - A) * (inv * inv);
+	}
+}
+__device__ void so3_exp_AB(V3 w, float A, float B, float R[9]) {  // rodrigues_so3_exp, LieDerivUtil.h:17-44
+	const float wx2 = w.x * w.x, wy2 = w.y * w.y, wz2 = w.z * w.z;
+	R[0] = 1.0f - B * (wy2 + wz2); R[4] = 1.0f - B * (wx2 + wz2); R[8] = 1.0f - B * (wx2 + wy2);
+	float a = A * w.z, b = B * (w.x * w.y); R[1] = b - a; R[3] = b + a;
+	a = A * w.y; b = B * (w.x * w.z); R[2] = b + a; R[6] = b - a;
+	a = A * w.x; b = B * (w.y * w.z); R[5] = b - a; R[7] = b + a;
+}
+// poseToMatrix (LieDerivUtil.h:150-194): T[12] = row-major 3x4 [R | t]
+__device__ void se3_exp(V3 rot, V3 trans, float T[12]) {
+	const float theta_sq = dot(rot, rot);
+	float A, B, C;
+	so3_coeffs(theta_sq, A, B, C);
+	const V3 cr = cross(rot, trans);
+	V3 t;
+	if (theta_sq < 1e-8f) t = trans + cr * 0.5f;
+	else t = trans + cr * B + cross(rot, cr) * C;
+	float R[9];
+	so3_exp_AB(rot, A, B, R);
+	T[0] = R[0]; T[1] = R[1]; T[2] = R[2]; T[3] = t.x;
+	T[4] = R[3]; T[5] = R[4]; T[6] = R[5]; T[7] = t.y;
+	T[8] = R[6]; T[9] = R[7]; T[10] = R[8]; T[11] = t.z;
+}
+// ln_rotation (LieDerivUtil.h:72-124)
+__device__ V3 so3_log(const float R[9]) {
+	V3 r = mk((R[7] - R[5]) * 0.5f, (R[2] - R[6]) * 0.5f, (R[3] - R[1]) * 0.5f);
+	const float cos_angle = (R[0] + R[4] + R[8] - 1.0f) * 0.5f;
+	const float s = sqrtf(dot(r, r));
+	if (cos_angle > 0.70710678118654752440f) {
+		if (s > 0.0f) r = r * (asinf(s) / s);
+	} else if (cos_angle > -0.70710678118654752440f) {
+		r = r * (acosf(cos_angle) / s);
+	} else {
+		const float angle = 3.14159265358979323846f - asinf(s);
+		const float d0 = R[0] - cos_angle, d1 = R[4] - cos_angle, d2 = R[8] - cos_angle;
+		V3 r2;
+		if (fabsf(d0) > fabsf(d1) && fabsf(d0) > fabsf(d2)) r2 = mk(d0, (R[3] + R[1]) * 0.5f, (R[2] + R[6]) * 0.5f);
+		else if (fabsf(d1) > fabsf(d2)) r2 = mk((R[3] + R[1]) * 0.5f, d1, (R[7] + R[5]) * 0.5f);
+		else r2 = mk((R[2] + R[6]) * 0.5f, (R[7] + R[5]) * 0.5f, d2);
+		if (dot(r2, r) < 0.0f) r2 = r2 * -1.0f;
+		r = r2 * (angle / sqrtf(dot(r2, r2)));
+	}
+	return r;
+}
+// matrixToPose (LieDerivUtil.h:126-148); T = row-major 3x4
+__device__ void se3_log(const float T[12], V3& rot, V3& trans) {
+	const float R[9] = { T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10] };
+	const V3 t = mk(T[3], T[7], T[11]);
+	rot = so3_log(R);
+	const float theta = sqrtf(dot(rot, rot));
+	float shtot = 0.5f;
+	if (theta > 0.00001f) shtot = sinf(theta * 0.5f) / theta;
+	const V3 half = rot * -0.5f;
+	float A, B, C, Hm[9];
+	so3_coeffs(dot(half, half), A, B, C);
+	so3_exp_AB(half, A, B, Hm);
+	V3 tr = mk(Hm[0] * t.x + Hm[1] * t.y + Hm[2] * t.z, Hm[3] * t.x + Hm[4] * t.y + Hm[5] * t.z, Hm[6] * t.x + Hm[7] * t.y + Hm[8] * t.z);
+	if (theta > 0.001f) tr = tr - rot * (dot(t, rot) * (1.0f - 2.0f * shtot) / dot(rot, rot));
+	else tr = tr - rot * (dot(t, rot) / 24.0f);
+	trans = tr * (1.0f / (2.0f * shtot));
+}
+__device__ __forceinline__ float huber_w(float e, float delta) {  // rho.y of huberLoss, SolverBundlingUtil.h:24-39
+	return (e <= delta * delta) ? 1.0f : delta / sqrtf(e);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+	int v;
+	asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+	asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ k_prep_frames
+// CUDACache::storeFrame fused (convertDepthFloatToCameraSpaceFloat4 + 2x resampleFloat4 nearest, CUDAImageUtil.cu:
+// 310-326,82-99) + compaction of the source list + matrixToPose/poseToMatrix of the incoming pose (SBA.cu:71-79).
+__global__ void __launch_bounds__(512) k_prep_frames(SolveArgs a) {
+	const int fs = blockIdx.x;
+	const WinDesc wd = a.wins[a.frame_win[fs]];
+	const int npix = wd.w * wd.h;
+	const float* __restrict__ depth = a.depth_ptr[fs];
+	const float4* __restrict__ normal = a.normal_ptr[fs];
+	float4* texel = a.texel + (size_t)fs * 2 * a.npix_max;
+	float4* src = a.src + (size_t)fs * 2 * a.npix_max;
+	__shared__ int s_warp[16];
+	__shared__ int s_base;
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	if (tid == 0) {
+		s_base = 0;
+		float Tm[12];
+		const float* P = a.pose_in + (size_t)fs * 16;
+		for (int k = 0; k < 12; k++) Tm[k] = P[k];
+		V3 rot, trans;
+		se3_log(Tm, rot, trans);
+		float* x = a.x + (size_t)fs * 6;
+		x[0] = rot.x; x[1] = rot.y; x[2] = rot.z; x[3] = trans.x; x[4] = trans.y; x[5] = trans.z;
+		se3_exp(rot, trans, Tm);
+		float* T = a.T + (size_t)fs * 12;
+		for (int k = 0; k < 12; k++) T[k] = Tm[k];
+	}
+	__syncthreads();
+	const bool use_dense = a.prm.w_dense > 0.0f;
+	if (!use_dense) { if (tid == 0) a.nsrc[fs] = 0; return; }
+	for (int base = 0; base < npix; base += blockDim.x) {
+		const int idx = base + tid;
+		float4 cp = make_float4(0.f, 0.f, 0.f, 0.f), nr = make_float4(0.f, 0.f, 0.f, 0.f);
+		bool valid = false;
+		if (idx < npix) {
+			const int x = idx % wd.w, y = idx / wd.w;
+			const unsigned xi = (unsigned)((float)x * wd.scaleW + 0.5f), yi = (unsigned)((float)y * wd.scaleH + 0.5f);
+			if (xi < (unsigned)wd.W && yi < (unsigned)wd.H) {
+				const size_t s = (size_t)yi * wd.W + xi;
+				const float d = __ldg(depth + s);
+				if (d >= 0.1f) cp = make_float4(wd.ifx * ((float)xi * d) + wd.icx * d, wd.ify * ((float)yi * d) + wd.icy * d, d, 1.0f);
+				nr = __ldg(normal + s);
+			}
+			texel[2 * idx] = cp;
+			texel[2 * idx + 1] = nr;
+			valid = (cp.z > a.prm.depth_min && cp.z < a.prm.depth_max);
+		}
+		const unsigned bal = __ballot_sync(0xffffffffu, valid);
+		if (lane == 0) s_warp[wid] = __popc(bal);
+		__syncthreads();
+		int off = s_base;
+		for (int k = 0; k < wid; k++) off += s_warp[k];
+		if (valid) {
+			const int o = off + __popc(bal & ((1u << lane) - 1u));
+			src[2 * o] = make_float4(cp.x, cp.y, cp.z, nr.x);
+			src[2 * o + 1] = make_float4(nr.y, nr.z, nr.w, 0.f);
+		}
+		__syncthreads();
+		if (tid == 0) { int t = 0; for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += s_warp[k]; s_base += t; }
+		__syncthreads();
+	}
+	if (tid == 0) a.nsrc[fs] = s_base;
+}
+
+// ------------------------------------------------------------------------------------------------ k_plan
+__device__ __forceinline__ int chunks_for(int n, int chunk, int& per) {
+	if (n <= 0) { per = 0; return 0; }
+	const int nch = (n + chunk - 1) / chunk;
+	per = (((n + nch - 1) / nch) + 31) & ~31;   // balanced, warp-aligned
+	return (n + per - 1) / per;
+}
+__global__ void __launch_bounds__(1024) k_plan(SolveArgs a, WinDesc* wins_rw) {
+	__shared__ int s_scan[1024];
+	__shared__ int s_carry;
+	__shared__ long long s_px;
+	const int tid = threadIdx.x;
+	if (tid == 0) { s_carry = 0; s_px = 0; *a.queue = 0; }
+	__syncthreads();
+	for (int base = 0; base < a.n_windows; base += blockDim.x) {
+		const int w = base + tid;
+		int cnt = 0;
+		long long px = 0;
+		if (w < a.n_windows) {
+			const WinDesc wd = a.wins[w];
+			for (int p = 0; p < wd.n_pairs; p++) {
+				const uint2 pr = a.pairs[wd.pair_off + p];
+				const int n = a.nsrc[wd.frame_off + pr.y];
+				int per;
+				cnt += chunks_for(n, a.chunk, per);
+				px += n;
+			}
+			if (cnt == 0) cnt = 1;   // dummy tile: the window still needs its tail every iteration
+			a.tiles_done[w] = 0;
+			a.iter_done[w] = 0;
+		}
+		s_scan[tid] = cnt;
+		__syncthreads();
+		for (int o = 1; o < (int)blockDim.x; o <<= 1) {   // Hillis-Steele inclusive scan
+			int v = (tid >= o) ? s_scan[tid - o] : 0;
+			__syncthreads();
+			s_scan[tid] += v;
+			__syncthreads();
+		}
+		const int excl = s_scan[tid] - cnt + s_carry;
+		if (w < a.n_windows) {
+			wins_rw[w].tile_off = excl;
+			wins_rw[w].n_tiles = cnt;
+			const WinDesc wd = a.wins[w];
+			int t = excl;
+			if (excl + cnt <= a.max_tiles) {
+				for (int p = 0; p < wd.n_pairs; p++) {
+					const uint2 pr = a.pairs[wd.pair_off + p];
+					const int n = a.nsrc[wd.frame_off + pr.y];
+					int per;
+					const int nch = chunks_for(n, a.chunk, per);
+					a.pair_tile0[wd.pair_off + p] = t - excl;
+					a.pair_ntile[wd.pair_off + p] = nch;
+					for (int c = 0; c < nch; c++) {
+						Tile tl; tl.win = w; tl.pair = p; tl.start = c * per; tl.count = min(per, n - c * per);
+						a.tiles[t++] = tl;
+					}
+				}
+				if (t == excl) { Tile tl; tl.win = w; tl.pair = -1; tl.start = 0; tl.count = 0; a.tiles[t++] = tl; }
+			}
+			atomicAdd((unsigned long long*)&s_px, (unsigned long long)px);
+		}
+		__syncthreads();
+		if (tid == blockDim.x - 1) s_carry += s_scan[tid];
+		__syncthreads();
+	}
+	if (tid == 0) {
+		*a.n_tiles_total = (s_carry <= a.max_tiles) ? s_carry : -1;   // -1 => capacity error reported by the host
+		*a.n_src_px = s_px;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ tile (dense term)
+// Evaluate one chunk of compacted source pixels of pair (tgt i, src j).  Accumulates, in the TARGET camera frame,
+// S' = sum w g' g'^T (upper triangle, 21) and b' = sum w g' r (6) with g' = (n_tgt, p' x n_tgt); the tail maps them to
+// the model frame with the 6x6 adjoint of T_i.
+struct TileAcc { float v[kTileVals]; };
+
+__device__ __forceinline__ void tile_pixels(const SolveArgs& a, const WinDesc& wd, const float4* __restrict__ src,
+                                            const float4* __restrict__ tex, const float* __restrict__ sM, int start, int count, TileAcc& acc) {
+	const float m00 = sM[0], m01 = sM[1], m02 = sM[2], m03 = sM[3];
+	const float m10 = sM[4], m11 = sM[5], m12 = sM[6], m13 = sM[7];
+	const float m20 = sM[8], m21 = sM[9], m22 = sM[10], m23 = sM[11];
+	const float fx = wd.fx, fy = wd.fy, cx = wd.cx, cy = wd.cy;
+	const unsigned W = (unsigned)wd.w, Hh = (unsigned)wd.h;
+	const float dmin = a.prm.depth_min, dmax = a.prm.depth_max, dist_t = a.prm.dense_dist_thresh, cos_t = a.prm.dense_cos_normal_thresh;
+	const float delta = a.prm.robust_delta, wdense = a.prm.w_dense;
+	for (int k = threadIdx.x; k < count; k += kThreads) {
+		const float4 s0 = __ldg(src + 2 * (size_t)(start + k)), s1 = __ldg(src + 2 * (size_t)(start + k) + 1);
+		const float px = s0.x, py = s0.y, pz = s0.z, nx = s0.w, ny = s1.x, nz = s1.y;
+		// camPosSrcToTgt = transform * camPosSrc ; nrmj = transform(3x3) * n  (w of the normal is 0)
+		const float tx = m00 * px + m01 * py + m02 * pz + m03;
+		const float ty = m10 * px + m11 * py + m12 * pz + m13;
+		const float tz = m20 * px + m21 * py + m22 * pz + m23;
+		const float rnx = m00 * nx + m01 * ny + m02 * nz;
+		const float rny = m10 * nx + m11 * ny + m12 * nz;
+		const float rnz = m20 * nx + m21 * ny + m22 * nz;
+		const float sx = tx * fx / tz + cx, sy = ty * fy / tz + cy;    // cameraToDepth, CUDACameraUtil.h:9-14
+		const int ix = (int)roundf(sx), iy = (int)roundf(sy);
+		if (!(ix >= 0 && iy >= 0 && ix < (int)W && iy < (int)Hh)) continue;
+		// bilinearInterpolationFloat4 on camera-space points AND normals (same taps, same weights)
+		const float fx0 = floorf(sx), fy0 = floorf(sy);
+		const int x0 = (int)fx0, y0 = (int)fy0;
+		const float al = sx - fx0, be = sy - fy0;
+		float c0[3] = { 0.f, 0.f, 0.f }, n0[3] = { 0.f, 0.f, 0.f }, c1[3] = { 0.f, 0.f, 0.f }, n1[3] = { 0.f, 0.f, 0.f };
+		float w0 = 0.f, w1 = 0.f;
+		const bool inx0 = (unsigned)x0 < W, inx1 = (unsigned)(x0 + 1) < W, iny0 = (unsigned)y0 < Hh, iny1 = (unsigned)(y0 + 1) < Hh;
+		if (iny0) {
+			const float4* row = tex + 2 * ((size_t)y0 * W);
+			if (inx0) { const float4 cp = __ldg(row + 2 * x0), nr = __ldg(row + 2 * x0 + 1); const float wt = 1.0f - al;
+				c0[0] += wt * cp.x; c0[1] += wt * cp.y; c0[2] += wt * cp.z; n0[0] += wt * nr.x; n0[1] += wt * nr.y; n0[2] += wt * nr.z; w0 += wt; }
+			if (inx1) { const float4 cp = __ldg(row + 2 * (x0 + 1)), nr = __ldg(row + 2 * (x0 + 1) + 1); const float wt = al;
+				c0[0] += wt * cp.x; c0[1] += wt * cp.y; c0[2] += wt * cp.z; n0[0] += wt * nr.x; n0[1] += wt * nr.y; n0[2] += wt * nr.z; w0 += wt; }
+		}
+		if (iny1) {
+			const float4* row = tex + 2 * ((size_t)(y0 + 1) * W);
+			if (inx0) { const float4 cp = __ldg(row + 2 * x0), nr = __ldg(row + 2 * x0 + 1); const float wt = 1.0f - al;
+				c1[0] += wt * cp.x; c1[1] += wt * cp.y; c1[2] += wt * cp.z; n1[0] += wt * nr.x; n1[1] += wt * nr.y; n1[2] += wt * nr.z; w1 += wt; }
+			if (inx1) { const float4 cp = __ldg(row + 2 * (x0 + 1)), nr = __ldg(row + 2 * (x0 + 1) + 1); const float wt = al;
+				c1[0] += wt * cp.x; c1[1] += wt * cp.y; c1[2] += wt * cp.z; n1[0] += wt * nr.x; n1[1] += wt * nr.y; n1[2] += wt * nr.z; w1 += wt; }
+		}
+		float ww = 0.f, cxs = 0.f, cys = 0.f, czs = 0.f, nxs = 0.f, nys = 0.f, nzs = 0.f;
+		if (w0 > 0.f) { const float r = (1.0f - be) / w0; cxs += r * c0[0]; cys += r * c0[1]; czs += r * c0[2]; nxs += r * n0[0]; nys += r * n0[1]; nzs += r * n0[2]; ww += (1.0f - be); }
+		if (w1 > 0.f) { const float r = be / w1; cxs += r * c1[0]; cys += r * c1[1]; czs += r * c1[2]; nxs += r * n1[0]; nys += r * n1[1]; nzs += r * n1[2]; ww += be; }
+		if (!(ww > 0.f)) continue;
+		const float rw = 1.0f / ww;
+		const float qx = cxs * rw, qy = cys * rw, qz = czs * rw;        // camPosTgt
+		if (!(qz > dmin && qz < dmax)) continue;
+		const float tnx = nxs * rw, tny = nys * rw, tnz = nzs * rw;     // normalTgt
+		const float dx = tx - qx, dy = ty - qy, dz = tz - qz;
+		const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+		const float dn = rnx * tnx + rny * tny + rnz * tnz;
+		if (!(dn >= cos_t && dist <= dist_t)) continue;
+		const float res = -(dx * tnx + dy * tny + dz * tnz);            // dot(camPosTgt - camPosSrcToTgt, normalTgt)
+		const float wgt = wdense * huber_w(res * res, delta);
+		float g[6];
+		g[0] = tnx; g[1] = tny; g[2] = tnz;
+		g[3] = ty * tnz - tz * tny; g[4] = tz * tnx - tx * tnz; g[5] = tx * tny - ty * tnx;   // p' x n_tgt
+		int e = 0;
+#pragma unroll
+		for (int r = 0; r < 6; r++) {
+			const float wg = wgt * g[r];
+#pragma unroll
+			for (int c = r; c < 6; c++) acc.v[e++] += wg * g[c];
+		}
+#pragma unroll
+		for (int r = 0; r < 6; r++) acc.v[21 + r] += wgt * g[r] * res;
+		acc.v[27] += 1.0f;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ tail (per window, per GN iteration)
+struct TailSmem {
+	float* T;      // [N][12]
+	float* A;      // [dimp][ld]
+	float* rhs; float* Minv; float* r; float* z; float* p; float* Ap; float* delta;   // [dimp] each
+	float* pairRaw;  // [P][28] target-frame sums
+	float* pairW;    // [P][28] model-frame sums (27 used)
+	float* grp;      // [G][44]
+	float* red;      // [32]
+	int dimp, ld;
+};
+__host__ __device__ inline size_t tail_smem_floats(int N, int P, int G) {
+	const int dimp = 6 * (N - 1), ld = dimp | 1;
+	return (size_t)N * 12 + (size_t)dimp * ld + 7 * (size_t)dimp + 2 * (size_t)P * kTileVals + (size_t)G * kGrpVals + 32 + 8;
+}
+__device__ inline void tail_carve(float* base, int N, int P, int G, TailSmem& s) {
+	s.dimp = 6 * (N - 1); s.ld = s.dimp | 1;
+	float* q = base;
+	s.T = q; q += N * 12;
+	s.A = q; q += s.dimp * s.ld;
+	s.rhs = q; q += s.dimp; s.Minv = q; q += s.dimp; s.r = q; q += s.dimp; s.z = q; q += s.dimp;
+	s.p = q; q += s.dimp; s.Ap = q; q += s.dimp; s.delta = q; q += s.dimp;
+	s.pairRaw = q; q += P * kTileVals; s.pairW = q; q += P * kTileVals;
+	s.grp = q; q += G * kGrpVals;
+	s.red = q;
+}
+__device__ __forceinline__ float block_sum(float v, float* red) {   // all kThreads threads; result broadcast
+	v = warp_sum(v);
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	__syncthreads();
+	if (lane == 0) red[wid] = v;
+	__syncthreads();
+	float t = 0.f;
+#pragma unroll
+	for (int k = 0; k < kWarps; k++) t += red[k];
+	return t;
+}
+// index of (r,c), r<=c, in the packed upper triangle of a symmetric 6x6
+__device__ __forceinline__ int sym6(int r, int c) { if (r > c) { const int t = r; r = c; c = t; } return r * 6 - (r * (r - 1)) / 2 + (c - r); }
+__device__ __forceinline__ float skew(const float v[3], int a, int b) {   // [v]x (a,b)
+	if (a == b) return 0.f;
+	const int k = 3 - a - b;                       // the remaining axis
+	const float s = ((b - a + 3) % 3 == 1) ? -1.f : 1.f;   // (0,1):-vz (1,2):-vx (2,0):-vy ; transposed: +
+	return s * v[k];
+}
+
+__device__ void window_tail(const SolveArgs& a, const WinDesc& wd, int w, int it, float* smem_base) {
+	const int tid = threadIdx.x, lane = tid & 31;
+	const int N = wd.n_frames, P = wd.n_pairs, G = wd.n_groups;
+	TailSmem s;
+	tail_carve(smem_base, N, P, G, s);
+	const int dimp = s.dimp, ld = s.ld;
+	const float wS = a.prm.w_sparse;
+	const bool use_dense = a.prm.w_dense > 0.f && P > 0;
+
+	// ---- P0: poses of this iteration + zero the system
+	for (int k = tid; k < N * 12; k += kThreads) s.T[k] = __ldcg(a.T + (size_t)wd.frame_off * 12 + k);
+	for (int k = tid; k < dimp * ld; k += kThreads) s.A[k] = 0.f;
+	__syncthreads();
+
+	// ---- P1: sparse moment sums, 8 lanes per (i,j) group of correspondences
+	{
+		const int sub = tid >> 3, sl = tid & 7, nsub = kThreads >> 3;
+		for (int g0 = 0; g0 < G; g0 += nsub) {
+			const int g = g0 + sub;
+			float m[kGrpVals];
+#pragma unroll
+			for (int k = 0; k < kGrpVals; k++) m[k] = 0.f;
+			if (g < G) {
+				const int gi = a.grp_i[wd.grp_off + g], gj = a.grp_j[wd.grp_off + g];
+				const int c0 = a.grp_start[wd.grp_off + w + g], c1 = a.grp_start[wd.grp_off + w + g + 1];
+				const float* Ti = s.T + gi * 12; const float* Tj = s.T + gj * 12;
+				for (int c = c0 + sl; c < c1; c += 8) {
+					const float4* e4 = reinterpret_cast<const float4*>(a.corr + wd.corr_off + c);
+					const float4 lo = __ldg(e4), hi = __ldg(e4 + 1);   // {i, j, pi.x, pi.y}, {pi.z, pj.x, pj.y, pj.z}
+					const float pix = lo.z, piy = lo.w, piz = hi.x, pjx = hi.y, pjy = hi.z, pjz = hi.w;
+					const V3 q = mk(Ti[0] * pix + Ti[1] * piy + Ti[2] * piz + Ti[3], Ti[4] * pix + Ti[5] * piy + Ti[6] * piz + Ti[7], Ti[8] * pix + Ti[9] * piy + Ti[10] * piz + Ti[11]);
+					const V3 sp = mk(Tj[0] * pjx + Tj[1] * pjy + Tj[2] * pjz + Tj[3], Tj[4] * pjx + Tj[5] * pjy + Tj[6] * pjz + Tj[7], Tj[8] * pjx + Tj[9] * pjy + Tj[10] * pjz + Tj[11]);
+					const V3 rr = q - sp;
+					const float rho = huber_w(dot(rr, rr), a.prm.robust_delta);
+					m[0] += 1.f;
+					m[1] += q.x; m[2] += q.y; m[3] += q.z;
+					m[4] += sp.x; m[5] += sp.y; m[6] += sp.z;
+					m[7] += q.x * q.x; m[8] += q.x * q.y; m[9] += q.x * q.z; m[10] += q.y * q.y; m[11] += q.y * q.z; m[12] += q.z * q.z;
+					m[13] += sp.x * sp.x; m[14] += sp.x * sp.y; m[15] += sp.x * sp.z; m[16] += sp.y * sp.y; m[17] += sp.y * sp.z; m[18] += sp.z * sp.z;
+					m[19] += sp.x * q.x; m[20] += sp.x * q.y; m[21] += sp.x * q.z;      // Qsq[a][b] = sum s_a q_b
+					m[22] += sp.y * q.x; m[23] += sp.y * q.y; m[24] += sp.y * q.z;
+					m[25] += sp.z * q.x; m[26] += sp.z * q.y; m[27] += sp.z * q.z;
+					const V3 gq = cross(q, rr), gs = cross(sp, rr);
+					m[28] += rho * gq.x; m[29] += rho * gq.y; m[30] += rho * gq.z;
+					m[31] += rho * gs.x; m[32] += rho * gs.y; m[33] += rho * gs.z;
+					m[34] += rho * rr.x; m[35] += rho * rr.y; m[36] += rho * rr.z;
+					m[37] += rho * q.x * q.x; m[38] += rho * q.y * q.y; m[39] += rho * q.z * q.z;
+					m[40] += rho * sp.x * sp.x; m[41] += rho * sp.y * sp.y; m[42] += rho * sp.z * sp.z;
+					m[43] += rho;
+				}
+			}
+#pragma unroll
+			for (int k = 0; k < kGrpVals; k++) {
+				float v = m[k];
+				v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 1);
+				if (g < G && sl == 0) s.grp[g * kGrpVals + k] = v;
+			}
+		}
+	}
+	// ---- P2a: per-pair sums over this window's tiles (target-frame)
+	if (use_dense) {
+		// a pair's tiles are consecutive in the window's tile list: fixed summation order => deterministic
+		for (int k = tid; k < P * kTileVals; k += kThreads) {
+			const int p = k / kTileVals, e = k - p * kTileVals;
+			const int t0 = wd.tile_off + a.pair_tile0[wd.pair_off + p], nt = a.pair_ntile[wd.pair_off + p];
+			float v = 0.f;
+			for (int c = 0; c < nt; c++) v += __ldcg(a.partial + (size_t)(t0 + c) * kTileVals + e);
+			s.pairRaw[k] = v;
+			if (a.dbg_cnt && e == 27 && it == a.prm.num_iter_outer - 1) a.dbg_cnt[(size_t)w * a.dbg_cnt_stride + p] = v;
+		}
+	}
+	__syncthreads();
+	// ---- P2b: target frame -> model frame:  S = X S' X^T, b = X b',  X = [[R,0],[[t]x R, R]]  (T of the TARGET frame)
+	if (use_dense) {
+		for (int k = tid; k < P * 27; k += kThreads) {
+			const int p = k / 27, e = k - p * 27;
+			const uint2 pr = a.pairs[wd.pair_off + p];
+			const float* Tt = s.T + pr.x * 12;
+			const float* raw = s.pairRaw + p * kTileVals;
+			// row r of X (6 entries)
+			auto Xrc = [&](int r, int c) -> float {
+				if (r < 3) return (c < 3) ? Tt[r * 4 + c] : 0.f;
+				const int rr = r - 3;
+				if (c >= 3) return Tt[rr * 4 + (c - 3)];
+				// ([t]x R)(rr, c) = sum_k [t]x(rr,k) R(k,c)
+				const float t3[3] = { Tt[3], Tt[7], Tt[11] };
+				float v = 0.f;
+				for (int kk = 0; kk < 3; kk++) v += skew(t3, rr, kk) * Tt[kk * 4 + c];
+				return v;
+			};
+			float out = 0.f;
+			if (e < 21) {
+				int r = 0, rem = e;
+				while (rem >= 6 - r) { rem -= 6 - r; r++; }
+				const int c = r + rem;
+				for (int u = 0; u < 6; u++) {
+					const float xr = Xrc(r, u);
+					if (xr == 0.f) continue;
+					float tsum = 0.f;
+					for (int v = 0; v < 6; v++) tsum += raw[sym6(u, v)] * Xrc(c, v);
+					out += xr * tsum;
+				}
+			} else {
+				const int r = e - 21;
+				for (int u = 0; u < 6; u++) out += Xrc(r, u) * raw[21 + u];
+			}
+			s.pairW[p * kTileVals + e] = out;
+		}
+	}
+	__syncthreads();
+	// ---- P3: diagonal blocks, right-hand side, Jacobi preconditioner — gathered per (frame, entry), no atomics
+	{
+		const int per = 21 + 6 + 6;
+		for (int k = tid; k < (N - 1) * per; k += kThreads) {
+			const int f = 1 + k / per, e = k % per;
+			const int base = (f - 1) * 6;
+			if (e < 21) {
+				int r = 0, rem = e;
+				while (rem >= 6 - r) { rem -= 6 - r; r++; }
+				const int c = r + rem;
+				float sp = 0.f, dn = 0.f;
+				for (int g = 0; g < G; g++) {
+					const int gi = a.grp_i[wd.grp_off + g], gj = a.grp_j[wd.grp_off + g];
+					if (gi != f && gj != f) continue;
+					const float* m = s.grp + g * kGrpVals;
+					const float* S1 = (gi == f) ? (m + 1) : (m + 4);       // sum of model-frame points on this frame's side
+					const float* Q = (gi == f) ? (m + 7) : (m + 13);       // xx xy xz yy yz zz
+					if (r < 3 && c < 3) sp += (r == c) ? m[0] : 0.f;                                   // TT = n I
+					else if (r < 3) sp += -skew(S1, r, c - 3);                                         // TR = -[S1]x
+					else { const int ra = r - 3, cb = c - 3; const float tr = Q[0] + Q[3] + Q[5];
+						const int qi = (ra == 0) ? cb : (ra == 1 ? 2 + cb : 5);                         // packed index of (ra,cb), ra<=cb
+						sp += ((ra == cb) ? tr : 0.f) - Q[qi]; }
+					if (gi == f && gj == f) { /* degenerate self pair: ignored */ }
+				}
+				if (use_dense) for (int p = 0; p < P; p++) {
+					const uint2 pr = a.pairs[wd.pair_off + p];
+					if ((int)pr.x == f || (int)pr.y == f) dn += s.pairW[p * kTileVals + e];
+				}
+				const float v = wS * sp + dn;
+				s.A[(base + r) * ld + base + c] = v;
+				s.A[(base + c) * ld + base + r] = v;
+				if (a.dbg_JtJ && it == a.prm.num_iter_outer - 1) {
+					float* D = a.dbg_JtJ + (size_t)w * a.dbg_stride * a.dbg_stride;
+					const int dim = 6 * N;
+					D[(f * 6 + r) * dim + f * 6 + c] = dn; D[(f * 6 + c) * dim + f * 6 + r] = dn;
+				}
+			} else if (e < 27) {
+				const int r = e - 21;
+				float gs = 0.f, dn = 0.f;
+				for (int g = 0; g < G; g++) {
+					const int gi = a.grp_i[wd.grp_off + g], gj = a.grp_j[wd.grp_off + g];
+					const float* m = s.grp + g * kGrpVals;
+					if (gi == f) gs += (r < 3) ? m[34 + r] : m[28 + (r - 3)];
+					else if (gj == f) gs -= (r < 3) ? m[34 + r] : m[31 + (r - 3)];
+				}
+				if (use_dense) for (int p = 0; p < P; p++) {
+					const uint2 pr = a.pairs[wd.pair_off + p];
+					if ((int)pr.x == f) dn += s.pairW[p * kTileVals + 21 + r];
+					else if ((int)pr.y == f) dn -= s.pairW[p * kTileVals + 21 + r];
+				}
+				s.rhs[base + r] = -wS * gs - dn;
+				if (a.dbg_Jtr && it == a.prm.num_iter_outer - 1) a.dbg_Jtr[(size_t)w * a.dbg_stride + f * 6 + r] = dn;
+			} else {
+				const int r = e - 27;
+				float pc = 0.f;
+				for (int g = 0; g < G; g++) {
+					const int gi = a.grp_i[wd.grp_off + g], gj = a.grp_j[wd.grp_off + g];
+					if (gi != f && gj != f) continue;
+					const float* m = s.grp + g * kGrpVals;
+					const float* Pw = (gi == f) ? (m + 37) : (m + 40);
+					if (r < 3) pc += m[43];
+					else { const int ax = r - 3; pc += Pw[(ax + 1) % 3] + Pw[(ax + 2) % 3]; }
+				}
+				s.Minv[base + r] = (pc > kEps) ? 1.0f / pc : 1.0f;
+			}
+		}
+	}
+	__syncthreads();
+	// ---- P4a: sparse cross blocks (i,j): J_i^T J_j, both frames free
+	for (int k = tid; k < G * 36; k += kThreads) {
+		const int g = k / 36, e = k - g * 36, r = e / 6, c = e - r * 6;
+		const int gi = a.grp_i[wd.grp_off + g], gj = a.grp_j[wd.grp_off + g];
+		if (gi < 1 || gj < 1 || gi == gj) continue;
+		const float* m = s.grp + g * kGrpVals;
+		float v;
+		if (r < 3 && c < 3) v = (r == c) ? -m[0] : 0.f;                 // TT = -n I
+		else if (r < 3) v = skew(m + 4, r, c - 3);                       // TR = [sum s]x
+		else if (c < 3) v = -skew(m + 1, r - 3, c);                      // RT = -[sum q]x
+		else { const int ra = r - 3, cb = c - 3; const float tr = m[19] + m[23] + m[27];
+			v = -(((ra == cb) ? tr : 0.f) - m[19 + ra * 3 + cb]); }        // RR = -((q.s) I - s q^T)
+		v *= wS;
+		atomicAdd(&s.A[((gi - 1) * 6 + r) * ld + (gj - 1) * 6 + c], v);
+		atomicAdd(&s.A[((gj - 1) * 6 + c) * ld + (gi - 1) * 6 + r], v);
+	}
+	__syncthreads();
+	// ---- P4b: dense cross blocks: -S for pairs whose cross block survives FlipJtJ (target < source) or all if !compat
+	if (use_dense) {
+		for (int k = tid; k < P * 36; k += kThreads) {
+			const int p = k / 36, e = k - p * 36, r = e / 6, c = e - r * 6;
+			const uint2 pr = a.pairs[wd.pair_off + p];
+			const int ti = (int)pr.x, sj = (int)pr.y;
+			if (ti < 1 || sj < 1) continue;
+			if (wd.compat_flip && !(ti < sj)) continue;
+			const float v = -s.pairW[p * kTileVals + sym6(r, c)];
+			atomicAdd(&s.A[((sj - 1) * 6 + r) * ld + (ti - 1) * 6 + c], v);
+			atomicAdd(&s.A[((ti - 1) * 6 + c) * ld + (sj - 1) * 6 + r], v);
+			if (a.dbg_JtJ && it == a.prm.num_iter_outer - 1) {
+				float* D = a.dbg_JtJ + (size_t)w * a.dbg_stride * a.dbg_stride;
+				const int dim = 6 * N;
+				atomicAdd(&D[(sj * 6 + r) * dim + ti * 6 + c], v);
+				atomicAdd(&D[(ti * 6 + c) * dim + sj * 6 + r], v);
+			}
+		}
+	}
+	__syncthreads();
+
+	// ---- PCG (PCGInit_Kernel1/2, PCGStep_Kernel*): SolverBundling.cu:575-818
+	float rz;
+	{
+		float d = 0.f;
+		for (int k = tid; k < dimp; k += kThreads) {
+			const float rv = s.rhs[k], pv = s.Minv[k] * rv;
+			s.r[k] = rv; s.p[k] = pv; s.delta[k] = 0.f;
+			d += rv * pv;
+		}
+		rz = block_sum(d, s.red);
+	}
+	for (int lin = 0; lin < a.prm.num_iter_inner; lin++) {
+		__syncthreads();
+		// Ap = A p : 4 lanes per row
+		{
+			const int row = tid >> 2, q4 = tid & 3;
+			for (int r0 = 0; r0 < dimp; r0 += kThreads / 4) {
+				const int r = r0 + row;
+				float acc = 0.f;
+				if (r < dimp) for (int c = q4; c < dimp; c += 4) acc += s.A[r * ld + c] * s.p[c];
+				acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+				acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+				if (r < dimp && q4 == 0) s.Ap[r] = acc;
+			}
+		}
+		__syncthreads();
+		float d = 0.f;
+		for (int k = tid; k < dimp; k += kThreads) d += s.p[k] * s.Ap[k];
+		const float pAp = block_sum(d, s.red);
+		const float alpha = (pAp > kEps) ? rz / pAp : 0.f;
+		float bsum = 0.f;
+		for (int k = tid; k < dimp; k += kThreads) {
+			s.delta[k] += alpha * s.p[k];
+			const float rv = s.r[k] - alpha * s.Ap[k];
+			s.r[k] = rv;
+			const float zv = s.Minv[k] * rv;
+			s.z[k] = zv;
+			bsum += zv * rv;
+		}
+		const float rz_new = block_sum(bsum, s.red);
+		const float beta = (rz > kEps) ? rz_new / rz : 0.f;
+		rz = rz_new;
+		for (int k = tid; k < dimp; k += kThreads) s.p[k] = s.z[k] + beta * s.p[k];
+	}
+	__syncthreads();
+	// ---- pose update: x <- log(exp(delta) * exp(x))  (computeLieUpdate), new T for the next iteration
+	const bool last = (it == a.prm.num_iter_outer - 1);
+	for (int f = tid; f < N; f += kThreads) {
+		float* xg = a.x + (size_t)(wd.frame_off + f) * 6;
+		V3 rot = mk(__ldcg(xg + 0), __ldcg(xg + 1), __ldcg(xg + 2)), trans = mk(__ldcg(xg + 3), __ldcg(xg + 4), __ldcg(xg + 5));
+		float Tn[12];
+		if (f >= 1) {
+			const float* dl = s.delta + (f - 1) * 6;
+			float U[12], Cm[12];
+			se3_exp(mk(dl[3], dl[4], dl[5]), mk(dl[0], dl[1], dl[2]), U);
+			se3_exp(rot, trans, Cm);
+			for (int r = 0; r < 3; r++) {
+				for (int c = 0; c < 4; c++) {
+					float v = U[r * 4 + 0] * Cm[0 * 4 + c] + U[r * 4 + 1] * Cm[1 * 4 + c] + U[r * 4 + 2] * Cm[2 * 4 + c];
+					if (c == 3) v += U[r * 4 + 3];
+					Tn[r * 4 + c] = v;
+				}
+			}
+			se3_log(Tn, rot, trans);
+			__stcg(xg + 0, rot.x); __stcg(xg + 1, rot.y); __stcg(xg + 2, rot.z); __stcg(xg + 3, trans.x); __stcg(xg + 4, trans.y); __stcg(xg + 5, trans.z);
+		}
+		se3_exp(rot, trans, Tn);
+		float* Tg = a.T + (size_t)(wd.frame_off + f) * 12;
+		for (int k = 0; k < 12; k++) __stcg(Tg + k, Tn[k]);
+		if (last) {   // convertPosesToMatricesCU (SBA.cu:97-104)
+			float* Po = a.pose_out + (size_t)(wd.frame_off + f) * 16;
+			for (int k = 0; k < 12; k++) Po[k] = Tn[k];
+			Po[12] = 0.f; Po[13] = 0.f; Po[14] = 0.f; Po[15] = 1.f;
+		}
+	}
+	(void)lane;
+}
+
+// ------------------------------------------------------------------------------------------------ k_solve
+__global__ void __launch_bounds__(kThreads, 2) k_solve(SolveArgs a) {
+	extern __shared__ __align__(16) float dyn_smem[];
+	__shared__ int s_tile;
+	__shared__ float s_M[12];
+	__shared__ float s_part[kWarps][kTileVals];
+	__shared__ int s_is_last;
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const int total = *a.n_tiles_total;
+	if (total <= 0) return;
+	const long long all = (long long)total * a.prm.num_iter_outer;
+	for (;;) {
+		__syncthreads();
+		if (tid == 0) s_tile = atomicAdd(a.queue, 1);
+		__syncthreads();
+		const long long t = s_tile;
+		if (t >= all) break;
+		const int it = (int)(t / total), tl_idx = (int)(t - (long long)it * total);
+		const Tile tl = a.tiles[tl_idx];
+		const WinDesc wd = a.wins[tl.win];
+		if (it > 0) {   // this window's previous GN iteration must have published its poses
+			if (tid == 0) { while (ld_acquire(a.iter_done + tl.win) < it) __nanosleep(64); }
+			__syncthreads();
+		}
+		TileAcc acc;
+#pragma unroll
+		for (int k = 0; k < kTileVals; k++) acc.v[k] = 0.f;
+		if (tl.pair >= 0) {
+			const uint2 pr = a.pairs[wd.pair_off + tl.pair];   // x = target i, y = source j
+			if (tid < 12) {   // transform = T_i^-1 T_j (rigid inverse), row r, col c
+				const float* Ti = a.T + (size_t)(wd.frame_off + pr.x) * 12;
+				const float* Tj = a.T + (size_t)(wd.frame_off + pr.y) * 12;
+				const int r = tid >> 2, c = tid & 3;
+				float v = 0.f;
+				for (int k = 0; k < 3; k++) {
+					const float rik = __ldcg(Ti + k * 4 + r);          // R_i^T (r,k) = R_i(k,r)
+					v += rik * ((c < 3) ? __ldcg(Tj + k * 4 + c) : (__ldcg(Tj + k * 4 + 3) - __ldcg(Ti + k * 4 + 3)));
+				}
+				s_M[tid] = v;
+			}
+			__syncthreads();
+			const float4* src = a.src + (size_t)(wd.frame_off + pr.y) * 2 * a.npix_max;
+			const float4* tex = a.texel + (size_t)(wd.frame_off + pr.x) * 2 * a.npix_max;
+			tile_pixels(a, wd, src, tex, s_M, tl.start, tl.count, acc);
+		}
+		// block reduction of the 28 sums -> this tile's slot
+#pragma unroll
+		for (int k = 0; k < kTileVals; k++) {
+			const float v = warp_sum(acc.v[k]);
+			if (lane == 0) s_part[wid][k] = v;
+		}
+		__syncthreads();
+		if (tid < kTileVals) {
+			float v = 0.f;
+#pragma unroll
+			for (int k = 0; k < kWarps; k++) v += s_part[k][tid];
+			__stcg(a.partial + (size_t)tl_idx * kTileVals + tid, v);
+		}
+		__threadfence();
+		__syncthreads();
+		if (tid == 0) {
+			const int done = atomicAdd(a.tiles_done + tl.win, 1) + 1;
+			s_is_last = (done == (it + 1) * wd.n_tiles);
+			if (s_is_last) __threadfence();
+		}
+		__syncthreads();
+		if (s_is_last) {
+			window_tail(a, wd, tl.win, it, dyn_smem);
+			__threadfence();
+			__syncthreads();
+			if (tid == 0) st_release(a.iter_done + tl.win, it + 1);
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct SolverState {
+	bt_solver_limits lim{};
+	int npix_max = 0, max_pairs = 0, max_frames_total = 0, max_tiles = 0, max_groups = 0;
+	DevBuf wins, depth_ptr, normal_ptr, frame_win, texel, src, nsrc, pose_in, x, T, pose_out, corr, grp_i, grp_j, grp_start, pairs,
+	    tiles, scalars, partial, tiles_done, iter_done, pair_tile0, pair_ntile, dbgJ, dbgR, dbgC;
+	PinnedBuf h_stage, h_poses;
+	// last staged batch
+	int n_windows = 0, frames_total = 0, smem_bytes = 0, chunk = 1024;
+	bt_solver_params prm{};
+	std::vector<int> frame_off;
+	std::vector<int> n_frames;
+	bool staged = false, debug = false, timing = false;
+	int launches = 0;
+	cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+};
+
+void solver_destroy(bt_ctx* ctx) {
+	SolverState* s = ctx->solver;
+	if (!s) return;
+	DevBuf* bufs[] = { &s->wins, &s->depth_ptr, &s->normal_ptr, &s->frame_win, &s->texel, &s->src, &s->nsrc, &s->pose_in, &s->x, &s->T,
+	                   &s->pose_out, &s->corr, &s->grp_i, &s->grp_j, &s->grp_start, &s->pairs, &s->tiles, &s->scalars, &s->partial,
+	                   &s->tiles_done, &s->iter_done, &s->pair_tile0, &s->pair_ntile, &s->dbgJ, &s->dbgR, &s->dbgC };
+	for (DevBuf* b : bufs) b->release();
+	s->h_stage.release(); s->h_poses.release();
+	for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+	delete s;
+	ctx->solver = nullptr;
+}
+
+static int reserve_impl(bt_ctx* ctx, const bt_solver_limits* lim) {
+	if (!ctx->solver) ctx->solver = new SolverState();
+	SolverState* s = ctx->solver;
+	BT_REQUIRE(lim->max_windows > 0 && lim->max_frames >= 2 && lim->max_frames <= kMaxFrames && lim->max_corr >= 0 && lim->H > 0 && lim->W > 0 && lim->image_downscale >= 1.0f,
+	           BT_ERR_INVALID_ARG, "bt_solver_reserve: bad limits (max_frames must be 2..%d)", kMaxFrames);
+	s->lim = *lim;
+	const int w = (int)(lim->W / lim->image_downscale), h = (int)(lim->H / lim->image_downscale);
+	s->npix_max = w * h;
+	const int F = lim->max_windows * lim->max_frames;
+	s->max_frames_total = F;
+	s->max_pairs = lim->max_frames * (lim->max_frames - 1);   // both directions allowed in custom lists
+	s->max_groups = lim->max_frames * lim->max_frames;
+	const int min_chunk = 256;   // worst case: every pixel valid at the smallest chunk the scheduler ever picks
+	s->max_tiles = lim->max_windows * (lim->max_frames * (lim->max_frames - 1) / 2) * ((s->npix_max + min_chunk - 1) / min_chunk + 1);
+	int rc;
+#define RES(buf, bytes) if ((rc = s->buf.alloc(bytes)) != BT_OK) return rc
+	RES(wins, sizeof(WinDesc) * lim->max_windows);
+	RES(depth_ptr, sizeof(void*) * F); RES(normal_ptr, sizeof(void*) * F); RES(frame_win, sizeof(int) * F);
+	RES(texel, sizeof(float4) * 2 * (size_t)s->npix_max * F);
+	RES(src, sizeof(float4) * 2 * (size_t)s->npix_max * F);
+	RES(nsrc, sizeof(int) * F);
+	RES(pose_in, sizeof(float) * 16 * F); RES(x, sizeof(float) * 6 * F); RES(T, sizeof(float) * 12 * F); RES(pose_out, sizeof(float) * 16 * F);
+	RES(corr, sizeof(bt_entryj) * (size_t)lim->max_corr * lim->max_windows + 32);
+	RES(grp_i, sizeof(int) * (size_t)s->max_groups * lim->max_windows);
+	RES(grp_j, sizeof(int) * (size_t)s->max_groups * lim->max_windows);
+	RES(grp_start, sizeof(int) * ((size_t)s->max_groups + 1) * lim->max_windows);
+	RES(pairs, sizeof(uint2) * (size_t)s->max_pairs * lim->max_windows);
+	RES(pair_tile0, sizeof(int) * (size_t)s->max_pairs * lim->max_windows);
+	RES(pair_ntile, sizeof(int) * (size_t)s->max_pairs * lim->max_windows);
+	RES(tiles, sizeof(Tile) * (size_t)s->max_tiles);
+	RES(partial, sizeof(float) * kTileVals * (size_t)s->max_tiles);
+	RES(scalars, 64);
+	RES(tiles_done, sizeof(int) * lim->max_windows); RES(iter_done, sizeof(int) * lim->max_windows);
+#undef RES
+	return BT_OK;
+}
+
+}  // namespace bt
+
+using namespace bt;
+
+extern "C" int bt_solver_reserve(bt_ctx* ctx, const bt_solver_limits* lim) {
+	BT_REQUIRE(ctx && lim, BT_ERR_INVALID_ARG, "bt_solver_reserve: NULL argument");
+	BT_CUDA(cudaSetDevice(ctx->device));
+	return reserve_impl(ctx, lim);
+}
+
+extern "C" int bt_solve_enable_debug(bt_ctx* ctx, int on) {
+	BT_REQUIRE(ctx && ctx->solver, BT_ERR_INVALID_ARG, "bt_solve_enable_debug: call bt_solver_reserve first");
+	ctx->solver->debug = on != 0;
+	return BT_OK;
+}
+
+extern "C" int bt_solve_enable_timing(bt_ctx* ctx, int on) {
+	BT_REQUIRE(ctx && ctx->solver, BT_ERR_INVALID_ARG, "bt_solve_enable_timing: call bt_solver_reserve first");
+	SolverState* s = ctx->solver;
+	if (on) for (auto& e : s->ev) if (!e) BT_CUDA(cudaEventCreate(&e));
+	s->timing = on != 0;
+	return BT_OK;
+}
+
+// Device time of the three kernels of the LAST bt_solve_run (prep, plan, solve), from CUDA events recorded on the
+// launching stream.  Synchronises on the last event.
+extern "C" int bt_solve_get_timing(bt_ctx* ctx, float* ms3) {
+	BT_REQUIRE(ctx && ctx->solver && ctx->solver->timing && ms3, BT_ERR_INVALID_ARG, "bt_solve_get_timing: timing not enabled");
+	SolverState* s = ctx->solver;
+	BT_CUDA(cudaEventSynchronize(s->ev[3]));
+	for (int k = 0; k < 3; k++) BT_CUDA(cudaEventElapsedTime(ms3 + k, s->ev[k], s->ev[k + 1]));
+	return BT_OK;
+}
+
+extern "C" int bt_solve_stage(bt_ctx* ctx, int n_windows, const bt_window* windows, const bt_solver_params* params,
+                              const float* poses_in, void* stream_) {
+	BT_REQUIRE(ctx && windows && params && poses_in, BT_ERR_INVALID_ARG, "bt_solve_stage: NULL argument");
+	BT_REQUIRE(ctx->solver, BT_ERR_INVALID_ARG, "bt_solve_stage: call bt_solver_reserve first");
+	SolverState* s = ctx->solver;
+	cudaStream_t stream = (cudaStream_t)stream_;
+	BT_CUDA(cudaSetDevice(ctx->device));
+	BT_REQUIRE(n_windows > 0 && n_windows <= s->lim.max_windows, BT_ERR_CAPACITY, "bt_solve_stage: %d windows > reserved %d", n_windows, s->lim.max_windows);
+	BT_REQUIRE(params->num_iter_outer > 0 && params->num_iter_inner > 0 && params->image_downscale == s->lim.image_downscale, BT_ERR_INVALID_ARG,
+	           "bt_solve_stage: iteration counts must be positive and image_downscale must equal the reserved value");
+	s->staged = false;
+	// ---- sizes
+	size_t F = 0, C = 0, G = 0, P = 0;
+	for (int w = 0; w < n_windows; w++) {
+		const bt_window& bw = windows[w];
+		BT_REQUIRE(bw.n_frames >= 2 && bw.n_frames <= s->lim.max_frames, BT_ERR_CAPACITY, "window %d: n_frames %d outside [2,%d]", w, bw.n_frames, s->lim.max_frames);
+		BT_REQUIRE(bw.n_corr >= 0 && bw.n_corr <= s->lim.max_corr, BT_ERR_CAPACITY, "window %d: n_corr %d > reserved %d", w, bw.n_corr, s->lim.max_corr);
+		BT_REQUIRE(bw.H > 0 && bw.W > 0 && bw.H <= s->lim.H && bw.W <= s->lim.W, BT_ERR_CAPACITY, "window %d: image %dx%d larger than reserved", w, bw.W, bw.H);
+		BT_REQUIRE((int)(bw.W / params->image_downscale) >= 2 && (int)(bw.H / params->image_downscale) >= 2, BT_ERR_INVALID_ARG, "window %d: image too small", w);
+		BT_REQUIRE(bw.n_corr == 0 || bw.corr, BT_ERR_INVALID_ARG, "window %d: corr is NULL", w);
+		BT_REQUIRE(params->w_dense <= 0.f || (bw.depth_dev && bw.normal_dev), BT_ERR_INVALID_ARG, "window %d: depth/normal pointers are NULL", w);
+		F += bw.n_frames; C += bw.n_corr;
+	}
+	// ---- host staging: one pinned block, one H2D per array
+	const size_t maxP = (size_t)s->max_pairs, maxG = (size_t)s->max_groups;
+	size_t off = 0;
+	auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+	const size_t o_wins = carve(sizeof(WinDesc) * n_windows), o_dp = carve(sizeof(void*) * F), o_np = carve(sizeof(void*) * F), o_fw = carve(sizeof(int) * F),
+	             o_pose = carve(sizeof(float) * 16 * F), o_corr = carve(sizeof(bt_entryj) * C + 32), o_gi = carve(sizeof(int) * maxG * n_windows),
+	             o_gj = carve(sizeof(int) * maxG * n_windows), o_gs = carve(sizeof(int) * (maxG + 1) * n_windows), o_pairs = carve(sizeof(uint2) * maxP * n_windows);
+	int rc = s->h_stage.alloc(off);
+	if (rc != BT_OK) return rc;
+	char* hb = s->h_stage.as<char>();
+	WinDesc* hw = (WinDesc*)(hb + o_wins);
+	const void** hdp = (const void**)(hb + o_dp); const void** hnp = (const void**)(hb + o_np);
+	int* hfw = (int*)(hb + o_fw); float* hpose = (float*)(hb + o_pose); bt_entryj* hcorr = (bt_entryj*)(hb + o_corr);
+	int* hgi = (int*)(hb + o_gi); int* hgj = (int*)(hb + o_gj); int* hgs = (int*)(hb + o_gs); uint2* hpairs = (uint2*)(hb + o_pairs);
+	s->frame_off.assign(n_windows, 0); s->n_frames.assign(n_windows, 0);
+	size_t f_off = 0, c_off = 0, g_off = 0, p_off = 0, smem_need = 0;
+	std::vector<int> bin, order;
+	for (int w = 0; w < n_windows; w++) {
+		const bt_window& bw = windows[w];
+		const int N = bw.n_frames;
+		WinDesc& d = hw[w];
+		memset(&d, 0, sizeof d);
+		d.n_frames = N; d.H = bw.H; d.W = bw.W;
+		d.w = (int)(bw.W / params->image_downscale); d.h = (int)(bw.H / params->image_downscale);   // LossGPU.cu:56-57
+		d.fx = bw.fx * ((float)d.w / (float)bw.W); d.fy = bw.fy * ((float)d.h / (float)bw.H);         // CUDACache.cpp:20-24
+		d.cx = bw.cx * ((float)(d.w - 1) / (float)(bw.W - 1)); d.cy = bw.cy * ((float)(d.h - 1) / (float)(bw.H - 1));
+		d.ifx = 1.0f / bw.fx; d.ify = 1.0f / bw.fy; d.icx = -bw.cx / bw.fx; d.icy = -bw.cy / bw.fy;
+		d.scaleW = (float)(bw.W - 1) / (float)(d.w - 1); d.scaleH = (float)(bw.H - 1) / (float)(d.h - 1);
+		d.compat_flip = bw.compat_flip;
+		d.frame_off = (int)f_off; d.corr_off = (int)c_off; d.grp_off = (int)g_off; d.pair_off = (int)p_off;
+		s->frame_off[w] = (int)f_off; s->n_frames[w] = N;
+		for (int f = 0; f < N; f++) {
+			hdp[f_off + f] = (params->w_dense > 0.f) ? bw.depth_dev[f] : nullptr;
+			hnp[f_off + f] = (params->w_dense > 0.f) ? bw.normal_dev[f] : nullptr;
+			hfw[f_off + f] = w;
+			memcpy(hpose + (f_off + f) * 16, poses_in + (f_off + f) * 16, sizeof(float) * 16);
+		}
+		// correspondences: stable counting sort by (i,j) so each pair's entries are contiguous (Bundler::optimizeGPU
+		// already emits them that way, /root/reference/src/Bundler.cpp:298-324); invalid entries are dropped.
+		bin.assign((size_t)N * N + 1, 0);
+		int n_valid = 0;
+		for (int c = 0; c < bw.n_corr; c++) {
+			const bt_entryj& e = bw.corr[c];
+			if (e.imgIdx_i == 0xFFFFFFFFu) continue;
+			BT_REQUIRE(e.imgIdx_i < (uint32_t)N && e.imgIdx_j < (uint32_t)N, BT_ERR_INVALID_ARG, "window %d: correspondence %d references frame outside [0,%d)", w, c, N);
+			bin[(size_t)e.imgIdx_i * N + e.imgIdx_j + 1]++;
+			n_valid++;
+		}
+		int ng = 0;
+		for (size_t b = 0; b < (size_t)N * N; b++) {
+			if (bin[b + 1] > 0) { hgi[g_off + ng] = (int)(b / N); hgj[g_off + ng] = (int)(b % N); ng++; }
+		}
+		for (size_t b = 0; b < (size_t)N * N; b++) bin[b + 1] += bin[b];
+		{   // group starts (relative to corr_off); stored at grp_off + w + g to leave room for the extra end entry
+			int gg = 0;
+			for (size_t b = 0; b < (size_t)N * N; b++) if (bin[b + 1] > bin[b]) hgs[g_off + w + gg++] = bin[b];
+			hgs[g_off + w + ng] = n_valid;
+		}
+		for (int c = 0; c < bw.n_corr; c++) {
+			const bt_entryj& e = bw.corr[c];
+			if (e.imgIdx_i == 0xFFFFFFFFu) continue;
+			hcorr[c_off + bin[(size_t)e.imgIdx_i * N + e.imgIdx_j]++] = e;
+		}
+		d.n_corr = n_valid; d.n_groups = ng;
+		// dense pairs
+		int np = 0;
+		if (params->w_dense > 0.f) {
+			if (bw.dense_pairs) {
+				BT_REQUIRE(bw.n_dense_pairs >= 0 && bw.n_dense_pairs <= s->max_pairs, BT_ERR_CAPACITY, "window %d: %d dense pairs > %d", w, bw.n_dense_pairs, s->max_pairs);
+				for (int p = 0; p < bw.n_dense_pairs; p++) {
+					const uint32_t ti = bw.dense_pairs[2 * p], sj = bw.dense_pairs[2 * p + 1];
+					BT_REQUIRE(ti < (uint32_t)N && sj < (uint32_t)N && ti != sj, BT_ERR_INVALID_ARG, "window %d: dense pair %d = (%u,%u) invalid", w, p, ti, sj);
+					hpairs[p_off + np++] = make_uint2(ti, sj);
+				}
+			} else {
+				for (int i = 0; i < N; i++) for (int j = 0; j < i; j++) hpairs[p_off + np++] = make_uint2((unsigned)i, (unsigned)j);
+			}
+		}
+		d.n_pairs = np;
+		smem_need = std::max(smem_need, tail_smem_floats(N, np, ng) * sizeof(float));
+		f_off += N; c_off += n_valid; g_off += ng; p_off += np;
+	}
+	BT_REQUIRE(smem_need <= 200 * 1024, BT_ERR_CAPACITY, "bt_solve_stage: window needs %zu bytes of shared memory (> 200 KB)", smem_need);
+	s->n_windows = n_windows; s->frames_total = (int)f_off; s->smem_bytes = (int)smem_need; s->prm = *params;
+	// chunk: aim for >= 4 tiles per SM-resident CTA over the batch, between 256 and 2048 source pixels
+	{
+		const long long est_px = (long long)p_off * (s->npix_max / 8);   // ~12 % valid
+		long long c = est_px / ((long long)ctx->sm_count * 2 * 4);
+		c = std::max(256LL, std::min(2048LL, c));
+		s->chunk = (int)((c + 255) / 256 * 256);
+	}
+#define UP(buf, ptr, bytes) BT_CUDA(cudaMemcpyAsync(s->buf.p, ptr, bytes, cudaMemcpyHostToDevice, stream))
+	UP(wins, hw, sizeof(WinDesc) * n_windows);
+	UP(depth_ptr, hdp, sizeof(void*) * F); UP(normal_ptr, hnp, sizeof(void*) * F); UP(frame_win, hfw, sizeof(int) * F);
+	UP(pose_in, hpose, sizeof(float) * 16 * F);
+	if (c_off) UP(corr, hcorr, sizeof(bt_entryj) * c_off);
+	UP(grp_i, hgi, sizeof(int) * std::max<size_t>(g_off, 1)); UP(grp_j, hgj, sizeof(int) * std::max<size_t>(g_off, 1));
+	UP(grp_start, hgs, sizeof(int) * (g_off + n_windows));
+	if (p_off) UP(pairs, hpairs, sizeof(uint2) * p_off);
+#undef UP
+	if (s->debug) {
+		const int st = 6 * s->lim.max_frames;
+		if ((rc = s->dbgJ.alloc(sizeof(float) * (size_t)st * st * s->lim.max_windows)) != BT_OK) return rc;
+		if ((rc = s->dbgR.alloc(sizeof(float) * (size_t)st * s->lim.max_windows)) != BT_OK) return rc;
+		if ((rc = s->dbgC.alloc(sizeof(float) * (size_t)s->max_pairs * s->lim.max_windows)) != BT_OK) return rc;
+	}
+	s->staged = true;
+	return BT_OK;
+}
+
+static SolveArgs make_args(bt_ctx* ctx) {
+	SolverState* s = ctx->solver;
+	SolveArgs a;
+	memset(&a, 0, sizeof a);
+	a.wins = s->wins.as<WinDesc>(); a.n_windows = s->n_windows;
+	a.depth_ptr = s->depth_ptr.as<const float*>(); a.normal_ptr = s->normal_ptr.as<const float4*>(); a.frame_win = s->frame_win.as<int>();
+	a.texel = s->texel.as<float4>(); a.src = s->src.as<float4>(); a.nsrc = s->nsrc.as<int>();
+	a.pose_in = s->pose_in.as<float>(); a.x = s->x.as<float>(); a.T = s->T.as<float>(); a.pose_out = s->pose_out.as<float>();
+	a.npix_max = s->npix_max;
+	a.corr = s->corr.as<bt_entryj>(); a.grp_i = s->grp_i.as<int>(); a.grp_j = s->grp_j.as<int>(); a.grp_start = s->grp_start.as<int>();
+	a.pairs = s->pairs.as<uint2>();
+	a.tiles = s->tiles.as<Tile>(); a.max_tiles = s->max_tiles; a.partial = s->partial.as<float>();
+	a.pair_tile0 = s->pair_tile0.as<int>(); a.pair_ntile = s->pair_ntile.as<int>();
+	a.n_tiles_total = s->scalars.as<int>(); a.queue = s->scalars.as<int>() + 1; a.n_src_px = (long long*)(s->scalars.as<char>() + 16);
+	a.tiles_done = s->tiles_done.as<int>(); a.iter_done = s->iter_done.as<int>();
+	a.chunk = s->chunk; a.prm = s->prm;
+	if (s->debug) { a.dbg_JtJ = s->dbgJ.as<float>(); a.dbg_Jtr = s->dbgR.as<float>(); a.dbg_stride = 6 * s->lim.max_frames; a.dbg_cnt = s->dbgC.as<float>(); a.dbg_cnt_stride = s->max_pairs; }
+	return a;
+}
+
+extern "C" int bt_solve_run(bt_ctx* ctx, void* stream_) {
+	BT_REQUIRE(ctx && ctx->solver && ctx->solver->staged, BT_ERR_INVALID_ARG, "bt_solve_run: nothing staged");
+	SolverState* s = ctx->solver;
+	cudaStream_t stream = (cudaStream_t)stream_;
+	BT_CUDA(cudaSetDevice(ctx->device));
+	SolveArgs a = make_args(ctx);
+	if (s->debug) {
+		BT_CUDA(cudaMemsetAsync(s->dbgJ.p, 0, s->dbgJ.bytes, stream));
+		BT_CUDA(cudaMemsetAsync(s->dbgR.p, 0, s->dbgR.bytes, stream));
+	}
+	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[0], stream));
+	k_prep_frames<<<s->frames_total, 512, 0, stream>>>(a);
+	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[1], stream));
+	k_plan<<<1, 1024, 0, stream>>>(a, s->wins.as<WinDesc>());
+	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[2], stream));
+	static bool attr_set = false;
+	static int attr_bytes = 0;
+	if (!attr_set || attr_bytes < s->smem_bytes) {
+		BT_CUDA(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(s->smem_bytes, 48 * 1024)));
+		attr_set = true; attr_bytes = std::max(s->smem_bytes, 48 * 1024);
+	}
+	int occ = 1;
+	BT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve, kThreads, s->smem_bytes));
+	if (occ < 1) occ = 1;
+	const int grid = ctx->sm_count * occ;
+	k_solve<<<grid, kThreads, s->smem_bytes, stream>>>(a);
+	BT_CUDA(cudaGetLastError());
+	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[3], stream));
+	s->launches = 3;
+	return BT_OK;
+}
+
+extern "C" int bt_solve_fetch(bt_ctx* ctx, float* poses_out, void* stream_) {
+	BT_REQUIRE(ctx && ctx->solver && ctx->solver->staged && poses_out, BT_ERR_INVALID_ARG, "bt_solve_fetch: nothing staged / NULL output");
+	SolverState* s = ctx->solver;
+	cudaStream_t stream = (cudaStream_t)stream_;
+	const size_t bytes = sizeof(float) * 16 * (size_t)s->frames_total;
+	int rc = s->h_poses.alloc(bytes + 64);
+	if (rc != BT_OK) return rc;
+	BT_CUDA(cudaMemcpyAsync(s->h_poses.p, s->pose_out.p, bytes, cudaMemcpyDeviceToHost, stream));
+	BT_CUDA(cudaMemcpyAsync(s->h_poses.as<char>() + bytes, s->scalars.p, 32, cudaMemcpyDeviceToHost, stream));
+	BT_CUDA(cudaStreamSynchronize(stream));
+	const int total = *(int*)(s->h_poses.as<char>() + bytes);
+	BT_REQUIRE(total >= 0, BT_ERR_CAPACITY, "bt_solve_fetch: tile list overflow (more dense tiles than reserved)");
+	memcpy(poses_out, s->h_poses.p, bytes);
+	return BT_OK;
+}
+
+extern "C" int bt_solve_windows(bt_ctx* ctx, int n_windows, const bt_window* windows, const bt_solver_params* params,
+                                float* poses_inout, void* stream) {
+	int rc = bt_solve_stage(ctx, n_windows, windows, params, poses_inout, stream);
+	if (rc != BT_OK) return rc;
+	rc = bt_solve_run(ctx, stream);
+	if (rc != BT_OK) return rc;
+	return bt_solve_fetch(ctx, poses_inout, stream);
+}
+
+extern "C" int bt_solve_get_stats(bt_ctx* ctx, bt_solve_stats* out) {
+	BT_REQUIRE(ctx && ctx->solver && out, BT_ERR_INVALID_ARG, "bt_solve_get_stats: NULL argument");
+	SolverState* s = ctx->solver;
+	char h[32];
+	BT_CUDA(cudaMemcpy(h, s->scalars.p, 32, cudaMemcpyDeviceToHost));
+	out->n_windows = s->n_windows;
+	out->n_tiles_total = *(int*)h;
+	out->n_kernel_launches = s->launches;
+	out->n_src_pixels = *(long long*)(h + 16);
+	return BT_OK;
+}
+
+extern "C" int bt_solve_debug_counts(bt_ctx* ctx, int w, int n_pairs, float* counts_out) {
+	BT_REQUIRE(ctx && ctx->solver && ctx->solver->debug && ctx->solver->staged && counts_out, BT_ERR_INVALID_ARG, "bt_solve_debug_counts: debug not enabled / nothing run");
+	SolverState* s = ctx->solver;
+	BT_REQUIRE(w >= 0 && w < s->n_windows && n_pairs >= 0 && n_pairs <= s->max_pairs, BT_ERR_INVALID_ARG, "bt_solve_debug_counts: bad index");
+	BT_CUDA(cudaDeviceSynchronize());
+	BT_CUDA(cudaMemcpy(counts_out, s->dbgC.as<float>() + (size_t)w * s->max_pairs, sizeof(float) * n_pairs, cudaMemcpyDeviceToHost));
+	return BT_OK;
+}
+
+extern "C" int bt_solve_debug_dense(bt_ctx* ctx, int w, float* JtJ_out, float* Jtr_out) {
+	BT_REQUIRE(ctx && ctx->solver && ctx->solver->debug && ctx->solver->staged, BT_ERR_INVALID_ARG, "bt_solve_debug_dense: debug not enabled / nothing run");
+	SolverState* s = ctx->solver;
+	BT_REQUIRE(w >= 0 && w < s->n_windows, BT_ERR_INVALID_ARG, "bt_solve_debug_dense: window %d out of range", w);
+	const int st = 6 * s->lim.max_frames, dim = 6 * s->n_frames[w];
+	BT_CUDA(cudaDeviceSynchronize());
+	if (JtJ_out) BT_CUDA(cudaMemcpy(JtJ_out, s->dbgJ.as<float>() + (size_t)w * st * st, sizeof(float) * dim * dim, cudaMemcpyDeviceToHost));
+	if (Jtr_out) BT_CUDA(cudaMemcpy(Jtr_out, s->dbgR.as<float>() + (size_t)w * st, sizeof(float) * dim, cudaMemcpyDeviceToHost));
+	return BT_OK;
+}

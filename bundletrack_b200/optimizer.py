@@ -1,0 +1,165 @@
+"""Host-side mirror of the reference's optimizer facade, on top of the C-ABI.
+
+`OptimizerGpu.optimizeFrames` keeps the reference's name, argument order and in-place pose semantics
+(/root/reference/src/cuda/LossGPU.h:50, LossGPU.cu:53-139): poses are cam->model 4x4, every frame of the window is
+overwritten with its optimised pose, frame 0 is the gauge.  `optimizeWindows` is the batched form (many independent
+windows in one persistent launch) that the reference does not have.  All arithmetic happens in
+lib/libbundletrack_b200.so on the GPU; this file only marshals pointers.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .config import solver_params
+from .synth import ENTRYJ_DTYPE
+
+
+def _ptr(x) -> int:
+    """Device pointer of a torch tensor / anything with data_ptr(), or a raw integer address."""
+    if hasattr(x, "data_ptr"):
+        return int(x.data_ptr())
+    return int(x)
+
+
+class SolveWindow:
+    """One window's inputs: device frame maps + host correspondences/poses (the reference's argument list)."""
+
+    def __init__(self, corr: np.ndarray, H: int, W: int, depths_gpu: Sequence, normals_gpu: Sequence, poses: np.ndarray, K,
+                 dense_pairs: Optional[np.ndarray] = None, compat_flip: bool = True):
+        self.corr = np.ascontiguousarray(corr, dtype=ENTRYJ_DTYPE)
+        self.H, self.W = int(H), int(W)
+        self.depths = [_ptr(d) for d in depths_gpu]
+        self.normals = [_ptr(n) for n in normals_gpu]
+        self.poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 4, 4)
+        K = np.asarray(K, np.float64)
+        self.K = (float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])) if K.ndim == 2 else tuple(float(v) for v in K)
+        self.dense_pairs = None if dense_pairs is None else np.ascontiguousarray(dense_pairs, np.uint32).reshape(-1, 2)
+        self.compat_flip = bool(compat_flip)
+        self._keep = (depths_gpu, normals_gpu)
+
+    @property
+    def n_frames(self) -> int:
+        return self.poses.shape[0]
+
+
+class OptimizerGpu:
+    def __init__(self, yml=None, device: int = 0, max_windows: int = 1, max_frames: int = 15, max_corr: int = 65536,
+                 H: int = 480, W: int = 640, stream: int = 0):
+        self.lib = _lib.load()
+        self.params = solver_params(yml)
+        self.stream = ctypes.c_void_p(stream)
+        self.ctx = ctypes.c_void_p()
+        _lib.check(self.lib.bt_ctx_create(ctypes.byref(self.ctx), ctypes.c_int(device)), "bt_ctx_create")
+        self.limits = _lib.SolverLimits(max_windows, max_frames, max_corr, H, W, self.params.image_downscale)
+        _lib.check(self.lib.bt_solver_reserve(self.ctx, ctypes.byref(self.limits)), "bt_solver_reserve")
+        self._staged = None
+
+    def close(self):
+        if self.ctx:
+            self.lib.bt_ctx_destroy(self.ctx)
+            self.ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- reference-shaped single-window call (LossGPU.h:50) -------------------------------------------------
+    def optimizeFrames(self, global_corres, n_match_per_pair, n_frames, H, W, depths_gpu, colors_gpu, normals_gpu, poses, K,
+                       dense_pairs=None, compat_flip=True):
+        """poses: [n_frames,4,4] float32, modified in place (the reference's in-out std::vector<Eigen::Matrix4f>).
+        n_match_per_pair and colors_gpu are accepted and ignored, as in the reference (LossGPU.cu:53, SBA.cpp:28-32)."""
+        poses_arr = np.asarray(poses)
+        win = SolveWindow(global_corres, H, W, depths_gpu[:n_frames], normals_gpu[:n_frames], poses_arr[:n_frames], K, dense_pairs, compat_flip)
+        out = self.optimizeWindows([win])[0]
+        poses_arr[:n_frames] = out
+        return poses_arr
+
+    # ---- batched form ---------------------------------------------------------------------------------------------
+    def _marshal(self, windows: List[SolveWindow]):
+        n = len(windows)
+        arr = (_lib.Window * n)()
+        keep = []
+        for i, w in enumerate(windows):
+            N = w.n_frames
+            dp = (ctypes.c_void_p * N)(*w.depths)
+            nq = (ctypes.c_void_p * N)(*w.normals)
+            keep += [dp, nq]
+            arr[i].n_frames, arr[i].H, arr[i].W, arr[i].n_corr = N, w.H, w.W, len(w.corr)
+            arr[i].corr = w.corr.ctypes.data if len(w.corr) else None
+            arr[i].depth_dev = ctypes.cast(dp, ctypes.POINTER(ctypes.c_void_p))
+            arr[i].normal_dev = ctypes.cast(nq, ctypes.POINTER(ctypes.c_void_p))
+            arr[i].fx, arr[i].fy, arr[i].cx, arr[i].cy = w.K
+            if w.dense_pairs is not None:
+                arr[i].dense_pairs = w.dense_pairs.ctypes.data if len(w.dense_pairs) else ctypes.addressof(ctypes.c_uint32(0))
+                arr[i].n_dense_pairs = len(w.dense_pairs)
+            else:
+                arr[i].dense_pairs, arr[i].n_dense_pairs = None, 0
+            arr[i].compat_flip = 1 if w.compat_flip else 0
+        poses = np.ascontiguousarray(np.concatenate([w.poses.reshape(-1, 16) for w in windows], 0), np.float32)
+        return arr, poses, keep
+
+    def optimizeWindows(self, windows: List[SolveWindow]) -> List[np.ndarray]:
+        arr, poses, keep = self._marshal(windows)
+        _lib.check(self.lib.bt_solve_windows(self.ctx, ctypes.c_int(len(windows)), arr, ctypes.byref(self.params),
+                                             poses.ctypes.data_as(ctypes.c_void_p), self.stream), "bt_solve_windows")
+        del keep
+        return self._split(windows, poses)
+
+    @staticmethod
+    def _split(windows, poses):
+        out, o = [], 0
+        for w in windows:
+            out.append(poses[o:o + w.n_frames].reshape(-1, 4, 4).copy())
+            o += w.n_frames
+        return out
+
+    # split API used by bench.py to time the resident-input kernel path separately from staging
+    def stage(self, windows: List[SolveWindow]):
+        arr, poses, keep = self._marshal(windows)
+        _lib.check(self.lib.bt_solve_stage(self.ctx, ctypes.c_int(len(windows)), arr, ctypes.byref(self.params),
+                                           poses.ctypes.data_as(ctypes.c_void_p), self.stream), "bt_solve_stage")
+        self._staged = (windows, poses, keep, arr)
+
+    def run(self):
+        _lib.check(self.lib.bt_solve_run(self.ctx, self.stream), "bt_solve_run")
+
+    def fetch(self) -> List[np.ndarray]:
+        windows, poses, _, _ = self._staged
+        out = np.empty_like(poses)
+        _lib.check(self.lib.bt_solve_fetch(self.ctx, out.ctypes.data_as(ctypes.c_void_p), self.stream), "bt_solve_fetch")
+        return self._split(windows, out)
+
+    def stats(self) -> dict:
+        st = _lib.SolveStats()
+        _lib.check(self.lib.bt_solve_get_stats(self.ctx, ctypes.byref(st)), "bt_solve_get_stats")
+        return {"n_windows": st.n_windows, "n_tiles_total": st.n_tiles_total, "n_kernel_launches": st.n_kernel_launches,
+                "n_src_pixels": int(st.n_src_pixels)}
+
+    def enable_timing(self, on=True):
+        _lib.check(self.lib.bt_solve_enable_timing(self.ctx, ctypes.c_int(1 if on else 0)), "bt_solve_enable_timing")
+
+    def timing_ms(self):
+        ms = (ctypes.c_float * 3)()
+        _lib.check(self.lib.bt_solve_get_timing(self.ctx, ms), "bt_solve_get_timing")
+        return {"prep": ms[0], "plan": ms[1], "solve": ms[2]}
+
+    def enable_debug(self, on=True):
+        _lib.check(self.lib.bt_solve_enable_debug(self.ctx, ctypes.c_int(1 if on else 0)), "bt_solve_enable_debug")
+
+    def debug_counts(self, w: int, n_pairs: int):
+        c = np.zeros(n_pairs, np.float32)
+        _lib.check(self.lib.bt_solve_debug_counts(self.ctx, ctypes.c_int(w), ctypes.c_int(n_pairs), c.ctypes.data_as(ctypes.c_void_p)), "bt_solve_debug_counts")
+        return c
+
+    def debug_dense(self, w: int, n_frames: int):
+        dim = 6 * n_frames
+        J = np.zeros((dim, dim), np.float32)
+        r = np.zeros(dim, np.float32)
+        _lib.check(self.lib.bt_solve_debug_dense(self.ctx, ctypes.c_int(w), J.ctypes.data_as(ctypes.c_void_p), r.ctypes.data_as(ctypes.c_void_p)), "bt_solve_debug_dense")
+        return J, r

@@ -1,0 +1,185 @@
+/*
+ * bundletrack_b200.h — C-ABI of the B200-native pose-graph optimizer + feature matcher that drops in behind
+ * BundleTrack's C++ surface.  Plain pointers and sizes only; no C++/torch types.  Every entry point returns
+ * BT_OK (0) or a negative bt_status — it never exits, throws or hangs (the reference does all three).
+ *
+ * The reference has no plugin/FFI layer; the "boundary" is the three C++ call sites where BundleTrack's host code
+ * hands device work to something replaceable.  Each entry point below names the call it replaces.
+ * INTEGRATION.md shows the reference-side shim a maintainer adds at each site.
+ *
+ * Threading: a bt_ctx may be used by one host thread at a time.  All work is enqueued on the cudaStream_t passed
+ * in (as void*); entry points that return host data synchronise that stream before returning.
+ */
+#ifndef BUNDLETRACK_B200_H
+#define BUNDLETRACK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#define BT_API __attribute__((visibility("default")))
+#else
+#define BT_API
+#endif
+
+typedef enum {
+	BT_OK = 0,
+	BT_ERR_INVALID_ARG = -1,
+	BT_ERR_CAPACITY = -2,     /* more windows / frames / correspondences / features than the context was created for */
+	BT_ERR_CUDA = -3,         /* a CUDA runtime call failed; bt_last_error() has the string */
+	BT_ERR_NO_DEVICE = -4,    /* no CUDA device, or not an sm_100 part: there is NO CPU fallback */
+	BT_ERR_UNSUPPORTED = -5
+} bt_status;
+
+typedef struct bt_ctx bt_ctx;
+
+/* One 3D-3D feature correspondence.  Layout-identical to the reference's `struct EntryJ`
+ * (/root/reference/src/cuda/SIFTImageManager.h:44-59): 32 bytes, invalid <=> imgIdx_i == 0xFFFFFFFF. */
+typedef struct {
+	uint32_t imgIdx_i;
+	uint32_t imgIdx_j;
+	float pos_i[3];   /* camera-frame point in frame i, metres */
+	float pos_j[3];
+} bt_entryj;
+
+/* Solver parameters, filled from the UNCHANGED config_*.yml keys:
+ *   num_iter_outer  <- bundle.num_iter_outter      (Solver/CUDASolverBundling.cpp:193)
+ *   num_iter_inner  <- bundle.num_iter_inner       (:210)
+ *   robust_delta    <- bundle.robust_delta         (:214)
+ *   image_downscale <- bundle.image_downscale      (LossGPU.cu:55)
+ *   dense_dist_thresh        <- p2p.max_dist                       (CUDASolverBundling.cpp:93)
+ *   dense_cos_normal_thresh  <- cos(p2p.max_normal_angle * pi/180) (:94)
+ *   depth_min / depth_max    =  0.1 / 9999 (hard-wired, :97-98)
+ *   w_sparse / w_dense       =  1 / 1      (hard-wired, SBA.cpp:28-30)                                   */
+typedef struct {
+	int num_iter_outer;
+	int num_iter_inner;
+	float robust_delta;
+	float image_downscale;
+	float dense_dist_thresh;
+	float dense_cos_normal_thresh;
+	float depth_min;
+	float depth_max;
+	float w_sparse;
+	float w_dense;
+} bt_solver_params;
+
+/* One tracking window = one OptimizerGpu::optimizeFrames call (/root/reference/src/cuda/LossGPU.cu:53). */
+typedef struct {
+	int n_frames;                     /* N, frame 0 is the gauge (never moves) */
+	int H, W;                         /* full-resolution image size */
+	int n_corr;
+	const bt_entryj* corr;            /* HOST pointer, n_corr entries (std::vector<EntryJ>::data()) */
+	const float* const* depth_dev;    /* HOST array of N DEVICE pointers: Frame::_depth_gpu, float[H*W], metres, 0 = invalid */
+	const float* const* normal_dev;   /* HOST array of N DEVICE pointers: Frame::_normal_gpu, float4[H*W], (nx,ny,nz,0) */
+	float fx, fy, cx, cy;             /* K at full resolution */
+	/* Dense point-to-plane pair list as (target, source) frame indices.  NULL => every unordered pair once with
+	 * target = the larger index, which is what the reference's FindImageImageCorr_Kernel produces when the
+	 * per-frame d_num_valid_points allocations have ascending addresses.  n_dense_pairs == 0 with a
+	 * non-NULL pointer disables the dense term for this window. */
+	const uint32_t* dense_pairs;
+	int n_dense_pairs;
+	/* 1 => reproduce the reference's FlipJtJ behaviour: a pair's cross block survives only when target < source
+	 * (SURVEY.md Q2).  0 => keep every cross block (the mathematically complete Gauss-Newton system). */
+	int compat_flip;
+} bt_window;
+
+typedef struct {
+	int max_windows;        /* windows per bt_solve_* call */
+	int max_frames;         /* frames per window (<= 32) */
+	int max_corr;           /* correspondences per window */
+	int H, W;               /* largest full-resolution frame */
+	float image_downscale;  /* bundle.image_downscale */
+} bt_solver_limits;
+
+BT_API const char* bt_last_error(void);
+BT_API int bt_version(void);
+
+/* Create / destroy.  `device` is a CUDA ordinal.  The context owns every scratch buffer, so the per-call path does
+ * no cudaMalloc/cudaFree (the reference does ~110 per call). */
+BT_API int bt_ctx_create(bt_ctx** out, int device);
+BT_API void bt_ctx_destroy(bt_ctx* ctx);
+BT_API int bt_solver_reserve(bt_ctx* ctx, const bt_solver_limits* lim);
+
+/* Replaces OptimizerGpu::optimizeFrames (/root/reference/src/cuda/LossGPU.cu:53-139; caller
+ * /root/reference/src/Bundler.cpp:350-351) for a BATCH of independent windows.
+ * poses_inout: HOST, row-major 4x4 cam->model per frame, windows concatenated (sum of n_frames * 16 floats);
+ * overwritten with the optimised poses of EVERY frame of the window, exactly like the reference's in-out vector.
+ * Equivalent to bt_solve_stage + bt_solve_run + bt_solve_fetch. */
+BT_API int bt_solve_windows(bt_ctx* ctx, int n_windows, const bt_window* windows, const bt_solver_params* params,
+                     float* poses_inout, void* stream);
+
+/* The same call split at the host<->device boundary, so a caller (and bench.py) can keep inputs resident:
+ *   stage : host -> device copies of correspondences, poses, window tables (async on `stream`)
+ *   run   : the kernels only (frame cache, plan, persistent GN/PCG solve); asynchronous
+ *   fetch : device -> host copy of the poses + stream synchronise                                       */
+BT_API int bt_solve_stage(bt_ctx* ctx, int n_windows, const bt_window* windows, const bt_solver_params* params,
+                   const float* poses_in, void* stream);
+BT_API int bt_solve_run(bt_ctx* ctx, void* stream);
+BT_API int bt_solve_fetch(bt_ctx* ctx, float* poses_out, void* stream);
+
+/* Introspection used by tests / bench (device pointers stay owned by the context). */
+typedef struct {
+	int n_windows;
+	int n_tiles_total;         /* dense tiles per GN iteration over the batch */
+	int n_kernel_launches;     /* kernels enqueued by the last bt_solve_run */
+	long long n_src_pixels;    /* valid quarter-res source pixels summed over (window, pair) */
+} bt_solve_stats;
+BT_API int bt_solve_get_stats(bt_ctx* ctx, bt_solve_stats* out);
+/* Copies the dense system (6N x 6N JtJ, row-major, reference ordering trans 0-2 / rot 3-5, and 6N Jtr) that the
+ * LAST Gauss-Newton iteration of window `w` assembled; debugging/parity aid. */
+/* Per-kernel device time of the last bt_solve_run (ms3 = {frame cache, plan, persistent solve}), CUDA events on the
+ * launching stream; opt-in because it adds four event records per run. */
+BT_API int bt_solve_enable_timing(bt_ctx* ctx, int on);
+BT_API int bt_solve_get_timing(bt_ctx* ctx, float* ms3);
+BT_API int bt_solve_enable_debug(bt_ctx* ctx, int on);
+BT_API int bt_solve_debug_dense(bt_ctx* ctx, int w, float* JtJ_out, float* Jtr_out);
+/* Number of dense correspondences each pair found in the last GN iteration of window `w` (gating parity aid). */
+BT_API int bt_solve_debug_counts(bt_ctx* ctx, int w, int n_pairs, float* counts_out);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Matcher.  Replaces the two cv::cuda::DescriptorMatcher::knnMatch calls in SiftManager::findCorresbyNN
+ * (/root/reference/src/FeatureManager.cpp:271-273) for a batch of frame pairs.
+ * Distances are sqrt(sum d^2) like cv::NORM_L2, ascending; ties -> lower train index first.                  */
+typedef struct {
+	const float* dev;      /* DEVICE pointer, row-major n x dim (cv::cuda::GpuMat data), fp32 */
+	int n;
+	int dim;               /* 256 for LF-Net; must be a multiple of 32 */
+	size_t pitch_bytes;    /* GpuMat::step; 0 => dim*4 */
+} bt_desc_view;
+
+BT_API int bt_matcher_reserve(bt_ctx* ctx, int max_pairs, int max_feats, int dim);
+/* idxAB/distAB: DEVICE [sum_p nA_p * k] results for queries in A against train B; idxBA/distBA the reverse
+ * direction, computed from the same tensor-core pass.  Pair p's block starts at k * (sum of nA over pairs < p)
+ * (resp. nB).  Rows with fewer than k candidates are padded with idx -1 / dist +inf. */
+BT_API int bt_knn_match_pairs(bt_ctx* ctx, int n_pairs, const bt_desc_view* A, const bt_desc_view* B, int k,
+                       int32_t* idxAB, float* distAB, int32_t* idxBA, float* distBA, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * RANSAC.  Replaces ransacMultiPairGPU (/root/reference/src/cuda/cuda_ransac.cu:1228-1323; caller
+ * /root/reference/src/FeatureManager.cpp:713).  ptsA/ptsB: HOST arrays of n_pairs DEVICE pointers to float4[n]
+ * model-frame points (w ignored).  seed 0 => the reference's sampling sequence (XORWOW, curand_init(0, trial, 0)).
+ * Winner = max inlier count, ties -> lowest trial id (the reference's findBestTrial is racy).
+ * inlier_ids_out: DEVICE int32 [sum n_pts] (pair p's list starts at sum of n_pts over pairs < p);
+ * n_inliers_out: DEVICE int32 [n_pairs]. */
+BT_API int bt_ransac_reserve(bt_ctx* ctx, int max_pairs, int max_pts, int max_trials);
+BT_API int bt_ransac_pairs(bt_ctx* ctx, int n_pairs, const float* const* ptsA, const float* const* ptsB, const int* n_pts,
+                    int n_trials, float dist_thresh, uint64_t seed, int32_t* inlier_ids_out, int32_t* n_inliers_out,
+                    void* stream);
+
+/* Small device-memory helpers so non-CUDA hosts (ctypes, cgo, JNI) can drive the library without another runtime. */
+BT_API int bt_dev_alloc(void** out, size_t bytes);
+BT_API int bt_dev_free(void* p);
+BT_API int bt_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes, void* stream);
+BT_API int bt_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes, void* stream);
+BT_API int bt_host_alloc_pinned(void** out, size_t bytes);
+BT_API int bt_host_free_pinned(void* p);
+BT_API int bt_stream_sync(void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BUNDLETRACK_B200_H */

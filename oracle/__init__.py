@@ -153,3 +153,57 @@ def pose_to_matrix(r, t):
     T = np.zeros((4, 4), np.float32)
     lib.oracle_pose_to_matrix(_fp(r), _fp(t), _fp(T))
     return T
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Oracle B: the reference's own CUDA kernels, compiled verbatim by oracle/Makefile (`make ref`) into oracle/_ref.
+# Needs a GPU; used by the `-m gpu` parity tests and by `bench.py --impl reference`.
+class RefParams(ctypes.Structure):
+    _fields_ = OracleParams._fields_
+
+
+_ref = None
+
+
+def build_ref(force: bool = False) -> bool:
+    """(Re)build oracle/_ref/libbt_ref.so from /root/reference when it is present (this container only)."""
+    out = os.path.join(_HERE, "_ref", "libbt_ref.so")
+    if os.path.isdir("/root/reference/src/cuda") and (force or not os.path.exists(out)):
+        subprocess.check_call(["make", "-C", _HERE, "ref", "-j4"], stdout=subprocess.DEVNULL)
+    return os.path.exists(out)
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        path = os.path.join(_HERE, "_ref", "libbt_ref.so")
+        if not os.path.exists(path):
+            raise RuntimeError("oracle/_ref/libbt_ref.so missing: run `make -C oracle ref` where /root/reference exists")
+        _ref = ctypes.CDLL(path)
+        _ref.ref_optimize_frames.restype = ctypes.c_int
+        _ref.ref_ransac_pairs.restype = ctypes.c_int
+    return _ref
+
+
+def ref_optimize_frames(depth_ptrs, normal_ptrs, H, W, K, corr, poses, params=None):
+    """Run the reference's optimizeFrames-equivalent on the current CUDA device.
+    depth_ptrs/normal_ptrs: lists of device addresses.  Returns (poses [N,4,4], pairs [(tgt,src)], t_outer_ms, t_solve_ms)."""
+    lib = ref_lib()
+    N = len(depth_ptrs)
+    params = params or default_params()
+    rp = RefParams(*[getattr(params, f[0]) for f in OracleParams._fields_])
+    dp = (ctypes.c_void_p * N)(*[int(p) for p in depth_ptrs])
+    nq = (ctypes.c_void_p * N)(*[int(p) for p in normal_ptrs])
+    corr = np.ascontiguousarray(corr)
+    poses = np.ascontiguousarray(poses, np.float32).copy()
+    pairs = np.zeros((N * (N - 1) // 2 + 1, 2), np.uint32)
+    npairs = ctypes.c_int(0)
+    t_outer = ctypes.c_double(0)
+    t_solve = ctypes.c_double(0)
+    rc = lib.ref_optimize_frames(ctypes.c_int(N), ctypes.c_int(H), ctypes.c_int(W), dp, nq,
+                                 ctypes.c_float(K[0]), ctypes.c_float(K[1]), ctypes.c_float(K[2]), ctypes.c_float(K[3]),
+                                 ctypes.c_int(len(corr)), _fp(corr), _fp(poses), ctypes.byref(rp),
+                                 _fp(pairs), ctypes.byref(npairs), ctypes.byref(t_outer), ctypes.byref(t_solve))
+    if rc != 0:
+        raise RuntimeError(f"ref_optimize_frames rc={rc}")
+    return poses, pairs[: npairs.value].copy(), t_outer.value, t_solve.value
