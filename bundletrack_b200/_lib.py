@@ -70,6 +70,27 @@ class SolveStats(ctypes.Structure):
     ]
 
 
+class MatchFrame(ctypes.Structure):
+    _fields_ = [
+        ("kpts_dev", ctypes.c_void_p),
+        ("n", ctypes.c_int),
+        ("depth_dev", ctypes.c_void_p),
+        ("normal_dev", ctypes.c_void_p),
+        ("pose", ctypes.c_float * 16),
+        ("frame_id", ctypes.c_int),
+        ("window_index", ctypes.c_int),
+    ]
+
+
+class PruneParams(ctypes.Structure):
+    _fields_ = [
+        ("max_dist_no_neighbor", ctypes.c_float),
+        ("cos_max_normal_no_neighbor", ctypes.c_float),
+        ("max_dist_neighbor", ctypes.c_float),
+        ("cos_max_normal_neighbor", ctypes.c_float),
+    ]
+
+
 class DescView(ctypes.Structure):
     _fields_ = [
         ("dev", ctypes.c_void_p),
@@ -83,8 +104,9 @@ class DescView(ctypes.Structure):
 EXPORTS = [
     "bt_last_error", "bt_version", "bt_ctx_create", "bt_ctx_destroy", "bt_solver_reserve",
     "bt_solve_windows", "bt_solve_stage", "bt_solve_run", "bt_solve_fetch", "bt_solve_get_stats",
-    "bt_solve_enable_debug", "bt_solve_debug_dense", "bt_solve_debug_counts", "bt_solve_enable_timing", "bt_solve_get_timing",
-    "bt_matcher_reserve", "bt_knn_match_pairs", "bt_ransac_reserve", "bt_ransac_pairs",
+    "bt_solve_enable_debug", "bt_solve_debug_dense", "bt_solve_debug_counts", "bt_solve_enable_timing", "bt_solve_get_timing", "bt_solve_enable_profile", "bt_solve_get_profile",
+    "bt_matcher_reserve", "bt_knn_match_pairs", "bt_knn_enable_timing", "bt_knn_get_timing", "bt_ransac_reserve", "bt_ransac_pairs", "bt_ransac_debug",
+    "bt_pipeline_reserve", "bt_prune_mutual_pairs", "bt_match_pairs",
     "bt_dev_alloc", "bt_dev_free", "bt_memcpy_h2d", "bt_memcpy_d2h", "bt_host_alloc_pinned", "bt_host_free_pinned",
     "bt_stream_sync",
 ]

@@ -47,6 +47,7 @@ extern "C" void bt_ctx_destroy(bt_ctx* ctx) {
 	bt::solver_destroy(ctx);
 	bt::matcher_destroy(ctx);
 	bt::ransac_destroy(ctx);
+	bt::prune_destroy(ctx);
 	delete ctx;
 }
 

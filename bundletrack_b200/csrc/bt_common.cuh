@@ -75,4 +75,5 @@ namespace bt {
 void solver_destroy(bt_ctx* ctx);
 void matcher_destroy(bt_ctx* ctx);
 void ransac_destroy(bt_ctx* ctx);
+void prune_destroy(bt_ctx* ctx);
 }

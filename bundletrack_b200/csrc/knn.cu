@@ -1,5 +1,711 @@
-// knn.cu — placeholder until the tcgen05 matcher lands (next milestone).
+// knn.cu — all-pairs L2 k-nearest-neighbour matching of 256-d LF-Net descriptors on the 5th-gen tensor cores.
+//
+// Replaces the two cv::cuda::DescriptorMatcher::knnMatch(…, k=5) calls of SiftManager::findCorresbyNN
+// (/root/reference/src/FeatureManager.cpp:271-273) for a BATCH of frame pairs, both directions.  OpenCV's CUDA matcher
+// materialises the nQ x nT fp32 distance matrix with a SIMT kernel and runs k row-min passes over it;
+// here the distance matrix is never written:
+//
+//   k_desc_prep   fp32 (pitched GpuMat rows) -> bf16 pool [rows padded to 256][D] + fp32 |x~|^2 of the ROUNDED rows
+//                 (padding rows are zero with norm = +inf so they can never be selected).
+//   k_knn_tc      persistent, warp-specialised tcgen05 kernel.  Work item = (pair, direction, 128-row query tile, train
+//                 split).  Warp 0 streams operands with TMA (SWIZZLE_128B, K-major); warp 1 issues
+//                 tcgen05.mma.cta_group::1.kind::f16 (bf16 x bf16 -> fp32, M=128, N=256, K=16 per instruction) into a
+//                 double-buffered TMEM accumulator (2 x 256 columns); eight epilogue warps read the accumulator with
+//                 tcgen05.ld (thread t of a lane quarter owns query row t), form key = |t~|^2 - 2 q~.t~ and keep a
+//                 per-thread top-8 of (key | train index packed in the low 13 mantissa bits) with a branch-free min/max
+//                 insertion network that only runs when a key beats the current 8th best.
+//   k_knn_rerank  per query row: the <= 16*splits candidates are re-scored EXACTLY (float64 sum of (a-b)^2 on the fp32
+//                 inputs), sorted (distance, index) and the top k written.  A rigorous bound on the bf16 pass
+//                 (| |q~-t~| - |q-t| | <= 2^-9 (|q|+|t|), plus key packing) proves the exact top-k lies inside the
+//                 candidate set; rows where the proof fails go to
+//   k_knn_exact   exact brute force for those rows only (rare).
+// Result == exact brute-force kNN (float64 distances, ties -> lower train index), distances returned as
+// float(sqrt(d2)) like cv::NORM_L2.
+#include <algorithm>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <map>
+#include <math.h>
 #include "bt_common.cuh"
-namespace bt { void matcher_destroy(bt_ctx*) {} }
-extern "C" int bt_matcher_reserve(bt_ctx*, int, int, int) { bt::set_error("matcher not built yet"); return BT_ERR_UNSUPPORTED; }
-extern "C" int bt_knn_match_pairs(bt_ctx*, int, const bt_desc_view*, const bt_desc_view*, int, int32_t*, float*, int32_t*, float*, void*) { bt::set_error("matcher not built yet"); return BT_ERR_UNSUPPORTED; }
+
+namespace bt {
+
+static constexpr int KD = 256;              // descriptor dimension handled by the tensor path
+static constexpr int BM = 128;              // query rows per tile (UMMA M)
+static constexpr int BN = 256;              // train rows per tile (UMMA N)
+static constexpr int BK = 64;               // K elements per smem chunk: 64 bf16 = 128 B = one SWIZZLE_128B atom row
+static constexpr int KCH = KD / BK;         // 4 chunks
+static constexpr int STAGES = 4;            // train-operand pipeline depth (32 KB each)
+static constexpr int KC = 8;                // candidates kept per epilogue thread (per column half)
+static constexpr int NCAND = 2 * KC;        // candidates per (query row, split)
+static constexpr int IDX_BITS = 13;         // train index (relative to the split) packed in the low mantissa bits
+static constexpr int MAX_SPLIT_ROWS = 1 << IDX_BITS;
+static constexpr int KNN_THREADS = 32 * 10; // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+static constexpr uint32_t SQ_BYTES = BM * BK * 2;     // 16 KB per K-chunk of the query tile
+static constexpr uint32_t SB_BYTES = BN * BK * 2;     // 32 KB per stage
+static constexpr uint32_t SMEM_Q = KCH * SQ_BYTES;    // 64 KB
+static constexpr uint32_t SMEM_B = STAGES * SB_BYTES; // 128 KB
+static constexpr uint32_t SMEM_NORM = 2 * BN * 4;     // 2 KB
+static constexpr uint32_t SMEM_BAR = 256;
+static constexpr uint32_t SMEM_TOTAL = SMEM_Q + SMEM_B + SMEM_NORM + SMEM_BAR + 1024;   // + alignment slack
+
+struct KnnItem {
+	int q_row0;      // pool row of the first query row of this tile
+	int q_valid;     // valid query rows in this tile (<= 128)
+	int t_row0;      // pool row of the first train row of this split
+	int t_tiles;     // number of 256-row train tiles in this split
+	int cand_off;    // index (in rows) into the candidate buffer for this tile's first row
+	int pad0, pad1, pad2;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "WAIT_LOOP:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	    "@p bra WAIT_DONE;\n"
+	    "bra WAIT_LOOP;\n"
+	    "WAIT_DONE:\n"
+	    "}\n" ::"r"(smem_u32(bar)),
+	    "r"(parity)
+	    : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+	             "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+	             : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "setp.ne.b32 p, %4, 0;\n"
+	    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+	    "}\n" ::"r"(d_tmem),
+	    "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+	    : "memory");
+}
+// UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B, rows at 128-byte pitch, 8-row groups 1024 B apart.
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major) | [32,46) stride byte
+//   offset >> 4 (= 1024 >> 4) | [46,48) descriptor version = 1 (sm_100) | [61,64) layout type (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
+	uint64_t d = 0;
+	d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+	d |= (uint64_t)(1024 >> 4) << 32;
+	d |= (uint64_t)1 << 46;
+	d |= (uint64_t)2 << 61;
+	return d;
+}
+// UMMA instruction descriptor (kind::f16): c_format F32 (1) @4, a_format BF16 (1) @7, b_format BF16 (1) @10,
+// a/b K-major (0) @15/@16, N>>3 @17, M>>4 @24.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+	return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+#define TMEM_LD32(taddr, v)                                                                                                   \
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                     \
+	             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                      \
+	             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                      \
+	             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),     \
+	               "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),          \
+	               "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),         \
+	               "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                       \
+	             : "r"(taddr))
+
+// ------------------------------------------------------------------------------------------------ k_desc_prep
+struct PrepSet { const float* src; size_t pitch_bytes; int n; int row0; int rows_padded; int pad; };
+
+__global__ void __launch_bounds__(256) k_desc_prep(const PrepSet* sets, __nv_bfloat16* pool, float* norms, float* errn, int* set_maxnorm2, int* set_maxerr) {
+	const PrepSet st = sets[blockIdx.y];
+	const int warps_per_block = blockDim.x >> 5, lane = threadIdx.x & 31;
+	for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < st.rows_padded; r += gridDim.x * warps_per_block) {
+		__nv_bfloat16* dst = pool + (size_t)(st.row0 + r) * KD;
+		float ss = 0.f, ee = 0.f;
+		if (r < st.n) {
+			const float* src = (const float*)((const char*)st.src + (size_t)r * st.pitch_bytes);
+			// each lane converts 8 consecutive floats (two float4 loads, one 16-byte store)
+			const float4 a = __ldg(reinterpret_cast<const float4*>(src) + lane * 2), b = __ldg(reinterpret_cast<const float4*>(src) + lane * 2 + 1);
+			const float v[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+			__nv_bfloat16 h[8];
+#pragma unroll
+			for (int k = 0; k < 8; k++) { h[k] = __float2bfloat16_rn(v[k]); const float f = __bfloat162float(h[k]); ss += f * f; const float dlt = v[k] - f; ee += dlt * dlt; }
+			*reinterpret_cast<uint4*>(dst + lane * 8) = *reinterpret_cast<const uint4*>(h);
+		} else {
+			*reinterpret_cast<uint4*>(dst + lane * 8) = make_uint4(0u, 0u, 0u, 0u);
+		}
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) { ss += __shfl_xor_sync(0xffffffffu, ss, o); ee += __shfl_xor_sync(0xffffffffu, ee, o); }
+		if (lane == 0) {
+			norms[st.row0 + r] = (r < st.n) ? ss : __int_as_float(0x7f800000);
+			const float en = sqrtf(ee) * 1.001f + 1e-7f;     // |x~ - x|, rounded up: the ACTUAL bf16 rounding error of this row
+			errn[st.row0 + r] = (r < st.n) ? en : 0.f;
+			if (r < st.n) { atomicMax(set_maxnorm2 + blockIdx.y, __float_as_int(ss)); atomicMax(set_maxerr + blockIdx.y, __float_as_int(en)); }   // non-negative floats order like ints
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ k_knn_tc
+// Branch-free insertion of x into the ascending list a[0..KC-1], dropping the largest.
+__device__ __forceinline__ void topk_insert(float (&a)[KC], float x) {
+	float prev = a[0];
+	a[0] = fminf(a[0], x);
+#pragma unroll
+	for (int j = 1; j < KC; j++) {
+		const float cur = a[j];
+		a[j] = fminf(cur, fmaxf(prev, x));
+		prev = cur;
+	}
+}
+
+__global__ void __launch_bounds__(KNN_THREADS, 1)
+k_knn_tc(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_t, const KnnItem* __restrict__ items, int n_items,
+         const float* __restrict__ norms, float* __restrict__ cand) {
+	extern __shared__ uint8_t smem_raw[];
+	uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024-B alignment
+	uint8_t* sQ = smem;
+	uint8_t* sB = smem + SMEM_Q;
+	float* sNorm = reinterpret_cast<float*>(smem + SMEM_Q + SMEM_B);
+	uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_Q + SMEM_B + SMEM_NORM);
+	uint64_t* q_full = bars + 0;
+	uint64_t* q_empty = bars + 1;
+	uint64_t* full = bars + 2;                 // [STAGES]
+	uint64_t* empty = bars + 2 + STAGES;       // [STAGES]
+	uint64_t* tm_full = bars + 2 + 2 * STAGES; // [2]
+	uint64_t* tm_empty = tm_full + 2;          // [2]
+	uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tm_empty + 2);
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	if (warp == 0 && lane == 0) {
+		asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
+		asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_t) : "memory");
+		mbar_init(q_full, 1); mbar_init(q_empty, 1);
+		for (int s = 0; s < STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+		for (int b = 0; b < 2; b++) { mbar_init(tm_full + b, 1); mbar_init(tm_empty + b, 8); }
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	if (warp == 1) {   // TMEM: all 512 columns (two 256-column accumulators); this kernel runs 1 CTA / SM
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_ptr_smem;
+
+	if (warp == 0) {
+		// ================================================= TMA producer
+		if (lane == 0) {
+			uint32_t stage = 0, sphase = 0, qphase = 0;
+			for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+				const KnnItem item = items[it];
+				mbar_wait(q_empty, qphase ^ 1);        // previous item's MMAs no longer read the query tile
+				mbar_expect_tx(q_full, SMEM_Q);
+				for (int kc = 0; kc < KCH; kc++) tma_load_2d(sQ + kc * SQ_BYTES, &tmap_q, q_full, kc * BK, item.q_row0);
+				qphase ^= 1;
+				for (int t = 0; t < item.t_tiles; t++) {
+					for (int kc = 0; kc < KCH; kc++) {
+						mbar_wait(empty + stage, sphase ^ 1);
+						mbar_expect_tx(full + stage, SB_BYTES);
+						tma_load_2d(sB + stage * SB_BYTES, &tmap_t, full + stage, kc * BK, item.t_row0 + t * BN);
+						if (++stage == STAGES) { stage = 0; sphase ^= 1; }
+					}
+				}
+			}
+		}
+	} else if (warp == 1) {
+		// ================================================= MMA issuer (one thread)
+		if (lane == 0) {
+			constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+			uint32_t stage = 0, sphase = 0, qphase = 0, tcount = 0;
+			for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+				const KnnItem item = items[it];
+				mbar_wait(q_full, qphase);
+				qphase ^= 1;
+				for (int t = 0; t < item.t_tiles; t++, tcount++) {
+					const uint32_t buf = tcount & 1, tphase = (tcount >> 1) & 1;
+					mbar_wait(tm_empty + buf, tphase ^ 1);      // epilogue drained this accumulator
+					tc_fence_after();
+					const uint32_t d_tmem = tmem_base + buf * BN;
+					for (int kc = 0; kc < KCH; kc++) {
+						mbar_wait(full + stage, sphase);
+						tc_fence_after();
+						const uint32_t a_base = smem_u32(sQ + kc * SQ_BYTES), b_base = smem_u32(sB + stage * SB_BYTES);
+#pragma unroll
+						for (int k = 0; k < BK / 16; k++) {      // UMMA K = 16 bf16 = 32 bytes inside the 128-byte swizzle row
+							tc_mma_bf16(d_tmem, umma_desc_k128(a_base + k * 32), umma_desc_k128(b_base + k * 32), idesc, (uint32_t)((kc | k) != 0));
+						}
+						tc_commit(empty + stage);                // frees the stage when these MMAs retire
+						if (++stage == STAGES) { stage = 0; sphase ^= 1; }
+					}
+					tc_commit(tm_full + buf);                    // accumulator complete -> epilogue
+				}
+				tc_commit(q_empty);                              // query tile may be overwritten
+			}
+		}
+	} else {
+		// ================================================= epilogue: 8 warps, lane quarter = warp % 4, column half = (warp-2) / 4
+		const int ew = warp - 2;
+		const int quarter = warp & 3;            // TMEM lanes [32*quarter, 32*quarter+32) are the only ones this warp may read
+		const int half = ew >> 2;                // columns [128*half, 128*half+128) of each 256-column tile
+		const int row = quarter * 32 + lane;     // query row inside the tile == TMEM lane
+		const int etid = threadIdx.x - 64;       // 0..255
+		uint32_t tcount = 0;
+		for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+			const KnnItem item = items[it];
+			float best[KC];
+#pragma unroll
+			for (int j = 0; j < KC; j++) best[j] = __int_as_float(0x7f800000);
+			for (int t = 0; t < item.t_tiles; t++, tcount++) {
+				const uint32_t buf = tcount & 1, tphase = (tcount >> 1) & 1;
+				// |t~|^2 of this train tile -> smem (one float per epilogue thread).  The previous user of sNorm[buf] (two
+				// tiles ago) finished before its tm_empty arrival, which the MMA warp waited for before this tile's MMAs;
+				// the named barrier below orders this store against the reads.
+				sNorm[buf * BN + etid] = __ldg(norms + item.t_row0 + t * BN + etid);
+				asm volatile("bar.sync 1, 256;" ::: "memory");
+				mbar_wait(tm_full + buf, tphase);
+				tc_fence_after();
+				const float* nrm = sNorm + buf * BN + half * 128;
+				const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + half * 128;
+				const int col_base = t * BN + half * 128;   // train index relative to the split
+				// TMEM -> registers, double-buffered: chunk c+1 is in flight while chunk c is scanned.  Within a 32-column
+				// chunk every key is tested against the threshold the chunk STARTED with (no loop-carried dependency, the
+				// compares schedule ahead of the rare inserts); inserting against a stale threshold is harmless because the
+				// min/max network leaves the list untouched when the key is not better than its current 8th entry.
+				auto scan = [&](const uint32_t (&v)[32], int c) {
+					const float thr = best[KC - 1];
+#pragma unroll
+					for (int e = 0; e < 32; e++) {
+						const float key = fmaf(-2.0f, __uint_as_float(v[e]), nrm[c * 32 + e]);
+						if (key < thr) {
+							const uint32_t packed = (__float_as_uint(key) & ~((1u << IDX_BITS) - 1u)) | (uint32_t)(col_base + c * 32 + e);
+							topk_insert(best, __uint_as_float(packed));
+						}
+					}
+				};
+				uint32_t va[32], vb[32];
+				TMEM_LD32(taddr0, va);
+				asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+				TMEM_LD32(taddr0 + 32, vb);
+				scan(va, 0);
+				asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+				TMEM_LD32(taddr0 + 64, va);
+				scan(vb, 1);
+				asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+				TMEM_LD32(taddr0 + 96, vb);
+				scan(va, 2);
+				asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+				scan(vb, 3);
+				tc_fence_before();
+				__syncwarp();
+				if (lane == 0) mbar_arrive(tm_empty + buf);
+			}
+			if (row < item.q_valid) {
+				float4* out = reinterpret_cast<float4*>(cand + ((size_t)(item.cand_off + row) * NCAND + half * KC));
+				out[0] = make_float4(best[0], best[1], best[2], best[3]);
+				out[1] = make_float4(best[4], best[5], best[6], best[7]);
+			}
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 1) {
+		tc_fence_after();
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ exact re-rank
+struct RerankJob {        // one per (pair, direction)
+	const float* q; size_t q_pitch; int nq; int q_pool_row0;
+	const float* t; size_t t_pitch; int nt; int t_set;
+	int n_splits; int split_rows;   // train rows per split (multiple of 256)
+	int cand_off;                   // candidate rows of (split s, query row r) start at cand_off + s*cand_split_stride + r
+	int cand_split_stride;
+	int out_off;                    // rows (x k) into the idx/dist outputs of this direction
+	int dir;                        // 0: A->B outputs, 1: B->A outputs
+};
+
+__device__ __forceinline__ double exact_d2(const float* __restrict__ a, const float* __restrict__ b, int lane) {
+	// warp-cooperative sum over KD floats: lane handles 8 consecutive elements; fixed order => deterministic
+	const float4 a0 = __ldg(reinterpret_cast<const float4*>(a) + lane * 2), a1 = __ldg(reinterpret_cast<const float4*>(a) + lane * 2 + 1);
+	const float4 b0 = __ldg(reinterpret_cast<const float4*>(b) + lane * 2), b1 = __ldg(reinterpret_cast<const float4*>(b) + lane * 2 + 1);
+	double s = 0.0, d;
+	d = (double)a0.x - (double)b0.x; s += d * d; d = (double)a0.y - (double)b0.y; s += d * d;
+	d = (double)a0.z - (double)b0.z; s += d * d; d = (double)a0.w - (double)b0.w; s += d * d;
+	d = (double)a1.x - (double)b1.x; s += d * d; d = (double)a1.y - (double)b1.y; s += d * d;
+	d = (double)a1.z - (double)b1.z; s += d * d; d = (double)a1.w - (double)b1.w; s += d * d;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+	return s;
+}
+__device__ __forceinline__ int find_job(const int* __restrict__ job_row_start, int n_jobs, int gw) {
+	int lo = 0, hi = n_jobs - 1;
+	while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (job_row_start[mid] <= gw) lo = mid; else hi = mid - 1; }
+	return lo;
+}
+struct KnnOut { int32_t* idx[2]; float* dist[2]; };
+
+// one warp per query row
+__global__ void __launch_bounds__(256) k_knn_rerank(const RerankJob* __restrict__ jobs, const int* __restrict__ job_row_start, int n_jobs, int total_rows,
+                                                     const float* __restrict__ cand, const float* __restrict__ norms, const float* __restrict__ errn,
+                                                     const int* __restrict__ set_maxnorm2, const int* __restrict__ set_maxerr,
+                                                     int k, KnnOut out, int* fallback_rows, int* fallback_count) {
+	const int lane = threadIdx.x & 31;
+	const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (gw >= total_rows) return;
+	const RerankJob jb = jobs[find_job(job_row_start, n_jobs, gw)];
+	const int r = gw - job_row_start[find_job(job_row_start, n_jobs, gw)];
+	const float* qrow = (const float*)((const char*)jb.q + (size_t)r * jb.q_pitch);
+	const int ncand_total = jb.n_splits * NCAND;
+	double best_d[8]; int best_i[8];          // warp-uniform values, kept redundantly by every lane
+#pragma unroll
+	for (int j = 0; j < 8; j++) { best_d[j] = 1e300; best_i[j] = 0x7fffffff; }
+	float thr_key = __int_as_float(0x7f800000);   // smallest (over splits/halves) of the KC-th best approximate keys
+	for (int c = 0; c < ncand_total; c++) {
+		const int s = c / NCAND, e = c - s * NCAND;
+		const float pk = __ldg(cand + ((size_t)(jb.cand_off + s * jb.cand_split_stride + r) * NCAND + e));
+		if ((e % KC) == KC - 1) thr_key = fminf(thr_key, pk);
+		if (!(pk < __int_as_float(0x7f800000))) continue;          // empty slot
+		const int ti = s * jb.split_rows + (int)(__float_as_uint(pk) & ((1u << IDX_BITS) - 1u));
+		if (ti >= jb.nt) continue;
+		bool dup = false;
+#pragma unroll
+		for (int j = 0; j < 8; j++) dup |= (best_i[j] == ti);
+		if (dup) continue;
+		const float* trow = (const float*)((const char*)jb.t + (size_t)ti * jb.t_pitch);
+		double cd = exact_d2(qrow, trow, lane); int ci = ti;
+#pragma unroll
+		for (int j = 0; j < 8; j++) {   // sorted insert, ties -> lower index
+			const bool lt = (cd < best_d[j]) || (cd == best_d[j] && ci < best_i[j]);
+			if (lt) { const double td = best_d[j]; const int tix = best_i[j]; best_d[j] = cd; best_i[j] = ci; cd = td; ci = tix; }
+		}
+	}
+	// Proof that no NON-candidate can enter the exact top-k.  Every non-candidate j has approximate key >= thr_key (up to
+	// the 2^-10 relative loss of packing the index into the mantissa), i.e. |q~ - t~_j|^2 >= |q~|^2 + key_j, and
+	// | |q~ - t~| - |q - t| | <= |q~ - q| + |t~ - t| <= 2^-9 (|q| + |t|)  (bf16 round-to-nearest, per component).
+	const int kk = min(k, jb.nt);
+	bool ok = true;
+	if (kk > 0 && thr_key < __int_as_float(0x7f800000)) {    // an unfilled list means every train row of that half was a candidate
+		const float qn2 = __ldg(norms + jb.q_pool_row0 + r);                                  // |q~|^2
+		const double key_lo = (double)thr_key - fabs((double)thr_key) * (1.0 / 1024.0) - 1e-6;
+		const double approx_d2 = (double)qn2 + key_lo;
+		if (approx_d2 <= 0.0) ok = false;
+		else {
+			// | |q~ - t~| - |q - t| | <= |q~ - q| + |t~ - t|: both rounding-error norms were measured by k_desc_prep (the
+			// train side through its per-set maximum); plus slack for the fp32 accumulation inside the tensor core.
+			const double qn = sqrt((double)qn2), tn = sqrt((double)__int_as_float(set_maxnorm2[jb.t_set]));
+			const double eps = (double)__ldg(errn + jb.q_pool_row0 + r) + (double)__int_as_float(set_maxerr[jb.t_set]) + 1e-4 * (qn + tn) + 1e-6;
+			const double lower = sqrt(approx_d2) - eps;
+			ok = (lower > 0.0) && (best_i[kk - 1] != 0x7fffffff) && (best_d[kk - 1] < lower * lower);
+		}
+	}
+	if (lane == 0) {
+		int32_t* io = out.idx[jb.dir] + ((size_t)jb.out_off + r) * k;
+		float* dd = out.dist[jb.dir] + ((size_t)jb.out_off + r) * k;
+		for (int j = 0; j < k; j++) {
+			const bool have = j < kk && best_i[j] != 0x7fffffff;
+			io[j] = have ? best_i[j] : -1;
+			dd[j] = have ? (float)sqrt(best_d[j]) : __int_as_float(0x7f800000);
+		}
+		if (!ok) { const int slot = atomicAdd(fallback_count, 1); fallback_rows[slot] = gw; }
+	}
+}
+
+// exact brute force for the rows the proof rejected: one CTA per row, persistent over the list
+__global__ void __launch_bounds__(256) k_knn_exact(const RerankJob* __restrict__ jobs, const int* __restrict__ job_row_start, int n_jobs,
+                                                    const int* __restrict__ fallback_rows, const int* __restrict__ fallback_count, int k, KnnOut out) {
+	__shared__ double s_d[8][8];
+	__shared__ int s_i[8][8];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int n = *fallback_count;
+	for (int f = blockIdx.x; f < n; f += gridDim.x) {
+		const int gw = fallback_rows[f];
+		const int ji = find_job(job_row_start, n_jobs, gw);
+		const RerankJob jb = jobs[ji];
+		const int r = gw - job_row_start[ji];
+		const float* qrow = (const float*)((const char*)jb.q + (size_t)r * jb.q_pitch);
+		double best_d[8]; int best_i[8];
+#pragma unroll
+		for (int j = 0; j < 8; j++) { best_d[j] = 1e300; best_i[j] = 0x7fffffff; }
+		for (int ti = warp; ti < jb.nt; ti += 8) {
+			const float* trow = (const float*)((const char*)jb.t + (size_t)ti * jb.t_pitch);
+			double cd = exact_d2(qrow, trow, lane); int ci = ti;
+#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				const bool lt = (cd < best_d[j]) || (cd == best_d[j] && ci < best_i[j]);
+				if (lt) { const double td = best_d[j]; const int tix = best_i[j]; best_d[j] = cd; best_i[j] = ci; cd = td; ci = tix; }
+			}
+		}
+		__syncthreads();
+		if (lane == 0) for (int j = 0; j < 8; j++) { s_d[warp][j] = best_d[j]; s_i[warp][j] = best_i[j]; }
+		__syncthreads();
+		if (threadIdx.x == 0) {   // 8-way merge of the per-warp sorted lists
+			int ptr[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+			int32_t* io = out.idx[jb.dir] + ((size_t)jb.out_off + r) * k;
+			float* dd = out.dist[jb.dir] + ((size_t)jb.out_off + r) * k;
+			for (int j = 0; j < k; j++) {
+				int bw = -1;
+				for (int w2 = 0; w2 < 8; w2++) {
+					if (ptr[w2] >= 8 || s_i[w2][ptr[w2]] == 0x7fffffff) continue;
+					if (bw < 0 || s_d[w2][ptr[w2]] < s_d[bw][ptr[bw]] || (s_d[w2][ptr[w2]] == s_d[bw][ptr[bw]] && s_i[w2][ptr[w2]] < s_i[bw][ptr[bw]])) bw = w2;
+				}
+				if (bw < 0) { io[j] = -1; dd[j] = __int_as_float(0x7f800000); }
+				else { io[j] = s_i[bw][ptr[bw]]; dd[j] = (float)sqrt(s_d[bw][ptr[bw]]); ptr[bw]++; }
+			}
+		}
+		__syncthreads();
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct MatcherState {
+	int max_pairs = 0, max_feats = 0, dim = 0;
+	int pool_rows = 0;                      // capacity of the bf16 pool (rows)
+	DevBuf pool, norms, errn, sets, set_max, set_err, items, cand, jobs, job_rows, fb_rows, fb_count;
+	PinnedBuf h_stage, h_small;
+	PFN_encodeTiled encode = nullptr;
+	CUtensorMap tmap_q, tmap_t;
+	bool maps_ready = false;
+	long long cand_rows_cap = 0;
+	int max_items = 0, max_jobs = 0, max_rows_total = 0;
+	int last_items = 0, last_rows = 0;
+	cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+	bool timing = false;
+};
+
+void matcher_destroy(bt_ctx* ctx) {
+	MatcherState* m = ctx->matcher;
+	if (!m) return;
+	DevBuf* bufs[] = { &m->pool, &m->norms, &m->errn, &m->sets, &m->set_max, &m->set_err, &m->items, &m->cand, &m->jobs, &m->job_rows, &m->fb_rows, &m->fb_count };
+	for (DevBuf* b : bufs) b->release();
+	m->h_stage.release(); m->h_small.release();
+	for (auto& e : m->ev) if (e) cudaEventDestroy(e);
+	delete m;
+	ctx->matcher = nullptr;
+}
+
+static int make_tmap(MatcherState* m, CUtensorMap* out, void* base, uint64_t rows, uint32_t box_rows) {
+	const cuuint64_t gdim[2] = { (cuuint64_t)KD, rows };
+	const cuuint64_t gstride[1] = { (cuuint64_t)KD * 2 };
+	const cuuint32_t box[2] = { (cuuint32_t)BK, box_rows };
+	const cuuint32_t estr[2] = { 1, 1 };
+	const CUresult r = m->encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+	                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return BT_ERR_CUDA; }
+	return BT_OK;
+}
+
+}  // namespace bt
+
+using namespace bt;
+
+extern "C" int bt_matcher_reserve(bt_ctx* ctx, int max_pairs, int max_feats, int dim) {
+	BT_REQUIRE(ctx, BT_ERR_INVALID_ARG, "bt_matcher_reserve: NULL ctx");
+	BT_REQUIRE(dim == KD, BT_ERR_UNSUPPORTED, "bt_matcher_reserve: descriptor dim %d unsupported (the tensor path is built for %d)", dim, KD);
+	BT_REQUIRE(max_pairs > 0 && max_feats > 0, BT_ERR_INVALID_ARG, "bt_matcher_reserve: bad limits");
+	BT_CUDA(cudaSetDevice(ctx->device));
+	if (!ctx->matcher) ctx->matcher = new MatcherState();
+	MatcherState* m = ctx->matcher;
+	m->max_pairs = max_pairs; m->max_feats = max_feats; m->dim = dim;
+	if (!m->encode) {
+		void* fn = nullptr;
+		cudaDriverEntryPointQueryResult qres;
+		BT_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+		BT_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, BT_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+		m->encode = (PFN_encodeTiled)fn;
+	}
+	const int padded = (max_feats + BN - 1) / BN * BN;
+	m->pool_rows = 2 * max_pairs * padded + BN;          // worst case: every pair uses two distinct descriptor sets
+	const int qtiles = (max_feats + BM - 1) / BM;
+	const int max_splits = 8;
+	m->max_items = 2 * max_pairs * qtiles * max_splits;
+	m->max_jobs = 2 * max_pairs;
+	m->max_rows_total = 2 * max_pairs * max_feats;
+	m->cand_rows_cap = (long long)2 * max_pairs * qtiles * BM * max_splits;
+	int rc;
+#define RES(buf, bytes) if ((rc = m->buf.alloc(bytes)) != BT_OK) return rc
+	RES(pool, (size_t)m->pool_rows * KD * 2);
+	RES(norms, (size_t)m->pool_rows * 4);
+	RES(errn, (size_t)m->pool_rows * 4);
+	RES(sets, sizeof(PrepSet) * 2 * max_pairs);
+	RES(set_max, sizeof(int) * 2 * max_pairs);
+	RES(set_err, sizeof(int) * 2 * max_pairs);
+	RES(items, sizeof(KnnItem) * (size_t)m->max_items);
+	RES(cand, sizeof(float) * NCAND * (size_t)m->cand_rows_cap);
+	RES(jobs, sizeof(RerankJob) * m->max_jobs);
+	RES(job_rows, sizeof(int) * (m->max_jobs + 1));
+	RES(fb_rows, sizeof(int) * (size_t)m->max_rows_total);
+	RES(fb_count, 16);
+#undef RES
+	if ((rc = m->h_small.alloc(64)) != BT_OK) return rc;
+	if ((rc = make_tmap(m, &m->tmap_q, m->pool.p, (uint64_t)m->pool_rows, BM)) != BT_OK) return rc;
+	if ((rc = make_tmap(m, &m->tmap_t, m->pool.p, (uint64_t)m->pool_rows, BN)) != BT_OK) return rc;
+	m->maps_ready = true;
+	BT_CUDA(cudaFuncSetAttribute(k_knn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
+	return BT_OK;
+}
+
+extern "C" int bt_knn_enable_timing(bt_ctx* ctx, int on) {
+	BT_REQUIRE(ctx && ctx->matcher, BT_ERR_INVALID_ARG, "bt_knn_enable_timing: call bt_matcher_reserve first");
+	MatcherState* m = ctx->matcher;
+	if (on) for (auto& e : m->ev) if (!e) BT_CUDA(cudaEventCreate(&e));
+	m->timing = on != 0;
+	return BT_OK;
+}
+// ms4 = {descriptor prep, tensor-core pass, exact re-rank, exact fallback}; info3 = {work items, query rows, fallback rows}
+extern "C" int bt_knn_get_timing(bt_ctx* ctx, float* ms4, int* info3) {
+	BT_REQUIRE(ctx && ctx->matcher && ctx->matcher->timing && ms4 && info3, BT_ERR_INVALID_ARG, "bt_knn_get_timing: timing not enabled");
+	MatcherState* m = ctx->matcher;
+	BT_CUDA(cudaEventSynchronize(m->ev[4]));
+	for (int k = 0; k < 4; k++) BT_CUDA(cudaEventElapsedTime(ms4 + k, m->ev[k], m->ev[k + 1]));
+	int fb = 0;
+	BT_CUDA(cudaMemcpy(&fb, m->fb_count.p, sizeof(int), cudaMemcpyDeviceToHost));
+	info3[0] = m->last_items; info3[1] = m->last_rows; info3[2] = fb;
+	return BT_OK;
+}
+
+extern "C" int bt_knn_match_pairs(bt_ctx* ctx, int n_pairs, const bt_desc_view* A, const bt_desc_view* B, int k,
+                                  int32_t* idxAB, float* distAB, int32_t* idxBA, float* distBA, void* stream_) {
+	BT_REQUIRE(ctx && ctx->matcher && ctx->matcher->maps_ready, BT_ERR_INVALID_ARG, "bt_knn_match_pairs: call bt_matcher_reserve first");
+	BT_REQUIRE(A && B && idxAB && distAB && idxBA && distBA, BT_ERR_INVALID_ARG, "bt_knn_match_pairs: NULL argument");
+	BT_REQUIRE(k >= 1 && k <= 8, BT_ERR_UNSUPPORTED, "bt_knn_match_pairs: k=%d outside [1,8]", k);
+	MatcherState* m = ctx->matcher;
+	cudaStream_t stream = (cudaStream_t)stream_;
+	BT_CUDA(cudaSetDevice(ctx->device));
+	BT_REQUIRE(n_pairs > 0 && n_pairs <= m->max_pairs, BT_ERR_CAPACITY, "bt_knn_match_pairs: %d pairs > reserved %d", n_pairs, m->max_pairs);
+	for (int p = 0; p < n_pairs; p++) {
+		for (const bt_desc_view* v : { &A[p], &B[p] }) {
+			BT_REQUIRE(v->dim == KD, BT_ERR_UNSUPPORTED, "pair %d: descriptor dim %d != %d", p, v->dim, KD);
+			BT_REQUIRE(v->n >= 0 && v->n <= m->max_feats, BT_ERR_CAPACITY, "pair %d: %d features > reserved %d", p, v->n, m->max_feats);
+			BT_REQUIRE(v->n == 0 || v->dev, BT_ERR_INVALID_ARG, "pair %d: NULL descriptor pointer", p);
+			BT_REQUIRE(((uintptr_t)v->dev & 15) == 0 && ((v->pitch_bytes ? v->pitch_bytes : (size_t)KD * 4) & 15) == 0, BT_ERR_INVALID_ARG, "pair %d: descriptors must be 16-byte aligned", p);
+		}
+	}
+	// ---- unique descriptor sets (a keyframe appears in many pairs) -> pool slots
+	std::map<std::pair<const float*, int>, int> slot_of;
+	std::vector<PrepSet> sets;
+	int pool_row = 0;
+	auto slot = [&](const bt_desc_view& v) -> int {
+		const auto key = std::make_pair(v.dev, v.n);
+		auto it = slot_of.find(key);
+		if (it != slot_of.end()) return it->second;
+		PrepSet s; s.src = v.dev; s.pitch_bytes = v.pitch_bytes ? v.pitch_bytes : (size_t)v.dim * 4; s.n = v.n; s.row0 = pool_row;
+		s.rows_padded = (std::max(v.n, 1) + BN - 1) / BN * BN; s.pad = 0;
+		pool_row += s.rows_padded;
+		sets.push_back(s);
+		slot_of[key] = (int)sets.size() - 1;
+		return (int)sets.size() - 1;
+	};
+	std::vector<int> sa(n_pairs), sb(n_pairs);
+	for (int p = 0; p < n_pairs; p++) { sa[p] = slot(A[p]); sb[p] = slot(B[p]); }
+	BT_REQUIRE(pool_row <= m->pool_rows, BT_ERR_CAPACITY, "bt_knn_match_pairs: descriptor pool overflow");
+	// ---- work items + re-rank jobs.  Train splits: enough items to fill the machine; each split <= 8192 rows (13 index bits).
+	long long base_items = 0;
+	for (int p = 0; p < n_pairs; p++) base_items += (A[p].n + BM - 1) / BM + (B[p].n + BM - 1) / BM;
+	std::vector<KnnItem> items;
+	std::vector<RerankJob> jobs;
+	std::vector<int> job_rows;
+	long long cand_rows = 0; int total_rows = 0;
+	size_t off_dir[2] = { 0, 0 };
+	for (int p = 0; p < n_pairs; p++) {
+		for (int dir = 0; dir < 2; dir++) {
+			const bt_desc_view& Q = dir == 0 ? A[p] : B[p];
+			const bt_desc_view& T = dir == 0 ? B[p] : A[p];
+			const int qset = dir == 0 ? sa[p] : sb[p], tset = dir == 0 ? sb[p] : sa[p];
+			const PrepSet& qs = sets[qset];
+			const PrepSet& ts = sets[tset];
+			const int qtiles = (Q.n + BM - 1) / BM, ttiles = ts.rows_padded / BN;
+			int splits = 1;
+			if (base_items < 2LL * ctx->sm_count) splits = (int)std::min<long long>(8, (2LL * ctx->sm_count + base_items - 1) / std::max<long long>(base_items, 1));
+			splits = std::max(splits, (ts.rows_padded + MAX_SPLIT_ROWS - 1) / MAX_SPLIT_ROWS);
+			splits = std::min(splits, std::max(ttiles, 1));
+			BT_REQUIRE(splits <= 8, BT_ERR_CAPACITY, "pair %d: %d train rows need more than 8 splits", p, T.n);
+			const int tiles_per_split = (ttiles + splits - 1) / splits;
+			splits = (ttiles + tiles_per_split - 1) / std::max(tiles_per_split, 1);
+			RerankJob jb; memset(&jb, 0, sizeof jb);
+			jb.q = Q.dev; jb.q_pitch = qs.pitch_bytes; jb.nq = Q.n; jb.q_pool_row0 = qs.row0;
+			jb.t = T.dev; jb.t_pitch = ts.pitch_bytes; jb.nt = T.n; jb.t_set = tset;
+			jb.n_splits = (Q.n > 0 && T.n > 0) ? splits : 0; jb.split_rows = tiles_per_split * BN;
+			jb.cand_off = (int)cand_rows; jb.cand_split_stride = qtiles * BM;
+			jb.out_off = (int)off_dir[dir]; jb.dir = dir;
+			if (Q.n > 0 && T.n > 0) {
+				for (int s = 0; s < splits; s++) {
+					for (int qt = 0; qt < qtiles; qt++) {
+						KnnItem it; memset(&it, 0, sizeof it);
+						it.q_row0 = qs.row0 + qt * BM; it.q_valid = std::min(BM, Q.n - qt * BM);
+						it.t_row0 = ts.row0 + s * tiles_per_split * BN;
+						it.t_tiles = std::min(tiles_per_split, ttiles - s * tiles_per_split);
+						it.cand_off = (int)(cand_rows + (long long)s * qtiles * BM + (long long)qt * BM);
+						items.push_back(it);
+					}
+				}
+				cand_rows += (long long)splits * qtiles * BM;
+			}
+			jobs.push_back(jb);
+			job_rows.push_back(total_rows);
+			total_rows += Q.n;
+			off_dir[dir] += Q.n;
+		}
+	}
+	job_rows.push_back(total_rows);
+	BT_REQUIRE((int)items.size() <= m->max_items && cand_rows <= m->cand_rows_cap && total_rows <= m->max_rows_total, BT_ERR_CAPACITY, "bt_knn_match_pairs: work list overflow");
+	// ---- upload tables (one pinned block)
+	const size_t b_sets = sizeof(PrepSet) * sets.size(), b_items = sizeof(KnnItem) * items.size(), b_jobs = sizeof(RerankJob) * jobs.size(), b_rows = sizeof(int) * job_rows.size();
+	int rc = m->h_stage.alloc(b_sets + b_items + b_jobs + b_rows + 1024);
+	if (rc != BT_OK) return rc;
+	char* hb = m->h_stage.as<char>();
+	memcpy(hb, sets.data(), b_sets);
+	memcpy(hb + b_sets, items.data(), b_items);
+	memcpy(hb + b_sets + b_items, jobs.data(), b_jobs);
+	memcpy(hb + b_sets + b_items + b_jobs, job_rows.data(), b_rows);
+	BT_CUDA(cudaMemcpyAsync(m->sets.p, hb, b_sets, cudaMemcpyHostToDevice, stream));
+	if (b_items) BT_CUDA(cudaMemcpyAsync(m->items.p, hb + b_sets, b_items, cudaMemcpyHostToDevice, stream));
+	BT_CUDA(cudaMemcpyAsync(m->jobs.p, hb + b_sets + b_items, b_jobs, cudaMemcpyHostToDevice, stream));
+	BT_CUDA(cudaMemcpyAsync(m->job_rows.p, hb + b_sets + b_items + b_jobs, b_rows, cudaMemcpyHostToDevice, stream));
+	BT_CUDA(cudaMemsetAsync(m->fb_count.p, 0, 16, stream));
+	BT_CUDA(cudaMemsetAsync(m->set_max.p, 0, sizeof(int) * sets.size(), stream));
+	BT_CUDA(cudaMemsetAsync(m->set_err.p, 0, sizeof(int) * sets.size(), stream));
+	// ---- kernels
+	if (m->timing) BT_CUDA(cudaEventRecord(m->ev[0], stream));
+	int max_padded = 0;
+	for (auto& s : sets) max_padded = std::max(max_padded, s.rows_padded);
+	k_desc_prep<<<dim3((unsigned)std::max(1, std::min((max_padded + 7) / 8, 64)), (unsigned)sets.size()), 256, 0, stream>>>(
+	    m->sets.as<PrepSet>(), m->pool.as<__nv_bfloat16>(), m->norms.as<float>(), m->errn.as<float>(), m->set_max.as<int>(), m->set_err.as<int>());
+	if (m->timing) BT_CUDA(cudaEventRecord(m->ev[1], stream));
+	if (!items.empty()) {
+		const int grid = std::min((int)items.size(), ctx->sm_count);
+		k_knn_tc<<<grid, KNN_THREADS, SMEM_TOTAL, stream>>>(m->tmap_q, m->tmap_t, m->items.as<KnnItem>(), (int)items.size(), m->norms.as<float>(), m->cand.as<float>());
+	}
+	if (m->timing) BT_CUDA(cudaEventRecord(m->ev[2], stream));
+	KnnOut out; out.idx[0] = idxAB; out.idx[1] = idxBA; out.dist[0] = distAB; out.dist[1] = distBA;
+	if (total_rows > 0) {
+		k_knn_rerank<<<(total_rows + 7) / 8, 256, 0, stream>>>(m->jobs.as<RerankJob>(), m->job_rows.as<int>(), (int)jobs.size(), total_rows, m->cand.as<float>(),
+		                                                     m->norms.as<float>(), m->errn.as<float>(), m->set_max.as<int>(), m->set_err.as<int>(), k, out, m->fb_rows.as<int>(), m->fb_count.as<int>());
+		if (m->timing) BT_CUDA(cudaEventRecord(m->ev[3], stream));
+		k_knn_exact<<<ctx->sm_count * 2, 256, 0, stream>>>(m->jobs.as<RerankJob>(), m->job_rows.as<int>(), (int)jobs.size(), m->fb_rows.as<int>(), m->fb_count.as<int>(), k, out);
+	} else if (m->timing) BT_CUDA(cudaEventRecord(m->ev[3], stream));
+	if (m->timing) BT_CUDA(cudaEventRecord(m->ev[4], stream));
+	BT_CUDA(cudaGetLastError());
+	m->last_items = (int)items.size(); m->last_rows = total_rows;
+	return BT_OK;
+}

@@ -37,6 +37,9 @@
 
 namespace bt {
 
+#ifndef BT_SOLVE_MIN_CTAS
+#define BT_SOLVE_MIN_CTAS 2
+#endif
 static constexpr int kThreads = 256;          // CTA size of k_solve
 static constexpr int kWarps = kThreads / 32;
 static constexpr int kTileVals = 28;          // 21 (sym 6x6) + 6 (rhs) + 1 (#correspondences found)
@@ -53,7 +56,7 @@ struct WinDesc {
 	float ifx, ify, icx, icy;         // inverse full-res intrinsics (m_inputIntrinsicsInv)
 	float scaleW, scaleH;             // (W-1)/(w-1), (H-1)/(h-1)  (CUDAImageUtil.cu:57-58)
 	int compat_flip;
-	int pad;
+	int mem_off;                      // per-frame membership CSR of this window (see SolveArgs::mem)
 };
 
 struct Tile { int win; int pair; int start; int count; };  // pair < 0 => dummy tile (window without dense work)
@@ -77,6 +80,10 @@ struct SolveArgs {
 	const bt_entryj* corr;
 	const int* grp_i; const int* grp_j; const int* grp_start;   // grp_start has n_groups+1 entries per window
 	const uint2* pairs;   // (target, source)
+	const int* pair_win;  // owning window of every entry of `pairs`
+	// per-window CSR built on the host: for every frame f, first the correspondence groups touching f, then the dense
+	// pairs touching f.  Layout at mem_off: fg_start[N+1], fp_start[N+1], items[2G] (g | role<<16), items[2P] (p | role<<16)
+	const int* mem;
 	// schedule
 	Tile* tiles; int* n_tiles_total; int max_tiles;
 	int* pair_tile0; int* pair_ntile;   // per (window, pair): first tile (relative to the window's tile_off) and tile count
@@ -89,6 +96,7 @@ struct SolveArgs {
 	bt_solver_params prm;
 	float* dbg_JtJ; float* dbg_Jtr; int dbg_stride;   // optional dense-system dump (last GN iteration)
 	float* dbg_cnt; int dbg_cnt_stride;               // optional per-pair #correspondences found (last GN iteration)
+	long long* prof; int prof_cap;                    // optional phase timestamps: [0] = record count, then 12 x int64 per record
 };
 
 // ------------------------------------------------------------------------------------------------ device math
@@ -122,7 +130,7 @@ __device__ void so3_exp_AB(V3 w, float A, float B, float R[9]) {  // rodrigues_s
 	a = A * w.x; b = B * (w.y * w.z); R[5] = b - a; R[7] = b + a;
 }
 // poseToMatrix (LieDerivUtil.h:150-194): T[12] = row-major 3x4 [R | t]
-__device__ void se3_exp(V3 rot, V3 trans, float T[12]) {
+__device__ __noinline__ void se3_exp(V3 rot, V3 trans, float T[12]) {
 	const float theta_sq = dot(rot, rot);
 	float A, B, C;
 	so3_coeffs(theta_sq, A, B, C);
@@ -158,7 +166,7 @@ __device__ V3 so3_log(const float R[9]) {
 	return r;
 }
 // matrixToPose (LieDerivUtil.h:126-148); T = row-major 3x4
-__device__ void se3_log(const float T[12], V3& rot, V3& trans) {
+__device__ __noinline__ void se3_log(const float T[12], V3& rot, V3& trans) {
 	const float R[9] = { T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10] };
 	const V3 t = mk(T[3], T[7], T[11]);
 	rot = so3_log(R);
@@ -191,6 +199,18 @@ __device__ __forceinline__ void st_release(int* p, int v) {
 	asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Optional in-kernel phase profile (developer aid): thread 0 stamps clock64() at phase boundaries.
+struct ProfRec { long long kind_cta, tile_win, t[10]; };
+__device__ __forceinline__ void prof_emit(const SolveArgs& a, const ProfRec& r) {
+	const unsigned long long k = atomicAdd((unsigned long long*)a.prof, 1ull);
+	if ((int)k < a.prof_cap) {
+		long long* o = a.prof + 1 + k * 12;
+		o[0] = r.kind_cta; o[1] = r.tile_win;
+		for (int i = 0; i < 10; i++) o[2 + i] = r.t[i];
+	}
+}
+#define PROF_T(i) do { if (a.prof && threadIdx.x == 0) prf.t[i] = clock64(); } while (0)
+
 // ------------------------------------------------------------------------------------------------ k_prep_frames
 // CUDACache::storeFrame fused (convertDepthFloatToCameraSpaceFloat4 + 2x resampleFloat4 nearest, CUDAImageUtil.cu:
 // 310-326,82-99) + compaction of the source list + matrixToPose/poseToMatrix of the incoming pose (SBA.cu:71-79).
@@ -221,32 +241,53 @@ __global__ void __launch_bounds__(512) k_prep_frames(SolveArgs a) {
 	__syncthreads();
 	const bool use_dense = a.prm.w_dense > 0.0f;
 	if (!use_dense) { if (tid == 0) a.nsrc[fs] = 0; return; }
-	for (int base = 0; base < npix; base += blockDim.x) {
-		const int idx = base + tid;
-		float4 cp = make_float4(0.f, 0.f, 0.f, 0.f), nr = make_float4(0.f, 0.f, 0.f, 0.f);
-		bool valid = false;
-		if (idx < npix) {
-			const int x = idx % wd.w, y = idx / wd.w;
-			const unsigned xi = (unsigned)((float)x * wd.scaleW + 0.5f), yi = (unsigned)((float)y * wd.scaleH + 0.5f);
-			if (xi < (unsigned)wd.W && yi < (unsigned)wd.H) {
-				const size_t s = (size_t)yi * wd.W + xi;
-				const float d = __ldg(depth + s);
-				if (d >= 0.1f) cp = make_float4(wd.ifx * ((float)xi * d) + wd.icx * d, wd.ify * ((float)yi * d) + wd.icy * d, d, 1.0f);
-				nr = __ldg(normal + s);
+	constexpr int PX = 4;   // consecutive quarter-res pixels per thread and iteration: 8 independent loads in flight
+	for (int base = 0; base < npix; base += blockDim.x * PX) {
+		const int idx0 = base + tid * PX;
+		float d[PX]; float4 nr[PX]; size_t sidx[PX]; bool inb[PX];
+#pragma unroll
+		for (int j = 0; j < PX; j++) {
+			const int idx = idx0 + j;
+			inb[j] = false; sidx[j] = 0; d[j] = 0.f; nr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (idx < npix) {
+				const int x = idx % wd.w, y = idx / wd.w;
+				const unsigned xi = (unsigned)((float)x * wd.scaleW + 0.5f), yi = (unsigned)((float)y * wd.scaleH + 0.5f);
+				if (xi < (unsigned)wd.W && yi < (unsigned)wd.H) { inb[j] = true; sidx[j] = (size_t)yi * wd.W + xi; }
 			}
-			texel[2 * idx] = cp;
-			texel[2 * idx + 1] = nr;
-			valid = (cp.z > a.prm.depth_min && cp.z < a.prm.depth_max);
 		}
-		const unsigned bal = __ballot_sync(0xffffffffu, valid);
-		if (lane == 0) s_warp[wid] = __popc(bal);
+#pragma unroll
+		for (int j = 0; j < PX; j++) if (inb[j]) { d[j] = __ldg(depth + sidx[j]); nr[j] = __ldg(normal + sidx[j]); }
+		float4 cp[PX]; bool valid[PX]; int cnt = 0;
+#pragma unroll
+		for (int j = 0; j < PX; j++) {
+			const int idx = idx0 + j;
+			cp[j] = make_float4(0.f, 0.f, 0.f, 0.f); valid[j] = false;
+			if (idx < npix) {
+				if (inb[j] && d[j] >= 0.1f) {
+					const int x = idx % wd.w, y = idx / wd.w;
+					const unsigned xi = (unsigned)((float)x * wd.scaleW + 0.5f), yi = (unsigned)((float)y * wd.scaleH + 0.5f);
+					cp[j] = make_float4(wd.ifx * ((float)xi * d[j]) + wd.icx * d[j], wd.ify * ((float)yi * d[j]) + wd.icy * d[j], d[j], 1.0f);
+				}
+				texel[2 * idx] = make_float4(cp[j].x, cp[j].y, cp[j].z, nr[j].x);      // 32-byte texel: point xyz + normal xyz (+ pad)
+				texel[2 * idx + 1] = make_float4(nr[j].y, nr[j].z, 0.f, 0.f);
+				valid[j] = (cp[j].z > a.prm.depth_min && cp[j].z < a.prm.depth_max);
+				cnt += valid[j] ? 1 : 0;
+			}
+		}
+		int incl = cnt;   // warp inclusive scan of the per-thread counts (order-preserving compaction)
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+		if (lane == 31) s_warp[wid] = incl;
 		__syncthreads();
-		int off = s_base;
+		int off = s_base + incl - cnt;
 		for (int k = 0; k < wid; k++) off += s_warp[k];
-		if (valid) {
-			const int o = off + __popc(bal & ((1u << lane) - 1u));
-			src[2 * o] = make_float4(cp.x, cp.y, cp.z, nr.x);
-			src[2 * o + 1] = make_float4(nr.y, nr.z, nr.w, 0.f);
+#pragma unroll
+		for (int j = 0; j < PX; j++) {
+			if (valid[j]) {
+				src[2 * off] = make_float4(cp[j].x, cp[j].y, cp[j].z, nr[j].x);
+				src[2 * off + 1] = make_float4(nr[j].y, nr[j].z, nr[j].w, 0.f);
+				off++;
+			}
 		}
 		__syncthreads();
 		if (tid == 0) { int t = 0; for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += s_warp[k]; s_base += t; }
@@ -263,67 +304,90 @@ __device__ __forceinline__ int chunks_for(int n, int chunk, int& per) {
 	return (n + per - 1) / per;
 }
 __global__ void __launch_bounds__(1024) k_plan(SolveArgs a, WinDesc* wins_rw) {
+	__shared__ int s_cnt[1024];
 	__shared__ int s_scan[1024];
 	__shared__ int s_carry;
-	__shared__ long long s_px;
+	__shared__ unsigned long long s_px;
 	const int tid = threadIdx.x;
-	if (tid == 0) { s_carry = 0; s_px = 0; *a.queue = 0; }
+	if (tid == 0) { s_carry = 0; s_px = 0ull; *a.queue = 0; }
 	__syncthreads();
-	for (int base = 0; base < a.n_windows; base += blockDim.x) {
-		const int w = base + tid;
-		int cnt = 0;
-		long long px = 0;
-		if (w < a.n_windows) {
-			const WinDesc wd = a.wins[w];
-			for (int p = 0; p < wd.n_pairs; p++) {
-				const uint2 pr = a.pairs[wd.pair_off + p];
-				const int n = a.nsrc[wd.frame_off + pr.y];
-				int per;
-				cnt += chunks_for(n, a.chunk, per);
-				px += n;
-			}
-			if (cnt == 0) cnt = 1;   // dummy tile: the window still needs its tail every iteration
-			a.tiles_done[w] = 0;
-			a.iter_done[w] = 0;
+	for (int base = 0; base < a.n_windows; base += 1024) {
+		const int nw = min(1024, a.n_windows - base);
+		s_cnt[tid] = 0;
+		__syncthreads();
+		// (1) chunk count of every (window, pair) of this block of windows, in parallel
+		const int first_pair = a.wins[base].pair_off;
+		const WinDesc wl = a.wins[base + nw - 1];
+		const int end_pair = wl.pair_off + wl.n_pairs;
+		unsigned long long px = 0;
+		for (int q = first_pair + tid; q < end_pair; q += 1024) {
+			const int lo = a.pair_win[q];
+			const uint2 pr = a.pairs[q];
+			const int n = a.nsrc[a.wins[lo].frame_off + pr.y];
+			int per;
+			const int nch = chunks_for(n, a.chunk, per);
+			a.pair_ntile[q] = nch;
+			atomicAdd(&s_cnt[lo - base], nch);
+			px += (unsigned long long)n;
 		}
+		if (px) atomicAdd(&s_px, px);
+		__syncthreads();
+		// (2) exclusive scan of the per-window tile counts (a window without dense work still gets one dummy tile)
+		int cnt = 0;
+		if (tid < nw) { cnt = s_cnt[tid]; if (cnt == 0) cnt = 1; a.tiles_done[base + tid] = 0; a.iter_done[base + tid] = 0; }
 		s_scan[tid] = cnt;
 		__syncthreads();
-		for (int o = 1; o < (int)blockDim.x; o <<= 1) {   // Hillis-Steele inclusive scan
-			int v = (tid >= o) ? s_scan[tid - o] : 0;
+		for (int o = 1; o < 1024; o <<= 1) {
+			const int v = (tid >= o) ? s_scan[tid - o] : 0;
 			__syncthreads();
 			s_scan[tid] += v;
 			__syncthreads();
 		}
 		const int excl = s_scan[tid] - cnt + s_carry;
-		if (w < a.n_windows) {
-			wins_rw[w].tile_off = excl;
-			wins_rw[w].n_tiles = cnt;
-			const WinDesc wd = a.wins[w];
-			int t = excl;
-			if (excl + cnt <= a.max_tiles) {
-				for (int p = 0; p < wd.n_pairs; p++) {
-					const uint2 pr = a.pairs[wd.pair_off + p];
-					const int n = a.nsrc[wd.frame_off + pr.y];
-					int per;
-					const int nch = chunks_for(n, a.chunk, per);
-					a.pair_tile0[wd.pair_off + p] = t - excl;
-					a.pair_ntile[wd.pair_off + p] = nch;
-					for (int c = 0; c < nch; c++) {
-						Tile tl; tl.win = w; tl.pair = p; tl.start = c * per; tl.count = min(per, n - c * per);
-						a.tiles[t++] = tl;
-					}
-				}
-				if (t == excl) { Tile tl; tl.win = w; tl.pair = -1; tl.start = 0; tl.count = 0; a.tiles[t++] = tl; }
-			}
-			atomicAdd((unsigned long long*)&s_px, (unsigned long long)px);
+		const bool fits = (s_carry + s_scan[1023] <= a.max_tiles);
+		// (3) per-window prefix over its pairs: one warp per window, lanes over pairs
+		if (tid < nw) {
+			wins_rw[base + tid].tile_off = excl;
+			wins_rw[base + tid].n_tiles = cnt;
+			s_cnt[tid] = excl;      // reuse: window -> tile_off for step (4)
 		}
 		__syncthreads();
-		if (tid == blockDim.x - 1) s_carry += s_scan[tid];
+		for (int wl = (tid >> 5); wl < nw; wl += 32) {
+			const int w = base + wl, lane = tid & 31;
+			const int poff = a.wins[w].pair_off, np = a.wins[w].n_pairs;
+			int carry = 0;
+			for (int p0 = 0; p0 < np; p0 += 32) {
+				const int p = p0 + lane;
+				const int v = (p < np) ? a.pair_ntile[poff + p] : 0;
+				int incl = v;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+				if (p < np) a.pair_tile0[poff + p] = carry + incl - v;
+				carry += __shfl_sync(0xffffffffu, incl, 31);
+			}
+			if (lane == 0 && carry == 0 && fits) { Tile tl; tl.win = w; tl.pair = -1; tl.start = 0; tl.count = 0; a.tiles[s_cnt[wl]] = tl; }
+		}
+		__syncthreads();
+		// (4) tile records, one (window, pair) per thread
+		if (fits) {
+			for (int q = first_pair + tid; q < end_pair; q += 1024) {
+				const int lo = a.pair_win[q];
+				const WinDesc wd = a.wins[lo];
+				const uint2 pr = a.pairs[q];
+				const int n = a.nsrc[wd.frame_off + pr.y];
+				int per;
+				const int nch = chunks_for(n, a.chunk, per);
+				int t = s_cnt[lo - base] + a.pair_tile0[q];
+				for (int c = 0; c < nch; c++) { Tile tl; tl.win = lo; tl.pair = q - wd.pair_off; tl.start = c * per; tl.count = min(per, n - c * per); a.tiles[t++] = tl; }
+			}
+		}
+		__syncthreads();
+		if (tid == 0) s_carry += s_scan[1023];
 		__syncthreads();
 	}
 	if (tid == 0) {
 		*a.n_tiles_total = (s_carry <= a.max_tiles) ? s_carry : -1;   // -1 => capacity error reported by the host
-		*a.n_src_px = s_px;
+		*a.n_src_px = (long long)s_px;
 	}
 }
 
@@ -333,6 +397,11 @@ __global__ void __launch_bounds__(1024) k_plan(SolveArgs a, WinDesc* wins_rw) {
 // the model frame with the 6x6 adjoint of T_i.
 struct TileAcc { float v[kTileVals]; };
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// Software-pipelined over a thread's pixels (stride kThreads): iteration i issues the source load of pixel i+2, projects
+// pixel i+1 (whose source arrived during the previous iteration) and prefetches its four bilinear taps into L1, then does
+// the full evaluation of pixel i with its taps already on chip.
 __device__ __forceinline__ void tile_pixels(const SolveArgs& a, const WinDesc& wd, const float4* __restrict__ src,
                                             const float4* __restrict__ tex, const float* __restrict__ sM, int start, int count, TileAcc& acc) {
 	const float m00 = sM[0], m01 = sM[1], m02 = sM[2], m03 = sM[3];
@@ -342,16 +411,40 @@ __device__ __forceinline__ void tile_pixels(const SolveArgs& a, const WinDesc& w
 	const unsigned W = (unsigned)wd.w, Hh = (unsigned)wd.h;
 	const float dmin = a.prm.depth_min, dmax = a.prm.depth_max, dist_t = a.prm.dense_dist_thresh, cos_t = a.prm.dense_cos_normal_thresh;
 	const float delta = a.prm.robust_delta, wdense = a.prm.w_dense;
-	for (int k = threadIdx.x; k < count; k += kThreads) {
-		const float4 s0 = __ldg(src + 2 * (size_t)(start + k)), s1 = __ldg(src + 2 * (size_t)(start + k) + 1);
+	const float4* sp = src + 2 * (size_t)start;
+	int k = threadIdx.x;
+	float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0, n0 = c0, n1 = c0, f0 = c0, f1 = c0;   // current, next, next-next source records
+	if (k < count) { c0 = __ldg(sp + 2 * k); c1 = __ldg(sp + 2 * k + 1); }
+	if (k + kThreads < count) { n0 = __ldg(sp + 2 * (k + kThreads)); n1 = __ldg(sp + 2 * (k + kThreads) + 1); }
+	// prefetch taps of the first pixel
+	auto project_prefetch = [&](const float4& s0) {
+		const float tx = m00 * s0.x + m01 * s0.y + m02 * s0.z + m03, ty = m10 * s0.x + m11 * s0.y + m12 * s0.z + m13, tz = m20 * s0.x + m21 * s0.y + m22 * s0.z + m23;
+		const float sx = tx * fx / tz + cx, sy = ty * fy / tz + cy;
+		const int x0 = (int)floorf(sx), y0 = (int)floorf(sy);
+		if (x0 >= -1 && y0 >= -1 && x0 < (int)W && y0 < (int)Hh) {
+			const int xa = max(x0, 0), ya = max(y0, 0), yb = min(y0 + 1, (int)Hh - 1);
+			prefetch_l1(tex + 2 * ((size_t)ya * W + xa));
+			prefetch_l1(tex + 2 * ((size_t)ya * W + min(xa + 1, (int)W - 1)) + 1);
+			prefetch_l1(tex + 2 * ((size_t)yb * W + xa));
+			prefetch_l1(tex + 2 * ((size_t)yb * W + min(xa + 1, (int)W - 1)) + 1);
+		}
+	};
+#ifndef BT_NO_L1_PREFETCH
+	if (k < count) project_prefetch(c0);
+#endif
+	for (; k < count; k += kThreads) {
+		const int k2 = k + 2 * kThreads;
+		if (k2 < count) { f0 = __ldg(sp + 2 * k2); f1 = __ldg(sp + 2 * k2 + 1); }
+#ifndef BT_NO_L1_PREFETCH
+		if (k + kThreads < count) project_prefetch(n0);
+#endif
+		const float4 s0 = c0, s1 = c1;
+		c0 = n0; c1 = n1; n0 = f0; n1 = f1;
 		const float px = s0.x, py = s0.y, pz = s0.z, nx = s0.w, ny = s1.x, nz = s1.y;
 		// camPosSrcToTgt = transform * camPosSrc ; nrmj = transform(3x3) * n  (w of the normal is 0)
 		const float tx = m00 * px + m01 * py + m02 * pz + m03;
 		const float ty = m10 * px + m11 * py + m12 * pz + m13;
 		const float tz = m20 * px + m21 * py + m22 * pz + m23;
-		const float rnx = m00 * nx + m01 * ny + m02 * nz;
-		const float rny = m10 * nx + m11 * ny + m12 * nz;
-		const float rnz = m20 * nx + m21 * ny + m22 * nz;
 		const float sx = tx * fx / tz + cx, sy = ty * fy / tz + cy;    // cameraToDepth, CUDACameraUtil.h:9-14
 		const int ix = (int)roundf(sx), iy = (int)roundf(sy);
 		if (!(ix >= 0 && iy >= 0 && ix < (int)W && iy < (int)Hh)) continue;
@@ -359,31 +452,34 @@ __device__ __forceinline__ void tile_pixels(const SolveArgs& a, const WinDesc& w
 		const float fx0 = floorf(sx), fy0 = floorf(sy);
 		const int x0 = (int)fx0, y0 = (int)fy0;
 		const float al = sx - fx0, be = sy - fy0;
-		float c0[3] = { 0.f, 0.f, 0.f }, n0[3] = { 0.f, 0.f, 0.f }, c1[3] = { 0.f, 0.f, 0.f }, n1[3] = { 0.f, 0.f, 0.f };
+		float a0[3] = { 0.f, 0.f, 0.f }, b0[3] = { 0.f, 0.f, 0.f }, a1[3] = { 0.f, 0.f, 0.f }, b1[3] = { 0.f, 0.f, 0.f };
 		float w0 = 0.f, w1 = 0.f;
 		const bool inx0 = (unsigned)x0 < W, inx1 = (unsigned)(x0 + 1) < W, iny0 = (unsigned)y0 < Hh, iny1 = (unsigned)(y0 + 1) < Hh;
 		if (iny0) {
 			const float4* row = tex + 2 * ((size_t)y0 * W);
-			if (inx0) { const float4 cp = __ldg(row + 2 * x0), nr = __ldg(row + 2 * x0 + 1); const float wt = 1.0f - al;
-				c0[0] += wt * cp.x; c0[1] += wt * cp.y; c0[2] += wt * cp.z; n0[0] += wt * nr.x; n0[1] += wt * nr.y; n0[2] += wt * nr.z; w0 += wt; }
-			if (inx1) { const float4 cp = __ldg(row + 2 * (x0 + 1)), nr = __ldg(row + 2 * (x0 + 1) + 1); const float wt = al;
-				c0[0] += wt * cp.x; c0[1] += wt * cp.y; c0[2] += wt * cp.z; n0[0] += wt * nr.x; n0[1] += wt * nr.y; n0[2] += wt * nr.z; w0 += wt; }
+			if (inx0) { const float4 cp = __ldg(row + 2 * x0); const float2 nr = __ldg(reinterpret_cast<const float2*>(row + 2 * x0 + 1)); const float wt = 1.0f - al;
+				a0[0] += wt * cp.x; a0[1] += wt * cp.y; a0[2] += wt * cp.z; b0[0] += wt * cp.w; b0[1] += wt * nr.x; b0[2] += wt * nr.y; w0 += wt; }
+			if (inx1) { const float4 cp = __ldg(row + 2 * (x0 + 1)); const float2 nr = __ldg(reinterpret_cast<const float2*>(row + 2 * (x0 + 1) + 1)); const float wt = al;
+				a0[0] += wt * cp.x; a0[1] += wt * cp.y; a0[2] += wt * cp.z; b0[0] += wt * cp.w; b0[1] += wt * nr.x; b0[2] += wt * nr.y; w0 += wt; }
 		}
 		if (iny1) {
 			const float4* row = tex + 2 * ((size_t)(y0 + 1) * W);
-			if (inx0) { const float4 cp = __ldg(row + 2 * x0), nr = __ldg(row + 2 * x0 + 1); const float wt = 1.0f - al;
-				c1[0] += wt * cp.x; c1[1] += wt * cp.y; c1[2] += wt * cp.z; n1[0] += wt * nr.x; n1[1] += wt * nr.y; n1[2] += wt * nr.z; w1 += wt; }
-			if (inx1) { const float4 cp = __ldg(row + 2 * (x0 + 1)), nr = __ldg(row + 2 * (x0 + 1) + 1); const float wt = al;
-				c1[0] += wt * cp.x; c1[1] += wt * cp.y; c1[2] += wt * cp.z; n1[0] += wt * nr.x; n1[1] += wt * nr.y; n1[2] += wt * nr.z; w1 += wt; }
+			if (inx0) { const float4 cp = __ldg(row + 2 * x0); const float2 nr = __ldg(reinterpret_cast<const float2*>(row + 2 * x0 + 1)); const float wt = 1.0f - al;
+				a1[0] += wt * cp.x; a1[1] += wt * cp.y; a1[2] += wt * cp.z; b1[0] += wt * cp.w; b1[1] += wt * nr.x; b1[2] += wt * nr.y; w1 += wt; }
+			if (inx1) { const float4 cp = __ldg(row + 2 * (x0 + 1)); const float2 nr = __ldg(reinterpret_cast<const float2*>(row + 2 * (x0 + 1) + 1)); const float wt = al;
+				a1[0] += wt * cp.x; a1[1] += wt * cp.y; a1[2] += wt * cp.z; b1[0] += wt * cp.w; b1[1] += wt * nr.x; b1[2] += wt * nr.y; w1 += wt; }
 		}
 		float ww = 0.f, cxs = 0.f, cys = 0.f, czs = 0.f, nxs = 0.f, nys = 0.f, nzs = 0.f;
-		if (w0 > 0.f) { const float r = (1.0f - be) / w0; cxs += r * c0[0]; cys += r * c0[1]; czs += r * c0[2]; nxs += r * n0[0]; nys += r * n0[1]; nzs += r * n0[2]; ww += (1.0f - be); }
-		if (w1 > 0.f) { const float r = be / w1; cxs += r * c1[0]; cys += r * c1[1]; czs += r * c1[2]; nxs += r * n1[0]; nys += r * n1[1]; nzs += r * n1[2]; ww += be; }
+		if (w0 > 0.f) { const float r = (1.0f - be) / w0; cxs += r * a0[0]; cys += r * a0[1]; czs += r * a0[2]; nxs += r * b0[0]; nys += r * b0[1]; nzs += r * b0[2]; ww += (1.0f - be); }
+		if (w1 > 0.f) { const float r = be / w1; cxs += r * a1[0]; cys += r * a1[1]; czs += r * a1[2]; nxs += r * b1[0]; nys += r * b1[1]; nzs += r * b1[2]; ww += be; }
 		if (!(ww > 0.f)) continue;
 		const float rw = 1.0f / ww;
 		const float qx = cxs * rw, qy = cys * rw, qz = czs * rw;        // camPosTgt
 		if (!(qz > dmin && qz < dmax)) continue;
 		const float tnx = nxs * rw, tny = nys * rw, tnz = nzs * rw;     // normalTgt
+		const float rnx = m00 * nx + m01 * ny + m02 * nz;
+		const float rny = m10 * nx + m11 * ny + m12 * nz;
+		const float rnz = m20 * nx + m21 * ny + m22 * nz;
 		const float dx = tx - qx, dy = ty - qy, dz = tz - qz;
 		const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
 		const float dn = rnx * tnx + rny * tny + rnz * tnz;
@@ -407,19 +503,28 @@ __device__ __forceinline__ void tile_pixels(const SolveArgs& a, const WinDesc& w
 }
 
 // ------------------------------------------------------------------------------------------------ tail (per window, per GN iteration)
+__constant__ unsigned char c_sym_r[21] = { 0,0,0,0,0,0, 1,1,1,1,1, 2,2,2,2, 3,3,3, 4,4, 5 };
+__constant__ unsigned char c_sym_c[21] = { 0,1,2,3,4,5, 1,2,3,4,5, 2,3,4,5, 3,4,5, 4,5, 5 };
+__constant__ unsigned char c_sym_idx[36] = { 0,1,2,3,4,5, 1,6,7,8,9,10, 2,7,11,12,13,14, 3,8,12,15,16,17, 4,9,13,16,18,19, 5,10,14,17,19,20 };
+
 struct TailSmem {
 	float* T;      // [N][12]
 	float* A;      // [dimp][ld]
 	float* rhs; float* Minv; float* r; float* z; float* p; float* Ap; float* delta;   // [dimp] each
-	float* pairRaw;  // [P][28] target-frame sums
-	float* pairW;    // [P][28] model-frame sums (27 used)
+	float* pairW;    // [P][28] per-pair sums over the pair's tiles (model frame; 27 used + count)
 	float* grp;      // [G][44]
-	float* red;      // [32]
+	float* fS;       // [N][20] per-frame sparse sums: n, S(3), Q(6), grad rot(3), grad trans(3), Pw(3), Pn
+	float* fD;       // [N][28] per-frame dense sums: S(21) + signed b(6)
+	int* gi; int* gj; int* gstart;     // [G], [G], [G+1]
+	int* pt; int* ps; int* pt0; int* pnt;   // [P] each: pair target, source, first tile, #tiles
+	int* fg_start; int* fp_start; int* fg_items; int* fp_items;   // per-frame membership CSR ([N+1], [N+1], [2G], [2P])
 	int dimp, ld;
 };
+static constexpr int kFS = 20, kFD = 28;
 __host__ __device__ inline size_t tail_smem_floats(int N, int P, int G) {
 	const int dimp = 6 * (N - 1), ld = dimp | 1;
-	return (size_t)N * 12 + (size_t)dimp * ld + 7 * (size_t)dimp + 2 * (size_t)P * kTileVals + (size_t)G * kGrpVals + 32 + 8;
+	return (size_t)N * 12 + (size_t)dimp * ld + 7 * (size_t)dimp + (size_t)P * kTileVals + (size_t)G * kGrpVals +
+	       (size_t)N * (kFS + kFD) + (size_t)(3 * G + 1 + 4 * P) + (size_t)(2 * (N + 1) + 2 * G + 2 * P) + 16;
 }
 __device__ inline void tail_carve(float* base, int N, int P, int G, TailSmem& s) {
 	s.dimp = 6 * (N - 1); s.ld = s.dimp | 1;
@@ -428,28 +533,26 @@ __device__ inline void tail_carve(float* base, int N, int P, int G, TailSmem& s)
 	s.A = q; q += s.dimp * s.ld;
 	s.rhs = q; q += s.dimp; s.Minv = q; q += s.dimp; s.r = q; q += s.dimp; s.z = q; q += s.dimp;
 	s.p = q; q += s.dimp; s.Ap = q; q += s.dimp; s.delta = q; q += s.dimp;
-	s.pairRaw = q; q += P * kTileVals; s.pairW = q; q += P * kTileVals;
+	s.pairW = q; q += P * kTileVals;
 	s.grp = q; q += G * kGrpVals;
-	s.red = q;
-}
-__device__ __forceinline__ float block_sum(float v, float* red) {   // all kThreads threads; result broadcast
-	v = warp_sum(v);
-	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	__syncthreads();
-	if (lane == 0) red[wid] = v;
-	__syncthreads();
-	float t = 0.f;
-#pragma unroll
-	for (int k = 0; k < kWarps; k++) t += red[k];
-	return t;
+	s.fS = q; q += N * kFS; s.fD = q; q += N * kFD;
+	int* iq = reinterpret_cast<int*>(q);
+	s.gi = iq; iq += G; s.gj = iq; iq += G; s.gstart = iq; iq += G + 1;
+	s.pt = iq; iq += P; s.ps = iq; iq += P; s.pt0 = iq; iq += P; s.pnt = iq; iq += P;
+	s.fg_start = iq; iq += N + 1; s.fp_start = iq; iq += N + 1; s.fg_items = iq; iq += 2 * G; s.fp_items = iq; iq += 2 * P;
 }
 // index of (r,c), r<=c, in the packed upper triangle of a symmetric 6x6
 __device__ __forceinline__ int sym6(int r, int c) { if (r > c) { const int t = r; r = c; c = t; } return r * 6 - (r * (r - 1)) / 2 + (c - r); }
-__device__ __forceinline__ float skew(const float v[3], int a, int b) {   // [v]x (a,b)
+__device__ __forceinline__ float skew(const float* v, int a, int b) {   // [v]x (a,b)
 	if (a == b) return 0.f;
-	const int k = 3 - a - b;                       // the remaining axis
-	const float s = ((b - a + 3) % 3 == 1) ? -1.f : 1.f;   // (0,1):-vz (1,2):-vx (2,0):-vy ; transposed: +
+	const int k = 3 - a - b;                                // the remaining axis
+	const float s = ((b - a + 3) % 3 == 1) ? -1.f : 1.f;    // (0,1):-vz (1,2):-vx (2,0):-vy ; transposed: +
 	return s * v[k];
+}
+__device__ __forceinline__ void unpack_sym(int e, int& r, int& c) {
+	r = 0;
+	while (e >= 6 - r) { e -= 6 - r; r++; }
+	c = r + e;
 }
 
 __device__ void window_tail(const SolveArgs& a, const WinDesc& wd, int w, int it, float* smem_base) {
@@ -460,13 +563,28 @@ __device__ void window_tail(const SolveArgs& a, const WinDesc& wd, int w, int it
 	const int dimp = s.dimp, ld = s.ld;
 	const float wS = a.prm.w_sparse;
 	const bool use_dense = a.prm.w_dense > 0.f && P > 0;
+	const bool dbg = a.dbg_JtJ && it == a.prm.num_iter_outer - 1;
+	ProfRec prf; prf.kind_cta = (1ll << 32) | blockIdx.x; prf.tile_win = ((long long)it << 32) | w;
+	PROF_T(0);
 
-	// ---- P0: poses of this iteration + zero the system
+	// ---- P0: everything the later phases index repeatedly goes to shared memory once (poses, group/pair tables)
 	for (int k = tid; k < N * 12; k += kThreads) s.T[k] = __ldcg(a.T + (size_t)wd.frame_off * 12 + k);
+	for (int k = tid; k < G; k += kThreads) { s.gi[k] = a.grp_i[wd.grp_off + k]; s.gj[k] = a.grp_j[wd.grp_off + k]; }
+	for (int k = tid; k <= G; k += kThreads) s.gstart[k] = a.grp_start[wd.grp_off + w + k];
+	for (int k = tid; k < P; k += kThreads) {
+		const uint2 pr = a.pairs[wd.pair_off + k];
+		s.pt[k] = (int)pr.x; s.ps[k] = (int)pr.y; s.pt0[k] = a.pair_tile0[wd.pair_off + k]; s.pnt[k] = a.pair_ntile[wd.pair_off + k];
+	}
+	{
+		const int* mem = a.mem + wd.mem_off;     // fg_start[N+1] fp_start[N+1] fg_items[2G] fp_items[2P], contiguous like the smem copy
+		const int nmem = 2 * (N + 1) + 2 * G + 2 * P;
+		for (int k = tid; k < nmem; k += kThreads) s.fg_start[k] = mem[k];
+	}
 	for (int k = tid; k < dimp * ld; k += kThreads) s.A[k] = 0.f;
 	__syncthreads();
+	PROF_T(1);
 
-	// ---- P1: sparse moment sums, 8 lanes per (i,j) group of correspondences
+	// ---- P1: sparse moment sums, 8 lanes per (i,j) group of correspondences, loads one iteration ahead
 	{
 		const int sub = tid >> 3, sl = tid & 7, nsub = kThreads >> 3;
 		for (int g0 = 0; g0 < G; g0 += nsub) {
@@ -475,15 +593,20 @@ __device__ void window_tail(const SolveArgs& a, const WinDesc& wd, int w, int it
 #pragma unroll
 			for (int k = 0; k < kGrpVals; k++) m[k] = 0.f;
 			if (g < G) {
-				const int gi = a.grp_i[wd.grp_off + g], gj = a.grp_j[wd.grp_off + g];
-				const int c0 = a.grp_start[wd.grp_off + w + g], c1 = a.grp_start[wd.grp_off + w + g + 1];
-				const float* Ti = s.T + gi * 12; const float* Tj = s.T + gj * 12;
-				for (int c = c0 + sl; c < c1; c += 8) {
-					const float4* e4 = reinterpret_cast<const float4*>(a.corr + wd.corr_off + c);
-					const float4 lo = __ldg(e4), hi = __ldg(e4 + 1);   // {i, j, pi.x, pi.y}, {pi.z, pj.x, pj.y, pj.z}
-					const float pix = lo.z, piy = lo.w, piz = hi.x, pjx = hi.y, pjy = hi.z, pjz = hi.w;
-					const V3 q = mk(Ti[0] * pix + Ti[1] * piy + Ti[2] * piz + Ti[3], Ti[4] * pix + Ti[5] * piy + Ti[6] * piz + Ti[7], Ti[8] * pix + Ti[9] * piy + Ti[10] * piz + Ti[11]);
-					const V3 sp = mk(Tj[0] * pjx + Tj[1] * pjy + Tj[2] * pjz + Tj[3], Tj[4] * pjx + Tj[5] * pjy + Tj[6] * pjz + Tj[7], Tj[8] * pjx + Tj[9] * pjy + Tj[10] * pjz + Tj[11]);
+				const int c1 = s.gstart[g + 1];
+				const float* Ti = s.T + s.gi[g] * 12; const float* Tj = s.T + s.gj[g] * 12;
+				const float t00 = Ti[0], t01 = Ti[1], t02 = Ti[2], t03 = Ti[3], t10 = Ti[4], t11 = Ti[5], t12 = Ti[6], t13 = Ti[7], t20 = Ti[8], t21 = Ti[9], t22 = Ti[10], t23 = Ti[11];
+				const float u00 = Tj[0], u01 = Tj[1], u02 = Tj[2], u03 = Tj[3], u10 = Tj[4], u11 = Tj[5], u12 = Tj[6], u13 = Tj[7], u20 = Tj[8], u21 = Tj[9], u22 = Tj[10], u23 = Tj[11];
+				int c = s.gstart[g] + sl;
+				float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+				if (c < c1) { const float4* e4 = reinterpret_cast<const float4*>(a.corr + wd.corr_off + c); lo = __ldg(e4); hi = __ldg(e4 + 1); }
+				while (c < c1) {
+					const int cn = c + 8;
+					float4 lo_n = lo, hi_n = hi;
+					if (cn < c1) { const float4* e4 = reinterpret_cast<const float4*>(a.corr + wd.corr_off + cn); lo_n = __ldg(e4); hi_n = __ldg(e4 + 1); }
+					const float pix = lo.z, piy = lo.w, piz = hi.x, pjx = hi.y, pjy = hi.z, pjz = hi.w;   // {i, j, pi.x, pi.y}, {pi.z, pj.x, pj.y, pj.z}
+					const V3 q = mk(t00 * pix + t01 * piy + t02 * piz + t03, t10 * pix + t11 * piy + t12 * piz + t13, t20 * pix + t21 * piy + t22 * piz + t23);
+					const V3 sp = mk(u00 * pjx + u01 * pjy + u02 * pjz + u03, u10 * pjx + u11 * pjy + u12 * pjz + u13, u20 * pjx + u21 * pjy + u22 * pjz + u23);
 					const V3 rr = q - sp;
 					const float rho = huber_w(dot(rr, rr), a.prm.robust_delta);
 					m[0] += 1.f;
@@ -501,6 +624,7 @@ __device__ void window_tail(const SolveArgs& a, const WinDesc& wd, int w, int it
 					m[37] += rho * q.x * q.x; m[38] += rho * q.y * q.y; m[39] += rho * q.z * q.z;
 					m[40] += rho * sp.x * sp.x; m[41] += rho * sp.y * sp.y; m[42] += rho * sp.z * sp.z;
 					m[43] += rho;
+					lo = lo_n; hi = hi_n; c = cn;
 				}
 			}
 #pragma unroll
@@ -511,129 +635,115 @@ __device__ void window_tail(const SolveArgs& a, const WinDesc& wd, int w, int it
 			}
 		}
 	}
-	// ---- P2a: per-pair sums over this window's tiles (target-frame)
+	PROF_T(2);
+	// ---- P2: per-pair sums over the pair's tiles (already in the model frame; the tile epilogue applied X S' X^T).  A pair's
+	//      tiles are consecutive and summed in order (deterministic); RI items per thread keep RI loads in flight.
 	if (use_dense) {
-		// a pair's tiles are consecutive in the window's tile list: fixed summation order => deterministic
-		for (int k = tid; k < P * kTileVals; k += kThreads) {
-			const int p = k / kTileVals, e = k - p * kTileVals;
-			const int t0 = wd.tile_off + a.pair_tile0[wd.pair_off + p], nt = a.pair_ntile[wd.pair_off + p];
-			float v = 0.f;
-			for (int c = 0; c < nt; c++) v += __ldcg(a.partial + (size_t)(t0 + c) * kTileVals + e);
-			s.pairRaw[k] = v;
-			if (a.dbg_cnt && e == 27 && it == a.prm.num_iter_outer - 1) a.dbg_cnt[(size_t)w * a.dbg_cnt_stride + p] = v;
-		}
-	}
-	__syncthreads();
-	// ---- P2b: target frame -> model frame:  S = X S' X^T, b = X b',  X = [[R,0],[[t]x R, R]]  (T of the TARGET frame)
-	if (use_dense) {
-		for (int k = tid; k < P * 27; k += kThreads) {
-			const int p = k / 27, e = k - p * 27;
-			const uint2 pr = a.pairs[wd.pair_off + p];
-			const float* Tt = s.T + pr.x * 12;
-			const float* raw = s.pairRaw + p * kTileVals;
-			// row r of X (6 entries)
-			auto Xrc = [&](int r, int c) -> float {
-				if (r < 3) return (c < 3) ? Tt[r * 4 + c] : 0.f;
-				const int rr = r - 3;
-				if (c >= 3) return Tt[rr * 4 + (c - 3)];
-				// ([t]x R)(rr, c) = sum_k [t]x(rr,k) R(k,c)
-				const float t3[3] = { Tt[3], Tt[7], Tt[11] };
-				float v = 0.f;
-				for (int kk = 0; kk < 3; kk++) v += skew(t3, rr, kk) * Tt[kk * 4 + c];
-				return v;
-			};
-			float out = 0.f;
-			if (e < 21) {
-				int r = 0, rem = e;
-				while (rem >= 6 - r) { rem -= 6 - r; r++; }
-				const int c = r + rem;
-				for (int u = 0; u < 6; u++) {
-					const float xr = Xrc(r, u);
-					if (xr == 0.f) continue;
-					float tsum = 0.f;
-					for (int v = 0; v < 6; v++) tsum += raw[sym6(u, v)] * Xrc(c, v);
-					out += xr * tsum;
-				}
-			} else {
-				const int r = e - 21;
-				for (int u = 0; u < 6; u++) out += Xrc(r, u) * raw[21 + u];
+		constexpr int RI = 5;
+		for (int k0 = tid; k0 < P * kTileVals; k0 += kThreads * RI) {
+			float v[RI]; const float* src[RI]; int nt[RI]; int mx = 0;
+#pragma unroll
+			for (int r = 0; r < RI; r++) {
+				const int k = k0 + r * kThreads;
+				v[r] = 0.f; nt[r] = 0; src[r] = a.partial;
+				if (k < P * kTileVals) { const int p = k / kTileVals, e = k - p * kTileVals; nt[r] = s.pnt[p]; src[r] = a.partial + (size_t)(wd.tile_off + s.pt0[p]) * kTileVals + e; mx = max(mx, nt[r]); }
 			}
-			s.pairW[p * kTileVals + e] = out;
+			for (int c = 0; c < mx; c++) {
+#pragma unroll
+				for (int r = 0; r < RI; r++) if (c < nt[r]) v[r] += __ldcg(src[r] + (size_t)c * kTileVals);
+			}
+#pragma unroll
+			for (int r = 0; r < RI; r++) {
+				const int k = k0 + r * kThreads;
+				if (k < P * kTileVals) {
+					s.pairW[k] = v[r];
+					if (a.dbg_cnt && (k % kTileVals) == 27 && it == a.prm.num_iter_outer - 1) a.dbg_cnt[(size_t)w * a.dbg_cnt_stride + k / kTileVals] = v[r];
+				}
+			}
 		}
 	}
 	__syncthreads();
-	// ---- P3: diagonal blocks, right-hand side, Jacobi preconditioner — gathered per (frame, entry), no atomics
+	PROF_T(3);
+	PROF_T(4);
+	// ---- P3a: per-frame gathers (no atomics, fixed order).  Branch-free inner loops: every output entry e reads one moment
+	//      from the q-side or the s-side of each group touching the frame (offset/sign chosen once, outside the loop).
+	for (int k = tid; k < N * (kFS + kFD); k += kThreads) {
+		const int f = k / (kFS + kFD), e = k - f * (kFS + kFD);
+		float acc = 0.f;
+		if (e < kFS) {
+			// fS layout: 0 n | 1-3 S | 4-9 Q | 10-12 grad rot | 13-15 grad trans | 16-18 Pw | 19 Pn
+			int oq, os; float sg = 1.f;
+			if (e == 0) { oq = 0; os = 0; }
+			else if (e < 4) { oq = e; os = 3 + e; }
+			else if (e < 10) { oq = 3 + e; os = 9 + e; }
+			else if (e < 13) { oq = 18 + e; os = 21 + e; sg = -1.f; }
+			else if (e < 16) { oq = 21 + e; os = 21 + e; sg = -1.f; }
+			else if (e < 19) { oq = 21 + e; os = 24 + e; }
+			else { oq = 43; os = 43; }
+			for (int q = s.fg_start[f]; q < s.fg_start[f + 1]; q++) {
+				const int item = s.fg_items[q];
+				const float* m = s.grp + (item & 0xffff) * kGrpVals;
+				acc += (item >> 16) ? sg * m[os] : m[oq];      // role 0: this frame is the group's i (q side); 1: j (s side)
+			}
+			s.fS[f * kFS + e] = acc;
+		} else {
+			const int d = e - kFS;
+			if (use_dense && d < 27) {
+				const float sgs = (d >= 21) ? -1.f : 1.f;      // Jtr_i += b, Jtr_j -= b ; S adds to both diagonal blocks
+				for (int q = s.fp_start[f]; q < s.fp_start[f + 1]; q++) {
+					const int item = s.fp_items[q];
+					const float v = s.pairW[(item & 0xffff) * kTileVals + d];
+					acc += (item >> 16) ? sgs * v : v;             // role 0: target, 1: source
+				}
+			}
+			s.fD[f * kFD + d] = acc;
+		}
+	}
+	__syncthreads();
+	// ---- P3b: diagonal blocks, right-hand side, Jacobi preconditioner from the per-frame sums
 	{
 		const int per = 21 + 6 + 6;
 		for (int k = tid; k < (N - 1) * per; k += kThreads) {
 			const int f = 1 + k / per, e = k % per;
 			const int base = (f - 1) * 6;
+			const float* F = s.fS + f * kFS;
+			const float* D = s.fD + f * kFD;
 			if (e < 21) {
-				int r = 0, rem = e;
-				while (rem >= 6 - r) { rem -= 6 - r; r++; }
-				const int c = r + rem;
-				float sp = 0.f, dn = 0.f;
-				for (int g = 0; g < G; g++) {
-					const int gi = a.grp_i[wd.grp_off + g], gj = a.grp_j[wd.grp_off + g];
-					if (gi != f && gj != f) continue;
-					const float* m = s.grp + g * kGrpVals;
-					const float* S1 = (gi == f) ? (m + 1) : (m + 4);       // sum of model-frame points on this frame's side
-					const float* Q = (gi == f) ? (m + 7) : (m + 13);       // xx xy xz yy yz zz
-					if (r < 3 && c < 3) sp += (r == c) ? m[0] : 0.f;                                   // TT = n I
-					else if (r < 3) sp += -skew(S1, r, c - 3);                                         // TR = -[S1]x
-					else { const int ra = r - 3, cb = c - 3; const float tr = Q[0] + Q[3] + Q[5];
-						const int qi = (ra == 0) ? cb : (ra == 1 ? 2 + cb : 5);                         // packed index of (ra,cb), ra<=cb
-						sp += ((ra == cb) ? tr : 0.f) - Q[qi]; }
-					if (gi == f && gj == f) { /* degenerate self pair: ignored */ }
-				}
-				if (use_dense) for (int p = 0; p < P; p++) {
-					const uint2 pr = a.pairs[wd.pair_off + p];
-					if ((int)pr.x == f || (int)pr.y == f) dn += s.pairW[p * kTileVals + e];
-				}
+				int r, c;
+				unpack_sym(e, r, c);
+				float sp;
+				if (r < 3 && c < 3) sp = (r == c) ? F[0] : 0.f;                                   // TT = n I
+				else if (r < 3) sp = -skew(F + 1, r, c - 3);                                       // TR = -[S]x
+				else { const int ra = r - 3, cb = c - 3; const float tr = F[4] + F[7] + F[9];
+					const int qi = (ra == 0) ? cb : (ra == 1 ? 2 + cb : 5);                          // packed (ra,cb), ra<=cb
+					sp = ((ra == cb) ? tr : 0.f) - F[4 + qi]; }
+				const float dn = D[e];
 				const float v = wS * sp + dn;
 				s.A[(base + r) * ld + base + c] = v;
 				s.A[(base + c) * ld + base + r] = v;
-				if (a.dbg_JtJ && it == a.prm.num_iter_outer - 1) {
-					float* D = a.dbg_JtJ + (size_t)w * a.dbg_stride * a.dbg_stride;
-					const int dim = 6 * N;
-					D[(f * 6 + r) * dim + f * 6 + c] = dn; D[(f * 6 + c) * dim + f * 6 + r] = dn;
-				}
+				if (dbg) { float* Dg = a.dbg_JtJ + (size_t)w * a.dbg_stride * a.dbg_stride; const int dim = 6 * N;
+					Dg[(f * 6 + r) * dim + f * 6 + c] = dn; Dg[(f * 6 + c) * dim + f * 6 + r] = dn; }
 			} else if (e < 27) {
 				const int r = e - 21;
-				float gs = 0.f, dn = 0.f;
-				for (int g = 0; g < G; g++) {
-					const int gi = a.grp_i[wd.grp_off + g], gj = a.grp_j[wd.grp_off + g];
-					const float* m = s.grp + g * kGrpVals;
-					if (gi == f) gs += (r < 3) ? m[34 + r] : m[28 + (r - 3)];
-					else if (gj == f) gs -= (r < 3) ? m[34 + r] : m[31 + (r - 3)];
-				}
-				if (use_dense) for (int p = 0; p < P; p++) {
-					const uint2 pr = a.pairs[wd.pair_off + p];
-					if ((int)pr.x == f) dn += s.pairW[p * kTileVals + 21 + r];
-					else if ((int)pr.y == f) dn -= s.pairW[p * kTileVals + 21 + r];
-				}
+				const float gs = (r < 3) ? F[13 + r] : F[10 + (r - 3)];
+				const float dn = D[21 + r];
 				s.rhs[base + r] = -wS * gs - dn;
-				if (a.dbg_Jtr && it == a.prm.num_iter_outer - 1) a.dbg_Jtr[(size_t)w * a.dbg_stride + f * 6 + r] = dn;
+				if (dbg && a.dbg_Jtr) a.dbg_Jtr[(size_t)w * a.dbg_stride + f * 6 + r] = dn;
 			} else {
 				const int r = e - 27;
-				float pc = 0.f;
-				for (int g = 0; g < G; g++) {
-					const int gi = a.grp_i[wd.grp_off + g], gj = a.grp_j[wd.grp_off + g];
-					if (gi != f && gj != f) continue;
-					const float* m = s.grp + g * kGrpVals;
-					const float* Pw = (gi == f) ? (m + 37) : (m + 40);
-					if (r < 3) pc += m[43];
-					else { const int ax = r - 3; pc += Pw[(ax + 1) % 3] + Pw[(ax + 2) % 3]; }
-				}
+				float pc;
+				if (r < 3) pc = F[19];
+				else { const int ax = r - 3; pc = F[16 + (ax + 1) % 3] + F[16 + (ax + 2) % 3]; }
 				s.Minv[base + r] = (pc > kEps) ? 1.0f / pc : 1.0f;
 			}
 		}
 	}
 	__syncthreads();
+	PROF_T(5);
 	// ---- P4a: sparse cross blocks (i,j): J_i^T J_j, both frames free
 	for (int k = tid; k < G * 36; k += kThreads) {
 		const int g = k / 36, e = k - g * 36, r = e / 6, c = e - r * 6;
-		const int gi = a.grp_i[wd.grp_off + g], gj = a.grp_j[wd.grp_off + g];
+		const int gi = s.gi[g], gj = s.gj[g];
 		if (gi < 1 || gj < 1 || gi == gj) continue;
 		const float* m = s.grp + g * kGrpVals;
 		float v;
@@ -651,68 +761,78 @@ __device__ void window_tail(const SolveArgs& a, const WinDesc& wd, int w, int it
 	if (use_dense) {
 		for (int k = tid; k < P * 36; k += kThreads) {
 			const int p = k / 36, e = k - p * 36, r = e / 6, c = e - r * 6;
-			const uint2 pr = a.pairs[wd.pair_off + p];
-			const int ti = (int)pr.x, sj = (int)pr.y;
+			const int ti = s.pt[p], sj = s.ps[p];
 			if (ti < 1 || sj < 1) continue;
 			if (wd.compat_flip && !(ti < sj)) continue;
 			const float v = -s.pairW[p * kTileVals + sym6(r, c)];
 			atomicAdd(&s.A[((sj - 1) * 6 + r) * ld + (ti - 1) * 6 + c], v);
 			atomicAdd(&s.A[((ti - 1) * 6 + c) * ld + (sj - 1) * 6 + r], v);
-			if (a.dbg_JtJ && it == a.prm.num_iter_outer - 1) {
-				float* D = a.dbg_JtJ + (size_t)w * a.dbg_stride * a.dbg_stride;
+			if (dbg) {
+				float* Dg = a.dbg_JtJ + (size_t)w * a.dbg_stride * a.dbg_stride;
 				const int dim = 6 * N;
-				atomicAdd(&D[(sj * 6 + r) * dim + ti * 6 + c], v);
-				atomicAdd(&D[(ti * 6 + c) * dim + sj * 6 + r], v);
+				atomicAdd(&Dg[(sj * 6 + r) * dim + ti * 6 + c], v);
+				atomicAdd(&Dg[(ti * 6 + c) * dim + sj * 6 + r], v);
 			}
 		}
 	}
 	__syncthreads();
+	PROF_T(6);
 
-	// ---- PCG (PCGInit_Kernel1/2, PCGStep_Kernel*): SolverBundling.cu:575-818
-	float rz;
+	// ---- PCG (PCGInit_Kernel1/2, PCGStep_Kernel*: SolverBundling.cu:575-818) on ONE warp: the system has <= 186 unknowns,
+	//      so warp shuffles replace every block-wide reduction/barrier of a multi-warp version.
 	{
-		float d = 0.f;
-		for (int k = tid; k < dimp; k += kThreads) {
-			const float rv = s.rhs[k], pv = s.Minv[k] * rv;
-			s.r[k] = rv; s.p[k] = pv; s.delta[k] = 0.f;
-			d += rv * pv;
+		float rz = 0.f;
+		if (tid < 32) {
+			for (int k = lane; k < dimp; k += 32) { const float rv = s.rhs[k], pv = s.Minv[k] * rv; s.r[k] = rv; s.p[k] = pv; s.delta[k] = 0.f; rz += rv * pv; }
+			rz = warp_sum(rz);
 		}
-		rz = block_sum(d, s.red);
-	}
-	for (int lin = 0; lin < a.prm.num_iter_inner; lin++) {
-		__syncthreads();
-		// Ap = A p : 4 lanes per row
-		{
-			const int row = tid >> 2, q4 = tid & 3;
-			for (int r0 = 0; r0 < dimp; r0 += kThreads / 4) {
-				const int r = r0 + row;
-				float acc = 0.f;
-				if (r < dimp) for (int c = q4; c < dimp; c += 4) acc += s.A[r * ld + c] * s.p[c];
-				acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-				acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-				if (r < dimp && q4 == 0) s.Ap[r] = acc;
+		const int wid = tid >> 5;
+#pragma unroll 1
+		for (int lin = 0; lin < a.prm.num_iter_inner; lin++) {
+			__syncthreads();
+			// Ap = A p: lanes over columns, four rows of a warp in flight at once (the reductions interleave)
+#pragma unroll 1
+			for (int r0 = wid; r0 < dimp; r0 += 4 * kWarps) {
+				float acc[4] = { 0.f, 0.f, 0.f, 0.f };
+				for (int c = lane; c < dimp; c += 32) {
+					const float pc = s.p[c];
+#pragma unroll
+					for (int j = 0; j < 4; j++) { const int r = r0 + j * kWarps; if (r < dimp) acc[j] += s.A[r * ld + c] * pc; }
+				}
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+					for (int j = 0; j < 4; j++) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+				}
+				if (lane == 0) {
+#pragma unroll
+					for (int j = 0; j < 4; j++) { const int r = r0 + j * kWarps; if (r < dimp) s.Ap[r] = acc[j]; }
+				}
+			}
+			__syncthreads();
+			if (tid < 32) {
+				float d = 0.f;
+				for (int k = lane; k < dimp; k += 32) d += s.p[k] * s.Ap[k];
+				const float pAp = warp_sum(d);
+				const float alpha = (pAp > kEps) ? rz / pAp : 0.f;
+				float bsum = 0.f;
+				for (int k = lane; k < dimp; k += 32) {
+					s.delta[k] += alpha * s.p[k];
+					const float rv = s.r[k] - alpha * s.Ap[k];
+					s.r[k] = rv;
+					const float zv = s.Minv[k] * rv;
+					s.z[k] = zv;
+					bsum += zv * rv;
+				}
+				const float rz_new = warp_sum(bsum);
+				const float beta = (rz > kEps) ? rz_new / rz : 0.f;
+				rz = rz_new;
+				for (int k = lane; k < dimp; k += 32) s.p[k] = s.z[k] + beta * s.p[k];
 			}
 		}
-		__syncthreads();
-		float d = 0.f;
-		for (int k = tid; k < dimp; k += kThreads) d += s.p[k] * s.Ap[k];
-		const float pAp = block_sum(d, s.red);
-		const float alpha = (pAp > kEps) ? rz / pAp : 0.f;
-		float bsum = 0.f;
-		for (int k = tid; k < dimp; k += kThreads) {
-			s.delta[k] += alpha * s.p[k];
-			const float rv = s.r[k] - alpha * s.Ap[k];
-			s.r[k] = rv;
-			const float zv = s.Minv[k] * rv;
-			s.z[k] = zv;
-			bsum += zv * rv;
-		}
-		const float rz_new = block_sum(bsum, s.red);
-		const float beta = (rz > kEps) ? rz_new / rz : 0.f;
-		rz = rz_new;
-		for (int k = tid; k < dimp; k += kThreads) s.p[k] = s.z[k] + beta * s.p[k];
 	}
 	__syncthreads();
+	PROF_T(7);
 	// ---- pose update: x <- log(exp(delta) * exp(x))  (computeLieUpdate), new T for the next iteration
 	const bool last = (it == a.prm.num_iter_outer - 1);
 	for (int f = tid; f < N; f += kThreads) {
@@ -721,9 +841,9 @@ __device__ void window_tail(const SolveArgs& a, const WinDesc& wd, int w, int it
 		float Tn[12];
 		if (f >= 1) {
 			const float* dl = s.delta + (f - 1) * 6;
-			float U[12], Cm[12];
+			float U[12];
 			se3_exp(mk(dl[3], dl[4], dl[5]), mk(dl[0], dl[1], dl[2]), U);
-			se3_exp(rot, trans, Cm);
+			const float* Cm = s.T + f * 12;    // exp(x) of this iteration, already in shared memory
 			for (int r = 0; r < 3; r++) {
 				for (int c = 0; c < 4; c++) {
 					float v = U[r * 4 + 0] * Cm[0 * 4 + c] + U[r * 4 + 1] * Cm[1 * 4 + c] + U[r * 4 + 2] * Cm[2 * 4 + c];
@@ -743,26 +863,34 @@ __device__ void window_tail(const SolveArgs& a, const WinDesc& wd, int w, int it
 			Po[12] = 0.f; Po[13] = 0.f; Po[14] = 0.f; Po[15] = 1.f;
 		}
 	}
-	(void)lane;
+	__syncthreads();
+	PROF_T(8);
+	if (a.prof && threadIdx.x == 0) { prf.t[9] = 0; prof_emit(a, prf); }
 }
 
 // ------------------------------------------------------------------------------------------------ k_solve
-__global__ void __launch_bounds__(kThreads, 2) k_solve(SolveArgs a) {
+__global__ void __launch_bounds__(kThreads, BT_SOLVE_MIN_CTAS) k_solve(SolveArgs a) {
 	extern __shared__ __align__(16) float dyn_smem[];
-	__shared__ int s_tile;
+	__shared__ int s_tile, s_next;
 	__shared__ float s_M[12];
+	__shared__ float s_X[36];
+	__shared__ float s_red[kTileVals];
 	__shared__ float s_part[kWarps][kTileVals];
 	__shared__ int s_is_last;
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const int total = *a.n_tiles_total;
 	if (total <= 0) return;
 	const long long all = (long long)total * a.prm.num_iter_outer;
+	if (tid == 0) s_tile = atomicAdd(a.queue, 1);
 	for (;;) {
-		__syncthreads();
-		if (tid == 0) s_tile = atomicAdd(a.queue, 1);
 		__syncthreads();
 		const long long t = s_tile;
 		if (t >= all) break;
+		__syncthreads();
+		// claim the NEXT tile now: the atomic's round trip hides behind this tile.  Safe for the iteration dependencies:
+		// a CTA only ever waits on tiles with a smaller index than the one it is processing, never on its look-ahead.
+		if (tid == 0) s_next = atomicAdd(a.queue, 1);
+		ProfRec prf; PROF_T(0);
 		const int it = (int)(t / total), tl_idx = (int)(t - (long long)it * total);
 		const Tile tl = a.tiles[tl_idx];
 		const WinDesc wd = a.wins[tl.win];
@@ -770,6 +898,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_solve(SolveArgs a) {
 			if (tid == 0) { while (ld_acquire(a.iter_done + tl.win) < it) __nanosleep(64); }
 			__syncthreads();
 		}
+		PROF_T(1);
 		TileAcc acc;
 #pragma unroll
 		for (int k = 0; k < kTileVals; k++) acc.v[k] = 0.f;
@@ -785,12 +914,22 @@ __global__ void __launch_bounds__(kThreads, 2) k_solve(SolveArgs a) {
 					v += rik * ((c < 3) ? __ldcg(Tj + k * 4 + c) : (__ldcg(Tj + k * 4 + 3) - __ldcg(Ti + k * 4 + 3)));
 				}
 				s_M[tid] = v;
+			} else if (tid >= 32 && tid < 68) {   // X_i = [[R,0],[[t]x R, R]] of the TARGET frame: maps the tile's sums to the model frame
+				const float* Ti = a.T + (size_t)(wd.frame_off + pr.x) * 12;
+				const int e = tid - 32, r = e / 6, c = e - r * 6;
+				float v;
+				if (r < 3) v = (c < 3) ? __ldcg(Ti + r * 4 + c) : 0.f;
+				else if (c >= 3) v = __ldcg(Ti + (r - 3) * 4 + (c - 3));
+				else { const float t3[3] = { __ldcg(Ti + 3), __ldcg(Ti + 7), __ldcg(Ti + 11) }; v = 0.f; for (int kk = 0; kk < 3; kk++) v += skew(t3, r - 3, kk) * __ldcg(Ti + kk * 4 + c); }
+				s_X[e] = v;
 			}
 			__syncthreads();
+			PROF_T(2);
 			const float4* src = a.src + (size_t)(wd.frame_off + pr.y) * 2 * a.npix_max;
 			const float4* tex = a.texel + (size_t)(wd.frame_off + pr.x) * 2 * a.npix_max;
 			tile_pixels(a, wd, src, tex, s_M, tl.start, tl.count, acc);
 		}
+		PROF_T(3);
 		// block reduction of the 28 sums -> this tile's slot
 #pragma unroll
 		for (int k = 0; k < kTileVals; k++) {
@@ -802,22 +941,51 @@ __global__ void __launch_bounds__(kThreads, 2) k_solve(SolveArgs a) {
 			float v = 0.f;
 #pragma unroll
 			for (int k = 0; k < kWarps; k++) v += s_part[k][tid];
-			__stcg(a.partial + (size_t)tl_idx * kTileVals + tid, v);
+			s_red[tid] = v;
+		}
+		__syncthreads();
+		if (tid < kTileVals) {   // S = X S' X^T, b = X b' (rows 0-2 of X have 3 non-zeros); entry 27 = #correspondences
+			float out = s_red[tid];
+			if (tl.pair >= 0 && tid < 27) {
+				out = 0.f;
+				if (tid < 21) {
+					const int r = c_sym_r[tid], c = c_sym_c[tid];
+					float xr[6], xc[6];
+#pragma unroll
+					for (int u = 0; u < 6; u++) { xr[u] = s_X[r * 6 + u]; xc[u] = s_X[c * 6 + u]; }   // zero entries make the short rows exact
+#pragma unroll
+					for (int u = 0; u < 6; u++) {
+						float tsum = 0.f;
+#pragma unroll
+						for (int v = 0; v < 6; v++) tsum += s_red[c_sym_idx[u * 6 + v]] * xc[v];
+						out += xr[u] * tsum;
+					}
+				} else {
+					const int r = tid - 21;
+#pragma unroll
+					for (int u = 0; u < 6; u++) out += s_X[r * 6 + u] * s_red[21 + u];
+				}
+			}
+			__stcg(a.partial + (size_t)tl_idx * kTileVals + tid, out);
 		}
 		__threadfence();
 		__syncthreads();
+		PROF_T(4);
 		if (tid == 0) {
 			const int done = atomicAdd(a.tiles_done + tl.win, 1) + 1;
 			s_is_last = (done == (it + 1) * wd.n_tiles);
 			if (s_is_last) __threadfence();
 		}
 		__syncthreads();
+		PROF_T(5);
+		if (a.prof && tid == 0) { prf.kind_cta = blockIdx.x; prf.tile_win = ((long long)tl_idx << 32) | ((long long)it << 16) | tl.count; prf.t[6] = prf.t[7] = prf.t[8] = prf.t[9] = 0; prof_emit(a, prf); }
 		if (s_is_last) {
 			window_tail(a, wd, tl.win, it, dyn_smem);
 			__threadfence();
 			__syncthreads();
 			if (tid == 0) st_release(a.iter_done + tl.win, it + 1);
 		}
+		if (tid == 0) s_tile = s_next;
 	}
 }
 
@@ -826,7 +994,8 @@ struct SolverState {
 	bt_solver_limits lim{};
 	int npix_max = 0, max_pairs = 0, max_frames_total = 0, max_tiles = 0, max_groups = 0;
 	DevBuf wins, depth_ptr, normal_ptr, frame_win, texel, src, nsrc, pose_in, x, T, pose_out, corr, grp_i, grp_j, grp_start, pairs,
-	    tiles, scalars, partial, tiles_done, iter_done, pair_tile0, pair_ntile, dbgJ, dbgR, dbgC;
+	    tiles, scalars, partial, tiles_done, iter_done, pair_tile0, pair_ntile, pair_win, mem, dbgJ, dbgR, dbgC, prof;
+	int prof_cap = 0;
 	PinnedBuf h_stage, h_poses;
 	// last staged batch
 	int n_windows = 0, frames_total = 0, smem_bytes = 0, chunk = 1024;
@@ -843,7 +1012,7 @@ void solver_destroy(bt_ctx* ctx) {
 	if (!s) return;
 	DevBuf* bufs[] = { &s->wins, &s->depth_ptr, &s->normal_ptr, &s->frame_win, &s->texel, &s->src, &s->nsrc, &s->pose_in, &s->x, &s->T,
 	                   &s->pose_out, &s->corr, &s->grp_i, &s->grp_j, &s->grp_start, &s->pairs, &s->tiles, &s->scalars, &s->partial,
-	                   &s->tiles_done, &s->iter_done, &s->pair_tile0, &s->pair_ntile, &s->dbgJ, &s->dbgR, &s->dbgC };
+	                   &s->tiles_done, &s->iter_done, &s->pair_tile0, &s->pair_ntile, &s->pair_win, &s->mem, &s->dbgJ, &s->dbgR, &s->dbgC, &s->prof };
 	for (DevBuf* b : bufs) b->release();
 	s->h_stage.release(); s->h_poses.release();
 	for (auto& e : s->ev) if (e) cudaEventDestroy(e);
@@ -880,6 +1049,8 @@ static int reserve_impl(bt_ctx* ctx, const bt_solver_limits* lim) {
 	RES(pairs, sizeof(uint2) * (size_t)s->max_pairs * lim->max_windows);
 	RES(pair_tile0, sizeof(int) * (size_t)s->max_pairs * lim->max_windows);
 	RES(pair_ntile, sizeof(int) * (size_t)s->max_pairs * lim->max_windows);
+	RES(pair_win, sizeof(int) * (size_t)s->max_pairs * lim->max_windows);
+	RES(mem, sizeof(int) * (size_t)(2 * (lim->max_frames + 1) + 2 * s->max_groups + 2 * s->max_pairs) * lim->max_windows);
 	RES(tiles, sizeof(Tile) * (size_t)s->max_tiles);
 	RES(partial, sizeof(float) * kTileVals * (size_t)s->max_tiles);
 	RES(scalars, 64);
@@ -951,7 +1122,8 @@ extern "C" int bt_solve_stage(bt_ctx* ctx, int n_windows, const bt_window* windo
 	auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
 	const size_t o_wins = carve(sizeof(WinDesc) * n_windows), o_dp = carve(sizeof(void*) * F), o_np = carve(sizeof(void*) * F), o_fw = carve(sizeof(int) * F),
 	             o_pose = carve(sizeof(float) * 16 * F), o_corr = carve(sizeof(bt_entryj) * C + 32), o_gi = carve(sizeof(int) * maxG * n_windows),
-	             o_gj = carve(sizeof(int) * maxG * n_windows), o_gs = carve(sizeof(int) * (maxG + 1) * n_windows), o_pairs = carve(sizeof(uint2) * maxP * n_windows);
+	             o_gj = carve(sizeof(int) * maxG * n_windows), o_gs = carve(sizeof(int) * (maxG + 1) * n_windows), o_pairs = carve(sizeof(uint2) * maxP * n_windows),
+	             o_pwin = carve(sizeof(int) * maxP * n_windows), o_mem = carve(sizeof(int) * (2 * ((size_t)s->lim.max_frames + 1) + 2 * maxG + 2 * maxP) * n_windows);
 	int rc = s->h_stage.alloc(off);
 	if (rc != BT_OK) return rc;
 	char* hb = s->h_stage.as<char>();
@@ -959,6 +1131,8 @@ extern "C" int bt_solve_stage(bt_ctx* ctx, int n_windows, const bt_window* windo
 	const void** hdp = (const void**)(hb + o_dp); const void** hnp = (const void**)(hb + o_np);
 	int* hfw = (int*)(hb + o_fw); float* hpose = (float*)(hb + o_pose); bt_entryj* hcorr = (bt_entryj*)(hb + o_corr);
 	int* hgi = (int*)(hb + o_gi); int* hgj = (int*)(hb + o_gj); int* hgs = (int*)(hb + o_gs); uint2* hpairs = (uint2*)(hb + o_pairs);
+	int* hpwin = (int*)(hb + o_pwin); int* hmem = (int*)(hb + o_mem);
+	size_t m_off = 0;
 	s->frame_off.assign(n_windows, 0); s->n_frames.assign(n_windows, 0);
 	size_t f_off = 0, c_off = 0, g_off = 0, p_off = 0, smem_need = 0;
 	std::vector<int> bin, order;
@@ -1024,6 +1198,30 @@ extern "C" int bt_solve_stage(bt_ctx* ctx, int n_windows, const bt_window* windo
 			}
 		}
 		d.n_pairs = np;
+		for (int p = 0; p < np; p++) hpwin[p_off + p] = w;
+		{   // per-frame membership CSR: groups then pairs touching each frame, in increasing index order (fixed summation order)
+			d.mem_off = (int)m_off;
+			int* fg_start = hmem + m_off; int* fp_start = fg_start + (N + 1); int* fg_items = fp_start + (N + 1); int* fp_items = fg_items + 2 * ng;
+			int q = 0;
+			for (int f = 0; f < N; f++) {
+				fg_start[f] = q;
+				for (int g = 0; g < ng; g++) {
+					if (hgi[g_off + g] == f) fg_items[q++] = g;
+					else if (hgj[g_off + g] == f) fg_items[q++] = g | (1 << 16);
+				}
+			}
+			fg_start[N] = q;
+			q = 0;
+			for (int f = 0; f < N; f++) {
+				fp_start[f] = q;
+				for (int p = 0; p < np; p++) {
+					if ((int)hpairs[p_off + p].x == f) fp_items[q++] = p;
+					else if ((int)hpairs[p_off + p].y == f) fp_items[q++] = p | (1 << 16);
+				}
+			}
+			fp_start[N] = q;
+			m_off += (size_t)(2 * (N + 1) + 2 * ng + 2 * np);
+		}
 		smem_need = std::max(smem_need, tail_smem_floats(N, np, ng) * sizeof(float));
 		f_off += N; c_off += n_valid; g_off += ng; p_off += np;
 	}
@@ -1044,6 +1242,8 @@ extern "C" int bt_solve_stage(bt_ctx* ctx, int n_windows, const bt_window* windo
 	UP(grp_i, hgi, sizeof(int) * std::max<size_t>(g_off, 1)); UP(grp_j, hgj, sizeof(int) * std::max<size_t>(g_off, 1));
 	UP(grp_start, hgs, sizeof(int) * (g_off + n_windows));
 	if (p_off) UP(pairs, hpairs, sizeof(uint2) * p_off);
+	if (p_off) UP(pair_win, hpwin, sizeof(int) * p_off);
+	UP(mem, hmem, sizeof(int) * m_off);
 #undef UP
 	if (s->debug) {
 		const int st = 6 * s->lim.max_frames;
@@ -1065,12 +1265,13 @@ static SolveArgs make_args(bt_ctx* ctx) {
 	a.pose_in = s->pose_in.as<float>(); a.x = s->x.as<float>(); a.T = s->T.as<float>(); a.pose_out = s->pose_out.as<float>();
 	a.npix_max = s->npix_max;
 	a.corr = s->corr.as<bt_entryj>(); a.grp_i = s->grp_i.as<int>(); a.grp_j = s->grp_j.as<int>(); a.grp_start = s->grp_start.as<int>();
-	a.pairs = s->pairs.as<uint2>();
+	a.pairs = s->pairs.as<uint2>(); a.pair_win = s->pair_win.as<int>(); a.mem = s->mem.as<int>();
 	a.tiles = s->tiles.as<Tile>(); a.max_tiles = s->max_tiles; a.partial = s->partial.as<float>();
 	a.pair_tile0 = s->pair_tile0.as<int>(); a.pair_ntile = s->pair_ntile.as<int>();
 	a.n_tiles_total = s->scalars.as<int>(); a.queue = s->scalars.as<int>() + 1; a.n_src_px = (long long*)(s->scalars.as<char>() + 16);
 	a.tiles_done = s->tiles_done.as<int>(); a.iter_done = s->iter_done.as<int>();
 	a.chunk = s->chunk; a.prm = s->prm;
+	if (s->prof_cap > 0) { a.prof = s->prof.as<long long>(); a.prof_cap = s->prof_cap; }
 	if (s->debug) { a.dbg_JtJ = s->dbgJ.as<float>(); a.dbg_Jtr = s->dbgR.as<float>(); a.dbg_stride = 6 * s->lim.max_frames; a.dbg_cnt = s->dbgC.as<float>(); a.dbg_cnt_stride = s->max_pairs; }
 	return a;
 }
@@ -1085,6 +1286,7 @@ extern "C" int bt_solve_run(bt_ctx* ctx, void* stream_) {
 		BT_CUDA(cudaMemsetAsync(s->dbgJ.p, 0, s->dbgJ.bytes, stream));
 		BT_CUDA(cudaMemsetAsync(s->dbgR.p, 0, s->dbgR.bytes, stream));
 	}
+	if (s->prof_cap > 0) BT_CUDA(cudaMemsetAsync(s->prof.p, 0, 8, stream));
 	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[0], stream));
 	k_prep_frames<<<s->frames_total, 512, 0, stream>>>(a);
 	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[1], stream));
@@ -1142,6 +1344,25 @@ extern "C" int bt_solve_get_stats(bt_ctx* ctx, bt_solve_stats* out) {
 	out->n_kernel_launches = s->launches;
 	out->n_src_pixels = *(long long*)(h + 16);
 	return BT_OK;
+}
+
+extern "C" int bt_solve_enable_profile(bt_ctx* ctx, int max_records) {
+	BT_REQUIRE(ctx && ctx->solver && max_records >= 0, BT_ERR_INVALID_ARG, "bt_solve_enable_profile: call bt_solver_reserve first");
+	SolverState* s = ctx->solver;
+	if (max_records > 0) { int rc = s->prof.alloc(8 + (size_t)max_records * 96); if (rc != BT_OK) return rc; }
+	s->prof_cap = max_records;
+	return BT_OK;
+}
+extern "C" int bt_solve_get_profile(bt_ctx* ctx, long long* out, int max_records) {
+	BT_REQUIRE(ctx && ctx->solver && ctx->solver->prof_cap > 0 && out, BT_ERR_INVALID_ARG, "bt_solve_get_profile: profiling not enabled");
+	SolverState* s = ctx->solver;
+	BT_CUDA(cudaDeviceSynchronize());
+	long long n = 0;
+	BT_CUDA(cudaMemcpy(&n, s->prof.p, 8, cudaMemcpyDeviceToHost));
+	if (n > s->prof_cap) n = s->prof_cap;
+	if (n > max_records) n = max_records;
+	if (n > 0) BT_CUDA(cudaMemcpy(out, s->prof.as<long long>() + 1, (size_t)n * 96, cudaMemcpyDeviceToHost));
+	return (int)n;
 }
 
 extern "C" int bt_solve_debug_counts(bt_ctx* ctx, int w, int n_pairs, float* counts_out) {

@@ -149,6 +149,17 @@ class OptimizerGpu:
         _lib.check(self.lib.bt_solve_get_timing(self.ctx, ms), "bt_solve_get_timing")
         return {"prep": ms[0], "plan": ms[1], "solve": ms[2]}
 
+    def enable_profile(self, max_records=200000):
+        _lib.check(self.lib.bt_solve_enable_profile(self.ctx, ctypes.c_int(max_records)), "bt_solve_enable_profile")
+        self._prof_cap = max_records
+
+    def get_profile(self):
+        out = np.zeros((self._prof_cap, 12), np.int64)
+        n = self.lib.bt_solve_get_profile(self.ctx, out.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(self._prof_cap))
+        if n < 0:
+            _lib.check(n, "bt_solve_get_profile")
+        return out[:n]
+
     def enable_debug(self, on=True):
         _lib.check(self.lib.bt_solve_enable_debug(self.ctx, ctypes.c_int(1 if on else 0)), "bt_solve_enable_debug")
 

@@ -135,6 +135,10 @@ BT_API int bt_solve_get_stats(bt_ctx* ctx, bt_solve_stats* out);
  * launching stream; opt-in because it adds four event records per run. */
 BT_API int bt_solve_enable_timing(bt_ctx* ctx, int on);
 BT_API int bt_solve_get_timing(bt_ctx* ctx, float* ms3);
+/* Developer aid: in-kernel phase timestamps (clock64) of every tile and tail of the next runs; 12 int64 per record:
+ * {kind<<32|cta, ids, t[10]}.  bt_solve_get_profile returns the number of records copied (>= 0) or a negative status. */
+BT_API int bt_solve_enable_profile(bt_ctx* ctx, int max_records);
+BT_API int bt_solve_get_profile(bt_ctx* ctx, long long* out, int max_records);
 BT_API int bt_solve_enable_debug(bt_ctx* ctx, int on);
 BT_API int bt_solve_debug_dense(bt_ctx* ctx, int w, float* JtJ_out, float* Jtr_out);
 /* Number of dense correspondences each pair found in the last GN iteration of window `w` (gating parity aid). */
@@ -157,6 +161,10 @@ BT_API int bt_matcher_reserve(bt_ctx* ctx, int max_pairs, int max_feats, int dim
  * (resp. nB).  Rows with fewer than k candidates are padded with idx -1 / dist +inf. */
 BT_API int bt_knn_match_pairs(bt_ctx* ctx, int n_pairs, const bt_desc_view* A, const bt_desc_view* B, int k,
                        int32_t* idxAB, float* distAB, int32_t* idxBA, float* distBA, void* stream);
+/* Device time of the last bt_knn_match_pairs: ms4 = {bf16 conversion, tensor-core pass, exact re-rank, exact fallback},
+ * info3 = {work items, query rows, rows that needed the exact fallback}. */
+BT_API int bt_knn_enable_timing(bt_ctx* ctx, int on);
+BT_API int bt_knn_get_timing(bt_ctx* ctx, float* ms4, int* info3);
 
 /* ------------------------------------------------------------------------------------------------------------
  * RANSAC.  Replaces ransacMultiPairGPU (/root/reference/src/cuda/cuda_ransac.cu:1228-1323; caller
@@ -169,6 +177,49 @@ BT_API int bt_ransac_reserve(bt_ctx* ctx, int max_pairs, int max_pts, int max_tr
 BT_API int bt_ransac_pairs(bt_ctx* ctx, int n_pairs, const float* const* ptsA, const float* const* ptsB, const int* n_pts,
                     int n_trials, float dist_thresh, uint64_t seed, int32_t* inlier_ids_out, int32_t* n_inliers_out,
                     void* stream);
+/* Parity aid: the three uniforms per trial the sampler used (same values as curand_uniform after
+ * curand_init(seed, trial, 0)) and the winning trial id of every pair of the last call. */
+BT_API int bt_ransac_debug(bt_ctx* ctx, float* u3_out, int n_trials, int32_t* best_trial_out, int n_pairs);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Geometric pruning + "mutual" union + the fused matcher pipeline.  Replaces SiftManager::pruneMatches and
+ * collectMutualMatches (/root/reference/src/FeatureManager.cpp:290-368) and, fused, everything findCorres does
+ * between the descriptors and the EntryJ loop of Bundler::optimizeGPU (/root/reference/src/Bundler.cpp:298-324). */
+typedef struct {
+	const float* kpts_dev;     /* DEVICE float2[n]: cv::KeyPoint::pt (x = column, y = row), Frame::_keypts */
+	int n;
+	const float* depth_dev;    /* DEVICE float[H*W]:  Frame::_depth_gpu */
+	const float* normal_dev;   /* DEVICE float4[H*W]: Frame::_normal_gpu */
+	float pose[16];            /* Frame::_pose_in_model, row-major cam->model */
+	int frame_id;              /* Frame::_id; |idA - idB| == 1 selects the *_neighbor thresholds */
+	int window_index;          /* index of this frame in the sorted BA window (EntryJ::imgIdx_*) */
+} bt_match_frame;
+
+typedef struct {               /* feature_corres.* of config_*.yml, angles already as cosines (FeatureManager.cpp:292-295) */
+	float max_dist_no_neighbor, cos_max_normal_no_neighbor, max_dist_neighbor, cos_max_normal_neighbor;
+} bt_prune_params;
+
+typedef struct {               /* the reference's `Correspondence` (uA,vA,uB,vB,ptA_cam,ptB_cam), 40 bytes */
+	float uA, vA, uB, vB;
+	float ptA_cam[3];
+	float ptB_cam[3];
+} bt_correspondence;
+
+BT_API int bt_pipeline_reserve(bt_ctx* ctx, int max_pairs, int max_feats, int dim, int max_trials);
+/* A[p] is the NEWER frame of pair p (frameA->_id > frameB->_id, FeatureManager.cpp:175).  idxAB/idxBA: DEVICE kNN indices
+ * as produced by bt_knn_match_pairs for the same pairs.  corr_out: DEVICE, pair p's block starts at sum_{q<p}(nA_q+nB_q)
+ * and holds n_corr_out[p] entries: survivors of A->B in query order, then those of B->A (duplicates kept). */
+BT_API int bt_prune_mutual_pairs(bt_ctx* ctx, int n_pairs, const bt_match_frame* A, const bt_match_frame* B, int H, int W,
+                          float fx, float fy, float cx, float cy, const int32_t* idxAB, const int32_t* idxBA, int k,
+                          const bt_prune_params* prm, bt_correspondence* corr_out, int32_t* n_corr_out, void* stream);
+/* kNN -> prune -> mutual -> RANSAC -> EntryJ without leaving the device.  entry_out: DEVICE, pairs back to back
+ * (entry_off_out[p], n_entry_out[p]; *total_out entries in all).  Pairs with <= 5 pruned matches or < 5 RANSAC
+ * inliers contribute nothing (FeatureManager.cpp:575-579,233-241). */
+BT_API int bt_match_pairs(bt_ctx* ctx, int n_pairs, const bt_match_frame* A, const bt_match_frame* B,
+                   const bt_desc_view* dA, const bt_desc_view* dB, int H, int W, float fx, float fy, float cx, float cy,
+                   const bt_prune_params* prune, int ransac_trials, float ransac_inlier_dist, uint64_t ransac_seed,
+                   bt_entryj* entry_out, int entry_capacity, int32_t* n_entry_out, int32_t* entry_off_out,
+                   int32_t* total_out, void* stream);
 
 /* Small device-memory helpers so non-CUDA hosts (ctypes, cgo, JNI) can drive the library without another runtime. */
 BT_API int bt_dev_alloc(void** out, size_t bytes);

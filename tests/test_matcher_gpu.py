@@ -1,0 +1,152 @@
+"""GPU parity tests of the matcher half of the hot path (through the C-ABI): tcgen05 kNN vs exact brute force,
+RANSAC vs its CPU restatement."""
+import os
+
+import numpy as np
+import pytest
+
+from bundletrack_b200 import synth
+from oracle import matcher_oracle as mo
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def matcher(cuda_device):
+    from bundletrack_b200.matcher import KnnMatcher
+    m = KnnMatcher(max_pairs=64, max_feats=5120)
+    yield m
+    m.close()
+
+
+def _check(matcher, dev, a, b, k=5):
+    import torch
+    ta, tb = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+    iAB, dAB, iBA, dBA = matcher.knn_match_pairs([(ta, tb)], k=k)
+    i1, d1 = mo.knn(a, b, k)
+    i2, d2 = mo.knn(b, a, k)
+    assert np.array_equal(iAB[0].cpu().numpy(), i1)
+    assert np.array_equal(iBA[0].cpu().numpy(), i2)
+    f = np.isfinite(d1)
+    assert np.array_equal(np.isfinite(dAB[0].cpu().numpy()), f)
+    if f.any():
+        assert np.abs(dAB[0].cpu().numpy()[f] - d1[f]).max() <= 1e-6
+    f2 = np.isfinite(d2)
+    if f2.any():
+        assert np.abs(dBA[0].cpu().numpy()[f2] - d2[f2]).max() <= 1e-6
+
+
+@pytest.mark.parametrize("na,nb", [(500, 500), (2000, 2000), (1000, 3000), (129, 257), (5, 3), (1, 700), (300, 2)])
+def test_knn_equals_exact_brute_force(matcher, cuda_device, na, nb):
+    a, b, _, _ = synth.make_descriptors(na * 7 + nb, na, nb)
+    _check(matcher, cuda_device, a, b)
+
+
+def test_knn_cfg5_5000x5000(matcher, cuda_device):
+    a, b, _, _ = synth.make_descriptors(55, 5000, 5000)
+    _check(matcher, cuda_device, a, b)
+
+
+def test_knn_duplicates_and_unnormalised(matcher, cuda_device):
+    """Exact ties (duplicate descriptors) must come out lowest-index-first; non-unit norms must not break the proof."""
+    rng = np.random.default_rng(3)
+    a = rng.normal(size=(300, 256)).astype(np.float32)
+    b = rng.normal(size=(400, 256)).astype(np.float32) * 3.0
+    b[10] = b[200]; b[11] = b[200]; b[350] = b[200]
+    a[5] = b[200] * 0.999
+    _check(matcher, cuda_device, a, b)
+
+
+def test_knn_pitched_rows_and_batch(matcher, cuda_device):
+    """GpuMat rows are pitched; a keyframe's descriptor set is shared by many pairs of one call."""
+    import torch
+    frames = []
+    for f in range(4):
+        d = synth.make_descriptors(200 + f, 600 + 50 * f, 8)[0]
+        buf = torch.zeros((d.shape[0], 320), device=cuda_device)      # pitch 1280 B
+        buf[:, :256] = torch.from_numpy(d).to(cuda_device)
+        frames.append((d, buf[:, :256]))
+    pairs = [(frames[j][1], frames[i][1]) for i in range(4) for j in range(i + 1, 4)]
+    iAB, dAB, iBA, dBA = matcher.knn_match_pairs(pairs)
+    p = 0
+    for i in range(4):
+        for j in range(i + 1, 4):
+            i1, _ = mo.knn(frames[j][0], frames[i][0])
+            i2, _ = mo.knn(frames[i][0], frames[j][0])
+            assert np.array_equal(iAB[p].cpu().numpy(), i1)
+            assert np.array_equal(iBA[p].cpu().numpy(), i2)
+            p += 1
+
+
+def test_knn_matches_opencv(matcher, cuda_device):
+    pytest.importorskip("cv2")
+    import torch
+    a, b, _, _ = synth.make_descriptors(9, 800, 700)
+    iAB, dAB, _, _ = matcher.knn_match_pairs([(torch.from_numpy(a).to(cuda_device), torch.from_numpy(b).to(cuda_device))])
+    ic, dc = mo.knn_cv2(a, b)
+    assert np.array_equal(iAB[0].cpu().numpy(), ic)
+    assert np.abs(dAB[0].cpu().numpy() - dc).max() < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------------------ RANSAC
+def _ransac_case(seed, n, inlier_frac=0.7, noise=0.0005, big=False):
+    rng = np.random.default_rng(seed)
+    A = rng.uniform(-0.1, 0.1, (n, 3)) + [0, 0, 0.7]
+    R = synth.so3_exp(rng.normal(0, 0.3, 3)); t = rng.normal(0, 0.05, 3)
+    B = A @ R.T + t + rng.normal(0, noise, (n, 3))
+    out = rng.uniform(size=n) > inlier_frac
+    B[out] += rng.normal(0, 1, (int(out.sum()), 3)) * 0.02 + 0.03
+    A4 = np.concatenate([A, np.ones((n, 1))], 1).astype(np.float32)
+    B4 = np.concatenate([B, np.ones((n, 1))], 1).astype(np.float32)
+    return A4, B4, ~out
+
+
+def test_ransac_sampler_is_curand_xorwow(cuda_device):
+    """The sampler's uniforms must be the reference's: curand_init(0, trial, 0) + 3 x curand_uniform (golden table made
+    with that very call on a B200 by scripts/make_golden_curand.py)."""
+    from bundletrack_b200.matcher import Ransac
+    import torch
+    r = Ransac(max_pairs=2, max_pts=256, max_trials=2000)
+    A4, B4, _ = _ransac_case(0, 50)
+    r.ransac_pairs([torch.from_numpy(A4).to(cuda_device)], [torch.from_numpy(B4).to(cuda_device)], 2000, 0.005)
+    u3, _ = r.debug(2000, 1)
+    gold = np.load(os.path.join(GOLD, "curand_xorwow_seed0.npy"))
+    assert np.array_equal(u3, gold[:2000])
+    r.close()
+
+
+@pytest.mark.parametrize("n", [8, 60, 400, 3000])
+def test_ransac_matches_oracle(cuda_device, n):
+    from bundletrack_b200.matcher import Ransac
+    import torch
+    r = Ransac(max_pairs=4, max_pts=4096, max_trials=2000)
+    cases = [_ransac_case(10 * n + k, n) for k in range(3)]
+    ids = r.ransac_pairs([torch.from_numpy(c[0]).to(cuda_device) for c in cases], [torch.from_numpy(c[1]).to(cuda_device) for c in cases], 2000, 0.005)
+    u3, best = r.debug(2000, 3)
+    for k, (A4, B4, truth) in enumerate(cases):
+        got = ids[k].cpu().numpy()
+        want, wbest, counts = mo.ransac_pair(A4, B4, u3, 0.005)
+        assert (np.diff(got) > 0).all()
+        # the winning count can differ by a borderline point or two (fp32 pose vs float64 SVD); the SET must be the true inliers
+        assert abs(len(got) - len(want)) <= max(2, len(want) // 200)
+        inter = len(np.intersect1d(got, want))
+        assert inter >= len(want) - max(2, len(want) // 200)
+        assert counts[best[k]] >= counts.max() - max(2, len(want) // 200)      # our winner is (near-)optimal for the oracle too
+        if n >= 60:
+            assert np.array_equal(np.nonzero(truth)[0], got) or inter >= truth.sum() - 2
+    r.close()
+
+
+def test_ransac_edge_cases(cuda_device):
+    from bundletrack_b200.matcher import Ransac
+    import torch
+    r = Ransac(max_pairs=4, max_pts=64, max_trials=500)
+    A4, B4, _ = _ransac_case(1, 2)          # fewer than 3 points: no model, no inliers
+    z = torch.zeros((0, 4), device=cuda_device)
+    ids = r.ransac_pairs([torch.from_numpy(A4).to(cuda_device), z], [torch.from_numpy(B4).to(cuda_device), z], 500, 0.005)
+    assert len(ids[0]) == 0 and len(ids[1]) == 0
+    A4, B4, _ = _ransac_case(2, 30, inlier_frac=0.0)   # all outliers: at most the 3 sampled points agree
+    ids = r.ransac_pairs([torch.from_numpy(A4).to(cuda_device)], [torch.from_numpy(B4).to(cuda_device)], 500, 0.0005)
+    assert len(ids[0]) <= 6
+    r.close()
