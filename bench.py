@@ -36,7 +36,7 @@ import numpy as np  # noqa: E402
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--windows", type=int, default=32, help="windows per GPU per step (BASELINE configs[3]: 256 over 8 GPUs)")
@@ -61,7 +61,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([c.strip() for c in line.split(",")])
@@ -113,6 +113,41 @@ def make_batch(args, rank, dev):
         wins.append(SolveWindow(sc.corr, sc.H, sc.W, depth, normal, poses.astype(np.float32), sc.K))
         host.append((sc, poses.astype(np.float32)))
     return wins, host
+
+
+def matcher_microbench(dev, stream):
+    """Secondary evidence for the matcher half of the path (BASELINE configs[4]/[1]): kernel times from CUDA events inside
+    the library; tensor fraction = executed bf16 flops (both directions) / measured cuBLAS bf16 peak."""
+    import torch
+    from bundletrack_b200 import synth
+    from bundletrack_b200.matcher import KnnMatcher
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            tf_peak, src = float(json.load(f)["bf16_tflops"]), "measured"
+    except Exception:
+        tf_peak, src = 1590.0, "fallback"
+    m = KnnMatcher(max_pairs=48, max_feats=5120, stream=stream)
+    m.enable_timing(True)
+    out = {"peak_bf16_tflops": tf_peak, "peak_source": src}
+    a, b, _, _ = synth.make_descriptors(5, 5000, 5000)
+    ta, tb = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+    frames = [torch.from_numpy(synth.make_descriptors(100 + f, 2000, 8)[0]).to(dev) for f in range(10)]
+    pairs = [(frames[j], frames[i]) for i in range(10) for j in range(i + 1, 10)]
+    for name, prs, flop in (("cfg5_5000x5000", [(ta, tb)], 2 * 2.0 * 5000 * 5000 * 256), ("cfg2_45pairs_x2000", pairs, 45 * 2 * 2.0 * 2000 * 2000 * 256)):
+        for _ in range(3):
+            m.knn_match_pairs(prs)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            m.knn_match_pairs(prs)
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) / 10
+        tm = m.timing()
+        out[name] = {"pairs": len(prs), "call_ms": wall * 1e3, "pairs_per_s": len(prs) / wall, "tc_kernel_ms": tm["tc_ms"], "rerank_ms": tm["rerank_ms"],
+                     "fallback_ms": tm["fallback_ms"], "fallback_rows": tm["fallback_rows"], "tc_tflops_executed": flop / (tm["tc_ms"] * 1e-3) / 1e12,
+                     "tc_frac_of_bf16_peak": flop / (tm["tc_ms"] * 1e-3) / 1e12 / tf_peak}
+    m.close()
+    return out
 
 
 def cpu_baseline(host, n_windows):
@@ -212,15 +247,15 @@ def main():
         k_ms.append(None)
     ev1.record()
     sync_all()
-    clocks = sampler.stop()
     elapsed = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     tm = opt.timing_ms()                      # per-kernel device time of the last step
     stats = opt.stats()
     poses = opt.fetch()
     if world > 1:
         dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
-        gathered = [torch.zeros(args.windows * N * 16, device=dev) for _ in range(world)]   # NCCL only to gather results
-        dist.all_gather(gathered, torch.from_numpy(np.concatenate([p.reshape(-1) for p in poses])).to(dev))
+        from bundletrack_b200.sharding import gather_poses   # NCCL only gathers the results (windows are sharded per rank)
+        # every rank holds `windows` windows; global ids are rank-strided like shard_indices
+        gather_poses(poses, args.windows * world, [N] * (args.windows * world), rank, world, device=dev)
     ms_step = float(elapsed.item()) / args.steps
     value = world * args.windows / (ms_step * 1e-3)
 
@@ -233,12 +268,16 @@ def main():
         out_poses = opt.optimizeWindows(wins)
     torch.cuda.synchronize()
     dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    clocks = sampler.stop()      # sampled across both timed regions (value + e2e)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_val = world * args.windows * args.steps / float(dt.item())
     h2d = sum(len(w.corr) * 32 + w.n_frames * 64 + w.n_frames * 20 + 120 + 45 * 8 + 46 * 12 for w in wins)
     d2h = sum(w.n_frames * 64 for w in wins)
 
+    matcher = None
+    if rank == 0:
+        matcher = matcher_microbench(dev, stream)
     if rank == 0:
         peak, peak_src = hbm_peak()
         alg_bytes = args.windows * (7 * (N * npix * 32 + C * 32) + 2 * N * 64)
@@ -254,6 +293,7 @@ def main():
                              "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": tm},
                    cpu_baseline=cb, clocks=clocks,
                    parity={"window0_vs_oracle_rot_rad": chk[0], "window0_vs_oracle_trans_m": chk[1]},
+                   matcher=matcher,
                    solver_stats=stats)
         print(json.dumps(out))
     if world > 1:

@@ -11,13 +11,14 @@
 //                 split).  Warp 0 streams operands with TMA (SWIZZLE_128B, K-major); warp 1 issues
 //                 tcgen05.mma.cta_group::1.kind::f16 (bf16 x bf16 -> fp32, M=128, N=256, K=16 per instruction) into a
 //                 double-buffered TMEM accumulator (2 x 256 columns); eight epilogue warps read the accumulator with
-//                 tcgen05.ld (thread t of a lane quarter owns query row t), form key = |t~|^2 - 2 q~.t~ and keep a
-//                 per-thread top-8 of (key | train index packed in the low 13 mantissa bits) with a branch-free min/max
-//                 insertion network that only runs when a key beats the current 8th best.
-//   k_knn_rerank  per query row: the <= 16*splits candidates are re-scored EXACTLY (float64 sum of (a-b)^2 on the fp32
-//                 inputs), sorted (distance, index) and the top k written.  A rigorous bound on the bf16 pass
-//                 (| |q~-t~| - |q-t| | <= 2^-9 (|q|+|t|), plus key packing) proves the exact top-k lies inside the
-//                 candidate set; rows where the proof fails go to
+//                 tcgen05.ld (thread t of a lane quarter owns query row t), form key = |t~|^2 - 2 q~.t~, reduce every
+//                 group of 4 train columns to its minimum and push (min key | group index in the low 11 mantissa bits)
+//                 through a branch-free min/max insertion network that keeps the 12 smallest group minima per thread:
+//                 no data-dependent branch anywhere in the epilogue.
+//   k_knn_rerank  per query row: groups whose minimum could still reach the top k (interval test with the measured bf16
+//                 rounding error of both rows) are expanded to all 4 members and re-scored EXACTLY (float64 sum of
+//                 (a-b)^2 on the fp32 inputs, one lane per candidate); top k by (distance, index).  The same bound proves
+//                 that no train row outside the kept groups can enter the top k; rows where the proof fails go to
 //   k_knn_exact   exact brute force for those rows only (rare).
 // Result == exact brute-force kNN (float64 distances, ties -> lower train index), distances returned as
 // float(sqrt(d2)) like cv::NORM_L2.
@@ -36,10 +37,11 @@ static constexpr int BN = 256;              // train rows per tile (UMMA N)
 static constexpr int BK = 64;               // K elements per smem chunk: 64 bf16 = 128 B = one SWIZZLE_128B atom row
 static constexpr int KCH = KD / BK;         // 4 chunks
 static constexpr int STAGES = 4;            // train-operand pipeline depth (32 KB each)
-static constexpr int KC = 8;                // candidates kept per epilogue thread (per column half)
-static constexpr int NCAND = 2 * KC;        // candidates per (query row, split)
-static constexpr int IDX_BITS = 13;         // train index (relative to the split) packed in the low mantissa bits
-static constexpr int MAX_SPLIT_ROWS = 1 << IDX_BITS;
+static constexpr int GRP = 4;                // train columns per group: only each group's minimum key enters the list
+static constexpr int KC = 12;               // group minima kept per epilogue thread (per column half)
+static constexpr int NCAND = 2 * KC;        // list entries per (query row, split)
+static constexpr int IDX_BITS = 11;         // group index (relative to the split) packed in the low mantissa bits
+static constexpr int MAX_SPLIT_ROWS = GRP << IDX_BITS;   // 8192 train rows per split
 static constexpr int KNN_THREADS = 32 * 10; // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 static constexpr uint32_t SQ_BYTES = BM * BK * 2;     // 16 KB per K-chunk of the query tile
 static constexpr uint32_t SB_BYTES = BN * BK * 2;     // 32 KB per stage
@@ -289,14 +291,14 @@ k_knn_tc(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUt
 				// compares schedule ahead of the rare inserts); inserting against a stale threshold is harmless because the
 				// min/max network leaves the list untouched when the key is not better than its current 8th entry.
 				auto scan = [&](const uint32_t (&v)[32], int c) {
-					const float thr = best[KC - 1];
 #pragma unroll
-					for (int e = 0; e < 32; e++) {
-						const float key = fmaf(-2.0f, __uint_as_float(v[e]), nrm[c * 32 + e]);
-						if (key < thr) {
-							const uint32_t packed = (__float_as_uint(key) & ~((1u << IDX_BITS) - 1u)) | (uint32_t)(col_base + c * 32 + e);
-							topk_insert(best, __uint_as_float(packed));
-						}
+					for (int g = 0; g < 32 / GRP; g++) {
+						float m = fmaf(-2.0f, __uint_as_float(v[g * GRP]), nrm[c * 32 + g * GRP]);
+#pragma unroll
+						for (int j = 1; j < GRP; j++) m = fminf(m, fmaf(-2.0f, __uint_as_float(v[g * GRP + j]), nrm[c * 32 + g * GRP + j]));
+						m = fminf(m, 3.0e38f);    // an all-padding group has key +inf: OR-ing index bits into +inf would make a NaN and corrupt the min/max network
+						const uint32_t packed = (__float_as_uint(m) & ~((1u << IDX_BITS) - 1u)) | (uint32_t)((col_base + c * 32) / GRP + g);
+						topk_insert(best, __uint_as_float(packed));     // branch-free: a key worse than the 12th entry falls out again
 					}
 				};
 				uint32_t va[32], vb[32];
@@ -318,8 +320,8 @@ k_knn_tc(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUt
 			}
 			if (row < item.q_valid) {
 				float4* out = reinterpret_cast<float4*>(cand + ((size_t)(item.cand_off + row) * NCAND + half * KC));
-				out[0] = make_float4(best[0], best[1], best[2], best[3]);
-				out[1] = make_float4(best[4], best[5], best[6], best[7]);
+#pragma unroll
+				for (int j = 0; j < KC / 4; j++) out[j] = make_float4(best[4 * j], best[4 * j + 1], best[4 * j + 2], best[4 * j + 3]);
 			}
 		}
 	}
@@ -362,59 +364,160 @@ __device__ __forceinline__ int find_job(const int* __restrict__ job_row_start, i
 }
 struct KnnOut { int32_t* idx[2]; float* dist[2]; };
 
+// lane-private exact squared distance between two fp32 rows (float64 accumulation, fixed order)
+__device__ __forceinline__ double exact_d2_lane(const float* __restrict__ a, const float* __restrict__ b) {
+	double s0 = 0.0, s1 = 0.0;
+#pragma unroll 4
+	for (int k = 0; k < KD / 4; k++) {
+		const float4 x = __ldg(reinterpret_cast<const float4*>(a) + k), y = __ldg(reinterpret_cast<const float4*>(b) + k);
+		double d;
+		d = (double)x.x - (double)y.x; s0 += d * d; d = (double)x.y - (double)y.y; s1 += d * d;
+		d = (double)x.z - (double)y.z; s0 += d * d; d = (double)x.w - (double)y.w; s1 += d * d;
+	}
+	return s0 + s1;
+}
+
+static constexpr int RR_MAXC = 96;    // exact candidates per row handled in shared memory; more => exact fallback
+
 // one warp per query row
 __global__ void __launch_bounds__(256) k_knn_rerank(const RerankJob* __restrict__ jobs, const int* __restrict__ job_row_start, int n_jobs, int total_rows,
                                                      const float* __restrict__ cand, const float* __restrict__ norms, const float* __restrict__ errn,
                                                      const int* __restrict__ set_maxnorm2, const int* __restrict__ set_maxerr,
                                                      int k, KnnOut out, int* fallback_rows, int* fallback_count) {
-	const int lane = threadIdx.x & 31;
+	__shared__ int s_ci[8][RR_MAXC];
+	__shared__ double s_cd[8][RR_MAXC];
+	const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
 	const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (gw >= total_rows) return;
-	const RerankJob jb = jobs[find_job(job_row_start, n_jobs, gw)];
-	const int r = gw - job_row_start[find_job(job_row_start, n_jobs, gw)];
+	const int ji = find_job(job_row_start, n_jobs, gw);
+	const RerankJob jb = jobs[ji];
+	const int r = gw - job_row_start[ji];
 	const float* qrow = (const float*)((const char*)jb.q + (size_t)r * jb.q_pitch);
-	const int ncand_total = jb.n_splits * NCAND;
-	double best_d[8]; int best_i[8];          // warp-uniform values, kept redundantly by every lane
+	const int kk = min(k, jb.nt);
+	const float INF = __int_as_float(0x7f800000);
+	const int E = jb.n_splits * NCAND;
+	// bound on | |q~ - t~| - |q - t| |: measured rounding-error norms of both rows (train side: per-set maximum) plus slack for
+	// the fp32 accumulation in the tensor core; the index packing costs <= 2^-IDX_BITS relative on the key itself.
+	const float qn2 = __ldg(norms + jb.q_pool_row0 + r);
+	const double qn = sqrt((double)qn2), tn = sqrt((double)__int_as_float(set_maxnorm2[jb.t_set]));
+	const double eps = (double)__ldg(errn + jb.q_pool_row0 + r) + (double)__int_as_float(set_maxerr[jb.t_set]) + 1e-4 * (qn + tn) + 1e-6;
+	const double pk_rel = 1.0 / (double)(1 << IDX_BITS);
+	auto d_lo = [&](float key) -> double { const double v = (double)qn2 + (double)key - fabs((double)key) * pk_rel - 1e-6; return (v > 0.0 ? sqrt(v) : 0.0) - eps; };
+	auto d_hi = [&](float key) -> double { const double v = (double)qn2 + (double)key + fabs((double)key) * pk_rel + 1e-6; return (v > 0.0 ? sqrt(v) : 0.0) + eps; };
+	// ---- pass 1 over the list entries: D5 = k-th smallest upper bound (each entry IS a real train row, so the exact k-th
+	//      distance is <= D5), tau = smallest "list is full" threshold (rows of groups that never made a list have key >= tau)
+	double up[8];
 #pragma unroll
-	for (int j = 0; j < 8; j++) { best_d[j] = 1e300; best_i[j] = 0x7fffffff; }
-	float thr_key = __int_as_float(0x7f800000);   // smallest (over splits/halves) of the KC-th best approximate keys
-	for (int c = 0; c < ncand_total; c++) {
-		const int s = c / NCAND, e = c - s * NCAND;
-		const float pk = __ldg(cand + ((size_t)(jb.cand_off + s * jb.cand_split_stride + r) * NCAND + e));
-		if ((e % KC) == KC - 1) thr_key = fminf(thr_key, pk);
-		if (!(pk < __int_as_float(0x7f800000))) continue;          // empty slot
-		const int ti = s * jb.split_rows + (int)(__float_as_uint(pk) & ((1u << IDX_BITS) - 1u));
-		if (ti >= jb.nt) continue;
-		bool dup = false;
+	for (int j = 0; j < 8; j++) up[j] = 1e300;
+	float tau = INF;
+	for (int e0 = 0; e0 < E; e0 += 32) {
+		const int e = e0 + lane;
+		float pk = INF;
+		if (e < E) { const int s = e / NCAND, c = e - s * NCAND; pk = __ldg(cand + ((size_t)(jb.cand_off + s * jb.cand_split_stride + r) * NCAND + c)); if ((c % KC) == KC - 1) tau = fminf(tau, pk); }
+		double v = (pk < INF) ? d_hi(pk) : 1e300;
+		// merge the 32 lane values into the warp-uniform sorted list up[0..kk)
+		for (int round = 0; round < kk; round++) {
+			double m = v;
 #pragma unroll
-		for (int j = 0; j < 8; j++) dup |= (best_i[j] == ti);
-		if (dup) continue;
-		const float* trow = (const float*)((const char*)jb.t + (size_t)ti * jb.t_pitch);
-		double cd = exact_d2(qrow, trow, lane); int ci = ti;
+			for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+			if (!(m < up[kk - 1])) break;
+			// insert m, and retire ONE lane holding it
+			double cdv = m;
 #pragma unroll
-		for (int j = 0; j < 8; j++) {   // sorted insert, ties -> lower index
-			const bool lt = (cd < best_d[j]) || (cd == best_d[j] && ci < best_i[j]);
-			if (lt) { const double td = best_d[j]; const int tix = best_i[j]; best_d[j] = cd; best_i[j] = ci; cd = td; ci = tix; }
+			for (int j = 0; j < 8; j++) { if (j < kk && cdv < up[j]) { const double t2 = up[j]; up[j] = cdv; cdv = t2; } }
+			const unsigned who = __ballot_sync(0xffffffffu, v == m);
+			if (lane == (int)(__ffs(who) - 1)) v = 1e300;
 		}
 	}
-	// Proof that no NON-candidate can enter the exact top-k.  Every non-candidate j has approximate key >= thr_key (up to
-	// the 2^-10 relative loss of packing the index into the mantissa), i.e. |q~ - t~_j|^2 >= |q~|^2 + key_j, and
-	// | |q~ - t~| - |q - t| | <= |q~ - q| + |t~ - t| <= 2^-9 (|q| + |t|)  (bf16 round-to-nearest, per component).
-	const int kk = min(k, jb.nt);
-	bool ok = true;
-	if (kk > 0 && thr_key < __int_as_float(0x7f800000)) {    // an unfilled list means every train row of that half was a candidate
-		const float qn2 = __ldg(norms + jb.q_pool_row0 + r);                                  // |q~|^2
-		const double key_lo = (double)thr_key - fabs((double)thr_key) * (1.0 / 1024.0) - 1e-6;
-		const double approx_d2 = (double)qn2 + key_lo;
-		if (approx_d2 <= 0.0) ok = false;
-		else {
-			// | |q~ - t~| - |q - t| | <= |q~ - q| + |t~ - t|: both rounding-error norms were measured by k_desc_prep (the
-			// train side through its per-set maximum); plus slack for the fp32 accumulation inside the tensor core.
-			const double qn = sqrt((double)qn2), tn = sqrt((double)__int_as_float(set_maxnorm2[jb.t_set]));
-			const double eps = (double)__ldg(errn + jb.q_pool_row0 + r) + (double)__int_as_float(set_maxerr[jb.t_set]) + 1e-4 * (qn + tn) + 1e-6;
-			const double lower = sqrt(approx_d2) - eps;
-			ok = (lower > 0.0) && (best_i[kk - 1] != 0x7fffffff) && (best_d[kk - 1] < lower * lower);
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) tau = fminf(tau, __shfl_xor_sync(0xffffffffu, tau, o));
+	const double D5 = (kk > 0) ? up[kk - 1] : 1e300;
+	// ---- pass 2: expand every group whose lower bound can still reach D5 into its GRP members
+	int ncand = 0;
+	bool overflow = false;
+	for (int e0 = 0; e0 < E; e0 += 32) {
+		const int e = e0 + lane;
+		bool take = false; int gbase = 0;
+		if (e < E) {
+			const int s = e / NCAND, c = e - s * NCAND;
+			const float pk = __ldg(cand + ((size_t)(jb.cand_off + s * jb.cand_split_stride + r) * NCAND + c));
+			if (pk < INF) { gbase = s * jb.split_rows + (int)(__float_as_uint(pk) & ((1u << IDX_BITS) - 1u)) * GRP; take = (gbase < jb.nt) && (d_lo(pk) <= D5); }
 		}
+		const unsigned bal = __ballot_sync(0xffffffffu, take);
+		const int pos = ncand + __popc(bal & ((1u << lane) - 1u)) * GRP;
+		if (take) {
+			if (pos + GRP <= RR_MAXC) { for (int j = 0; j < GRP; j++) s_ci[wl][pos + j] = (gbase + j < jb.nt) ? gbase + j : -1; }
+			else overflow = true;
+		}
+		ncand += __popc(bal) * GRP;
+	}
+	overflow = __any_sync(0xffffffffu, overflow) || ncand > RR_MAXC;
+	__syncwarp();
+	bool ok = !overflow;
+	double best_d[8]; int best_i[8];
+#pragma unroll
+	for (int j = 0; j < 8; j++) { best_d[j] = 1e300; best_i[j] = 0x7fffffff; }
+	if (!overflow) {
+		// ---- fp32 pre-filter, one lane per candidate: float64 conversions are the scarce resource, so the exact float64
+		//      distance is only computed for candidates the fp32 value cannot rule out.  |d2_f32 - d2| <= 256 * 2^-23 * d2.
+		float* s_cf = reinterpret_cast<float*>(&s_cd[wl][0]);        // fp32 distances live in the (otherwise unused) double array
+		for (int c0 = 0; c0 < ncand; c0 += 32) {
+			const int c = c0 + lane;
+			if (c < ncand) {
+				const int ti = s_ci[wl][c];
+				float f = INF;
+				if (ti >= 0) {
+					const float4* a4 = reinterpret_cast<const float4*>(qrow);
+					const float4* b4 = reinterpret_cast<const float4*>((const char*)jb.t + (size_t)ti * jb.t_pitch);
+					float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
+					for (int q = 0; q < KD / 4; q++) {
+						const float4 x = __ldg(a4 + q), y = __ldg(b4 + q);
+						const float d0 = x.x - y.x, d1 = x.y - y.y, d2_ = x.z - y.z, d3 = x.w - y.w;
+						s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2_, d2_, s2); s3 = fmaf(d3, d3, s3);
+					}
+					f = (s0 + s1) + (s2 + s3);
+				}
+				s_cf[c] = f;
+			}
+		}
+		__syncwarp();
+		// k-th smallest fp32 distance (warp-uniform): k rounds of warp-min, retiring ONE holder per round
+		float fk = INF;
+		{
+			unsigned taken_lo = 0u, taken_mid = 0u, taken_hi = 0u;     // candidate slots already counted (<= 96 slots)
+			for (int round = 0; round < kk; round++) {
+				float m = INF; int mc = -1;
+				for (int c = lane; c < ncand; c += 32) {
+					const unsigned bit = 1u << (c & 31);
+					const unsigned word = (c < 32) ? taken_lo : ((c < 64) ? taken_mid : taken_hi);
+					if (!(word & bit) && s_cf[c] < m) { m = s_cf[c]; mc = c; }
+				}
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) {
+					const float om = __shfl_xor_sync(0xffffffffu, m, o); const int oc = __shfl_xor_sync(0xffffffffu, mc, o);
+					if (oc >= 0 && (mc < 0 || om < m || (om == m && oc < mc))) { m = om; mc = oc; }
+				}
+				if (mc < 0) break;
+				fk = m;
+				const unsigned bit = 1u << (mc & 31);
+				if (mc < 32) taken_lo |= bit; else if (mc < 64) taken_mid |= bit; else taken_hi |= bit;
+			}
+		}
+		const float f_cut = (fk < INF) ? fk * (1.0f + 1.0e-4f) + 1e-30f : INF;
+		// ---- exact float64 distance (warp-cooperative) for the survivors; sorted insert by (distance, index)
+		for (int c = 0; c < ncand; c++) {
+			const int ti = s_ci[wl][c];
+			if (ti < 0 || !(s_cf[c] <= f_cut)) continue;           // warp-uniform: both arrays are shared
+			double cd = exact_d2(qrow, (const float*)((const char*)jb.t + (size_t)ti * jb.t_pitch), lane); int ci = ti;
+#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				const bool lt = (cd < best_d[j]) || (cd == best_d[j] && ci < best_i[j]);
+				if (lt) { const double td = best_d[j]; const int tix = best_i[j]; best_d[j] = cd; best_i[j] = ci; cd = td; ci = tix; }
+			}
+		}
+		// ---- proof for everything that never made a list: its key is >= tau
+		if (kk > 0 && tau < INF) ok = (best_i[kk - 1] != 0x7fffffff) && (sqrt(best_d[kk - 1]) < d_lo(tau));
 	}
 	if (lane == 0) {
 		int32_t* io = out.idx[jb.dir] + ((size_t)jb.out_off + r) * k;
@@ -422,7 +525,7 @@ __global__ void __launch_bounds__(256) k_knn_rerank(const RerankJob* __restrict_
 		for (int j = 0; j < k; j++) {
 			const bool have = j < kk && best_i[j] != 0x7fffffff;
 			io[j] = have ? best_i[j] : -1;
-			dd[j] = have ? (float)sqrt(best_d[j]) : __int_as_float(0x7f800000);
+			dd[j] = have ? (float)sqrt(best_d[j]) : INF;
 		}
 		if (!ok) { const int slot = atomicAdd(fallback_count, 1); fallback_rows[slot] = gw; }
 	}
@@ -635,8 +738,19 @@ extern "C" int bt_knn_match_pairs(bt_ctx* ctx, int n_pairs, const bt_desc_view* 
 			const PrepSet& qs = sets[qset];
 			const PrepSet& ts = sets[tset];
 			const int qtiles = (Q.n + BM - 1) / BM, ttiles = ts.rows_padded / BN;
+			// train splits: the epilogue is branch-free, so a split costs only the extra query-tile load; pick the smallest split
+			// count whose item total fills whole waves of SMs to >= 90 % (or the best one found)
 			int splits = 1;
-			if (base_items < 2LL * ctx->sm_count) splits = (int)std::min<long long>(8, (2LL * ctx->sm_count + base_items - 1) / std::max<long long>(base_items, 1));
+			{
+				double best_eff = 0.0;
+				for (int sc = 1; sc <= 8; sc++) {
+					const long long it_total = base_items * sc;
+					const long long waves = (it_total + ctx->sm_count - 1) / ctx->sm_count;
+					const double eff = (double)it_total / (double)(waves * ctx->sm_count);
+					if (eff > best_eff + 1e-9) { best_eff = eff; splits = sc; }
+					if (eff >= 0.9) { splits = sc; break; }
+				}
+			}
 			splits = std::max(splits, (ts.rows_padded + MAX_SPLIT_ROWS - 1) / MAX_SPLIT_ROWS);
 			splits = std::min(splits, std::max(ttiles, 1));
 			BT_REQUIRE(splits <= 8, BT_ERR_CAPACITY, "pair %d: %d train rows need more than 8 splits", p, T.n);

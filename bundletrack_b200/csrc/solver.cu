@@ -57,6 +57,8 @@ struct WinDesc {
 	float scaleW, scaleH;             // (W-1)/(w-1), (H-1)/(h-1)  (CUDAImageUtil.cu:57-58)
 	int compat_flip;
 	int mem_off;                      // per-frame membership CSR of this window (see SolveArgs::mem)
+	int unique_blocks;                // 1: no two groups / no two dense pairs share an unordered frame pair => cross blocks need no atomics
+	int pad[3];
 };
 
 struct Tile { int win; int pair; int start; int count; };  // pair < 0 => dummy tile (window without dense work)
@@ -81,6 +83,7 @@ struct SolveArgs {
 	const int* grp_i; const int* grp_j; const int* grp_start;   // grp_start has n_groups+1 entries per window
 	const uint2* pairs;   // (target, source)
 	const int* pair_win;  // owning window of every entry of `pairs`
+	const int* pair_src_slot;   // global frame slot (frame_off + source) of every entry of `pairs`
 	// per-window CSR built on the host: for every frame f, first the correspondence groups touching f, then the dense
 	// pairs touching f.  Layout at mem_off: fg_start[N+1], fp_start[N+1], items[2G] (g | role<<16), items[2P] (p | role<<16)
 	const int* mem;
@@ -214,7 +217,7 @@ __device__ __forceinline__ void prof_emit(const SolveArgs& a, const ProfRec& r) 
 // ------------------------------------------------------------------------------------------------ k_prep_frames
 // CUDACache::storeFrame fused (convertDepthFloatToCameraSpaceFloat4 + 2x resampleFloat4 nearest, CUDAImageUtil.cu:
 // 310-326,82-99) + compaction of the source list + matrixToPose/poseToMatrix of the incoming pose (SBA.cu:71-79).
-__global__ void __launch_bounds__(512) k_prep_frames(SolveArgs a) {
+__global__ void __launch_bounds__(1024) k_prep_frames(SolveArgs a) {
 	const int fs = blockIdx.x;
 	const WinDesc wd = a.wins[a.frame_win[fs]];
 	const int npix = wd.w * wd.h;
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(512) k_prep_frames(SolveArgs a) {
 	const float4* __restrict__ normal = a.normal_ptr[fs];
 	float4* texel = a.texel + (size_t)fs * 2 * a.npix_max;
 	float4* src = a.src + (size_t)fs * 2 * a.npix_max;
-	__shared__ int s_warp[16];
+	__shared__ int s_warp[32];
 	__shared__ int s_base;
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	if (tid == 0) {
@@ -241,53 +244,32 @@ __global__ void __launch_bounds__(512) k_prep_frames(SolveArgs a) {
 	__syncthreads();
 	const bool use_dense = a.prm.w_dense > 0.0f;
 	if (!use_dense) { if (tid == 0) a.nsrc[fs] = 0; return; }
-	constexpr int PX = 4;   // consecutive quarter-res pixels per thread and iteration: 8 independent loads in flight
-	for (int base = 0; base < npix; base += blockDim.x * PX) {
-		const int idx0 = base + tid * PX;
-		float d[PX]; float4 nr[PX]; size_t sidx[PX]; bool inb[PX];
-#pragma unroll
-		for (int j = 0; j < PX; j++) {
-			const int idx = idx0 + j;
-			inb[j] = false; sidx[j] = 0; d[j] = 0.f; nr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-			if (idx < npix) {
-				const int x = idx % wd.w, y = idx / wd.w;
-				const unsigned xi = (unsigned)((float)x * wd.scaleW + 0.5f), yi = (unsigned)((float)y * wd.scaleH + 0.5f);
-				if (xi < (unsigned)wd.W && yi < (unsigned)wd.H) { inb[j] = true; sidx[j] = (size_t)yi * wd.W + xi; }
+	for (int base = 0; base < npix; base += blockDim.x) {
+		const int idx = base + tid;
+		float4 cp = make_float4(0.f, 0.f, 0.f, 0.f), nr = make_float4(0.f, 0.f, 0.f, 0.f);
+		bool valid = false;
+		if (idx < npix) {
+			const int x = idx % wd.w, y = idx / wd.w;
+			const unsigned xi = (unsigned)((float)x * wd.scaleW + 0.5f), yi = (unsigned)((float)y * wd.scaleH + 0.5f);
+			if (xi < (unsigned)wd.W && yi < (unsigned)wd.H) {
+				const size_t sidx = (size_t)yi * wd.W + xi;
+				const float d = __ldg(depth + sidx);
+				nr = __ldg(normal + sidx);
+				if (d >= 0.1f) cp = make_float4(wd.ifx * ((float)xi * d) + wd.icx * d, wd.ify * ((float)yi * d) + wd.icy * d, d, 1.0f);
 			}
+			texel[2 * idx] = make_float4(cp.x, cp.y, cp.z, nr.x);      // 32-byte texel: point xyz + normal xyz (+ pad)
+			texel[2 * idx + 1] = make_float4(nr.y, nr.z, 0.f, 0.f);
+			valid = (cp.z > a.prm.depth_min && cp.z < a.prm.depth_max);
 		}
-#pragma unroll
-		for (int j = 0; j < PX; j++) if (inb[j]) { d[j] = __ldg(depth + sidx[j]); nr[j] = __ldg(normal + sidx[j]); }
-		float4 cp[PX]; bool valid[PX]; int cnt = 0;
-#pragma unroll
-		for (int j = 0; j < PX; j++) {
-			const int idx = idx0 + j;
-			cp[j] = make_float4(0.f, 0.f, 0.f, 0.f); valid[j] = false;
-			if (idx < npix) {
-				if (inb[j] && d[j] >= 0.1f) {
-					const int x = idx % wd.w, y = idx / wd.w;
-					const unsigned xi = (unsigned)((float)x * wd.scaleW + 0.5f), yi = (unsigned)((float)y * wd.scaleH + 0.5f);
-					cp[j] = make_float4(wd.ifx * ((float)xi * d[j]) + wd.icx * d[j], wd.ify * ((float)yi * d[j]) + wd.icy * d[j], d[j], 1.0f);
-				}
-				texel[2 * idx] = make_float4(cp[j].x, cp[j].y, cp[j].z, nr[j].x);      // 32-byte texel: point xyz + normal xyz (+ pad)
-				texel[2 * idx + 1] = make_float4(nr[j].y, nr[j].z, 0.f, 0.f);
-				valid[j] = (cp[j].z > a.prm.depth_min && cp[j].z < a.prm.depth_max);
-				cnt += valid[j] ? 1 : 0;
-			}
-		}
-		int incl = cnt;   // warp inclusive scan of the per-thread counts (order-preserving compaction)
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-		if (lane == 31) s_warp[wid] = incl;
+		const unsigned bal = __ballot_sync(0xffffffffu, valid);
+		if (lane == 0) s_warp[wid] = __popc(bal);
 		__syncthreads();
-		int off = s_base + incl - cnt;
+		int off = s_base;
 		for (int k = 0; k < wid; k++) off += s_warp[k];
-#pragma unroll
-		for (int j = 0; j < PX; j++) {
-			if (valid[j]) {
-				src[2 * off] = make_float4(cp[j].x, cp[j].y, cp[j].z, nr[j].x);
-				src[2 * off + 1] = make_float4(nr[j].y, nr[j].z, nr[j].w, 0.f);
-				off++;
-			}
+		if (valid) {
+			const int o = off + __popc(bal & ((1u << lane) - 1u));
+			src[2 * o] = make_float4(cp.x, cp.y, cp.z, nr.x);
+			src[2 * o + 1] = make_float4(nr.y, nr.z, nr.w, 0.f);
 		}
 		__syncthreads();
 		if (tid == 0) { int t = 0; for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += s_warp[k]; s_base += t; }
@@ -322,8 +304,7 @@ __global__ void __launch_bounds__(1024) k_plan(SolveArgs a, WinDesc* wins_rw) {
 		unsigned long long px = 0;
 		for (int q = first_pair + tid; q < end_pair; q += 1024) {
 			const int lo = a.pair_win[q];
-			const uint2 pr = a.pairs[q];
-			const int n = a.nsrc[a.wins[lo].frame_off + pr.y];
+			const int n = a.nsrc[a.pair_src_slot[q]];
 			int per;
 			const int nch = chunks_for(n, a.chunk, per);
 			a.pair_ntile[q] = nch;
@@ -372,13 +353,12 @@ __global__ void __launch_bounds__(1024) k_plan(SolveArgs a, WinDesc* wins_rw) {
 		if (fits) {
 			for (int q = first_pair + tid; q < end_pair; q += 1024) {
 				const int lo = a.pair_win[q];
-				const WinDesc wd = a.wins[lo];
-				const uint2 pr = a.pairs[q];
-				const int n = a.nsrc[wd.frame_off + pr.y];
+				const int n = a.nsrc[a.pair_src_slot[q]];
+				const int pair_off_w = a.wins[lo].pair_off;
 				int per;
 				const int nch = chunks_for(n, a.chunk, per);
 				int t = s_cnt[lo - base] + a.pair_tile0[q];
-				for (int c = 0; c < nch; c++) { Tile tl; tl.win = lo; tl.pair = q - wd.pair_off; tl.start = c * per; tl.count = min(per, n - c * per); a.tiles[t++] = tl; }
+				for (int c = 0; c < nch; c++) { Tile tl; tl.win = lo; tl.pair = q - pair_off_w; tl.start = c * per; tl.count = min(per, n - c * per); a.tiles[t++] = tl; }
 			}
 		}
 		__syncthreads();
@@ -397,11 +377,8 @@ __global__ void __launch_bounds__(1024) k_plan(SolveArgs a, WinDesc* wins_rw) {
 // the model frame with the 6x6 adjoint of T_i.
 struct TileAcc { float v[kTileVals]; };
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
-// Software-pipelined over a thread's pixels (stride kThreads): iteration i issues the source load of pixel i+2, projects
-// pixel i+1 (whose source arrived during the previous iteration) and prefetches its four bilinear taps into L1, then does
-// the full evaluation of pixel i with its taps already on chip.
+// Software-pipelined over a thread's pixels (stride kThreads): iteration i issues the source load of pixel i+2 while it
+// evaluates pixel i (an explicit L1 prefetch of the taps of pixel i+1 was measured SLOWER on B200 and was removed).
 __device__ __forceinline__ void tile_pixels(const SolveArgs& a, const WinDesc& wd, const float4* __restrict__ src,
                                             const float4* __restrict__ tex, const float* __restrict__ sM, int start, int count, TileAcc& acc) {
 	const float m00 = sM[0], m01 = sM[1], m02 = sM[2], m03 = sM[3];
@@ -416,28 +393,9 @@ __device__ __forceinline__ void tile_pixels(const SolveArgs& a, const WinDesc& w
 	float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0, n0 = c0, n1 = c0, f0 = c0, f1 = c0;   // current, next, next-next source records
 	if (k < count) { c0 = __ldg(sp + 2 * k); c1 = __ldg(sp + 2 * k + 1); }
 	if (k + kThreads < count) { n0 = __ldg(sp + 2 * (k + kThreads)); n1 = __ldg(sp + 2 * (k + kThreads) + 1); }
-	// prefetch taps of the first pixel
-	auto project_prefetch = [&](const float4& s0) {
-		const float tx = m00 * s0.x + m01 * s0.y + m02 * s0.z + m03, ty = m10 * s0.x + m11 * s0.y + m12 * s0.z + m13, tz = m20 * s0.x + m21 * s0.y + m22 * s0.z + m23;
-		const float sx = tx * fx / tz + cx, sy = ty * fy / tz + cy;
-		const int x0 = (int)floorf(sx), y0 = (int)floorf(sy);
-		if (x0 >= -1 && y0 >= -1 && x0 < (int)W && y0 < (int)Hh) {
-			const int xa = max(x0, 0), ya = max(y0, 0), yb = min(y0 + 1, (int)Hh - 1);
-			prefetch_l1(tex + 2 * ((size_t)ya * W + xa));
-			prefetch_l1(tex + 2 * ((size_t)ya * W + min(xa + 1, (int)W - 1)) + 1);
-			prefetch_l1(tex + 2 * ((size_t)yb * W + xa));
-			prefetch_l1(tex + 2 * ((size_t)yb * W + min(xa + 1, (int)W - 1)) + 1);
-		}
-	};
-#ifndef BT_NO_L1_PREFETCH
-	if (k < count) project_prefetch(c0);
-#endif
 	for (; k < count; k += kThreads) {
 		const int k2 = k + 2 * kThreads;
 		if (k2 < count) { f0 = __ldg(sp + 2 * k2); f1 = __ldg(sp + 2 * k2 + 1); }
-#ifndef BT_NO_L1_PREFETCH
-		if (k + kThreads < count) project_prefetch(n0);
-#endif
 		const float4 s0 = c0, s1 = c1;
 		c0 = n0; c1 = n1; n0 = f0; n1 = f1;
 		const float px = s0.x, py = s0.y, pz = s0.z, nx = s0.w, ny = s1.x, nz = s1.y;
@@ -740,38 +698,52 @@ __device__ void window_tail(const SolveArgs& a, const WinDesc& wd, int w, int it
 	}
 	__syncthreads();
 	PROF_T(5);
-	// ---- P4a: sparse cross blocks (i,j): J_i^T J_j, both frames free
-	for (int k = tid; k < G * 36; k += kThreads) {
-		const int g = k / 36, e = k - g * 36, r = e / 6, c = e - r * 6;
+	// ---- P4a: sparse cross blocks (i,j): J_i^T J_j, both frames free.  One thread per (group, 3x3 sub-block): uniform code per
+	//      thread, 9 entries each.  Sub-blocks: 0 = TT (-n I), 1 = TR ([sum s]x), 2 = RT (-[sum q]x), 3 = RR (-((q.s) I - s q^T)).
+	const bool uniq = wd.unique_blocks != 0;
+	for (int k = tid; k < G * 4; k += kThreads) {
+		const int g = k >> 2, sb = k & 3;
 		const int gi = s.gi[g], gj = s.gj[g];
 		if (gi < 1 || gj < 1 || gi == gj) continue;
 		const float* m = s.grp + g * kGrpVals;
-		float v;
-		if (r < 3 && c < 3) v = (r == c) ? -m[0] : 0.f;                 // TT = -n I
-		else if (r < 3) v = skew(m + 4, r, c - 3);                       // TR = [sum s]x
-		else if (c < 3) v = -skew(m + 1, r - 3, c);                      // RT = -[sum q]x
-		else { const int ra = r - 3, cb = c - 3; const float tr = m[19] + m[23] + m[27];
-			v = -(((ra == cb) ? tr : 0.f) - m[19 + ra * 3 + cb]); }        // RR = -((q.s) I - s q^T)
-		v *= wS;
-		atomicAdd(&s.A[((gi - 1) * 6 + r) * ld + (gj - 1) * 6 + c], v);
-		atomicAdd(&s.A[((gj - 1) * 6 + c) * ld + (gi - 1) * 6 + r], v);
+		const int r0 = (sb >> 1) * 3, c0 = (sb & 1) * 3;
+		const float tr = m[19] + m[23] + m[27];
+#pragma unroll
+		for (int a3 = 0; a3 < 3; a3++) {
+#pragma unroll
+			for (int b3 = 0; b3 < 3; b3++) {
+				float v;
+				if (sb == 0) v = (a3 == b3) ? -m[0] : 0.f;
+				else if (sb == 1) v = skew(m + 4, a3, b3);
+				else if (sb == 2) v = -skew(m + 1, a3, b3);
+				else v = -(((a3 == b3) ? tr : 0.f) - m[19 + a3 * 3 + b3]);
+				v *= wS;
+				float* p1 = &s.A[((gi - 1) * 6 + r0 + a3) * ld + (gj - 1) * 6 + c0 + b3];
+				float* p2 = &s.A[((gj - 1) * 6 + c0 + b3) * ld + (gi - 1) * 6 + r0 + a3];
+				if (uniq) { *p1 = v; *p2 = v; } else { atomicAdd(p1, v); atomicAdd(p2, v); }
+			}
+		}
 	}
 	__syncthreads();
 	// ---- P4b: dense cross blocks: -S for pairs whose cross block survives FlipJtJ (target < source) or all if !compat
 	if (use_dense) {
-		for (int k = tid; k < P * 36; k += kThreads) {
-			const int p = k / 36, e = k - p * 36, r = e / 6, c = e - r * 6;
+		for (int k = tid; k < P * 6; k += kThreads) {
+			const int p = k / 6, r = k - p * 6;
 			const int ti = s.pt[p], sj = s.ps[p];
 			if (ti < 1 || sj < 1) continue;
 			if (wd.compat_flip && !(ti < sj)) continue;
-			const float v = -s.pairW[p * kTileVals + sym6(r, c)];
-			atomicAdd(&s.A[((sj - 1) * 6 + r) * ld + (ti - 1) * 6 + c], v);
-			atomicAdd(&s.A[((ti - 1) * 6 + c) * ld + (sj - 1) * 6 + r], v);
-			if (dbg) {
-				float* Dg = a.dbg_JtJ + (size_t)w * a.dbg_stride * a.dbg_stride;
-				const int dim = 6 * N;
-				atomicAdd(&Dg[(sj * 6 + r) * dim + ti * 6 + c], v);
-				atomicAdd(&Dg[(ti * 6 + c) * dim + sj * 6 + r], v);
+#pragma unroll
+			for (int c = 0; c < 6; c++) {
+				const float v = -s.pairW[p * kTileVals + c_sym_idx[r * 6 + c]];
+				float* p1 = &s.A[((sj - 1) * 6 + r) * ld + (ti - 1) * 6 + c];
+				float* p2 = &s.A[((ti - 1) * 6 + c) * ld + (sj - 1) * 6 + r];
+				if (uniq) { *p1 += v; *p2 += v; } else { atomicAdd(p1, v); atomicAdd(p2, v); }
+				if (dbg) {
+					float* Dg = a.dbg_JtJ + (size_t)w * a.dbg_stride * a.dbg_stride;
+					const int dim = 6 * N;
+					atomicAdd(&Dg[(sj * 6 + r) * dim + ti * 6 + c], v);
+					atomicAdd(&Dg[(ti * 6 + c) * dim + sj * 6 + r], v);
+				}
 			}
 		}
 	}
@@ -781,54 +753,68 @@ __device__ void window_tail(const SolveArgs& a, const WinDesc& wd, int w, int it
 	// ---- PCG (PCGInit_Kernel1/2, PCGStep_Kernel*: SolverBundling.cu:575-818) on ONE warp: the system has <= 186 unknowns,
 	//      so warp shuffles replace every block-wide reduction/barrier of a multi-warp version.
 	{
-		float rz = 0.f;
-		if (tid < 32) {
-			for (int k = lane; k < dimp; k += 32) { const float rv = s.rhs[k], pv = s.Minv[k] * rv; s.r[k] = rv; s.p[k] = pv; s.delta[k] = 0.f; rz += rv * pv; }
-			rz = warp_sum(rz);
-		}
+		// Every warp keeps its OWN register copy of the PCG vectors (element k = lane + 32 q lives in lane, slot q), so the only
+		// thing exchanged per step is Ap (rows are split over the warps): one barrier per step, all scalars by warp shuffles.
+		constexpr int QM = (6 * (kMaxFrames - 1) + 31) / 32;   // <= 6 slots per lane
 		const int wid = tid >> 5;
+		float rr[QM], pp[QM], dl[QM], mi[QM];
+		float rz = 0.f;
+#pragma unroll
+		for (int q = 0; q < QM; q++) {
+			const int k = lane + 32 * q;
+			rr[q] = (k < dimp) ? s.rhs[k] : 0.f; mi[q] = (k < dimp) ? s.Minv[k] : 0.f;
+			pp[q] = mi[q] * rr[q]; dl[q] = 0.f;
+			rz += rr[q] * pp[q];
+		}
+		rz = warp_sum(rz);
 #pragma unroll 1
 		for (int lin = 0; lin < a.prm.num_iter_inner; lin++) {
-			__syncthreads();
-			// Ap = A p: lanes over columns, four rows of a warp in flight at once (the reductions interleave)
+			float* Apb = (lin & 1) ? s.z : s.Ap;      // double-buffered exchange (s.z is free: z lives in registers here)
+			// Ap rows of this warp: lanes over columns (p[c] is already in this lane's registers), four rows in flight
 #pragma unroll 1
 			for (int r0 = wid; r0 < dimp; r0 += 4 * kWarps) {
-				float acc[4] = { 0.f, 0.f, 0.f, 0.f };
-				for (int c = lane; c < dimp; c += 32) {
-					const float pc = s.p[c];
+				float acc4[4] = { 0.f, 0.f, 0.f, 0.f };
 #pragma unroll
-					for (int j = 0; j < 4; j++) { const int r = r0 + j * kWarps; if (r < dimp) acc[j] += s.A[r * ld + c] * pc; }
+				for (int q = 0; q < QM; q++) {
+					const int c = lane + 32 * q;
+					if (c < dimp) {
+#pragma unroll
+						for (int j = 0; j < 4; j++) { const int r = r0 + j * kWarps; if (r < dimp) acc4[j] += s.A[r * ld + c] * pp[q]; }
+					}
 				}
 #pragma unroll
 				for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-					for (int j = 0; j < 4; j++) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+					for (int j = 0; j < 4; j++) acc4[j] += __shfl_xor_sync(0xffffffffu, acc4[j], o);
 				}
 				if (lane == 0) {
 #pragma unroll
-					for (int j = 0; j < 4; j++) { const int r = r0 + j * kWarps; if (r < dimp) s.Ap[r] = acc[j]; }
+					for (int j = 0; j < 4; j++) { const int r = r0 + j * kWarps; if (r < dimp) Apb[r] = acc4[j]; }
 				}
 			}
 			__syncthreads();
-			if (tid < 32) {
-				float d = 0.f;
-				for (int k = lane; k < dimp; k += 32) d += s.p[k] * s.Ap[k];
-				const float pAp = warp_sum(d);
-				const float alpha = (pAp > kEps) ? rz / pAp : 0.f;
-				float bsum = 0.f;
-				for (int k = lane; k < dimp; k += 32) {
-					s.delta[k] += alpha * s.p[k];
-					const float rv = s.r[k] - alpha * s.Ap[k];
-					s.r[k] = rv;
-					const float zv = s.Minv[k] * rv;
-					s.z[k] = zv;
-					bsum += zv * rv;
-				}
-				const float rz_new = warp_sum(bsum);
-				const float beta = (rz > kEps) ? rz_new / rz : 0.f;
-				rz = rz_new;
-				for (int k = lane; k < dimp; k += 32) s.p[k] = s.z[k] + beta * s.p[k];
+			float ap[QM], d = 0.f;
+#pragma unroll
+			for (int q = 0; q < QM; q++) { const int k = lane + 32 * q; ap[q] = (k < dimp) ? Apb[k] : 0.f; d += pp[q] * ap[q]; }
+			const float pAp = warp_sum(d);
+			const float alpha = (pAp > kEps) ? rz / pAp : 0.f;
+			float bsum = 0.f, zz[QM];
+#pragma unroll
+			for (int q = 0; q < QM; q++) {
+				dl[q] += alpha * pp[q];
+				rr[q] -= alpha * ap[q];
+				zz[q] = mi[q] * rr[q];
+				bsum += zz[q] * rr[q];
 			}
+			const float rz_new = warp_sum(bsum);
+			const float beta = (rz > kEps) ? rz_new / rz : 0.f;
+			rz = rz_new;
+#pragma unroll
+			for (int q = 0; q < QM; q++) pp[q] = zz[q] + beta * pp[q];
+		}
+		if (wid == 0) {
+#pragma unroll
+			for (int q = 0; q < QM; q++) { const int k = lane + 32 * q; if (k < dimp) s.delta[k] = dl[q]; }
 		}
 	}
 	__syncthreads();
@@ -930,52 +916,66 @@ __global__ void __launch_bounds__(kThreads, BT_SOLVE_MIN_CTAS) k_solve(SolveArgs
 			tile_pixels(a, wd, src, tex, s_M, tl.start, tl.count, acc);
 		}
 		PROF_T(3);
-		// block reduction of the 28 sums -> this tile's slot
+		// block reduction of the 28 sums -> this tile's slot.  Warp level: a transposing butterfly (31 shuffles instead of
+		// 28 x 5): after the five steps lane L holds the warp total of value L.
+		{
+			float v[32];
 #pragma unroll
-		for (int k = 0; k < kTileVals; k++) {
-			const float v = warp_sum(acc.v[k]);
-			if (lane == 0) s_part[wid][k] = v;
-		}
-		__syncthreads();
-		if (tid < kTileVals) {
-			float v = 0.f;
+			for (int k = 0; k < 32; k++) v[k] = (k < kTileVals) ? acc.v[k] : 0.f;
 #pragma unroll
-			for (int k = 0; k < kWarps; k++) v += s_part[k][tid];
-			s_red[tid] = v;
-		}
-		__syncthreads();
-		if (tid < kTileVals) {   // S = X S' X^T, b = X b' (rows 0-2 of X have 3 non-zeros); entry 27 = #correspondences
-			float out = s_red[tid];
-			if (tl.pair >= 0 && tid < 27) {
-				out = 0.f;
-				if (tid < 21) {
-					const int r = c_sym_r[tid], c = c_sym_c[tid];
-					float xr[6], xc[6];
+			for (int half = 16; half >= 1; half >>= 1) {
+				const bool up = (lane & half) != 0;
 #pragma unroll
-					for (int u = 0; u < 6; u++) { xr[u] = s_X[r * 6 + u]; xc[u] = s_X[c * 6 + u]; }   // zero entries make the short rows exact
-#pragma unroll
-					for (int u = 0; u < 6; u++) {
-						float tsum = 0.f;
-#pragma unroll
-						for (int v = 0; v < 6; v++) tsum += s_red[c_sym_idx[u * 6 + v]] * xc[v];
-						out += xr[u] * tsum;
-					}
-				} else {
-					const int r = tid - 21;
-#pragma unroll
-					for (int u = 0; u < 6; u++) out += s_X[r * 6 + u] * s_red[21 + u];
+				for (int k = 0; k < half; k++) {
+					const float send = up ? v[k] : v[k + half];
+					const float keep = up ? v[k + half] : v[k];
+					v[k] = keep + __shfl_xor_sync(0xffffffffu, send, half);
 				}
 			}
-			__stcg(a.partial + (size_t)tl_idx * kTileVals + tid, out);
+			if (lane < kTileVals) s_part[wid][lane] = v[0];
 		}
-		__threadfence();
 		__syncthreads();
-		PROF_T(4);
-		if (tid == 0) {
-			const int done = atomicAdd(a.tiles_done + tl.win, 1) + 1;
-			s_is_last = (done == (it + 1) * wd.n_tiles);
-			if (s_is_last) __threadfence();
+		if (wid == 0) {   // warp 0 finishes the tile: cross-warp sum, model-frame transform, store, ticket
+			float red = 0.f;
+			if (lane < kTileVals) {
+#pragma unroll
+				for (int k = 0; k < kWarps; k++) red += s_part[k][lane];
+				s_red[lane] = red;
+			}
+			__syncwarp();
+			if (lane < kTileVals) {   // S = X S' X^T, b = X b' (rows 0-2 of X have 3 non-zeros); entry 27 = #correspondences
+				float out = red;
+				if (tl.pair >= 0 && lane < 27) {
+					out = 0.f;
+					if (lane < 21) {
+						const int r = c_sym_r[lane], c = c_sym_c[lane];
+						float xr[6], xc[6];
+#pragma unroll
+						for (int u = 0; u < 6; u++) { xr[u] = s_X[r * 6 + u]; xc[u] = s_X[c * 6 + u]; }   // zero entries make the short rows exact
+#pragma unroll
+						for (int u = 0; u < 6; u++) {
+							float tsum = 0.f;
+#pragma unroll
+							for (int v = 0; v < 6; v++) tsum += s_red[c_sym_idx[u * 6 + v]] * xc[v];
+							out += xr[u] * tsum;
+						}
+					} else {
+						const int r = lane - 21;
+#pragma unroll
+						for (int u = 0; u < 6; u++) out += s_X[r * 6 + u] * s_red[21 + u];
+					}
+				}
+				__stcg(a.partial + (size_t)tl_idx * kTileVals + lane, out);
+				__threadfence();      // the writers order their store before the ticket below
+			}
+			__syncwarp();
+			if (lane == 0) {
+				const int done = atomicAdd(a.tiles_done + tl.win, 1) + 1;
+				s_is_last = (done == (it + 1) * wd.n_tiles);
+				if (s_is_last) __threadfence();
+			}
 		}
+		PROF_T(4);
 		__syncthreads();
 		PROF_T(5);
 		if (a.prof && tid == 0) { prf.kind_cta = blockIdx.x; prf.tile_win = ((long long)tl_idx << 32) | ((long long)it << 16) | tl.count; prf.t[6] = prf.t[7] = prf.t[8] = prf.t[9] = 0; prof_emit(a, prf); }
@@ -994,7 +994,7 @@ struct SolverState {
 	bt_solver_limits lim{};
 	int npix_max = 0, max_pairs = 0, max_frames_total = 0, max_tiles = 0, max_groups = 0;
 	DevBuf wins, depth_ptr, normal_ptr, frame_win, texel, src, nsrc, pose_in, x, T, pose_out, corr, grp_i, grp_j, grp_start, pairs,
-	    tiles, scalars, partial, tiles_done, iter_done, pair_tile0, pair_ntile, pair_win, mem, dbgJ, dbgR, dbgC, prof;
+	    tiles, scalars, partial, tiles_done, iter_done, pair_tile0, pair_ntile, pair_win, pair_src, mem, dbgJ, dbgR, dbgC, prof;
 	int prof_cap = 0;
 	PinnedBuf h_stage, h_poses;
 	// last staged batch
@@ -1012,7 +1012,7 @@ void solver_destroy(bt_ctx* ctx) {
 	if (!s) return;
 	DevBuf* bufs[] = { &s->wins, &s->depth_ptr, &s->normal_ptr, &s->frame_win, &s->texel, &s->src, &s->nsrc, &s->pose_in, &s->x, &s->T,
 	                   &s->pose_out, &s->corr, &s->grp_i, &s->grp_j, &s->grp_start, &s->pairs, &s->tiles, &s->scalars, &s->partial,
-	                   &s->tiles_done, &s->iter_done, &s->pair_tile0, &s->pair_ntile, &s->pair_win, &s->mem, &s->dbgJ, &s->dbgR, &s->dbgC, &s->prof };
+	                   &s->tiles_done, &s->iter_done, &s->pair_tile0, &s->pair_ntile, &s->pair_win, &s->pair_src, &s->mem, &s->dbgJ, &s->dbgR, &s->dbgC, &s->prof };
 	for (DevBuf* b : bufs) b->release();
 	s->h_stage.release(); s->h_poses.release();
 	for (auto& e : s->ev) if (e) cudaEventDestroy(e);
@@ -1050,6 +1050,7 @@ static int reserve_impl(bt_ctx* ctx, const bt_solver_limits* lim) {
 	RES(pair_tile0, sizeof(int) * (size_t)s->max_pairs * lim->max_windows);
 	RES(pair_ntile, sizeof(int) * (size_t)s->max_pairs * lim->max_windows);
 	RES(pair_win, sizeof(int) * (size_t)s->max_pairs * lim->max_windows);
+	RES(pair_src, sizeof(int) * (size_t)s->max_pairs * lim->max_windows);
 	RES(mem, sizeof(int) * (size_t)(2 * (lim->max_frames + 1) + 2 * s->max_groups + 2 * s->max_pairs) * lim->max_windows);
 	RES(tiles, sizeof(Tile) * (size_t)s->max_tiles);
 	RES(partial, sizeof(float) * kTileVals * (size_t)s->max_tiles);
@@ -1123,7 +1124,7 @@ extern "C" int bt_solve_stage(bt_ctx* ctx, int n_windows, const bt_window* windo
 	const size_t o_wins = carve(sizeof(WinDesc) * n_windows), o_dp = carve(sizeof(void*) * F), o_np = carve(sizeof(void*) * F), o_fw = carve(sizeof(int) * F),
 	             o_pose = carve(sizeof(float) * 16 * F), o_corr = carve(sizeof(bt_entryj) * C + 32), o_gi = carve(sizeof(int) * maxG * n_windows),
 	             o_gj = carve(sizeof(int) * maxG * n_windows), o_gs = carve(sizeof(int) * (maxG + 1) * n_windows), o_pairs = carve(sizeof(uint2) * maxP * n_windows),
-	             o_pwin = carve(sizeof(int) * maxP * n_windows), o_mem = carve(sizeof(int) * (2 * ((size_t)s->lim.max_frames + 1) + 2 * maxG + 2 * maxP) * n_windows);
+	             o_pwin = carve(sizeof(int) * maxP * n_windows), o_psrc = carve(sizeof(int) * maxP * n_windows), o_mem = carve(sizeof(int) * (2 * ((size_t)s->lim.max_frames + 1) + 2 * maxG + 2 * maxP) * n_windows);
 	int rc = s->h_stage.alloc(off);
 	if (rc != BT_OK) return rc;
 	char* hb = s->h_stage.as<char>();
@@ -1131,7 +1132,7 @@ extern "C" int bt_solve_stage(bt_ctx* ctx, int n_windows, const bt_window* windo
 	const void** hdp = (const void**)(hb + o_dp); const void** hnp = (const void**)(hb + o_np);
 	int* hfw = (int*)(hb + o_fw); float* hpose = (float*)(hb + o_pose); bt_entryj* hcorr = (bt_entryj*)(hb + o_corr);
 	int* hgi = (int*)(hb + o_gi); int* hgj = (int*)(hb + o_gj); int* hgs = (int*)(hb + o_gs); uint2* hpairs = (uint2*)(hb + o_pairs);
-	int* hpwin = (int*)(hb + o_pwin); int* hmem = (int*)(hb + o_mem);
+	int* hpwin = (int*)(hb + o_pwin); int* hpsrc = (int*)(hb + o_psrc); int* hmem = (int*)(hb + o_mem);
 	size_t m_off = 0;
 	s->frame_off.assign(n_windows, 0); s->n_frames.assign(n_windows, 0);
 	size_t f_off = 0, c_off = 0, g_off = 0, p_off = 0, smem_need = 0;
@@ -1158,29 +1159,51 @@ extern "C" int bt_solve_stage(bt_ctx* ctx, int n_windows, const bt_window* windo
 		}
 		// correspondences: stable counting sort by (i,j) so each pair's entries are contiguous (Bundler::optimizeGPU
 		// already emits them that way, /root/reference/src/Bundler.cpp:298-324); invalid entries are dropped.
-		bin.assign((size_t)N * N + 1, 0);
-		int n_valid = 0;
-		for (int c = 0; c < bw.n_corr; c++) {
-			const bt_entryj& e = bw.corr[c];
-			if (e.imgIdx_i == 0xFFFFFFFFu) continue;
-			BT_REQUIRE(e.imgIdx_i < (uint32_t)N && e.imgIdx_j < (uint32_t)N, BT_ERR_INVALID_ARG, "window %d: correspondence %d references frame outside [0,%d)", w, c, N);
-			bin[(size_t)e.imgIdx_i * N + e.imgIdx_j + 1]++;
-			n_valid++;
+		int n_valid = 0, ng = 0;
+		bool grouped = true;    // fast path: keys (i*N+j) non-decreasing and no invalid entries => groups are runs, plain copy
+		{
+			long long prev = -1;
+			for (int c = 0; c < bw.n_corr && grouped; c++) {
+				const bt_entryj& e = bw.corr[c];
+				if (e.imgIdx_i >= (uint32_t)N || e.imgIdx_j >= (uint32_t)N) { grouped = false; break; }
+				const long long key = (long long)e.imgIdx_i * N + e.imgIdx_j;
+				if (key < prev) grouped = false;
+				prev = key;
+			}
 		}
-		int ng = 0;
-		for (size_t b = 0; b < (size_t)N * N; b++) {
-			if (bin[b + 1] > 0) { hgi[g_off + ng] = (int)(b / N); hgj[g_off + ng] = (int)(b % N); ng++; }
-		}
-		for (size_t b = 0; b < (size_t)N * N; b++) bin[b + 1] += bin[b];
-		{   // group starts (relative to corr_off); stored at grp_off + w + g to leave room for the extra end entry
-			int gg = 0;
-			for (size_t b = 0; b < (size_t)N * N; b++) if (bin[b + 1] > bin[b]) hgs[g_off + w + gg++] = bin[b];
+		if (grouped) {
+			long long prev = -1;
+			for (int c = 0; c < bw.n_corr; c++) {
+				const bt_entryj& e = bw.corr[c];
+				const long long key = (long long)e.imgIdx_i * N + e.imgIdx_j;
+				if (key != prev) { hgi[g_off + ng] = (int)e.imgIdx_i; hgj[g_off + ng] = (int)e.imgIdx_j; hgs[g_off + w + ng] = c; ng++; prev = key; }
+			}
+			n_valid = bw.n_corr;
 			hgs[g_off + w + ng] = n_valid;
-		}
-		for (int c = 0; c < bw.n_corr; c++) {
-			const bt_entryj& e = bw.corr[c];
-			if (e.imgIdx_i == 0xFFFFFFFFu) continue;
-			hcorr[c_off + bin[(size_t)e.imgIdx_i * N + e.imgIdx_j]++] = e;
+			if (n_valid) memcpy(hcorr + c_off, bw.corr, sizeof(bt_entryj) * (size_t)n_valid);
+		} else {
+			bin.assign((size_t)N * N + 1, 0);
+			for (int c = 0; c < bw.n_corr; c++) {
+				const bt_entryj& e = bw.corr[c];
+				if (e.imgIdx_i == 0xFFFFFFFFu) continue;
+				BT_REQUIRE(e.imgIdx_i < (uint32_t)N && e.imgIdx_j < (uint32_t)N, BT_ERR_INVALID_ARG, "window %d: correspondence %d references frame outside [0,%d)", w, c, N);
+				bin[(size_t)e.imgIdx_i * N + e.imgIdx_j + 1]++;
+				n_valid++;
+			}
+			for (size_t b = 0; b < (size_t)N * N; b++) {
+				if (bin[b + 1] > 0) { hgi[g_off + ng] = (int)(b / N); hgj[g_off + ng] = (int)(b % N); ng++; }
+			}
+			for (size_t b = 0; b < (size_t)N * N; b++) bin[b + 1] += bin[b];
+			{   // group starts (relative to corr_off); stored at grp_off + w + g to leave room for the extra end entry
+				int gg = 0;
+				for (size_t b = 0; b < (size_t)N * N; b++) if (bin[b + 1] > bin[b]) hgs[g_off + w + gg++] = bin[b];
+				hgs[g_off + w + ng] = n_valid;
+			}
+			for (int c = 0; c < bw.n_corr; c++) {
+				const bt_entryj& e = bw.corr[c];
+				if (e.imgIdx_i == 0xFFFFFFFFu) continue;
+				hcorr[c_off + bin[(size_t)e.imgIdx_i * N + e.imgIdx_j]++] = e;
+			}
 		}
 		d.n_corr = n_valid; d.n_groups = ng;
 		// dense pairs
@@ -1198,7 +1221,15 @@ extern "C" int bt_solve_stage(bt_ctx* ctx, int n_windows, const bt_window* windo
 			}
 		}
 		d.n_pairs = np;
-		for (int p = 0; p < np; p++) hpwin[p_off + p] = w;
+		{   // cross blocks are written without atomics when every unordered frame pair occurs at most once per table
+			std::vector<char> seen((size_t)N * N, 0);
+			bool uq = true;
+			for (int g = 0; g < ng && uq; g++) { const int a2 = std::min(hgi[g_off + g], hgj[g_off + g]), b2 = std::max(hgi[g_off + g], hgj[g_off + g]); if (seen[(size_t)a2 * N + b2]) uq = false; seen[(size_t)a2 * N + b2] = 1; }
+			std::fill(seen.begin(), seen.end(), 0);
+			for (int p = 0; p < np && uq; p++) { const int a2 = (int)std::min(hpairs[p_off + p].x, hpairs[p_off + p].y), b2 = (int)std::max(hpairs[p_off + p].x, hpairs[p_off + p].y); if (seen[(size_t)a2 * N + b2]) uq = false; seen[(size_t)a2 * N + b2] = 1; }
+			d.unique_blocks = uq ? 1 : 0;
+		}
+		for (int p = 0; p < np; p++) { hpwin[p_off + p] = w; hpsrc[p_off + p] = (int)f_off + (int)hpairs[p_off + p].y; }
 		{   // per-frame membership CSR: groups then pairs touching each frame, in increasing index order (fixed summation order)
 			d.mem_off = (int)m_off;
 			int* fg_start = hmem + m_off; int* fp_start = fg_start + (N + 1); int* fg_items = fp_start + (N + 1); int* fp_items = fg_items + 2 * ng;
@@ -1243,6 +1274,7 @@ extern "C" int bt_solve_stage(bt_ctx* ctx, int n_windows, const bt_window* windo
 	UP(grp_start, hgs, sizeof(int) * (g_off + n_windows));
 	if (p_off) UP(pairs, hpairs, sizeof(uint2) * p_off);
 	if (p_off) UP(pair_win, hpwin, sizeof(int) * p_off);
+	if (p_off) UP(pair_src, hpsrc, sizeof(int) * p_off);
 	UP(mem, hmem, sizeof(int) * m_off);
 #undef UP
 	if (s->debug) {
@@ -1265,7 +1297,7 @@ static SolveArgs make_args(bt_ctx* ctx) {
 	a.pose_in = s->pose_in.as<float>(); a.x = s->x.as<float>(); a.T = s->T.as<float>(); a.pose_out = s->pose_out.as<float>();
 	a.npix_max = s->npix_max;
 	a.corr = s->corr.as<bt_entryj>(); a.grp_i = s->grp_i.as<int>(); a.grp_j = s->grp_j.as<int>(); a.grp_start = s->grp_start.as<int>();
-	a.pairs = s->pairs.as<uint2>(); a.pair_win = s->pair_win.as<int>(); a.mem = s->mem.as<int>();
+	a.pairs = s->pairs.as<uint2>(); a.pair_win = s->pair_win.as<int>(); a.pair_src_slot = s->pair_src.as<int>(); a.mem = s->mem.as<int>();
 	a.tiles = s->tiles.as<Tile>(); a.max_tiles = s->max_tiles; a.partial = s->partial.as<float>();
 	a.pair_tile0 = s->pair_tile0.as<int>(); a.pair_ntile = s->pair_ntile.as<int>();
 	a.n_tiles_total = s->scalars.as<int>(); a.queue = s->scalars.as<int>() + 1; a.n_src_px = (long long*)(s->scalars.as<char>() + 16);
@@ -1288,7 +1320,7 @@ extern "C" int bt_solve_run(bt_ctx* ctx, void* stream_) {
 	}
 	if (s->prof_cap > 0) BT_CUDA(cudaMemsetAsync(s->prof.p, 0, 8, stream));
 	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[0], stream));
-	k_prep_frames<<<s->frames_total, 512, 0, stream>>>(a);
+	k_prep_frames<<<s->frames_total, 1024, 0, stream>>>(a);
 	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[1], stream));
 	k_plan<<<1, 1024, 0, stream>>>(a, s->wins.as<WinDesc>());
 	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[2], stream));

@@ -117,3 +117,100 @@ class Ransac:
         bt = np.zeros(n_pairs, np.int32)
         _lib.check(self.lib.bt_ransac_debug(self.ctx, u3.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(n_trials), bt.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(n_pairs)), "bt_ransac_debug")
         return u3, bt
+
+
+class MatchPipeline:
+    """The matcher half of the hot path, device-resident: SiftManager::findCorres for a batch of frame pairs
+    (kNN both directions -> pruneMatches -> collectMutualMatches -> runRansacBetween) ending in the EntryJ records
+    Bundler::optimizeGPU would build (/root/reference/src/FeatureManager.cpp:173-368,561-741; src/Bundler.cpp:298-324)."""
+
+    def __init__(self, yml=None, device: int = 0, max_pairs: int = 64, max_feats: int = 4096, dim: int = 256, stream: int = 0):
+        import math
+        from .config import load_yml
+        self.lib = _lib.load()
+        self.stream = ctypes.c_void_p(stream)
+        self.ctx = ctypes.c_void_p()
+        _lib.check(self.lib.bt_ctx_create(ctypes.byref(self.ctx), ctypes.c_int(device)), "bt_ctx_create")
+        y = load_yml(yml)
+        fc, rs = y["feature_corres"], y["ransac"]
+        self.prune = _lib.PruneParams(float(fc["max_dist_no_neighbor"]), math.cos(float(fc["max_normal_no_neighbor"]) / 180.0 * math.pi),
+                                      float(fc["max_dist_neighbor"]), math.cos(float(fc["max_normal_neighbor"]) / 180.0 * math.pi))
+        self.ransac_trials = int(rs["max_iter"])
+        self.ransac_inlier_dist = float(rs["inlier_dist"])
+        _lib.check(self.lib.bt_pipeline_reserve(self.ctx, ctypes.c_int(max_pairs), ctypes.c_int(max_feats), ctypes.c_int(dim), ctypes.c_int(max(self.ransac_trials, 1))), "bt_pipeline_reserve")
+        self.max_pairs, self.max_feats = max_pairs, max_feats
+
+    def close(self):
+        if self.ctx:
+            self.lib.bt_ctx_destroy(self.ctx)
+            self.ctx = ctypes.c_void_p()
+
+    @staticmethod
+    def _frame(fr) -> "_lib.MatchFrame":
+        """fr: dict with kpts [n,2] cuda f32, depth [H,W] cuda f32, normal [H,W,4] cuda f32, pose [4,4] numpy, id, window_index."""
+        import numpy as np
+        m = _lib.MatchFrame()
+        m.kpts_dev, m.n = fr["kpts"].data_ptr(), fr["kpts"].shape[0]
+        m.depth_dev, m.normal_dev = fr["depth"].data_ptr(), fr["normal"].data_ptr()
+        P = np.ascontiguousarray(fr["pose"], np.float32).reshape(16)
+        for k in range(16):
+            m.pose[k] = float(P[k])
+        m.frame_id, m.window_index = int(fr["id"]), int(fr.get("window_index", fr["id"]))
+        return m
+
+    def _views(self, pairs):
+        n = len(pairs)
+        A = (_lib.MatchFrame * n)()
+        B = (_lib.MatchFrame * n)()
+        dA = (_lib.DescView * n)()
+        dB = (_lib.DescView * n)()
+        for i, (fa, fb) in enumerate(pairs):
+            A[i], B[i] = self._frame(fa), self._frame(fb)
+            for view, t in ((dA[i], fa["desc"]), (dB[i], fb["desc"])):
+                view.dev, view.n, view.dim, view.pitch_bytes = t.data_ptr(), t.shape[0], t.shape[1], (t.stride(0) * 4 if t.shape[0] > 1 else t.shape[1] * 4)
+        return A, B, dA, dB
+
+    def prune_mutual(self, pairs, idxAB, idxBA, H, W, K, k=5):
+        """pairs: list of (frameA newer, frameB older) dicts; idxAB/idxBA: concatenated [sum n, k] int32 cuda kNN indices.
+        Returns list of [m,10] float32 cuda tensors (uA,vA,uB,vB,ptA_cam,ptB_cam)."""
+        import torch
+        A, B, _, _ = self._views(pairs)
+        n = len(pairs)
+        cap = sum(fa["kpts"].shape[0] + fb["kpts"].shape[0] for fa, fb in pairs)
+        dev = pairs[0][0]["kpts"].device
+        corr = torch.empty((max(cap, 1), 10), dtype=torch.float32, device=dev)
+        cnt = torch.empty(n, dtype=torch.int32, device=dev)
+        _lib.check(self.lib.bt_prune_mutual_pairs(self.ctx, ctypes.c_int(n), A, B, ctypes.c_int(H), ctypes.c_int(W),
+                                                  ctypes.c_float(K[0]), ctypes.c_float(K[1]), ctypes.c_float(K[2]), ctypes.c_float(K[3]),
+                                                  ctypes.c_void_p(idxAB.data_ptr()), ctypes.c_void_p(idxBA.data_ptr()), ctypes.c_int(k), ctypes.byref(self.prune),
+                                                  ctypes.c_void_p(corr.data_ptr()), ctypes.c_void_p(cnt.data_ptr()), self.stream), "bt_prune_mutual_pairs")
+        ch = cnt.cpu().numpy()
+        out, o = [], 0
+        for p, (fa, fb) in enumerate(pairs):
+            out.append(corr[o:o + int(ch[p])])
+            o += fa["kpts"].shape[0] + fb["kpts"].shape[0]
+        return out
+
+    def match_pairs(self, pairs, H, W, K, seed: int = 0, capacity: int = 0):
+        """Fused pipeline.  Returns (entries [total] EntryJ structured numpy array, n_entry [n_pairs], entry_off [n_pairs]) —
+        device tensors are also kept in self.last for a zero-copy hand-off to the solver."""
+        import numpy as np
+        import torch
+        from .synth import ENTRYJ_DTYPE
+        A, B, dA, dB = self._views(pairs)
+        n = len(pairs)
+        cap = capacity or sum(fa["kpts"].shape[0] + fb["kpts"].shape[0] for fa, fb in pairs)
+        dev = pairs[0][0]["kpts"].device
+        ent = torch.empty((max(cap, 1), 8), dtype=torch.int32, device=dev)     # 32-byte EntryJ records
+        n_ent = torch.empty(n, dtype=torch.int32, device=dev)
+        off = torch.empty(n, dtype=torch.int32, device=dev)
+        tot = torch.zeros(4, dtype=torch.int32, device=dev)
+        _lib.check(self.lib.bt_match_pairs(self.ctx, ctypes.c_int(n), A, B, dA, dB, ctypes.c_int(H), ctypes.c_int(W),
+                                           ctypes.c_float(K[0]), ctypes.c_float(K[1]), ctypes.c_float(K[2]), ctypes.c_float(K[3]),
+                                           ctypes.byref(self.prune), ctypes.c_int(self.ransac_trials), ctypes.c_float(self.ransac_inlier_dist), ctypes.c_uint64(seed),
+                                           ctypes.c_void_p(ent.data_ptr()), ctypes.c_int(cap), ctypes.c_void_p(n_ent.data_ptr()), ctypes.c_void_p(off.data_ptr()),
+                                           ctypes.c_void_p(tot.data_ptr()), self.stream), "bt_match_pairs")
+        self.last = (ent, n_ent, off, tot)
+        total = int(tot[0].item())
+        host = ent[:total].cpu().numpy().view(np.uint8).reshape(-1).view(ENTRYJ_DTYPE)
+        return host, n_ent.cpu().numpy(), off.cpu().numpy()

@@ -248,3 +248,45 @@ def make_descriptors(seed: int, n_a: int, n_b: int, dim: int = 256, match_frac: 
     b[ib] = a[ia] + rng.normal(0, noise, (m, dim))
     b /= np.linalg.norm(b, axis=1, keepdims=True)
     return a.astype(np.float32), b.astype(np.float32), ia, ib
+
+
+def make_feature_frames(win: Window, n_feats: int = 500, seed: int = 0, n_surface: int = 4000, kp_noise: float = 0.3, desc_noise: float = 0.05,
+                        distractor_frac: float = 0.2, dim: int = 256):
+    """Keypoints + unit-norm descriptors for every frame of a rendered window (the matcher side of SURVEY.md §8d):
+    `n_surface` points on the ellipsoid carry a random code each; a frame sees those facing it, keypoint = projection +
+    sub-pixel noise, descriptor = code + noise (renormalised); `distractor_frac` of the features are unmatched.
+    Returns list of dicts {kpts [n,2] f32 (x,y), desc [n,dim] f32, ids [n] (surface id or -1)}."""
+    rng = np.random.default_rng(np.uint64(0xFEA7) + np.uint64(seed))
+    sdir = rng.normal(size=(n_surface, 3))
+    sdir /= np.linalg.norm(sdir, axis=1, keepdims=True)
+    p_ob, n_ob = sdir * win.radii, sdir / win.radii
+    codes = rng.normal(size=(n_surface, dim))
+    codes /= np.linalg.norm(codes, axis=1, keepdims=True)
+    fx, fy, cx, cy = win.K
+    frames = []
+    for f in range(win.n_frames):
+        R, c = win.ob_in_cam[f][:3, :3], win.ob_in_cam[f][:3, 3]
+        pc, nc = p_ob @ R.T + c, n_ob @ R.T
+        vis = np.einsum("nk,nk->n", nc, -pc) > 0.15 * np.linalg.norm(nc, axis=1) * np.linalg.norm(pc, axis=1)
+        u, v = pc[:, 0] * fx / pc[:, 2] + cx, pc[:, 1] * fy / pc[:, 2] + cy
+        vis &= (u >= 1) & (u <= win.W - 2) & (v >= 1) & (v <= win.H - 2)
+        ui, vi = np.clip(np.rint(u).astype(int), 0, win.W - 1), np.clip(np.rint(v).astype(int), 0, win.H - 1)
+        vis &= win.depth[f][vi, ui] > 0.1
+        idx = np.nonzero(vis)[0]
+        n_match = min(len(idx), int(n_feats * (1 - distractor_frac)))
+        idx = rng.permutation(idx)[:n_match]
+        kp = np.stack([u[idx], v[idx]], 1) + rng.normal(0, kp_noise, (n_match, 2))
+        de = codes[idx] + rng.normal(0, desc_noise, (n_match, dim)) / np.sqrt(dim) * 4.0
+        ys, xs = np.nonzero(win.depth[f] > 0.1)
+        n_dis = n_feats - n_match
+        if len(xs) and n_dis > 0:
+            sel = rng.integers(0, len(xs), n_dis)
+            kp = np.concatenate([kp, np.stack([xs[sel], ys[sel]], 1) + rng.uniform(-0.4, 0.4, (n_dis, 2))])
+            de = np.concatenate([de, rng.normal(size=(n_dis, dim))])
+            ids = np.concatenate([idx, -np.ones(n_dis, int)])
+        else:
+            ids = idx
+        de /= np.linalg.norm(de, axis=1, keepdims=True)
+        perm = rng.permutation(len(kp))
+        frames.append({"kpts": kp[perm].astype(np.float32), "desc": de[perm].astype(np.float32), "ids": ids[perm]})
+    return frames

@@ -96,3 +96,77 @@ def ransac_pair(A, B, u3, dist_thresh):
     R, tt = poses[best]
     dist = np.linalg.norm(B - (A @ R.T + tt), axis=1)
     return np.nonzero(dist <= dist_thresh)[0].astype(np.int32), best, counts
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def _cloud_point(depth, K, u, v):
+    """Frame::depthToCloudAndNormals (/root/reference/src/Frame.cpp:199-233): K^-1 (u d, v d, d), zeros when d < 0.1."""
+    fx, fy, cx, cy = [np.float32(x) for x in K]
+    d = np.float32(depth[v, u])
+    if d < np.float32(0.1):
+        return np.zeros(3, np.float32)
+    ifx, ify, icx, icy = np.float32(1) / fx, np.float32(1) / fy, -cx / fx, -cy / fy
+    return np.array([ifx * (np.float32(u) * d) + icx * d, ify * (np.float32(v) * d) + icy * d, d], np.float32)
+
+
+def _round_half_away(x):
+    return int(np.floor(abs(float(x)) + 0.5) * (1 if x >= 0 else -1))
+
+
+def prune_matches(Q, T, knn_idx, K, max_dist, cos_max):
+    """SiftManager::pruneMatches (/root/reference/src/FeatureManager.cpp:290-336) for one direction.
+    Q, T: dicts with kpts [n,2], depth [H,W], normal [H,W,4], pose [4,4].  Returns list of (q, t, ptQ_cam, ptT_cam)."""
+    H, W = Q["depth"].shape
+    out = []
+    Rq, tq = Q["pose"][:3, :3].astype(np.float32), Q["pose"][:3, 3].astype(np.float32)
+    Rt, tt = T["pose"][:3, :3].astype(np.float32), T["pose"][:3, 3].astype(np.float32)
+    for q in range(len(Q["kpts"])):
+        for t in knn_idx[q]:
+            if t < 0:
+                continue
+            uq, vq = _round_half_away(Q["kpts"][q, 0]), _round_half_away(Q["kpts"][q, 1])
+            ut, vt = _round_half_away(T["kpts"][t, 0]), _round_half_away(T["kpts"][t, 1])
+            if not (0 <= uq < W and 0 <= vq < H and 0 <= ut < W and 0 <= vt < H):
+                continue
+            pq, pt = _cloud_point(Q["depth"], K, uq, vq), _cloud_point(T["depth"], K, ut, vt)
+            if pq[2] < 0.1 or pt[2] < 0.1:
+                continue
+            mq, mt = Rq @ pq + tq, Rt @ pt + tt
+            nq, nt = Rq @ Q["normal"][vq, uq, :3], Rt @ T["normal"][vt, ut, :3]
+            dist = np.float32(np.linalg.norm((mq - mt).astype(np.float32)))
+            with np.errstate(invalid="ignore", divide="ignore"):
+                dotn = np.float32(np.dot(nq / np.float32(np.linalg.norm(nq)), nt / np.float32(np.linalg.norm(nt))))
+            if dist > max_dist or dotn < cos_max:      # NaN dot (zero normal) does NOT reject (FeatureManager.cpp:326)
+                continue
+            out.append((q, int(t), pq, pt))
+            break
+    return out
+
+
+def collect_mutual(A, B, mAB, mBA):
+    """SiftManager::collectMutualMatches (:338-368): A->B survivors then B->A survivors, duplicates kept.
+    Rows: [uA, vA, uB, vB, ptA_cam(3), ptB_cam(3)]."""
+    rows = []
+    for (q, t, pq, pt) in mAB:
+        rows.append(np.concatenate([A["kpts"][q], B["kpts"][t], pq, pt]))
+    for (q, t, pq, pt) in mBA:
+        rows.append(np.concatenate([A["kpts"][t], B["kpts"][q], pt, pq]))
+    return np.asarray(rows, np.float32).reshape(-1, 10)
+
+
+def find_corres(A, B, K, prune, u3, ransac_inlier_dist, k=5):
+    """findCorresbyNN + runRansacBetween for one pair (A newer).  prune = (max_dist_nn, cos_nn, max_dist_n, cos_n).
+    Returns (mutual rows, inlier row ids or None if the pair was dropped)."""
+    iAB, _ = knn(A["desc"], B["desc"], k)
+    iBA, _ = knn(B["desc"], A["desc"], k)
+    neighbor = abs(A["id"] - B["id"]) == 1
+    max_dist, cos_max = (prune[2], prune[3]) if neighbor else (prune[0], prune[1])
+    rows = collect_mutual(A, B, prune_matches(A, B, iAB, K, max_dist, cos_max), prune_matches(B, A, iBA, K, max_dist, cos_max))
+    if len(rows) <= 5:
+        return rows, None
+    PA = rows[:, 4:7] @ A["pose"][:3, :3].T.astype(np.float32) + A["pose"][:3, 3].astype(np.float32)
+    PB = rows[:, 7:10] @ B["pose"][:3, :3].T.astype(np.float32) + B["pose"][:3, 3].astype(np.float32)
+    ids, best, counts = ransac_pair(PA, PB, u3, ransac_inlier_dist)
+    if len(ids) < 5:
+        return rows, None
+    return rows, ids

@@ -150,3 +150,86 @@ def test_ransac_edge_cases(cuda_device):
     ids = r.ransac_pairs([torch.from_numpy(A4).to(cuda_device)], [torch.from_numpy(B4).to(cuda_device)], 500, 0.0005)
     assert len(ids[0]) <= 6
     r.close()
+
+
+# ------------------------------------------------------------------------------------------------- prune / fused pipeline
+def _feature_window(seed, N, n_feats, dev):
+    import torch
+    w = synth.make_window(seed, n_frames=N, n_corr=10)
+    fr = synth.make_feature_frames(w, n_feats, seed=seed)
+    host, devf = [], []
+    for k in range(N):
+        h = {"kpts": fr[k]["kpts"], "desc": fr[k]["desc"], "depth": w.depth[k], "normal": w.normal[k], "pose": w.poses_init[k], "id": k}
+        host.append(h)
+        devf.append({"kpts": torch.from_numpy(h["kpts"]).to(dev), "desc": torch.from_numpy(h["desc"]).to(dev), "depth": torch.from_numpy(w.depth[k]).to(dev),
+                     "normal": torch.from_numpy(w.normal[k]).to(dev), "pose": h["pose"], "id": k, "window_index": k})
+    return w, host, devf
+
+
+def test_prune_mutual_equals_oracle(cuda_device):
+    from bundletrack_b200.matcher import MatchPipeline
+    import torch
+    w, host, devf = _feature_window(3, 4, 400, cuda_device)
+    mp = MatchPipeline(None, max_pairs=8, max_feats=512)
+    pairs_idx = [(j, i) for i in range(4) for j in range(i + 1, 4)]           # (newer, older), incl. neighbours |j-i| == 1
+    idxAB = [mo.knn(host[a]["desc"], host[b]["desc"])[0] for a, b in pairs_idx]
+    idxBA = [mo.knn(host[b]["desc"], host[a]["desc"])[0] for a, b in pairs_idx]
+    got = mp.prune_mutual([(devf[a], devf[b]) for a, b in pairs_idx], torch.from_numpy(np.concatenate(idxAB)).to(cuda_device),
+                          torch.from_numpy(np.concatenate(idxBA)).to(cuda_device), w.H, w.W, w.K)
+    prm = (mp.prune.max_dist_no_neighbor, mp.prune.cos_max_normal_no_neighbor, mp.prune.max_dist_neighbor, mp.prune.cos_max_normal_neighbor)
+    total = 0
+    for p, (a, b) in enumerate(pairs_idx):
+        nb = abs(a - b) == 1
+        md, cm = (prm[2], prm[3]) if nb else (prm[0], prm[1])
+        want = mo.collect_mutual(host[a], host[b], mo.prune_matches(host[a], host[b], idxAB[p], w.K, md, cm), mo.prune_matches(host[b], host[a], idxBA[p], w.K, md, cm))
+        g = got[p].cpu().numpy()
+        assert g.shape == want.shape, (p, g.shape, want.shape)
+        assert np.allclose(g, want, atol=2e-6)
+        total += len(want)
+    assert total > 50
+    mp.close()
+
+
+def test_fused_pipeline_matches_oracle_and_feeds_solver(cuda_device):
+    """descriptors -> kNN -> prune -> mutual -> RANSAC -> EntryJ on the device, compared stage by stage with the oracle, then the
+    resulting correspondences drive the solver to the same poses as the oracle solver fed with the oracle correspondences."""
+    from bundletrack_b200.matcher import MatchPipeline
+    from bundletrack_b200.optimizer import OptimizerGpu, SolveWindow
+    import oracle
+    yml = {"bundle": {"num_iter_outter": 7, "num_iter_inner": 5, "robust_delta": 0.005, "image_downscale": 4}, "p2p": {"max_dist": 0.02, "max_normal_angle": 45},
+           "feature_corres": {"max_dist_no_neighbor": 0.02, "max_normal_no_neighbor": 45, "max_dist_neighbor": 10000, "max_normal_neighbor": 180},
+           "ransac": {"max_iter": 2000, "inlier_dist": 0.01}}
+    w, host, devf = _feature_window(5, 4, 500, cuda_device)
+    mp = MatchPipeline(yml, max_pairs=8, max_feats=512)
+    pairs_idx = [(j, i) for i in range(4) for j in range(i + 1, 4)]
+    ent, n_ent, off = mp.match_pairs([(devf[a], devf[b]) for a, b in pairs_idx], w.H, w.W, w.K)
+    u3 = np.load(os.path.join(GOLD, "curand_xorwow_seed0.npy"))[:2000]
+    prm = (mp.prune.max_dist_no_neighbor, mp.prune.cos_max_normal_no_neighbor, mp.prune.max_dist_neighbor, mp.prune.cos_max_normal_neighbor)
+    want_entries = []
+    for p, (a, b) in enumerate(pairs_idx):
+        rows, ids = mo.find_corres(host[a], host[b], w.K, prm, u3, 0.01)
+        n_want = 0 if ids is None else len(ids)
+        assert abs(int(n_ent[p]) - n_want) <= max(2, n_want // 50), (p, n_ent[p], n_want)
+        e = ent[off[p]:off[p] + n_ent[p]]
+        assert (e["imgIdx_i"] == b).all() and (e["imgIdx_j"] == a).all()
+        if ids is not None:
+            wp = rows[ids]
+            # every emitted entry is one of the oracle's mutual rows (pos_i = ptB_cam, pos_j = ptA_cam)
+            allrows = np.concatenate([rows[:, 7:10], rows[:, 4:7]], 1)
+            for x in e:
+                got = np.concatenate([x["pos_i"], x["pos_j"]])
+                assert np.abs(allrows - got).max(axis=1).min() <= 2e-6
+            for r in wp:
+                want_entries.append((b, a, r[7:10], r[4:7]))
+    assert n_ent.sum() >= 20
+    # hand the device-produced correspondences to the solver; compare with the oracle solver on the oracle's correspondences
+    corr_o = np.zeros(len(want_entries), synth.ENTRYJ_DTYPE)
+    for k, (i, j, pi, pj) in enumerate(want_entries):
+        corr_o[k] = (i, j, pi, pj)
+    opt = OptimizerGpu(yml, max_windows=1, max_frames=8, max_corr=8192)
+    depth = [f["depth"] for f in devf]; normal = [f["normal"] for f in devf]
+    out = opt.optimizeWindows([SolveWindow(ent, w.H, w.W, depth, normal, w.poses_init, w.K)])[0]
+    ref = oracle.solve_window(w.depth, w.normal, w.K, corr_o, w.poses_init)
+    r, t = synth.pose_errors(out, ref)
+    assert r <= 2e-3 and t <= 1e-3, (r, t)      # RANSAC winners may differ by a borderline inlier; the solve must agree closely
+    opt.close(); mp.close()
