@@ -287,7 +287,7 @@ def main():
         import oracle
         sc, p0 = host[0]
         chk = synth.pose_errors(out_poses[0], oracle.solve_window(sc.depth, sc.normal, sc.K, sc.corr, p0))
-        out = dict(base, value=value, ms_per_step=ms_step, gpu_launches=3 * args.steps,
+        out = dict(base, value=value, ms_per_step=ms_step, gpu_launches=int(stats["n_kernel_launches"]) * args.steps,
                    e2e={"value": e2e_val, "unit": "windows/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                    roofline={"bound": "hbm", "kernel": "k_solve", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                              "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": tm},

@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbundletrack_b200.so")
+# BT_B200_LIB selects another BUILD of the same library (kernel experiments); there is still no non-CUDA path behind it
+LIB_PATH = os.environ.get("BT_B200_LIB") or os.path.join(_HERE, "lib", "libbundletrack_b200.so")
 
 BT_OK = 0
 

@@ -342,6 +342,7 @@ struct RerankJob {        // one per (pair, direction)
 	int cand_split_stride;
 	int out_off;                    // rows (x k) into the idx/dist outputs of this direction
 	int dir;                        // 0: A->B outputs, 1: B->A outputs
+	int t_pool_row0;                // first row of the train set in the bf16 pool / norms / errn
 };
 
 __device__ __forceinline__ double exact_d2(const float* __restrict__ a, const float* __restrict__ b, int lane) {
@@ -377,15 +378,23 @@ __device__ __forceinline__ double exact_d2_lane(const float* __restrict__ a, con
 	return s0 + s1;
 }
 
-static constexpr int RR_MAXC = 96;    // exact candidates per row handled in shared memory; more => exact fallback
+static constexpr int RR_MAXG = 24;            // groups expanded per row in shared memory; more => exact fallback
+static constexpr int RR_MAXC = RR_MAXG * GRP; // = 96 candidate train rows
 
-// one warp per query row
-__global__ void __launch_bounds__(256) k_knn_rerank(const RerankJob* __restrict__ jobs, const int* __restrict__ job_row_start, int n_jobs, int total_rows,
-                                                     const float* __restrict__ cand, const float* __restrict__ norms, const float* __restrict__ errn,
-                                                     const int* __restrict__ set_maxnorm2, const int* __restrict__ set_maxerr,
+// one warp per query row.  Three filters of increasing cost, each with a rigorous interval so that no true neighbour is lost:
+//   (1) group keys from k_knn_tc (min over GRP train rows, index packed into the mantissa)   -> groups that can reach the k-th
+//   (2) the GRP members of those groups re-evaluated on the bf16 pool rows (coalesced 512 B per row, fp32 accumulation;
+//       |d~ - d| <= errn[q] + errn[t], both measured by k_desc_prep)                           -> rows that can reach the k-th
+//   (3) exact float64 distance on the caller's fp32 rows for the survivors (typically k + 1..3 rows)
+// Traffic per query row: ~8 groups x 2 KB + ~7 x 1 KB instead of ~32 uncoalesced fp32 rows.
+__global__ void __launch_bounds__(256, 2) k_knn_rerank(const RerankJob* __restrict__ jobs, const int* __restrict__ job_row_start, int n_jobs, int total_rows,
+                                                     const float* __restrict__ cand, const __nv_bfloat16* __restrict__ pool, const float* __restrict__ norms,
+                                                     const float* __restrict__ errn, const int* __restrict__ set_maxnorm2, const int* __restrict__ set_maxerr,
                                                      int k, KnnOut out, int* fallback_rows, int* fallback_count) {
-	__shared__ int s_ci[8][RR_MAXC];
-	__shared__ double s_cd[8][RR_MAXC];
+	__shared__ int s_g[8][RR_MAXG];
+	__shared__ float s_lo[8][RR_MAXC];
+	__shared__ float s_hi[8][RR_MAXC];
+	__shared__ int s_sv[8][RR_MAXC];
 	const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
 	const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (gw >= total_rows) return;
@@ -396,45 +405,46 @@ __global__ void __launch_bounds__(256) k_knn_rerank(const RerankJob* __restrict_
 	const int kk = min(k, jb.nt);
 	const float INF = __int_as_float(0x7f800000);
 	const int E = jb.n_splits * NCAND;
+	// the query's bf16 row (8 consecutive elements per lane), issued early
+	const uint4 qraw = __ldg(reinterpret_cast<const uint4*>(pool + (size_t)(jb.q_pool_row0 + r) * KD) + lane);
 	// bound on | |q~ - t~| - |q - t| |: measured rounding-error norms of both rows (train side: per-set maximum) plus slack for
 	// the fp32 accumulation in the tensor core; the index packing costs <= 2^-IDX_BITS relative on the key itself.
 	const float qn2 = __ldg(norms + jb.q_pool_row0 + r);
+	const float qerr = __ldg(errn + jb.q_pool_row0 + r);
 	const double qn = sqrt((double)qn2), tn = sqrt((double)__int_as_float(set_maxnorm2[jb.t_set]));
-	const double eps = (double)__ldg(errn + jb.q_pool_row0 + r) + (double)__int_as_float(set_maxerr[jb.t_set]) + 1e-4 * (qn + tn) + 1e-6;
+	const double eps = (double)qerr + (double)__int_as_float(set_maxerr[jb.t_set]) + 1e-4 * (qn + tn) + 1e-6;
 	const double pk_rel = 1.0 / (double)(1 << IDX_BITS);
 	auto d_lo = [&](float key) -> double { const double v = (double)qn2 + (double)key - fabs((double)key) * pk_rel - 1e-6; return (v > 0.0 ? sqrt(v) : 0.0) - eps; };
 	auto d_hi = [&](float key) -> double { const double v = (double)qn2 + (double)key + fabs((double)key) * pk_rel + 1e-6; return (v > 0.0 ? sqrt(v) : 0.0) + eps; };
-	// ---- pass 1 over the list entries: D5 = k-th smallest upper bound (each entry IS a real train row, so the exact k-th
-	//      distance is <= D5), tau = smallest "list is full" threshold (rows of groups that never made a list have key >= tau)
-	double up[8];
+	// ---- pass 1 over the list entries: k-th smallest key (d_hi is monotone in the key, and every entry IS a real train row, so
+	//      the exact k-th distance is <= D5 = d_hi(k-th key)); tau = smallest "list is full" threshold (rows of groups that
+	//      never made a list have key >= tau)
+	float up[8];
 #pragma unroll
-	for (int j = 0; j < 8; j++) up[j] = 1e300;
-	float tau = INF;
+	for (int j = 0; j < 8; j++) up[j] = INF;
+	float tau = INF, upk = INF;                     // upk mirrors up[kk-1] (no dynamic register indexing)
 	for (int e0 = 0; e0 < E; e0 += 32) {
 		const int e = e0 + lane;
-		float pk = INF;
-		if (e < E) { const int s = e / NCAND, c = e - s * NCAND; pk = __ldg(cand + ((size_t)(jb.cand_off + s * jb.cand_split_stride + r) * NCAND + c)); if ((c % KC) == KC - 1) tau = fminf(tau, pk); }
-		double v = (pk < INF) ? d_hi(pk) : 1e300;
-		// merge the 32 lane values into the warp-uniform sorted list up[0..kk)
-		for (int round = 0; round < kk; round++) {
-			double m = v;
+		float v = INF;
+		if (e < E) { const int s = e / NCAND, c = e - s * NCAND; v = __ldg(cand + ((size_t)(jb.cand_off + s * jb.cand_split_stride + r) * NCAND + c)); if ((c % KC) == KC - 1) tau = fminf(tau, v); }
+		for (int round = 0; round < kk; round++) {       // merge the 32 lane values into the warp-uniform sorted list up[0..kk)
+			float m = v;
 #pragma unroll
-			for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
-			if (!(m < up[kk - 1])) break;
-			// insert m, and retire ONE lane holding it
-			double cdv = m;
+			for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+			if (!(m < upk)) break;
+			float cdv = m;
 #pragma unroll
-			for (int j = 0; j < 8; j++) { if (j < kk && cdv < up[j]) { const double t2 = up[j]; up[j] = cdv; cdv = t2; } }
+			for (int j = 0; j < 8; j++) { if (j < kk && cdv < up[j]) { const float t2 = up[j]; up[j] = cdv; cdv = t2; } if (j == kk - 1) upk = up[j]; }
 			const unsigned who = __ballot_sync(0xffffffffu, v == m);
-			if (lane == (int)(__ffs(who) - 1)) v = 1e300;
+			if (lane == (int)(__ffs(who) - 1)) v = INF;   // retire ONE lane holding it
 		}
 	}
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) tau = fminf(tau, __shfl_xor_sync(0xffffffffu, tau, o));
-	const double D5 = (kk > 0) ? up[kk - 1] : 1e300;
-	// ---- pass 2: expand every group whose lower bound can still reach D5 into its GRP members
-	int ncand = 0;
-	bool overflow = false;
+	const float key_k = upk;
+	const double D5 = (kk > 0 && key_k < INF) ? d_hi(key_k) : 1e300;
+	// ---- pass 2: every group whose lower bound can still reach D5
+	int ng = 0;
 	for (int e0 = 0; e0 < E; e0 += 32) {
 		const int e = e0 + lane;
 		bool take = false; int gbase = 0;
@@ -444,88 +454,145 @@ __global__ void __launch_bounds__(256) k_knn_rerank(const RerankJob* __restrict_
 			if (pk < INF) { gbase = s * jb.split_rows + (int)(__float_as_uint(pk) & ((1u << IDX_BITS) - 1u)) * GRP; take = (gbase < jb.nt) && (d_lo(pk) <= D5); }
 		}
 		const unsigned bal = __ballot_sync(0xffffffffu, take);
-		const int pos = ncand + __popc(bal & ((1u << lane) - 1u)) * GRP;
-		if (take) {
-			if (pos + GRP <= RR_MAXC) { for (int j = 0; j < GRP; j++) s_ci[wl][pos + j] = (gbase + j < jb.nt) ? gbase + j : -1; }
-			else overflow = true;
-		}
-		ncand += __popc(bal) * GRP;
+		const int pos = ng + __popc(bal & ((1u << lane) - 1u));
+		if (take && pos < RR_MAXG) s_g[wl][pos] = gbase;
+		ng += __popc(bal);
 	}
-	overflow = __any_sync(0xffffffffu, overflow) || ncand > RR_MAXC;
+	const bool overflow = ng > RR_MAXG;
 	__syncwarp();
 	bool ok = !overflow;
 	double best_d[8]; int best_i[8];
 #pragma unroll
 	for (int j = 0; j < 8; j++) { best_d[j] = 1e300; best_i[j] = 0x7fffffff; }
 	if (!overflow) {
-		// ---- fp32 pre-filter, one lane per candidate: float64 conversions are the scarce resource, so the exact float64
-		//      distance is only computed for candidates the fp32 value cannot rule out.  |d2_f32 - d2| <= 256 * 2^-23 * d2.
-		float* s_cf = reinterpret_cast<float*>(&s_cd[wl][0]);        // fp32 distances live in the (otherwise unused) double array
-		for (int c0 = 0; c0 < ncand; c0 += 32) {
-			const int c = c0 + lane;
-			if (c < ncand) {
-				const int ti = s_ci[wl][c];
-				float f = INF;
-				if (ti >= 0) {
-					const float4* a4 = reinterpret_cast<const float4*>(qrow);
-					const float4* b4 = reinterpret_cast<const float4*>((const char*)jb.t + (size_t)ti * jb.t_pitch);
-					float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll 4
-					for (int q = 0; q < KD / 4; q++) {
-						const float4 x = __ldg(a4 + q), y = __ldg(b4 + q);
-						const float d0 = x.x - y.x, d1 = x.y - y.y, d2_ = x.z - y.z, d3 = x.w - y.w;
-						s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2_, d2_, s2); s3 = fmaf(d3, d3, s3);
-					}
-					f = (s0 + s1) + (s2 + s3);
+		// ---- filter 2: the members of the taken groups on the bf16 pool rows, two groups (8 rows, 4 KB) per step
+		float qf[8];
+		{
+			const uint32_t w[4] = { qraw.x, qraw.y, qraw.z, qraw.w };
+#pragma unroll
+			for (int i = 0; i < 4; i++) { qf[2 * i] = __uint_as_float(w[i] << 16); qf[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+		}
+		const __nv_bfloat16* tpool = pool + (size_t)jb.t_pool_row0 * KD;
+		for (int g0 = 0; g0 < ng; g0 += 2) {
+			const int gA = s_g[wl][g0], gB = (g0 + 1 < ng) ? s_g[wl][g0 + 1] : gA;
+			const uint4* pa = reinterpret_cast<const uint4*>(tpool + (size_t)gA * KD) + lane;     // consecutive rows are 32 uint4 apart
+			const uint4* pb = reinterpret_cast<const uint4*>(tpool + (size_t)gB * KD) + lane;
+			uint4 w[8];
+#pragma unroll
+			for (int j = 0; j < 4; j++) { w[j] = __ldg(pa + j * 32); w[4 + j] = __ldg(pb + j * 32); }
+			const int trow = ((lane & 4) ? gB : gA) + (lane & 3);                             // the row lane (L & 7) will own after the reduction
+			const float tn2 = __ldg(norms + jb.t_pool_row0 + trow), terr = __ldg(errn + jb.t_pool_row0 + trow);
+			float v[8];
+#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				const uint32_t x[4] = { w[j].x, w[j].y, w[j].z, w[j].w };
+				float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+				for (int i = 0; i < 4; i++) { a0 = fmaf(qf[2 * i], __uint_as_float(x[i] << 16), a0); a1 = fmaf(qf[2 * i + 1], __uint_as_float(x[i] & 0xffff0000u), a1); }
+				v[j] = a0 + a1;
+			}
+			// transposing butterfly over lane bits 2,1,0, then plain sums over bits 3,4: lane L ends with the total of value (L & 7)
+#pragma unroll
+			for (int half = 4; half >= 1; half >>= 1) {
+				const bool upper = (lane & half) != 0;
+#pragma unroll
+				for (int j = 0; j < half; j++) {
+					const float send = upper ? v[j] : v[j + half];
+					const float keep = upper ? v[j + half] : v[j];
+					v[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
 				}
-				s_cf[c] = f;
+			}
+			v[0] += __shfl_xor_sync(0xffffffffu, v[0], 8);
+			v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
+			const int gi = g0 + ((lane >> 2) & 1);
+			if (lane < 8 && gi < ng) {
+				float lo = INF, hi = INF;
+				if (trow < jb.nt) {
+					// fp32 evaluation of |q~ - t~|^2 from 256 exact products: absolute error <= 4e-5 (|q~|^2 + |t~|^2) (sum of 256 terms,
+					// the two norms, the final combination); sqrtf is correctly rounded, the factors (1 +- 1e-6) cover it and the adds
+					const float d2 = qn2 + tn2 - 2.0f * v[0];
+					const float slack = 4.0e-5f * (qn2 + tn2) + 1.0e-12f;
+					const float e = (qerr + terr) * 1.0001f + 1.0e-9f;
+					hi = sqrtf(fmaxf(d2 + slack, 0.f)) * (1.0f + 1.0e-6f) + e;
+					lo = sqrtf(fmaxf(d2 - slack, 0.f)) * (1.0f - 1.0e-6f) - e;
+				}
+				s_lo[wl][gi * GRP + (lane & 3)] = lo;
+				s_hi[wl][gi * GRP + (lane & 3)] = hi;
 			}
 		}
 		__syncwarp();
-		// k-th smallest fp32 distance (warp-uniform): k rounds of warp-min, retiring ONE holder per round
-		float fk = INF;
-		{
-			unsigned taken_lo = 0u, taken_mid = 0u, taken_hi = 0u;     // candidate slots already counted (<= 96 slots)
-			for (int round = 0; round < kk; round++) {
-				float m = INF; int mc = -1;
-				for (int c = lane; c < ncand; c += 32) {
-					const unsigned bit = 1u << (c & 31);
-					const unsigned word = (c < 32) ? taken_lo : ((c < 64) ? taken_mid : taken_hi);
-					if (!(word & bit) && s_cf[c] < m) { m = s_cf[c]; mc = c; }
-				}
+		const int nc = ng * GRP;
+		// k-th smallest upper bound over the members (warp-uniform): kk rounds of warp-min, retiring ONE holder per round
+		float h[3];
 #pragma unroll
-				for (int o = 16; o > 0; o >>= 1) {
-					const float om = __shfl_xor_sync(0xffffffffu, m, o); const int oc = __shfl_xor_sync(0xffffffffu, mc, o);
-					if (oc >= 0 && (mc < 0 || om < m || (om == m && oc < mc))) { m = om; mc = oc; }
-				}
-				if (mc < 0) break;
-				fk = m;
-				const unsigned bit = 1u << (mc & 31);
-				if (mc < 32) taken_lo |= bit; else if (mc < 64) taken_mid |= bit; else taken_hi |= bit;
-			}
+		for (int j = 0; j < 3; j++) { const int c = lane + 32 * j; h[j] = (c < nc) ? s_hi[wl][c] : INF; }
+		float hk = INF;
+		for (int round = 0; round < kk; round++) {
+			const float mine = fminf(h[0], fminf(h[1], h[2]));
+			float m = mine;
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+			hk = m;
+			if (!(m < INF)) break;
+			const unsigned who = __ballot_sync(0xffffffffu, mine == m);
+			if (lane == (int)(__ffs(who) - 1)) { if (h[0] == m) h[0] = INF; else if (h[1] == m) h[1] = INF; else h[2] = INF; }
 		}
-		const float f_cut = (fk < INF) ? fk * (1.0f + 1.0e-4f) + 1e-30f : INF;
-		// ---- exact float64 distance (warp-cooperative) for the survivors; sorted insert by (distance, index)
-		for (int c = 0; c < ncand; c++) {
-			const int ti = s_ci[wl][c];
-			if (ti < 0 || !(s_cf[c] <= f_cut)) continue;           // warp-uniform: both arrays are shared
-			double cd = exact_d2(qrow, (const float*)((const char*)jb.t + (size_t)ti * jb.t_pitch), lane); int ci = ti;
+		// survivors: members whose lower bound can still reach the k-th upper bound
+		int nsv = 0;
+#pragma unroll
+		for (int j = 0; j < 3; j++) {
+			const int c = lane + 32 * j;
+			const bool keep = (c < nc) && (s_lo[wl][c] <= hk) && (s_lo[wl][c] < INF);
+			const unsigned bal = __ballot_sync(0xffffffffu, keep);
+			if (keep) s_sv[wl][nsv + __popc(bal & ((1u << lane) - 1u))] = s_g[wl][c / GRP] + (c % GRP);
+			nsv += __popc(bal);
+		}
+		__syncwarp();
+		// ---- filter 3: exact float64 distance (warp-cooperative, two rows in flight); sorted insert by (distance, index)
+		const float4 qa = __ldg(reinterpret_cast<const float4*>(qrow) + lane * 2), qb = __ldg(reinterpret_cast<const float4*>(qrow) + lane * 2 + 1);
+		auto d2_exact = [&](const float4& b0, const float4& b1) -> double {
+			double s = 0.0, d;
+			d = (double)qa.x - (double)b0.x; s += d * d; d = (double)qa.y - (double)b0.y; s += d * d;
+			d = (double)qa.z - (double)b0.z; s += d * d; d = (double)qa.w - (double)b0.w; s += d * d;
+			d = (double)qb.x - (double)b1.x; s += d * d; d = (double)qb.y - (double)b1.y; s += d * d;
+			d = (double)qb.z - (double)b1.z; s += d * d; d = (double)qb.w - (double)b1.w; s += d * d;
+			return s;
+		};
+		auto insert = [&](double cd, int ci) {
 #pragma unroll
 			for (int j = 0; j < 8; j++) {
 				const bool lt = (cd < best_d[j]) || (cd == best_d[j] && ci < best_i[j]);
 				if (lt) { const double td = best_d[j]; const int tix = best_i[j]; best_d[j] = cd; best_i[j] = ci; cd = td; ci = tix; }
 			}
+		};
+		for (int c = 0; c < nsv; c += 2) {
+			const int t0 = s_sv[wl][c], t1 = (c + 1 < nsv) ? s_sv[wl][c + 1] : t0;
+			const float4* r0 = reinterpret_cast<const float4*>((const char*)jb.t + (size_t)t0 * jb.t_pitch) + lane * 2;
+			const float4* r1 = reinterpret_cast<const float4*>((const char*)jb.t + (size_t)t1 * jb.t_pitch) + lane * 2;
+			const float4 x0 = __ldg(r0), x1 = __ldg(r0 + 1), y0 = __ldg(r1), y1 = __ldg(r1 + 1);
+			double sa = d2_exact(x0, x1), sb = d2_exact(y0, y1);
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
+			insert(sa, t0);
+			if (c + 1 < nsv) insert(sb, t1);
 		}
 		// ---- proof for everything that never made a list: its key is >= tau
-		if (kk > 0 && tau < INF) ok = (best_i[kk - 1] != 0x7fffffff) && (sqrt(best_d[kk - 1]) < d_lo(tau));
+		double bk = 1e300; int bi = 0x7fffffff;
+#pragma unroll
+		for (int j = 0; j < 8; j++) if (j == kk - 1) { bk = best_d[j]; bi = best_i[j]; }
+		if (kk > 0 && tau < INF) ok = (bi != 0x7fffffff) && (sqrt(bk) < d_lo(tau));
+		if (kk > 0 && bi == 0x7fffffff) ok = false;      // fewer than k survivors can only mean a broken bound: recompute exactly
 	}
 	if (lane == 0) {
 		int32_t* io = out.idx[jb.dir] + ((size_t)jb.out_off + r) * k;
 		float* dd = out.dist[jb.dir] + ((size_t)jb.out_off + r) * k;
-		for (int j = 0; j < k; j++) {
-			const bool have = j < kk && best_i[j] != 0x7fffffff;
-			io[j] = have ? best_i[j] : -1;
-			dd[j] = have ? (float)sqrt(best_d[j]) : INF;
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			if (j < k) {
+				const bool have = j < kk && best_i[j] != 0x7fffffff;
+				io[j] = have ? best_i[j] : -1;
+				dd[j] = have ? (float)sqrt(best_d[j]) : INF;
+			}
 		}
 		if (!ok) { const int slot = atomicAdd(fallback_count, 1); fallback_rows[slot] = gw; }
 	}
@@ -758,7 +825,7 @@ extern "C" int bt_knn_match_pairs(bt_ctx* ctx, int n_pairs, const bt_desc_view* 
 			splits = (ttiles + tiles_per_split - 1) / std::max(tiles_per_split, 1);
 			RerankJob jb; memset(&jb, 0, sizeof jb);
 			jb.q = Q.dev; jb.q_pitch = qs.pitch_bytes; jb.nq = Q.n; jb.q_pool_row0 = qs.row0;
-			jb.t = T.dev; jb.t_pitch = ts.pitch_bytes; jb.nt = T.n; jb.t_set = tset;
+			jb.t = T.dev; jb.t_pitch = ts.pitch_bytes; jb.nt = T.n; jb.t_set = tset; jb.t_pool_row0 = ts.row0;
 			jb.n_splits = (Q.n > 0 && T.n > 0) ? splits : 0; jb.split_rows = tiles_per_split * BN;
 			jb.cand_off = (int)cand_rows; jb.cand_split_stride = qtiles * BM;
 			jb.out_off = (int)off_dir[dir]; jb.dir = dir;
@@ -814,7 +881,7 @@ extern "C" int bt_knn_match_pairs(bt_ctx* ctx, int n_pairs, const bt_desc_view* 
 	KnnOut out; out.idx[0] = idxAB; out.idx[1] = idxBA; out.dist[0] = distAB; out.dist[1] = distBA;
 	if (total_rows > 0) {
 		k_knn_rerank<<<(total_rows + 7) / 8, 256, 0, stream>>>(m->jobs.as<RerankJob>(), m->job_rows.as<int>(), (int)jobs.size(), total_rows, m->cand.as<float>(),
-		                                                     m->norms.as<float>(), m->errn.as<float>(), m->set_max.as<int>(), m->set_err.as<int>(), k, out, m->fb_rows.as<int>(), m->fb_count.as<int>());
+		                                                     m->pool.as<__nv_bfloat16>(), m->norms.as<float>(), m->errn.as<float>(), m->set_max.as<int>(), m->set_err.as<int>(), k, out, m->fb_rows.as<int>(), m->fb_count.as<int>());
 		if (m->timing) BT_CUDA(cudaEventRecord(m->ev[3], stream));
 		k_knn_exact<<<ctx->sm_count * 2, 256, 0, stream>>>(m->jobs.as<RerankJob>(), m->job_rows.as<int>(), (int)jobs.size(), m->fb_rows.as<int>(), m->fb_count.as<int>(), k, out);
 	} else if (m->timing) BT_CUDA(cudaEventRecord(m->ev[3], stream));

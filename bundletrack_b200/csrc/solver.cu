@@ -4,12 +4,12 @@
 // (/root/reference/src/cuda/LossGPU.cu:53-139) -> CUDACache::storeFrame (CUDACache.cpp:76-88) -> SBA::align
 // (SBA.cpp:81-139) -> CUDASolverBundling::solve (Solver/CUDASolverBundling.cpp:190-288) -> solveBundlingStub
 // (Solver/SolverBundling.cu:931-1003): ~260 kernel launches, ~75 memsets, 7 blocking copies and ~110 cudaMalloc per
-// window there; THREE launches per BATCH here, none of them allocating:
+// window there; TWO launches per BATCH here, none of them allocating:
 //
 //   k_prep_frames  one CTA per (window, frame): quarter-res cache (camera-space point + normal interleaved in one
 //                  32-byte texel so a bilinear tap is a single sector) + an order-preserving COMPACTED list of the
 //                  valid source pixels (the object mask leaves ~10 % of the image valid), + se(3) of the input pose.
-//   k_plan         one CTA: per-window tile counts -> exclusive scan -> flat tile list.
+//   (plan)         the LAST CTA of k_prep_frames to finish: per-window tile counts -> exclusive scan -> flat tile list.
 //   k_solve        persistent, dynamically scheduled: tiles are (GN iteration, window, pair, pixel chunk); a tile
 //                  evaluates point-to-plane residuals/Jacobians for its chunk and reduces a 6x6 system in the TARGET
 //                  camera frame; the CTA that retires a window's last tile of an iteration runs that window's "tail":
@@ -217,7 +217,16 @@ __device__ __forceinline__ void prof_emit(const SolveArgs& a, const ProfRec& r) 
 // ------------------------------------------------------------------------------------------------ k_prep_frames
 // CUDACache::storeFrame fused (convertDepthFloatToCameraSpaceFloat4 + 2x resampleFloat4 nearest, CUDAImageUtil.cu:
 // 310-326,82-99) + compaction of the source list + matrixToPose/poseToMatrix of the incoming pose (SBA.cu:71-79).
-__global__ void __launch_bounds__(1024) k_prep_frames(SolveArgs a) {
+__device__ void plan_body(const SolveArgs& a, WinDesc* wins_rw);
+
+// One CTA per frame.  The compacted source list keeps pixel order (fixed summation order downstream), so the CTA needs
+// an ordered prefix over its pixels; instead of one block-wide scan per 1024 pixels (19 x 3 barriers per frame, the loads
+// of each round exposed) it runs two sweeps around ONE scan: sweep 1 counts the valid pixels of every (round, warp) from
+// the depth map alone, the scan turns the counts into offsets, sweep 2 loads depth + normal, writes the texel map and the
+// source records at their final position.  No barrier inside either sweep, so the loads of consecutive rounds overlap.
+static constexpr int kPrepRounds = 64;      // rounds of 1024 pixels per scan (one scan covers 65536 quarter-res pixels)
+
+__global__ void __launch_bounds__(1024) k_prep_frames(SolveArgs a, WinDesc* wins_rw, int* prep_ticket) {
 	const int fs = blockIdx.x;
 	const WinDesc wd = a.wins[a.frame_win[fs]];
 	const int npix = wd.w * wd.h;
@@ -225,11 +234,84 @@ __global__ void __launch_bounds__(1024) k_prep_frames(SolveArgs a) {
 	const float4* __restrict__ normal = a.normal_ptr[fs];
 	float4* texel = a.texel + (size_t)fs * 2 * a.npix_max;
 	float4* src = a.src + (size_t)fs * 2 * a.npix_max;
-	__shared__ int s_warp[32];
-	__shared__ int s_base;
+	__shared__ int s_cnt[kPrepRounds * 32];
+	__shared__ int s_wt[32];
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-	if (tid == 0) {
-		s_base = 0;
+	const bool use_dense = a.prm.w_dense > 0.0f;
+	const float dmin = a.prm.depth_min, dmax = a.prm.depth_max;
+	// nearest-neighbour sample position of quarter-res pixel idx in the full-res maps, or -1 (resampleFloat4, CUDAImageUtil.cu:82-99)
+	auto sample = [&](int idx, unsigned& xi, unsigned& yi) -> bool {
+		const int x = idx % wd.w, y = idx / wd.w;
+		xi = (unsigned)((float)x * wd.scaleW + 0.5f); yi = (unsigned)((float)y * wd.scaleH + 0.5f);
+		return xi < (unsigned)wd.W && yi < (unsigned)wd.H;
+	};
+	int base = 0;
+	for (int sb = 0; use_dense && sb < npix; sb += kPrepRounds * 1024) {
+		const int rounds = min(kPrepRounds, (npix - sb + 1023) >> 10);
+		// ---- sweep 1: valid counts per (round, warp)
+#pragma unroll 4
+		for (int r = 0; r < rounds; r++) {
+			const int idx = sb + (r << 10) + tid;
+			bool valid = false;
+			if (idx < npix) {       // must agree bit for bit with sweep 2: z = 0 for a missing / too-near sample
+				unsigned xi, yi;
+				float z = 0.f;
+				if (sample(idx, xi, yi)) { const float d = __ldg(depth + (size_t)yi * wd.W + xi); if (d >= 0.1f) z = d; }
+				valid = (z > dmin && z < dmax);
+			}
+			const unsigned bal = __ballot_sync(0xffffffffu, valid);
+			if (lane == 0) s_cnt[r * 32 + wid] = __popc(bal);
+		}
+		__syncthreads();
+		// ---- exclusive scan of the rounds*32 counts in (round, warp) order: two entries per thread
+		const int n = rounds * 32;
+		const int v0 = (2 * tid < n) ? s_cnt[2 * tid] : 0, v1 = (2 * tid + 1 < n) ? s_cnt[2 * tid + 1] : 0;
+		int incl = v0 + v1;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+		if (lane == 31) s_wt[wid] = incl;
+		__syncthreads();
+		if (wid == 0) {
+			int t = s_wt[lane];
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += u; }
+			s_wt[lane] = t;
+		}
+		__syncthreads();
+		const int excl = base + incl - (v0 + v1) + (wid ? s_wt[wid - 1] : 0);
+		if (2 * tid < n) s_cnt[2 * tid] = excl;
+		if (2 * tid + 1 < n) s_cnt[2 * tid + 1] = excl + v0;
+		base += s_wt[31];
+		__syncthreads();
+		// ---- sweep 2: texel map + source records at their final offsets
+#pragma unroll 2
+		for (int r = 0; r < rounds; r++) {
+			const int idx = sb + (r << 10) + tid;
+			float4 cp = make_float4(0.f, 0.f, 0.f, 0.f), nr = make_float4(0.f, 0.f, 0.f, 0.f);
+			bool valid = false;
+			if (idx < npix) {
+				unsigned xi, yi;
+				if (sample(idx, xi, yi)) {
+					const size_t sidx = (size_t)yi * wd.W + xi;
+					const float d = __ldg(depth + sidx);
+					nr = __ldg(normal + sidx);
+					if (d >= 0.1f) cp = make_float4(wd.ifx * ((float)xi * d) + wd.icx * d, wd.ify * ((float)yi * d) + wd.icy * d, d, 1.0f);
+				}
+				texel[2 * idx] = make_float4(cp.x, cp.y, cp.z, nr.x);      // 32-byte texel: point xyz + normal xyz (+ pad)
+				texel[2 * idx + 1] = make_float4(nr.y, nr.z, 0.f, 0.f);
+				valid = (cp.z > dmin && cp.z < dmax);
+			}
+			const unsigned bal = __ballot_sync(0xffffffffu, valid);
+			if (valid) {
+				const int o = s_cnt[r * 32 + wid] + __popc(bal & ((1u << lane) - 1u));
+				src[2 * o] = make_float4(cp.x, cp.y, cp.z, nr.x);
+				src[2 * o + 1] = make_float4(nr.y, nr.z, nr.w, 0.f);
+			}
+		}
+		__syncthreads();
+	}
+	if (tid == 0) a.nsrc[fs] = base;
+	if (tid == 1023) {      // pose -> (rot, trans) -> T of iteration 0, off the critical path of the sweeps (last warp, one lane)
 		float Tm[12];
 		const float* P = a.pose_in + (size_t)fs * 16;
 		for (int k = 0; k < 12; k++) Tm[k] = P[k];
@@ -241,41 +323,13 @@ __global__ void __launch_bounds__(1024) k_prep_frames(SolveArgs a) {
 		float* T = a.T + (size_t)fs * 12;
 		for (int k = 0; k < 12; k++) T[k] = Tm[k];
 	}
+	// the last CTA to finish plans the dense tiles of the whole batch (saves a launch and its dependency gap)
+	__shared__ int s_last;
+	__threadfence();
 	__syncthreads();
-	const bool use_dense = a.prm.w_dense > 0.0f;
-	if (!use_dense) { if (tid == 0) a.nsrc[fs] = 0; return; }
-	for (int base = 0; base < npix; base += blockDim.x) {
-		const int idx = base + tid;
-		float4 cp = make_float4(0.f, 0.f, 0.f, 0.f), nr = make_float4(0.f, 0.f, 0.f, 0.f);
-		bool valid = false;
-		if (idx < npix) {
-			const int x = idx % wd.w, y = idx / wd.w;
-			const unsigned xi = (unsigned)((float)x * wd.scaleW + 0.5f), yi = (unsigned)((float)y * wd.scaleH + 0.5f);
-			if (xi < (unsigned)wd.W && yi < (unsigned)wd.H) {
-				const size_t sidx = (size_t)yi * wd.W + xi;
-				const float d = __ldg(depth + sidx);
-				nr = __ldg(normal + sidx);
-				if (d >= 0.1f) cp = make_float4(wd.ifx * ((float)xi * d) + wd.icx * d, wd.ify * ((float)yi * d) + wd.icy * d, d, 1.0f);
-			}
-			texel[2 * idx] = make_float4(cp.x, cp.y, cp.z, nr.x);      // 32-byte texel: point xyz + normal xyz (+ pad)
-			texel[2 * idx + 1] = make_float4(nr.y, nr.z, 0.f, 0.f);
-			valid = (cp.z > a.prm.depth_min && cp.z < a.prm.depth_max);
-		}
-		const unsigned bal = __ballot_sync(0xffffffffu, valid);
-		if (lane == 0) s_warp[wid] = __popc(bal);
-		__syncthreads();
-		int off = s_base;
-		for (int k = 0; k < wid; k++) off += s_warp[k];
-		if (valid) {
-			const int o = off + __popc(bal & ((1u << lane) - 1u));
-			src[2 * o] = make_float4(cp.x, cp.y, cp.z, nr.x);
-			src[2 * o + 1] = make_float4(nr.y, nr.z, nr.w, 0.f);
-		}
-		__syncthreads();
-		if (tid == 0) { int t = 0; for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += s_warp[k]; s_base += t; }
-		__syncthreads();
-	}
-	if (tid == 0) a.nsrc[fs] = s_base;
+	if (tid == 0) { const int t = atomicAdd(prep_ticket, 1); s_last = (t == (int)gridDim.x - 1); if (s_last) { *prep_ticket = 0; __threadfence(); } }
+	__syncthreads();
+	if (s_last) plan_body(a, wins_rw);
 }
 
 // ------------------------------------------------------------------------------------------------ k_plan
@@ -285,7 +339,8 @@ __device__ __forceinline__ int chunks_for(int n, int chunk, int& per) {
 	per = (((n + nch - 1) / nch) + 31) & ~31;   // balanced, warp-aligned
 	return (n + per - 1) / per;
 }
-__global__ void __launch_bounds__(1024) k_plan(SolveArgs a, WinDesc* wins_rw) {
+// Runs on the LAST CTA of k_prep_frames to finish (1024 threads): per-window tile counts -> scans -> flat tile list.
+__device__ void plan_body(const SolveArgs& a, WinDesc* wins_rw) {
 	__shared__ int s_cnt[1024];
 	__shared__ int s_scan[1024];
 	__shared__ int s_carry;
@@ -316,12 +371,21 @@ __global__ void __launch_bounds__(1024) k_plan(SolveArgs a, WinDesc* wins_rw) {
 		// (2) exclusive scan of the per-window tile counts (a window without dense work still gets one dummy tile)
 		int cnt = 0;
 		if (tid < nw) { cnt = s_cnt[tid]; if (cnt == 0) cnt = 1; a.tiles_done[base + tid] = 0; a.iter_done[base + tid] = 0; }
-		s_scan[tid] = cnt;
-		__syncthreads();
-		for (int o = 1; o < 1024; o <<= 1) {
-			const int v = (tid >= o) ? s_scan[tid - o] : 0;
+		{   // inclusive scan over the 1024 per-window counts: warp shuffles + one pass over the 32 warp totals
+			__shared__ int s_wtot[32];
+			int incl = cnt;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += u; }
+			if ((tid & 31) == 31) s_wtot[tid >> 5] = incl;
 			__syncthreads();
-			s_scan[tid] += v;
+			if (tid < 32) {
+				int t = s_wtot[tid];
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, t, o); if (tid >= o) t += u; }
+				s_wtot[tid] = t;
+			}
+			__syncthreads();
+			s_scan[tid] = incl + ((tid >> 5) ? s_wtot[(tid >> 5) - 1] : 0);
 			__syncthreads();
 		}
 		const int excl = s_scan[tid] - cnt + s_carry;
@@ -990,11 +1054,31 @@ __global__ void __launch_bounds__(kThreads, BT_SOLVE_MIN_CTAS) k_solve(SolveArgs
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+// Everything bt_solve_stage uploads lives in ONE pinned block mirrored by ONE device block (same offsets), so staging is a
+// single H2D copy: the small tables first (carved for the worst case of this window count), the correspondences last so
+// that the copy length follows the actual number of entries.
+struct StageLayout {
+	size_t wins, dp, np, fw, pose, gi, gj, gs, pairs, pwin, psrc, mem, corr, total;
+};
+static StageLayout stage_layout(int n_windows, size_t F, size_t C, int max_frames, size_t maxG, size_t maxP) {
+	StageLayout L;
+	size_t off = 0;
+	auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+	const size_t nw = (size_t)n_windows;
+	L.wins = carve(sizeof(WinDesc) * nw); L.dp = carve(sizeof(void*) * F); L.np = carve(sizeof(void*) * F); L.fw = carve(sizeof(int) * F);
+	L.pose = carve(sizeof(float) * 16 * F); L.gi = carve(sizeof(int) * maxG * nw); L.gj = carve(sizeof(int) * maxG * nw);
+	L.gs = carve(sizeof(int) * (maxG + 1) * nw); L.pairs = carve(sizeof(uint2) * maxP * nw); L.pwin = carve(sizeof(int) * maxP * nw);
+	L.psrc = carve(sizeof(int) * maxP * nw); L.mem = carve(sizeof(int) * (2 * ((size_t)max_frames + 1) + 2 * maxG + 2 * maxP) * nw);
+	L.corr = carve(sizeof(bt_entryj) * C + 32);
+	L.total = off;
+	return L;
+}
+
 struct SolverState {
 	bt_solver_limits lim{};
 	int npix_max = 0, max_pairs = 0, max_frames_total = 0, max_tiles = 0, max_groups = 0;
-	DevBuf wins, depth_ptr, normal_ptr, frame_win, texel, src, nsrc, pose_in, x, T, pose_out, corr, grp_i, grp_j, grp_start, pairs,
-	    tiles, scalars, partial, tiles_done, iter_done, pair_tile0, pair_ntile, pair_win, pair_src, mem, dbgJ, dbgR, dbgC, prof;
+	DevBuf stage_dev, texel, src, nsrc, x, T, pose_out, tiles, scalars, partial, tiles_done, iter_done, pair_tile0, pair_ntile, dbgJ, dbgR, dbgC, prof;
+	StageLayout layout{};
 	int prof_cap = 0;
 	PinnedBuf h_stage, h_poses;
 	// last staged batch
@@ -1004,18 +1088,23 @@ struct SolverState {
 	std::vector<int> n_frames;
 	bool staged = false, debug = false, timing = false;
 	int launches = 0;
+	int attr_bytes = 0, occ = 1, occ_smem = -1;
+	bool prep_launched = false;
+	cudaStream_t copy_stream = nullptr;
+	cudaEvent_t ev_prev = nullptr, ev_corr = nullptr, ev_h2d = nullptr;
 	cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
 };
 
 void solver_destroy(bt_ctx* ctx) {
 	SolverState* s = ctx->solver;
 	if (!s) return;
-	DevBuf* bufs[] = { &s->wins, &s->depth_ptr, &s->normal_ptr, &s->frame_win, &s->texel, &s->src, &s->nsrc, &s->pose_in, &s->x, &s->T,
-	                   &s->pose_out, &s->corr, &s->grp_i, &s->grp_j, &s->grp_start, &s->pairs, &s->tiles, &s->scalars, &s->partial,
-	                   &s->tiles_done, &s->iter_done, &s->pair_tile0, &s->pair_ntile, &s->pair_win, &s->pair_src, &s->mem, &s->dbgJ, &s->dbgR, &s->dbgC, &s->prof };
+	DevBuf* bufs[] = { &s->stage_dev, &s->texel, &s->src, &s->nsrc, &s->x, &s->T, &s->pose_out, &s->tiles, &s->scalars, &s->partial,
+	                   &s->tiles_done, &s->iter_done, &s->pair_tile0, &s->pair_ntile, &s->dbgJ, &s->dbgR, &s->dbgC, &s->prof };
 	for (DevBuf* b : bufs) b->release();
 	s->h_stage.release(); s->h_poses.release();
 	for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+	for (cudaEvent_t e : { s->ev_prev, s->ev_corr, s->ev_h2d }) if (e) cudaEventDestroy(e);
+	if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
 	delete s;
 	ctx->solver = nullptr;
 }
@@ -1036,25 +1125,20 @@ static int reserve_impl(bt_ctx* ctx, const bt_solver_limits* lim) {
 	s->max_tiles = lim->max_windows * (lim->max_frames * (lim->max_frames - 1) / 2) * ((s->npix_max + min_chunk - 1) / min_chunk + 1);
 	int rc;
 #define RES(buf, bytes) if ((rc = s->buf.alloc(bytes)) != BT_OK) return rc
-	RES(wins, sizeof(WinDesc) * lim->max_windows);
-	RES(depth_ptr, sizeof(void*) * F); RES(normal_ptr, sizeof(void*) * F); RES(frame_win, sizeof(int) * F);
+	{   // worst case over every window count <= max_windows (the table offsets grow with the count, so the maximum is at max_windows)
+		const StageLayout L = stage_layout(lim->max_windows, (size_t)F, (size_t)lim->max_corr * lim->max_windows, lim->max_frames, (size_t)s->max_groups, (size_t)s->max_pairs);
+		RES(stage_dev, L.total);
+	}
 	RES(texel, sizeof(float4) * 2 * (size_t)s->npix_max * F);
 	RES(src, sizeof(float4) * 2 * (size_t)s->npix_max * F);
 	RES(nsrc, sizeof(int) * F);
-	RES(pose_in, sizeof(float) * 16 * F); RES(x, sizeof(float) * 6 * F); RES(T, sizeof(float) * 12 * F); RES(pose_out, sizeof(float) * 16 * F);
-	RES(corr, sizeof(bt_entryj) * (size_t)lim->max_corr * lim->max_windows + 32);
-	RES(grp_i, sizeof(int) * (size_t)s->max_groups * lim->max_windows);
-	RES(grp_j, sizeof(int) * (size_t)s->max_groups * lim->max_windows);
-	RES(grp_start, sizeof(int) * ((size_t)s->max_groups + 1) * lim->max_windows);
-	RES(pairs, sizeof(uint2) * (size_t)s->max_pairs * lim->max_windows);
+	RES(x, sizeof(float) * 6 * F); RES(T, sizeof(float) * 12 * F); RES(pose_out, sizeof(float) * 16 * F);
 	RES(pair_tile0, sizeof(int) * (size_t)s->max_pairs * lim->max_windows);
 	RES(pair_ntile, sizeof(int) * (size_t)s->max_pairs * lim->max_windows);
-	RES(pair_win, sizeof(int) * (size_t)s->max_pairs * lim->max_windows);
-	RES(pair_src, sizeof(int) * (size_t)s->max_pairs * lim->max_windows);
-	RES(mem, sizeof(int) * (size_t)(2 * (lim->max_frames + 1) + 2 * s->max_groups + 2 * s->max_pairs) * lim->max_windows);
 	RES(tiles, sizeof(Tile) * (size_t)s->max_tiles);
 	RES(partial, sizeof(float) * kTileVals * (size_t)s->max_tiles);
 	RES(scalars, 64);
+	BT_CUDA(cudaMemset(s->scalars.p, 0, 64));
 	RES(tiles_done, sizeof(int) * lim->max_windows); RES(iter_done, sizeof(int) * lim->max_windows);
 #undef RES
 	return BT_OK;
@@ -1094,8 +1178,15 @@ extern "C" int bt_solve_get_timing(bt_ctx* ctx, float* ms3) {
 	return BT_OK;
 }
 
-extern "C" int bt_solve_stage(bt_ctx* ctx, int n_windows, const bt_window* windows, const bt_solver_params* params,
-                              const float* poses_in, void* stream_) {
+static SolveArgs make_args(bt_ctx* ctx);
+static int launch_prep(bt_ctx* ctx, cudaStream_t stream);
+
+// Staging order (what makes the fused call fast): everything the frame preparation needs (window descriptors, frame
+// pointers, poses, pair tables - ~100 KB) is built and uploaded first and, in the fused call, k_prep_frames is launched
+// right there; only then are the correspondences (the bulk: 32 B each) copied into pinned memory and uploaded in
+// chunks on a private copy stream, overlapping the kernel.  k_solve waits on the last chunk's event.
+static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, const bt_solver_params* params,
+                      const float* poses_in, void* stream_, bool early_prep) {
 	BT_REQUIRE(ctx && windows && params && poses_in, BT_ERR_INVALID_ARG, "bt_solve_stage: NULL argument");
 	BT_REQUIRE(ctx->solver, BT_ERR_INVALID_ARG, "bt_solve_stage: call bt_solver_reserve first");
 	SolverState* s = ctx->solver;
@@ -1104,9 +1195,10 @@ extern "C" int bt_solve_stage(bt_ctx* ctx, int n_windows, const bt_window* windo
 	BT_REQUIRE(n_windows > 0 && n_windows <= s->lim.max_windows, BT_ERR_CAPACITY, "bt_solve_stage: %d windows > reserved %d", n_windows, s->lim.max_windows);
 	BT_REQUIRE(params->num_iter_outer > 0 && params->num_iter_inner > 0 && params->image_downscale == s->lim.image_downscale, BT_ERR_INVALID_ARG,
 	           "bt_solve_stage: iteration counts must be positive and image_downscale must equal the reserved value");
-	s->staged = false;
+	s->staged = false; s->prep_launched = false;
+	if (s->ev_h2d) BT_CUDA(cudaEventSynchronize(s->ev_h2d));     // the previous upload still reads the pinned block
 	// ---- sizes
-	size_t F = 0, C = 0, G = 0, P = 0;
+	size_t F = 0, C = 0;
 	for (int w = 0; w < n_windows; w++) {
 		const bt_window& bw = windows[w];
 		BT_REQUIRE(bw.n_frames >= 2 && bw.n_frames <= s->lim.max_frames, BT_ERR_CAPACITY, "window %d: n_frames %d outside [2,%d]", w, bw.n_frames, s->lim.max_frames);
@@ -1119,13 +1211,11 @@ extern "C" int bt_solve_stage(bt_ctx* ctx, int n_windows, const bt_window* windo
 	}
 	// ---- host staging: one pinned block, one H2D per array
 	const size_t maxP = (size_t)s->max_pairs, maxG = (size_t)s->max_groups;
-	size_t off = 0;
-	auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-	const size_t o_wins = carve(sizeof(WinDesc) * n_windows), o_dp = carve(sizeof(void*) * F), o_np = carve(sizeof(void*) * F), o_fw = carve(sizeof(int) * F),
-	             o_pose = carve(sizeof(float) * 16 * F), o_corr = carve(sizeof(bt_entryj) * C + 32), o_gi = carve(sizeof(int) * maxG * n_windows),
-	             o_gj = carve(sizeof(int) * maxG * n_windows), o_gs = carve(sizeof(int) * (maxG + 1) * n_windows), o_pairs = carve(sizeof(uint2) * maxP * n_windows),
-	             o_pwin = carve(sizeof(int) * maxP * n_windows), o_psrc = carve(sizeof(int) * maxP * n_windows), o_mem = carve(sizeof(int) * (2 * ((size_t)s->lim.max_frames + 1) + 2 * maxG + 2 * maxP) * n_windows);
-	int rc = s->h_stage.alloc(off);
+	const StageLayout L = stage_layout(n_windows, F, C, s->lim.max_frames, maxG, maxP);
+	BT_REQUIRE(L.total <= s->stage_dev.bytes, BT_ERR_CAPACITY, "bt_solve_stage: staging block %zu > reserved %zu bytes", L.total, s->stage_dev.bytes);
+	const size_t o_wins = L.wins, o_dp = L.dp, o_np = L.np, o_fw = L.fw, o_pose = L.pose, o_corr = L.corr, o_gi = L.gi, o_gj = L.gj, o_gs = L.gs, o_pairs = L.pairs,
+	             o_pwin = L.pwin, o_psrc = L.psrc, o_mem = L.mem;
+	int rc = s->h_stage.alloc(L.total);
 	if (rc != BT_OK) return rc;
 	char* hb = s->h_stage.as<char>();
 	WinDesc* hw = (WinDesc*)(hb + o_wins);
@@ -1136,7 +1226,9 @@ extern "C" int bt_solve_stage(bt_ctx* ctx, int n_windows, const bt_window* windo
 	size_t m_off = 0;
 	s->frame_off.assign(n_windows, 0); s->n_frames.assign(n_windows, 0);
 	size_t f_off = 0, c_off = 0, g_off = 0, p_off = 0, smem_need = 0;
-	std::vector<int> bin, order;
+	struct CorrJob { const bt_entryj* src; int n_in; size_t dst; int N; std::vector<int> bin; };   // bin non-empty => stable counting sort
+	std::vector<CorrJob> jobs;
+	jobs.reserve(n_windows);
 	for (int w = 0; w < n_windows; w++) {
 		const bt_window& bw = windows[w];
 		const int N = bw.n_frames;
@@ -1163,25 +1255,21 @@ extern "C" int bt_solve_stage(bt_ctx* ctx, int n_windows, const bt_window* windo
 		bool grouped = true;    // fast path: keys (i*N+j) non-decreasing and no invalid entries => groups are runs, plain copy
 		{
 			long long prev = -1;
-			for (int c = 0; c < bw.n_corr && grouped; c++) {
+			for (int c = 0; c < bw.n_corr; c++) {
 				const bt_entryj& e = bw.corr[c];
 				if (e.imgIdx_i >= (uint32_t)N || e.imgIdx_j >= (uint32_t)N) { grouped = false; break; }
 				const long long key = (long long)e.imgIdx_i * N + e.imgIdx_j;
-				if (key < prev) grouped = false;
-				prev = key;
-			}
-		}
-		if (grouped) {
-			long long prev = -1;
-			for (int c = 0; c < bw.n_corr; c++) {
-				const bt_entryj& e = bw.corr[c];
-				const long long key = (long long)e.imgIdx_i * N + e.imgIdx_j;
+				if (key < prev) { grouped = false; break; }
 				if (key != prev) { hgi[g_off + ng] = (int)e.imgIdx_i; hgj[g_off + ng] = (int)e.imgIdx_j; hgs[g_off + w + ng] = c; ng++; prev = key; }
 			}
+		}
+		CorrJob job; job.src = bw.corr; job.n_in = bw.n_corr; job.dst = c_off; job.N = N;
+		if (grouped) {
 			n_valid = bw.n_corr;
 			hgs[g_off + w + ng] = n_valid;
-			if (n_valid) memcpy(hcorr + c_off, bw.corr, sizeof(bt_entryj) * (size_t)n_valid);
 		} else {
+			ng = 0;
+			std::vector<int>& bin = job.bin;
 			bin.assign((size_t)N * N + 1, 0);
 			for (int c = 0; c < bw.n_corr; c++) {
 				const bt_entryj& e = bw.corr[c];
@@ -1199,12 +1287,8 @@ extern "C" int bt_solve_stage(bt_ctx* ctx, int n_windows, const bt_window* windo
 				for (size_t b = 0; b < (size_t)N * N; b++) if (bin[b + 1] > bin[b]) hgs[g_off + w + gg++] = bin[b];
 				hgs[g_off + w + ng] = n_valid;
 			}
-			for (int c = 0; c < bw.n_corr; c++) {
-				const bt_entryj& e = bw.corr[c];
-				if (e.imgIdx_i == 0xFFFFFFFFu) continue;
-				hcorr[c_off + bin[(size_t)e.imgIdx_i * N + e.imgIdx_j]++] = e;
-			}
 		}
+		jobs.push_back(std::move(job));
 		d.n_corr = n_valid; d.n_groups = ng;
 		// dense pairs
 		int np = 0;
@@ -1265,18 +1349,43 @@ extern "C" int bt_solve_stage(bt_ctx* ctx, int n_windows, const bt_window* windo
 		c = std::max(256LL, std::min(2048LL, c));
 		s->chunk = (int)((c + 255) / 256 * 256);
 	}
-#define UP(buf, ptr, bytes) BT_CUDA(cudaMemcpyAsync(s->buf.p, ptr, bytes, cudaMemcpyHostToDevice, stream))
-	UP(wins, hw, sizeof(WinDesc) * n_windows);
-	UP(depth_ptr, hdp, sizeof(void*) * F); UP(normal_ptr, hnp, sizeof(void*) * F); UP(frame_win, hfw, sizeof(int) * F);
-	UP(pose_in, hpose, sizeof(float) * 16 * F);
-	if (c_off) UP(corr, hcorr, sizeof(bt_entryj) * c_off);
-	UP(grp_i, hgi, sizeof(int) * std::max<size_t>(g_off, 1)); UP(grp_j, hgj, sizeof(int) * std::max<size_t>(g_off, 1));
-	UP(grp_start, hgs, sizeof(int) * (g_off + n_windows));
-	if (p_off) UP(pairs, hpairs, sizeof(uint2) * p_off);
-	if (p_off) UP(pair_win, hpwin, sizeof(int) * p_off);
-	if (p_off) UP(pair_src, hpsrc, sizeof(int) * p_off);
-	UP(mem, hmem, sizeof(int) * m_off);
-#undef UP
+	(void)p_off; (void)g_off; (void)m_off;
+	s->layout = L;
+	if (!s->copy_stream) {
+		BT_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+		BT_CUDA(cudaEventCreateWithFlags(&s->ev_prev, cudaEventDisableTiming));
+		BT_CUDA(cudaEventCreateWithFlags(&s->ev_corr, cudaEventDisableTiming));
+		BT_CUDA(cudaEventCreateWithFlags(&s->ev_h2d, cudaEventDisableTiming));
+	}
+	// (1) tables, in stream order behind whatever the caller's stream still runs on the previous batch
+	BT_CUDA(cudaMemcpyAsync(s->stage_dev.p, hb, o_corr, cudaMemcpyHostToDevice, stream));
+	BT_CUDA(cudaEventRecord(s->ev_prev, stream));
+	BT_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_prev, 0));
+	if (early_prep) { if ((rc = launch_prep(ctx, stream)) != BT_OK) return rc; }
+	// (2) correspondences: pinned copy (or stable counting sort) per window, uploaded in chunks of >= 256 KB on the copy stream
+	{
+		size_t sent = 0;      // entries already handed to the copy engine
+		for (size_t j = 0; j < jobs.size(); j++) {
+			CorrJob& jb = jobs[j];
+			if (jb.bin.empty()) {
+				if (jb.n_in) memcpy(hcorr + jb.dst, jb.src, sizeof(bt_entryj) * (size_t)jb.n_in);
+			} else {
+				for (int c = 0; c < jb.n_in; c++) {
+					const bt_entryj& e = jb.src[c];
+					if (e.imgIdx_i == 0xFFFFFFFFu) continue;
+					hcorr[jb.dst + jb.bin[(size_t)e.imgIdx_i * jb.N + e.imgIdx_j]++] = e;
+				}
+			}
+			const size_t done = (j + 1 < jobs.size()) ? jobs[j + 1].dst : c_off;
+			if ((done - sent) * sizeof(bt_entryj) >= 256 * 1024 || (j + 1 == jobs.size() && done > sent)) {
+				BT_CUDA(cudaMemcpyAsync(s->stage_dev.as<char>() + o_corr + sent * sizeof(bt_entryj), hcorr + sent, (done - sent) * sizeof(bt_entryj), cudaMemcpyHostToDevice, s->copy_stream));
+				sent = done;
+			}
+		}
+	}
+	BT_CUDA(cudaEventRecord(s->ev_corr, s->copy_stream));
+	BT_CUDA(cudaEventRecord(s->ev_h2d, s->copy_stream));
+	BT_CUDA(cudaStreamWaitEvent(stream, s->ev_corr, 0));     // everything later on the caller's stream sees the correspondences
 	if (s->debug) {
 		const int st = 6 * s->lim.max_frames;
 		if ((rc = s->dbgJ.alloc(sizeof(float) * (size_t)st * st * s->lim.max_windows)) != BT_OK) return rc;
@@ -1287,17 +1396,24 @@ extern "C" int bt_solve_stage(bt_ctx* ctx, int n_windows, const bt_window* windo
 	return BT_OK;
 }
 
+extern "C" int bt_solve_stage(bt_ctx* ctx, int n_windows, const bt_window* windows, const bt_solver_params* params,
+                              const float* poses_in, void* stream_) {
+	return stage_impl(ctx, n_windows, windows, params, poses_in, stream_, false);
+}
+
 static SolveArgs make_args(bt_ctx* ctx) {
 	SolverState* s = ctx->solver;
 	SolveArgs a;
 	memset(&a, 0, sizeof a);
-	a.wins = s->wins.as<WinDesc>(); a.n_windows = s->n_windows;
-	a.depth_ptr = s->depth_ptr.as<const float*>(); a.normal_ptr = s->normal_ptr.as<const float4*>(); a.frame_win = s->frame_win.as<int>();
+	char* sd = s->stage_dev.as<char>();
+	const StageLayout& L = s->layout;
+	a.wins = (WinDesc*)(sd + L.wins); a.n_windows = s->n_windows;
+	a.depth_ptr = (const float**)(sd + L.dp); a.normal_ptr = (const float4**)(sd + L.np); a.frame_win = (int*)(sd + L.fw);
 	a.texel = s->texel.as<float4>(); a.src = s->src.as<float4>(); a.nsrc = s->nsrc.as<int>();
-	a.pose_in = s->pose_in.as<float>(); a.x = s->x.as<float>(); a.T = s->T.as<float>(); a.pose_out = s->pose_out.as<float>();
+	a.pose_in = (float*)(sd + L.pose); a.x = s->x.as<float>(); a.T = s->T.as<float>(); a.pose_out = s->pose_out.as<float>();
 	a.npix_max = s->npix_max;
-	a.corr = s->corr.as<bt_entryj>(); a.grp_i = s->grp_i.as<int>(); a.grp_j = s->grp_j.as<int>(); a.grp_start = s->grp_start.as<int>();
-	a.pairs = s->pairs.as<uint2>(); a.pair_win = s->pair_win.as<int>(); a.pair_src_slot = s->pair_src.as<int>(); a.mem = s->mem.as<int>();
+	a.corr = (bt_entryj*)(sd + L.corr); a.grp_i = (int*)(sd + L.gi); a.grp_j = (int*)(sd + L.gj); a.grp_start = (int*)(sd + L.gs);
+	a.pairs = (uint2*)(sd + L.pairs); a.pair_win = (int*)(sd + L.pwin); a.pair_src_slot = (int*)(sd + L.psrc); a.mem = (int*)(sd + L.mem);
 	a.tiles = s->tiles.as<Tile>(); a.max_tiles = s->max_tiles; a.partial = s->partial.as<float>();
 	a.pair_tile0 = s->pair_tile0.as<int>(); a.pair_ntile = s->pair_ntile.as<int>();
 	a.n_tiles_total = s->scalars.as<int>(); a.queue = s->scalars.as<int>() + 1; a.n_src_px = (long long*)(s->scalars.as<char>() + 16);
@@ -1306,6 +1422,17 @@ static SolveArgs make_args(bt_ctx* ctx) {
 	if (s->prof_cap > 0) { a.prof = s->prof.as<long long>(); a.prof_cap = s->prof_cap; }
 	if (s->debug) { a.dbg_JtJ = s->dbgJ.as<float>(); a.dbg_Jtr = s->dbgR.as<float>(); a.dbg_stride = 6 * s->lim.max_frames; a.dbg_cnt = s->dbgC.as<float>(); a.dbg_cnt_stride = s->max_pairs; }
 	return a;
+}
+
+static int launch_prep(bt_ctx* ctx, cudaStream_t stream) {
+	SolverState* s = ctx->solver;
+	SolveArgs a = make_args(ctx);
+	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[0], stream));
+	k_prep_frames<<<s->frames_total, 1024, 0, stream>>>(a, const_cast<WinDesc*>(a.wins), s->scalars.as<int>() + 8);
+	BT_CUDA(cudaGetLastError());
+	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[1], stream));
+	s->prep_launched = true;
+	return BT_OK;
 }
 
 extern "C" int bt_solve_run(bt_ctx* ctx, void* stream_) {
@@ -1319,25 +1446,24 @@ extern "C" int bt_solve_run(bt_ctx* ctx, void* stream_) {
 		BT_CUDA(cudaMemsetAsync(s->dbgR.p, 0, s->dbgR.bytes, stream));
 	}
 	if (s->prof_cap > 0) BT_CUDA(cudaMemsetAsync(s->prof.p, 0, 8, stream));
-	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[0], stream));
-	k_prep_frames<<<s->frames_total, 1024, 0, stream>>>(a);
-	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[1], stream));
-	k_plan<<<1, 1024, 0, stream>>>(a, s->wins.as<WinDesc>());
+	if (!s->prep_launched) { int rcp = launch_prep(ctx, stream); if (rcp != BT_OK) return rcp; }
+	s->prep_launched = false;       // a second bt_solve_run on the same staged batch prepares again (poses restart from the staged input)
 	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[2], stream));
-	static bool attr_set = false;
-	static int attr_bytes = 0;
-	if (!attr_set || attr_bytes < s->smem_bytes) {
-		BT_CUDA(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(s->smem_bytes, 48 * 1024)));
-		attr_set = true; attr_bytes = std::max(s->smem_bytes, 48 * 1024);
+	if (s->attr_bytes < s->smem_bytes || s->attr_bytes == 0) {      // per context (= per device), not per process
+		s->attr_bytes = std::max(s->smem_bytes, 48 * 1024);
+		BT_CUDA(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, s->attr_bytes));
 	}
-	int occ = 1;
-	BT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve, kThreads, s->smem_bytes));
-	if (occ < 1) occ = 1;
+	if (s->occ_smem != s->smem_bytes) {
+		int occ_q = 1;
+		BT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_q, k_solve, kThreads, s->smem_bytes));
+		s->occ = std::max(occ_q, 1); s->occ_smem = s->smem_bytes;
+	}
+	const int occ = s->occ;
 	const int grid = ctx->sm_count * occ;
 	k_solve<<<grid, kThreads, s->smem_bytes, stream>>>(a);
 	BT_CUDA(cudaGetLastError());
 	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[3], stream));
-	s->launches = 3;
+	s->launches = 2;
 	return BT_OK;
 }
 
@@ -1359,7 +1485,7 @@ extern "C" int bt_solve_fetch(bt_ctx* ctx, float* poses_out, void* stream_) {
 
 extern "C" int bt_solve_windows(bt_ctx* ctx, int n_windows, const bt_window* windows, const bt_solver_params* params,
                                 float* poses_inout, void* stream) {
-	int rc = bt_solve_stage(ctx, n_windows, windows, params, poses_inout, stream);
+	int rc = stage_impl(ctx, n_windows, windows, params, poses_inout, stream, true);
 	if (rc != BT_OK) return rc;
 	rc = bt_solve_run(ctx, stream);
 	if (rc != BT_OK) return rc;

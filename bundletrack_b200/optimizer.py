@@ -41,6 +41,38 @@ class SolveWindow:
         self.compat_flip = bool(compat_flip)
         self._keep = (depths_gpu, normals_gpu)
 
+    _MARSHALLED = frozenset(("corr", "H", "W", "depths", "normals", "poses", "K", "dense_pairs", "compat_flip"))
+
+    def __setattr__(self, name, value):
+        if name in SolveWindow._MARSHALLED:
+            self.__dict__.pop("_cwin", None)        # the cached bt_window is rebuilt on the next call
+        object.__setattr__(self, name, value)
+
+    def c_window(self) -> "_lib.Window":
+        """The bt_window of this object (built once: per-call ctypes field stores cost more than the GPU work)."""
+        cw = self.__dict__.get("_cwin")
+        if cw is None:
+            N = self.n_frames
+            dp = (ctypes.c_void_p * N)(*self.depths)
+            nq = (ctypes.c_void_p * N)(*self.normals)
+            cw = _lib.Window()
+            cw.n_frames, cw.H, cw.W, cw.n_corr = N, self.H, self.W, len(self.corr)
+            cw.corr = self.corr.ctypes.data if len(self.corr) else None
+            cw.depth_dev = ctypes.cast(dp, ctypes.POINTER(ctypes.c_void_p))
+            cw.normal_dev = ctypes.cast(nq, ctypes.POINTER(ctypes.c_void_p))
+            cw.fx, cw.fy, cw.cx, cw.cy = self.K
+            zero = None
+            if self.dense_pairs is not None:
+                zero = ctypes.c_uint32(0)
+                cw.dense_pairs = self.dense_pairs.ctypes.data if len(self.dense_pairs) else ctypes.addressof(zero)
+                cw.n_dense_pairs = len(self.dense_pairs)
+            else:
+                cw.dense_pairs, cw.n_dense_pairs = None, 0
+            cw.compat_flip = 1 if self.compat_flip else 0
+            self.__dict__["_cwin"] = cw
+            self.__dict__["_cwin_keep"] = (dp, nq, zero, self.corr, self.dense_pairs)
+        return cw
+
     @property
     def n_frames(self) -> int:
         return self.poses.shape[0]
@@ -84,25 +116,12 @@ class OptimizerGpu:
     def _marshal(self, windows: List[SolveWindow]):
         n = len(windows)
         arr = (_lib.Window * n)()
-        keep = []
+        sz = ctypes.sizeof(_lib.Window)
+        base = ctypes.addressof(arr)
         for i, w in enumerate(windows):
-            N = w.n_frames
-            dp = (ctypes.c_void_p * N)(*w.depths)
-            nq = (ctypes.c_void_p * N)(*w.normals)
-            keep += [dp, nq]
-            arr[i].n_frames, arr[i].H, arr[i].W, arr[i].n_corr = N, w.H, w.W, len(w.corr)
-            arr[i].corr = w.corr.ctypes.data if len(w.corr) else None
-            arr[i].depth_dev = ctypes.cast(dp, ctypes.POINTER(ctypes.c_void_p))
-            arr[i].normal_dev = ctypes.cast(nq, ctypes.POINTER(ctypes.c_void_p))
-            arr[i].fx, arr[i].fy, arr[i].cx, arr[i].cy = w.K
-            if w.dense_pairs is not None:
-                arr[i].dense_pairs = w.dense_pairs.ctypes.data if len(w.dense_pairs) else ctypes.addressof(ctypes.c_uint32(0))
-                arr[i].n_dense_pairs = len(w.dense_pairs)
-            else:
-                arr[i].dense_pairs, arr[i].n_dense_pairs = None, 0
-            arr[i].compat_flip = 1 if w.compat_flip else 0
-        poses = np.ascontiguousarray(np.concatenate([w.poses.reshape(-1, 16) for w in windows], 0), np.float32)
-        return arr, poses, keep
+            ctypes.memmove(base + i * sz, ctypes.addressof(w.c_window()), sz)
+        poses = np.concatenate([w.poses.reshape(-1, 16) for w in windows], 0)
+        return arr, poses, windows
 
     def optimizeWindows(self, windows: List[SolveWindow]) -> List[np.ndarray]:
         arr, poses, keep = self._marshal(windows)

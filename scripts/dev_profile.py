@@ -25,12 +25,20 @@ for nw in nwin:
     rec = opt.get_profile()
     kind = rec[:, 0] >> 32
     tiles, tails = rec[kind == 0], rec[kind == 1]
-    d = np.diff(tiles[:, 2:8], axis=1)
-    names = ["wait", "Msetup", "pixels", "reduce+store", "ticket"]
-    print(f" tiles: n={len(tiles)} mean px/tile {np.mean(tiles[:,1] & 0xffff):.0f}; cycles mean/p50/p95 per phase:")
-    for i, nm in enumerate(names):
-        print(f"   {nm:14s} {d[:, i].mean():9.0f} {np.percentile(d[:, i], 50):9.0f} {np.percentile(d[:, i], 95):9.0f}")
-    print(f"   total          {(tiles[:,7]-tiles[:,2]).mean():9.0f}")
+    if len(tiles):
+        d = np.diff(tiles[:, 2:8], axis=1)
+        names = ["wait", "Msetup", "pixels", "reduce+store", "ticket"]
+        print(f" tiles: n={len(tiles)} mean px/tile {np.mean(tiles[:,1] & 0xffff):.0f}; cycles mean/p50/p95 per phase:")
+        for i, nm in enumerate(names):
+            print(f"   {nm:14s} {d[:, i].mean():9.0f} {np.percentile(d[:, i], 50):9.0f} {np.percentile(d[:, i], 95):9.0f}")
+        print(f"   total          {(tiles[:,7]-tiles[:,2]).mean():9.0f}")
+    ws = rec[kind == 2]
+    if len(ws):
+        px = ws[:, 1] >> 32
+        print(f" ws tiles: n={len(ws)} mean px {px.mean():.0f} ready-frac {np.mean(ws[:,1] & 1):.3f}")
+        for nm, v in (("pixels", ws[:, 3] - ws[:, 2]), ("phaseA total", ws[:, 4] - ws[:, 2]), ("h reduce", ws[:, 6] - ws[:, 5]), ("h claim", ws[:, 7] - ws[:, 6]),
+                      ("h dep+setup", ws[:, 8] - ws[:, 7]), ("h total", ws[:, 8] - ws[:, 5])):
+            print(f"   {nm:14s} {v.mean():9.0f} {np.percentile(v, 50):9.0f} {np.percentile(v, 95):9.0f}")
     d = np.diff(tails[:, 2:11], axis=1)
     names = ["P0 zero/T", "P1 sparse", "P2a pairsum", "P2b xform", "P3 diag/rhs", "P4 cross", "PCG", "update"]
     print(f" tails: n={len(tails)}")

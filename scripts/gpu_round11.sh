@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 300 python scripts/dev_profile.py 1,32 > gpurun_out/prof_main.log 2>&1
+for v in ws wsni; do
+  BT_B200_LIB=$PWD/bundletrack_b200/lib/variants/libbt_$v.so timeout 300 python scripts/dev_profile.py 1,32 > gpurun_out/prof_$v.log 2>&1
+done
+timeout 600 python bench.py --steps 100 --warmup 3 > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err; echo "rc=$?" >> gpurun_out/bench_ours.err

@@ -46,6 +46,16 @@ def test_matches_oracle_a(opt, cuda_device, seed, N, C):
     assert np.allclose(out[:, 3], [0, 0, 0, 1])
 
 
+def test_cfg3_occluded_pool_window(opt, cuda_device):
+    """BASELINE config 2: window of max_BA_frames=15 keyframes out of a 30-KF pool, 3000 correspondences, YCBInEOAT-style
+    occlusion (a half-plane of every silhouette zeroed)."""
+    w = synth.make_window(62, n_frames=15, n_corr=3000, occlusion=True)
+    out = _solve(opt, w, cuda_device)
+    ref = oracle.solve_window(w.depth, w.normal, w.K, w.corr, w.poses_init)
+    r, t = synth.pose_errors(out, ref)
+    assert r <= TOL and t <= TOL, (r, t)
+
+
 def test_gate_sensitive_window(opt, cuda_device):
     """seed 9 / N=15 is a window where the reference's hard gates (dense distance / normal thresholds) amplify
     rounding-level differences: the reference's own kernels and the IEEE restatement of them differ by 1.5e-4 rad there
