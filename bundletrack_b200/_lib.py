@@ -48,6 +48,18 @@ class Window(ctypes.Structure):
         ("dense_pairs", ctypes.c_void_p),
         ("n_dense_pairs", ctypes.c_int),
         ("compat_flip", ctypes.c_int),
+        ("cache_slots", ctypes.c_void_p),
+    ]
+
+
+class DepthParams(ctypes.Structure):
+    _fields_ = [
+        ("erode_radius", ctypes.c_int),
+        ("erode_diff", ctypes.c_float),
+        ("erode_ratio", ctypes.c_float),
+        ("bf_radius", ctypes.c_int),
+        ("sigma_D", ctypes.c_float),
+        ("sigma_R", ctypes.c_float),
     ]
 
 
@@ -107,7 +119,8 @@ EXPORTS = [
     "bt_solve_windows", "bt_solve_stage", "bt_solve_run", "bt_solve_fetch", "bt_solve_get_stats",
     "bt_solve_enable_debug", "bt_solve_debug_dense", "bt_solve_debug_counts", "bt_solve_enable_timing", "bt_solve_get_timing", "bt_solve_enable_profile", "bt_solve_get_profile",
     "bt_matcher_reserve", "bt_knn_match_pairs", "bt_knn_enable_timing", "bt_knn_get_timing", "bt_ransac_reserve", "bt_ransac_pairs", "bt_ransac_debug",
-    "bt_pipeline_reserve", "bt_prune_mutual_pairs", "bt_match_pairs",
+    "bt_pipeline_reserve", "bt_prune_mutual_pairs", "bt_match_pairs", "bt_frames_preprocess",
+    "bt_frame_cache_reserve", "bt_frame_cache_store",
     "bt_dev_alloc", "bt_dev_free", "bt_memcpy_h2d", "bt_memcpy_d2h", "bt_host_alloc_pinned", "bt_host_free_pinned",
     "bt_stream_sync",
 ]

@@ -29,6 +29,8 @@ NOCS_DEFAULTS = {
                "max_trans_neighbor": 0.2, "max_rot_deg_neighbor": 25, "max_trans_no_neighbor": 0.02,
                "max_rot_no_neighbor": 10},
     "p2p": {"max_dist": 0.02, "max_normal_angle": 45},
+    "depth_processing": {"erode": {"radius": 1, "diff": 0.001, "ratio": 0.8},
+                         "bilateral_filter": {"radius": 2, "sigma_D": 2, "sigma_R": 100000}},
 }
 
 
@@ -52,3 +54,12 @@ def solver_params(yml: Union[None, str, Mapping[str, Any]] = None) -> SolverPara
         0.1, 9999.0,   # denseDepthMin / denseDepthMax, hard-wired (CUDASolverBundling.cpp:97-98)
         1.0, 1.0,      # m_localWeightsSparse / m_localWeightsDenseDepth (SBA.cpp:28-30)
     )
+
+
+def depth_params(yml: Union[None, str, Mapping[str, Any]] = None):
+    """config "depth_processing" -> bt_depth_params (read where Frame::processDepth reads it, Frame.cpp:160-165)."""
+    from ._lib import DepthParams
+    y = load_yml(yml)
+    dp = y.get("depth_processing", NOCS_DEFAULTS["depth_processing"])
+    e, b = dp["erode"], dp["bilateral_filter"]
+    return DepthParams(int(e["radius"]), float(e["diff"]), float(e["ratio"]), int(b["radius"]), float(b["sigma_D"]), float(b["sigma_R"]))

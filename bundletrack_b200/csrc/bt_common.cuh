@@ -59,6 +59,7 @@ struct PinnedBuf {
 struct SolverState;   // solver.cu
 struct MatcherState;  // knn.cu
 struct RansacState;   // ransac.cu
+struct FrontState;    // frontend.cu
 
 }  // namespace bt
 
@@ -69,6 +70,7 @@ struct bt_ctx {
 	bt::SolverState* solver = nullptr;
 	bt::MatcherState* matcher = nullptr;
 	bt::RansacState* ransac = nullptr;
+	bt::FrontState* front = nullptr;
 };
 
 namespace bt {
@@ -76,4 +78,5 @@ void solver_destroy(bt_ctx* ctx);
 void matcher_destroy(bt_ctx* ctx);
 void ransac_destroy(bt_ctx* ctx);
 void prune_destroy(bt_ctx* ctx);
+void front_destroy(bt_ctx* ctx);
 }

@@ -70,9 +70,12 @@ struct SolveArgs {
 	const float* const* depth_ptr;
 	const float4* const* normal_ptr;
 	const int* frame_win;
-	float4* texel;        // [F][2*npix_max]
+	float4* texel;        // [F][2*npix_max]  the context's own maps (frames prepared by this call)
 	float4* src;          // [F][2*npix_max]
 	int* nsrc;            // [F]
+	const float4* const* texel_tab;   // [F] where each frame slot's texel map / source list lives: the arrays above, or a
+	const float4* const* src_tab;     //     frame-cache slot built earlier by bt_frame_cache_store
+	const int* const* nsrc_cached;    // [F] cached frame: address of its source count, else nullptr
 	const float* pose_in; // [F][16]
 	float* x;             // [F][6]  rot, trans
 	float* T;             // [F][12] row-major 3x4 cam->model
@@ -226,27 +229,21 @@ __device__ void plan_body(const SolveArgs& a, WinDesc* wins_rw);
 // source records at their final position.  No barrier inside either sweep, so the loads of consecutive rounds overlap.
 static constexpr int kPrepRounds = 64;      // rounds of 1024 pixels per scan (one scan covers 65536 quarter-res pixels)
 
-__global__ void __launch_bounds__(1024) k_prep_frames(SolveArgs a, WinDesc* wins_rw, int* prep_ticket) {
-	const int fs = blockIdx.x;
-	const WinDesc wd = a.wins[a.frame_win[fs]];
-	const int npix = wd.w * wd.h;
-	const float* __restrict__ depth = a.depth_ptr[fs];
-	const float4* __restrict__ normal = a.normal_ptr[fs];
-	float4* texel = a.texel + (size_t)fs * 2 * a.npix_max;
-	float4* src = a.src + (size_t)fs * 2 * a.npix_max;
-	__shared__ int s_cnt[kPrepRounds * 32];
-	__shared__ int s_wt[32];
+struct FrameGeom { int W, H, w, h; float ifx, ify, icx, icy, scaleW, scaleH; };
+
+// Builds one frame's quarter-resolution texel map and compacted source list (1024 threads); returns the source count.
+__device__ int build_frame_maps(const FrameGeom& g, const float* __restrict__ depth, const float4* __restrict__ normal, float4* texel, float4* src,
+                                float dmin, float dmax, int* s_cnt, int* s_wt) {
+	const int npix = g.w * g.h;
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-	const bool use_dense = a.prm.w_dense > 0.0f;
-	const float dmin = a.prm.depth_min, dmax = a.prm.depth_max;
 	// nearest-neighbour sample position of quarter-res pixel idx in the full-res maps, or -1 (resampleFloat4, CUDAImageUtil.cu:82-99)
 	auto sample = [&](int idx, unsigned& xi, unsigned& yi) -> bool {
-		const int x = idx % wd.w, y = idx / wd.w;
-		xi = (unsigned)((float)x * wd.scaleW + 0.5f); yi = (unsigned)((float)y * wd.scaleH + 0.5f);
-		return xi < (unsigned)wd.W && yi < (unsigned)wd.H;
+		const int x = idx % g.w, y = idx / g.w;
+		xi = (unsigned)((float)x * g.scaleW + 0.5f); yi = (unsigned)((float)y * g.scaleH + 0.5f);
+		return xi < (unsigned)g.W && yi < (unsigned)g.H;
 	};
 	int base = 0;
-	for (int sb = 0; use_dense && sb < npix; sb += kPrepRounds * 1024) {
+	for (int sb = 0; sb < npix; sb += kPrepRounds * 1024) {
 		const int rounds = min(kPrepRounds, (npix - sb + 1023) >> 10);
 		// ---- sweep 1: valid counts per (round, warp)
 #pragma unroll 4
@@ -256,7 +253,7 @@ __global__ void __launch_bounds__(1024) k_prep_frames(SolveArgs a, WinDesc* wins
 			if (idx < npix) {       // must agree bit for bit with sweep 2: z = 0 for a missing / too-near sample
 				unsigned xi, yi;
 				float z = 0.f;
-				if (sample(idx, xi, yi)) { const float d = __ldg(depth + (size_t)yi * wd.W + xi); if (d >= 0.1f) z = d; }
+				if (sample(idx, xi, yi)) { const float d = __ldg(depth + (size_t)yi * g.W + xi); if (d >= 0.1f) z = d; }
 				valid = (z > dmin && z < dmax);
 			}
 			const unsigned bal = __ballot_sync(0xffffffffu, valid);
@@ -292,10 +289,10 @@ __global__ void __launch_bounds__(1024) k_prep_frames(SolveArgs a, WinDesc* wins
 			if (idx < npix) {
 				unsigned xi, yi;
 				if (sample(idx, xi, yi)) {
-					const size_t sidx = (size_t)yi * wd.W + xi;
+					const size_t sidx = (size_t)yi * g.W + xi;
 					const float d = __ldg(depth + sidx);
 					nr = __ldg(normal + sidx);
-					if (d >= 0.1f) cp = make_float4(wd.ifx * ((float)xi * d) + wd.icx * d, wd.ify * ((float)yi * d) + wd.icy * d, d, 1.0f);
+					if (d >= 0.1f) cp = make_float4(g.ifx * ((float)xi * d) + g.icx * d, g.ify * ((float)yi * d) + g.icy * d, d, 1.0f);
 				}
 				texel[2 * idx] = make_float4(cp.x, cp.y, cp.z, nr.x);      // 32-byte texel: point xyz + normal xyz (+ pad)
 				texel[2 * idx + 1] = make_float4(nr.y, nr.z, 0.f, 0.f);
@@ -309,6 +306,23 @@ __global__ void __launch_bounds__(1024) k_prep_frames(SolveArgs a, WinDesc* wins
 			}
 		}
 		__syncthreads();
+	}
+	return base;
+}
+
+__global__ void __launch_bounds__(1024, 2) k_prep_frames(SolveArgs a, WinDesc* wins_rw, int* prep_ticket) {
+	const int fs = blockIdx.x;
+	const WinDesc wd = a.wins[a.frame_win[fs]];
+	__shared__ int s_cnt[kPrepRounds * 32];
+	__shared__ int s_wt[32];
+	const int tid = threadIdx.x;
+	int base = 0;
+	const int* cached = a.nsrc_cached[fs];
+	if (cached) base = *cached;                      // maps and source list were built by bt_frame_cache_store
+	else if (a.prm.w_dense > 0.0f) {
+		FrameGeom g; g.W = wd.W; g.H = wd.H; g.w = wd.w; g.h = wd.h; g.ifx = wd.ifx; g.ify = wd.ify; g.icx = wd.icx; g.icy = wd.icy; g.scaleW = wd.scaleW; g.scaleH = wd.scaleH;
+		base = build_frame_maps(g, a.depth_ptr[fs], a.normal_ptr[fs], a.texel + (size_t)fs * 2 * a.npix_max, a.src + (size_t)fs * 2 * a.npix_max,
+		                        a.prm.depth_min, a.prm.depth_max, s_cnt, s_wt);
 	}
 	if (tid == 0) a.nsrc[fs] = base;
 	if (tid == 1023) {      // pose -> (rot, trans) -> T of iteration 0, off the critical path of the sweeps (last warp, one lane)
@@ -332,6 +346,22 @@ __global__ void __launch_bounds__(1024) k_prep_frames(SolveArgs a, WinDesc* wins
 	if (s_last) plan_body(a, wins_rw);
 }
 
+// bt_frame_cache_store: the same maps, built once per keyframe into a slot of the context's frame cache.
+struct CacheStoreArgs {
+	FrameGeom g;
+	const float* const* depth; const float4* const* normal; const int* slots;
+	float4* texel; float4* src; int* nsrc; size_t slot_stride;   // float4 per slot (2 * npix_max)
+	float dmin, dmax;
+};
+__global__ void __launch_bounds__(1024, 2) k_frame_cache_store(CacheStoreArgs c) {
+	__shared__ int s_cnt[kPrepRounds * 32];
+	__shared__ int s_wt[32];
+	const int slot = c.slots[blockIdx.x];
+	const int n = build_frame_maps(c.g, c.depth[blockIdx.x], c.normal[blockIdx.x], c.texel + (size_t)slot * c.slot_stride, c.src + (size_t)slot * c.slot_stride,
+	                               c.dmin, c.dmax, s_cnt, s_wt);
+	if (threadIdx.x == 0) c.nsrc[slot] = n;
+}
+
 // ------------------------------------------------------------------------------------------------ k_plan
 __device__ __forceinline__ int chunks_for(int n, int chunk, int& per) {
 	if (n <= 0) { per = 0; return 0; }
@@ -346,6 +376,9 @@ __device__ void plan_body(const SolveArgs& a, WinDesc* wins_rw) {
 	__shared__ int s_carry;
 	__shared__ unsigned long long s_px;
 	const int tid = threadIdx.x;
+	ProfRec prf; prf.kind_cta = (3ll << 32) | blockIdx.x; prf.tile_win = a.n_windows;
+	for (int i = 0; i < 10; i++) prf.t[i] = 0;
+	PROF_T(0);
 	if (tid == 0) { s_carry = 0; s_px = 0ull; *a.queue = 0; }
 	__syncthreads();
 	for (int base = 0; base < a.n_windows; base += 1024) {
@@ -366,8 +399,12 @@ __device__ void plan_body(const SolveArgs& a, WinDesc* wins_rw) {
 			atomicAdd(&s_cnt[lo - base], nch);
 			px += (unsigned long long)n;
 		}
-		if (px) atomicAdd(&s_px, px);
+		// one 64-bit shared atomic per warp: 1024 threads hammering one 64-bit shared word (a CAS loop in hardware) cost 30 us here
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) px += __shfl_xor_sync(0xffffffffu, px, o);
+		if ((tid & 31) == 0 && px) atomicAdd(&s_px, px);
 		__syncthreads();
+		PROF_T(1);
 		// (2) exclusive scan of the per-window tile counts (a window without dense work still gets one dummy tile)
 		int cnt = 0;
 		if (tid < nw) { cnt = s_cnt[tid]; if (cnt == 0) cnt = 1; a.tiles_done[base + tid] = 0; a.iter_done[base + tid] = 0; }
@@ -388,6 +425,7 @@ __device__ void plan_body(const SolveArgs& a, WinDesc* wins_rw) {
 			s_scan[tid] = incl + ((tid >> 5) ? s_wtot[(tid >> 5) - 1] : 0);
 			__syncthreads();
 		}
+		PROF_T(2);
 		const int excl = s_scan[tid] - cnt + s_carry;
 		const bool fits = (s_carry + s_scan[1023] <= a.max_tiles);
 		// (3) per-window prefix over its pairs: one warp per window, lanes over pairs
@@ -413,6 +451,7 @@ __device__ void plan_body(const SolveArgs& a, WinDesc* wins_rw) {
 			if (lane == 0 && carry == 0 && fits) { Tile tl; tl.win = w; tl.pair = -1; tl.start = 0; tl.count = 0; a.tiles[s_cnt[wl]] = tl; }
 		}
 		__syncthreads();
+		PROF_T(3);
 		// (4) tile records, one (window, pair) per thread
 		if (fits) {
 			for (int q = first_pair + tid; q < end_pair; q += 1024) {
@@ -426,6 +465,7 @@ __device__ void plan_body(const SolveArgs& a, WinDesc* wins_rw) {
 			}
 		}
 		__syncthreads();
+		PROF_T(4);
 		if (tid == 0) s_carry += s_scan[1023];
 		__syncthreads();
 	}
@@ -433,6 +473,8 @@ __device__ void plan_body(const SolveArgs& a, WinDesc* wins_rw) {
 		*a.n_tiles_total = (s_carry <= a.max_tiles) ? s_carry : -1;   // -1 => capacity error reported by the host
 		*a.n_src_px = (long long)s_px;
 	}
+	PROF_T(5);
+	if (a.prof && tid == 0) prof_emit(a, prf);
 }
 
 // ------------------------------------------------------------------------------------------------ tile (dense term)
@@ -975,8 +1017,8 @@ __global__ void __launch_bounds__(kThreads, BT_SOLVE_MIN_CTAS) k_solve(SolveArgs
 			}
 			__syncthreads();
 			PROF_T(2);
-			const float4* src = a.src + (size_t)(wd.frame_off + pr.y) * 2 * a.npix_max;
-			const float4* tex = a.texel + (size_t)(wd.frame_off + pr.x) * 2 * a.npix_max;
+			const float4* src = a.src_tab[wd.frame_off + pr.y];
+			const float4* tex = a.texel_tab[wd.frame_off + pr.x];
 			tile_pixels(a, wd, src, tex, s_M, tl.start, tl.count, acc);
 		}
 		PROF_T(3);
@@ -1058,7 +1100,7 @@ __global__ void __launch_bounds__(kThreads, BT_SOLVE_MIN_CTAS) k_solve(SolveArgs
 // single H2D copy: the small tables first (carved for the worst case of this window count), the correspondences last so
 // that the copy length follows the actual number of entries.
 struct StageLayout {
-	size_t wins, dp, np, fw, pose, gi, gj, gs, pairs, pwin, psrc, mem, corr, total;
+	size_t wins, dp, np, fw, texp, srcp, nsrcp, pose, gi, gj, gs, pairs, pwin, psrc, mem, corr, total;
 };
 static StageLayout stage_layout(int n_windows, size_t F, size_t C, int max_frames, size_t maxG, size_t maxP) {
 	StageLayout L;
@@ -1066,6 +1108,7 @@ static StageLayout stage_layout(int n_windows, size_t F, size_t C, int max_frame
 	auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
 	const size_t nw = (size_t)n_windows;
 	L.wins = carve(sizeof(WinDesc) * nw); L.dp = carve(sizeof(void*) * F); L.np = carve(sizeof(void*) * F); L.fw = carve(sizeof(int) * F);
+	L.texp = carve(sizeof(void*) * F); L.srcp = carve(sizeof(void*) * F); L.nsrcp = carve(sizeof(void*) * F);
 	L.pose = carve(sizeof(float) * 16 * F); L.gi = carve(sizeof(int) * maxG * nw); L.gj = carve(sizeof(int) * maxG * nw);
 	L.gs = carve(sizeof(int) * (maxG + 1) * nw); L.pairs = carve(sizeof(uint2) * maxP * nw); L.pwin = carve(sizeof(int) * maxP * nw);
 	L.psrc = carve(sizeof(int) * maxP * nw); L.mem = carve(sizeof(int) * (2 * ((size_t)max_frames + 1) + 2 * maxG + 2 * maxP) * nw);
@@ -1079,6 +1122,14 @@ struct SolverState {
 	int npix_max = 0, max_pairs = 0, max_frames_total = 0, max_tiles = 0, max_groups = 0;
 	DevBuf stage_dev, texel, src, nsrc, x, T, pose_out, tiles, scalars, partial, tiles_done, iter_done, pair_tile0, pair_ntile, dbgJ, dbgR, dbgC, prof;
 	StageLayout layout{};
+	// frame cache (bt_frame_cache_*): quarter-res maps of keyframes, built once, referenced by bt_window::cache_slots
+	struct CacheMeta { bool valid = false; int H = 0, W = 0; float fx = 0, fy = 0, cx = 0, cy = 0, dmin = 0, dmax = 0; };
+	DevBuf c_texel, c_src, c_nsrc, c_tables;
+	PinnedBuf c_htables;
+	cudaEvent_t c_ev = nullptr;
+	int c_capacity = 0, c_npix = 0;
+	float c_downscale = 0.f;
+	std::vector<CacheMeta> c_meta;
 	int prof_cap = 0;
 	PinnedBuf h_stage, h_poses;
 	// last staged batch
@@ -1098,10 +1149,11 @@ struct SolverState {
 void solver_destroy(bt_ctx* ctx) {
 	SolverState* s = ctx->solver;
 	if (!s) return;
-	DevBuf* bufs[] = { &s->stage_dev, &s->texel, &s->src, &s->nsrc, &s->x, &s->T, &s->pose_out, &s->tiles, &s->scalars, &s->partial,
+	DevBuf* bufs[] = { &s->c_texel, &s->c_src, &s->c_nsrc, &s->c_tables, &s->stage_dev, &s->texel, &s->src, &s->nsrc, &s->x, &s->T, &s->pose_out, &s->tiles, &s->scalars, &s->partial,
 	                   &s->tiles_done, &s->iter_done, &s->pair_tile0, &s->pair_ntile, &s->dbgJ, &s->dbgR, &s->dbgC, &s->prof };
 	for (DevBuf* b : bufs) b->release();
-	s->h_stage.release(); s->h_poses.release();
+	s->h_stage.release(); s->h_poses.release(); s->c_htables.release();
+	if (s->c_ev) cudaEventDestroy(s->c_ev);
 	for (auto& e : s->ev) if (e) cudaEventDestroy(e);
 	for (cudaEvent_t e : { s->ev_prev, s->ev_corr, s->ev_h2d }) if (e) cudaEventDestroy(e);
 	if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
@@ -1206,7 +1258,7 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 		BT_REQUIRE(bw.H > 0 && bw.W > 0 && bw.H <= s->lim.H && bw.W <= s->lim.W, BT_ERR_CAPACITY, "window %d: image %dx%d larger than reserved", w, bw.W, bw.H);
 		BT_REQUIRE((int)(bw.W / params->image_downscale) >= 2 && (int)(bw.H / params->image_downscale) >= 2, BT_ERR_INVALID_ARG, "window %d: image too small", w);
 		BT_REQUIRE(bw.n_corr == 0 || bw.corr, BT_ERR_INVALID_ARG, "window %d: corr is NULL", w);
-		BT_REQUIRE(params->w_dense <= 0.f || (bw.depth_dev && bw.normal_dev), BT_ERR_INVALID_ARG, "window %d: depth/normal pointers are NULL", w);
+		BT_REQUIRE(params->w_dense <= 0.f || bw.cache_slots || (bw.depth_dev && bw.normal_dev), BT_ERR_INVALID_ARG, "window %d: depth/normal pointers are NULL and no cache slots given", w);
 		F += bw.n_frames; C += bw.n_corr;
 	}
 	// ---- host staging: one pinned block, one H2D per array
@@ -1220,6 +1272,7 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 	char* hb = s->h_stage.as<char>();
 	WinDesc* hw = (WinDesc*)(hb + o_wins);
 	const void** hdp = (const void**)(hb + o_dp); const void** hnp = (const void**)(hb + o_np);
+	const void** htex = (const void**)(hb + L.texp); const void** hsrc = (const void**)(hb + L.srcp); const void** hnsrc = (const void**)(hb + L.nsrcp);
 	int* hfw = (int*)(hb + o_fw); float* hpose = (float*)(hb + o_pose); bt_entryj* hcorr = (bt_entryj*)(hb + o_corr);
 	int* hgi = (int*)(hb + o_gi); int* hgj = (int*)(hb + o_gj); int* hgs = (int*)(hb + o_gs); uint2* hpairs = (uint2*)(hb + o_pairs);
 	int* hpwin = (int*)(hb + o_pwin); int* hpsrc = (int*)(hb + o_psrc); int* hmem = (int*)(hb + o_mem);
@@ -1244,8 +1297,23 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 		d.frame_off = (int)f_off; d.corr_off = (int)c_off; d.grp_off = (int)g_off; d.pair_off = (int)p_off;
 		s->frame_off[w] = (int)f_off; s->n_frames[w] = N;
 		for (int f = 0; f < N; f++) {
-			hdp[f_off + f] = (params->w_dense > 0.f) ? bw.depth_dev[f] : nullptr;
-			hnp[f_off + f] = (params->w_dense > 0.f) ? bw.normal_dev[f] : nullptr;
+			const size_t fs = f_off + f;
+			if (bw.cache_slots && params->w_dense > 0.f) {     // maps built earlier by bt_frame_cache_store
+				const int cs = bw.cache_slots[f];
+				BT_REQUIRE(cs >= 0 && cs < s->c_capacity && s->c_meta[cs].valid, BT_ERR_INVALID_ARG, "window %d frame %d: cache slot %d is empty or out of range", w, f, cs);
+				const SolverState::CacheMeta& m = s->c_meta[cs];
+				BT_REQUIRE(m.H == bw.H && m.W == bw.W && m.fx == bw.fx && m.fy == bw.fy && m.cx == bw.cx && m.cy == bw.cy && m.dmin == params->depth_min && m.dmax == params->depth_max
+				               && s->c_downscale == params->image_downscale,
+				           BT_ERR_INVALID_ARG, "window %d frame %d: cache slot %d was stored with another image size, K, depth range or downscale", w, f, cs);
+				hdp[fs] = nullptr; hnp[fs] = nullptr;
+				htex[fs] = s->c_texel.as<float4>() + (size_t)cs * 2 * s->c_npix; hsrc[fs] = s->c_src.as<float4>() + (size_t)cs * 2 * s->c_npix;
+				hnsrc[fs] = s->c_nsrc.as<int>() + cs;
+			} else {
+				hdp[fs] = (params->w_dense > 0.f) ? bw.depth_dev[f] : nullptr;
+				hnp[fs] = (params->w_dense > 0.f) ? bw.normal_dev[f] : nullptr;
+				htex[fs] = s->texel.as<float4>() + fs * 2 * (size_t)s->npix_max; hsrc[fs] = s->src.as<float4>() + fs * 2 * (size_t)s->npix_max;
+				hnsrc[fs] = nullptr;
+			}
 			hfw[f_off + f] = w;
 			memcpy(hpose + (f_off + f) * 16, poses_in + (f_off + f) * 16, sizeof(float) * 16);
 		}
@@ -1410,6 +1478,7 @@ static SolveArgs make_args(bt_ctx* ctx) {
 	a.wins = (WinDesc*)(sd + L.wins); a.n_windows = s->n_windows;
 	a.depth_ptr = (const float**)(sd + L.dp); a.normal_ptr = (const float4**)(sd + L.np); a.frame_win = (int*)(sd + L.fw);
 	a.texel = s->texel.as<float4>(); a.src = s->src.as<float4>(); a.nsrc = s->nsrc.as<int>();
+	a.texel_tab = (const float4* const*)(sd + L.texp); a.src_tab = (const float4* const*)(sd + L.srcp); a.nsrc_cached = (const int* const*)(sd + L.nsrcp);
 	a.pose_in = (float*)(sd + L.pose); a.x = s->x.as<float>(); a.T = s->T.as<float>(); a.pose_out = s->pose_out.as<float>();
 	a.npix_max = s->npix_max;
 	a.corr = (bt_entryj*)(sd + L.corr); a.grp_i = (int*)(sd + L.gi); a.grp_j = (int*)(sd + L.gj); a.grp_start = (int*)(sd + L.gs);
@@ -1490,6 +1559,65 @@ extern "C" int bt_solve_windows(bt_ctx* ctx, int n_windows, const bt_window* win
 	rc = bt_solve_run(ctx, stream);
 	if (rc != BT_OK) return rc;
 	return bt_solve_fetch(ctx, poses_inout, stream);
+}
+
+extern "C" int bt_frame_cache_reserve(bt_ctx* ctx, int capacity, int H, int W, float image_downscale) {
+	BT_REQUIRE(ctx && ctx->solver, BT_ERR_INVALID_ARG, "bt_frame_cache_reserve: call bt_solver_reserve first");
+	BT_REQUIRE(capacity > 0 && H > 0 && W > 0 && image_downscale >= 1.0f, BT_ERR_INVALID_ARG, "bt_frame_cache_reserve: bad arguments");
+	SolverState* s = ctx->solver;
+	BT_CUDA(cudaSetDevice(ctx->device));
+	const int w = (int)(W / image_downscale), h = (int)(H / image_downscale);
+	BT_REQUIRE(w >= 2 && h >= 2, BT_ERR_INVALID_ARG, "bt_frame_cache_reserve: image too small");
+	int rc;
+	if ((rc = s->c_texel.alloc(sizeof(float4) * 2 * (size_t)w * h * capacity)) != BT_OK) return rc;
+	if ((rc = s->c_src.alloc(sizeof(float4) * 2 * (size_t)w * h * capacity)) != BT_OK) return rc;
+	if ((rc = s->c_nsrc.alloc(sizeof(int) * (size_t)capacity)) != BT_OK) return rc;
+	s->c_capacity = capacity; s->c_npix = w * h; s->c_downscale = image_downscale;
+	s->c_meta.assign(capacity, SolverState::CacheMeta());
+	return BT_OK;
+}
+
+extern "C" int bt_frame_cache_store(bt_ctx* ctx, int n_frames, const int32_t* slots, const float* const* depth_dev, const float* const* normal_dev,
+                                    int H, int W, float fx, float fy, float cx, float cy, float depth_min, float depth_max, void* stream_) {
+	BT_REQUIRE(ctx && ctx->solver && slots && depth_dev && normal_dev, BT_ERR_INVALID_ARG, "bt_frame_cache_store: NULL argument");
+	SolverState* s = ctx->solver;
+	BT_REQUIRE(s->c_capacity > 0, BT_ERR_INVALID_ARG, "bt_frame_cache_store: call bt_frame_cache_reserve first");
+	BT_REQUIRE(n_frames > 0 && n_frames <= s->c_capacity, BT_ERR_CAPACITY, "bt_frame_cache_store: %d frames > capacity %d", n_frames, s->c_capacity);
+	const int w = (int)(W / s->c_downscale), h = (int)(H / s->c_downscale);
+	BT_REQUIRE(H > 0 && W > 0 && w >= 2 && h >= 2 && w * h <= s->c_npix, BT_ERR_CAPACITY, "bt_frame_cache_store: image %dx%d does not fit the reserved cache", W, H);
+	cudaStream_t stream = (cudaStream_t)stream_;
+	BT_CUDA(cudaSetDevice(ctx->device));
+	const size_t b_ptr = sizeof(void*) * (size_t)n_frames, bytes = 2 * b_ptr + sizeof(int) * (size_t)n_frames;
+	int rc;
+	if ((rc = s->c_tables.alloc(bytes)) != BT_OK) return rc;
+	if (s->c_ev) BT_CUDA(cudaEventSynchronize(s->c_ev));
+	if ((rc = s->c_htables.alloc(bytes)) != BT_OK) return rc;
+	if (!s->c_ev) BT_CUDA(cudaEventCreateWithFlags(&s->c_ev, cudaEventDisableTiming));
+	char* hb = s->c_htables.as<char>();
+	const void** hd = (const void**)hb; const void** hn = (const void**)(hb + b_ptr); int* hs = (int*)(hb + 2 * b_ptr);
+	for (int f = 0; f < n_frames; f++) {
+		BT_REQUIRE(slots[f] >= 0 && slots[f] < s->c_capacity, BT_ERR_INVALID_ARG, "bt_frame_cache_store: slot %d out of range [0,%d)", slots[f], s->c_capacity);
+		BT_REQUIRE(depth_dev[f] && normal_dev[f], BT_ERR_INVALID_ARG, "bt_frame_cache_store: frame %d has a NULL map", f);
+		for (int g = 0; g < f; g++) BT_REQUIRE(slots[g] != slots[f], BT_ERR_INVALID_ARG, "bt_frame_cache_store: slot %d listed twice", slots[f]);
+		hd[f] = depth_dev[f]; hn[f] = normal_dev[f]; hs[f] = slots[f];
+	}
+	BT_CUDA(cudaMemcpyAsync(s->c_tables.p, hb, bytes, cudaMemcpyHostToDevice, stream));
+	BT_CUDA(cudaEventRecord(s->c_ev, stream));
+	CacheStoreArgs c;
+	c.g.W = W; c.g.H = H; c.g.w = w; c.g.h = h;                                                   // same expressions as bt_solve_stage (CUDACache.cpp:20-24)
+	c.g.ifx = 1.0f / fx; c.g.ify = 1.0f / fy; c.g.icx = -cx / fx; c.g.icy = -cy / fy;
+	c.g.scaleW = (float)(W - 1) / (float)(w - 1); c.g.scaleH = (float)(H - 1) / (float)(h - 1);
+	char* db = s->c_tables.as<char>();
+	c.depth = (const float* const*)db; c.normal = (const float4* const*)(db + b_ptr); c.slots = (const int*)(db + 2 * b_ptr);
+	c.texel = s->c_texel.as<float4>(); c.src = s->c_src.as<float4>(); c.nsrc = s->c_nsrc.as<int>(); c.slot_stride = 2 * (size_t)s->c_npix;
+	c.dmin = depth_min; c.dmax = depth_max;
+	k_frame_cache_store<<<n_frames, 1024, 0, stream>>>(c);
+	BT_CUDA(cudaGetLastError());
+	for (int f = 0; f < n_frames; f++) {
+		SolverState::CacheMeta& m = s->c_meta[slots[f]];
+		m.valid = true; m.H = H; m.W = W; m.fx = fx; m.fy = fy; m.cx = cx; m.cy = cy; m.dmin = depth_min; m.dmax = depth_max;
+	}
+	return BT_OK;
 }
 
 extern "C" int bt_solve_get_stats(bt_ctx* ctx, bt_solve_stats* out) {

@@ -29,19 +29,20 @@ class SolveWindow:
     """One window's inputs: device frame maps + host correspondences/poses (the reference's argument list)."""
 
     def __init__(self, corr: np.ndarray, H: int, W: int, depths_gpu: Sequence, normals_gpu: Sequence, poses: np.ndarray, K,
-                 dense_pairs: Optional[np.ndarray] = None, compat_flip: bool = True):
+                 dense_pairs: Optional[np.ndarray] = None, compat_flip: bool = True, cache_slots: Optional[Sequence[int]] = None):
         self.corr = np.ascontiguousarray(corr, dtype=ENTRYJ_DTYPE)
         self.H, self.W = int(H), int(W)
-        self.depths = [_ptr(d) for d in depths_gpu]
-        self.normals = [_ptr(n) for n in normals_gpu]
+        self.depths = [_ptr(d) for d in (depths_gpu or [])]
+        self.normals = [_ptr(n) for n in (normals_gpu or [])]
         self.poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 4, 4)
         K = np.asarray(K, np.float64)
         self.K = (float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])) if K.ndim == 2 else tuple(float(v) for v in K)
         self.dense_pairs = None if dense_pairs is None else np.ascontiguousarray(dense_pairs, np.uint32).reshape(-1, 2)
         self.compat_flip = bool(compat_flip)
+        self.cache_slots = None if cache_slots is None else np.ascontiguousarray(cache_slots, np.int32)
         self._keep = (depths_gpu, normals_gpu)
 
-    _MARSHALLED = frozenset(("corr", "H", "W", "depths", "normals", "poses", "K", "dense_pairs", "compat_flip"))
+    _MARSHALLED = frozenset(("corr", "H", "W", "depths", "normals", "poses", "K", "dense_pairs", "compat_flip", "cache_slots"))
 
     def __setattr__(self, name, value):
         if name in SolveWindow._MARSHALLED:
@@ -53,13 +54,18 @@ class SolveWindow:
         cw = self.__dict__.get("_cwin")
         if cw is None:
             N = self.n_frames
-            dp = (ctypes.c_void_p * N)(*self.depths)
-            nq = (ctypes.c_void_p * N)(*self.normals)
+            dp = (ctypes.c_void_p * N)(*self.depths) if self.depths else None
+            nq = (ctypes.c_void_p * N)(*self.normals) if self.normals else None
             cw = _lib.Window()
             cw.n_frames, cw.H, cw.W, cw.n_corr = N, self.H, self.W, len(self.corr)
             cw.corr = self.corr.ctypes.data if len(self.corr) else None
-            cw.depth_dev = ctypes.cast(dp, ctypes.POINTER(ctypes.c_void_p))
-            cw.normal_dev = ctypes.cast(nq, ctypes.POINTER(ctypes.c_void_p))
+            if dp is not None:
+                cw.depth_dev = ctypes.cast(dp, ctypes.POINTER(ctypes.c_void_p))
+                cw.normal_dev = ctypes.cast(nq, ctypes.POINTER(ctypes.c_void_p))
+            if self.cache_slots is not None:
+                if len(self.cache_slots) != N:
+                    raise ValueError("cache_slots needs one slot per frame")
+                cw.cache_slots = self.cache_slots.ctypes.data
             cw.fx, cw.fy, cw.cx, cw.cy = self.K
             zero = None
             if self.dense_pairs is not None:
@@ -70,7 +76,7 @@ class SolveWindow:
                 cw.dense_pairs, cw.n_dense_pairs = None, 0
             cw.compat_flip = 1 if self.compat_flip else 0
             self.__dict__["_cwin"] = cw
-            self.__dict__["_cwin_keep"] = (dp, nq, zero, self.corr, self.dense_pairs)
+            self.__dict__["_cwin_keep"] = (dp, nq, zero, self.corr, self.dense_pairs, self.cache_slots)
         return cw
 
     @property
@@ -100,6 +106,22 @@ class OptimizerGpu:
             self.close()
         except Exception:
             pass
+
+    # ---- frame cache: quarter-res maps built once per keyframe instead of once per call (CUDACache.cpp:76-88) ----------
+    def reserve_frame_cache(self, capacity: int, H: int = None, W: int = None):
+        _lib.check(self.lib.bt_frame_cache_reserve(self.ctx, ctypes.c_int(capacity), ctypes.c_int(H or self.limits.H), ctypes.c_int(W or self.limits.W),
+                                                   ctypes.c_float(self.params.image_downscale)), "bt_frame_cache_reserve")
+
+    def store_frames(self, slots: Sequence[int], depths_gpu: Sequence, normals_gpu: Sequence, H: int, W: int, K):
+        n = len(slots)
+        K = np.asarray(K, np.float64)
+        fx, fy, cx, cy = (K[0, 0], K[1, 1], K[0, 2], K[1, 2]) if K.ndim == 2 else K
+        sl = (ctypes.c_int32 * n)(*[int(v) for v in slots])
+        dp = (ctypes.c_void_p * n)(*[_ptr(d) for d in depths_gpu])
+        nq = (ctypes.c_void_p * n)(*[_ptr(d) for d in normals_gpu])
+        _lib.check(self.lib.bt_frame_cache_store(self.ctx, ctypes.c_int(n), sl, dp, nq, ctypes.c_int(H), ctypes.c_int(W), ctypes.c_float(fx), ctypes.c_float(fy),
+                                                 ctypes.c_float(cx), ctypes.c_float(cy), ctypes.c_float(self.params.depth_min), ctypes.c_float(self.params.depth_max),
+                                                 self.stream), "bt_frame_cache_store")
 
     # ---- reference-shaped single-window call (LossGPU.h:50) -------------------------------------------------
     def optimizeFrames(self, global_corres, n_match_per_pair, n_frames, H, W, depths_gpu, colors_gpu, normals_gpu, poses, K,

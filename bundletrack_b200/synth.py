@@ -290,3 +290,19 @@ def make_feature_frames(win: Window, n_feats: int = 500, seed: int = 0, n_surfac
         perm = rng.permutation(len(kp))
         frames.append({"kpts": kp[perm].astype(np.float32), "desc": de[perm].astype(np.float32), "ids": ids[perm]})
     return frames
+
+
+def make_raw_depth(seed: int, H: int = 480, W: int = 640, K=None, noise: float = 0.0003, hole_frac: float = 0.02, flying_frac: float = 0.01):
+    """A raw sensor-like depth image for the frame front end: a rendered ellipsoid (the window
+    generator's frame 0) + N(0, noise) on valid pixels + random holes + isolated "flying" pixels displaced by 2-6 cm that
+    the erosion must remove.  Returns (raw [H,W] float32, K)."""
+    K = tuple(v * W / 640.0 for v in NOCS_K) if K is None else K
+    w = make_window(seed, n_frames=2, n_corr=10, H=H, W=W, K=K)
+    rng = np.random.default_rng(np.uint64(0xDE97) + np.uint64(seed))
+    d = w.depth[0].astype(np.float32).copy()
+    valid = d > 0
+    raw = d + valid * rng.normal(0, noise, d.shape).astype(np.float32)
+    fly = valid & (rng.random(d.shape) < flying_frac)
+    raw = raw + fly * rng.uniform(0.02, 0.06, d.shape).astype(np.float32) * rng.choice([-1.0, 1.0], d.shape).astype(np.float32)
+    raw[rng.random(d.shape) < hole_frac] = 0.0
+    return raw.astype(np.float32), K

@@ -85,6 +85,10 @@ typedef struct {
 	/* 1 => reproduce the reference's FlipJtJ behaviour: a pair's cross block survives only when target < source
 	 * (SURVEY.md Q2).  0 => keep every cross block (the mathematically complete Gauss-Newton system). */
 	int compat_flip;
+	/* Optional: N slots of the context's frame cache (bt_frame_cache_store).  When non-NULL, depth_dev / normal_dev are not
+	 * read: the quarter-resolution maps CUDACache::storeFrame (CUDACache.cpp:76-88) would rebuild for this call were built
+	 * once per keyframe.  Results are bit-identical either way. */
+	const int32_t* cache_slots;
 } bt_window;
 
 typedef struct {
@@ -220,6 +224,33 @@ BT_API int bt_match_pairs(bt_ctx* ctx, int n_pairs, const bt_match_frame* A, con
                    const bt_prune_params* prune, int ransac_trials, float ransac_inlier_dist, uint64_t ransac_seed,
                    bt_entryj* entry_out, int entry_capacity, int32_t* n_entry_out, int32_t* entry_off_out,
                    int32_t* total_out, void* stream);
+
+/* ---- frame front end: Frame::processDepth + Frame::depthToCloudAndNormals -------------------------
+ * /root/reference/src/Frame.cpp:152-233 -> CUDAImageUtil::erodeDepthMap, gaussFilterDepthMap x2,
+ * convertDepthFloatToCameraSpaceFloat4, computeNormals (src/cuda/CUDAImageUtil.cu:676-806,310-336,342-423), fused into
+ * one kernel per batch of frames.  Parameters are config_*.yml "depth_processing" (erode.radius/diff/ratio,
+ * bilateral_filter.radius/sigma_D/sigma_R). */
+typedef struct {
+	int erode_radius; float erode_diff, erode_ratio;
+	int bf_radius; float sigma_D, sigma_R;
+} bt_depth_params;
+/* All map pointers are DEVICE memory; the pointer ARRAYS are host memory.  depth_raw/depth_out: H*W float (metres);
+ * xyz_out (may be NULL: not wanted) and normal_out: H*W float4 = 4 floats per pixel ((x,y,z,1) / (nx,ny,nz,0), zeros
+ * where undefined) - depth_out and normal_out are exactly Frame::_depth_gpu / _normal_gpu as the solver reads them.
+ * Out of place: depth_out[f] must differ from depth_raw[f]. */
+BT_API int bt_frames_preprocess(bt_ctx* ctx, int n_frames, const float* const* depth_raw_dev, int H, int W,
+                         float fx, float fy, float cx, float cy, const bt_depth_params* prm,
+                         float* const* depth_out_dev, float* const* xyz_out_dev, float* const* normal_out_dev, void* stream);
+
+/* Frame cache (second half).  The reference re-creates a CUDACache and re-downsamples every keyframe of
+ * the window in EVERY optimizeFrames call (/root/reference/src/cuda/LossGPU.cu:74-101, CUDACache.cpp:76-88); a keyframe
+ * takes part in many windows, so its quarter-resolution point/normal texel map and compacted source list are built here
+ * once, when the keyframe enters the pool, and referenced by slot from bt_window::cache_slots.  The cache belongs to the
+ * solver of this context: call bt_solver_reserve first.  Slots stay valid until overwritten.  depth_min/depth_max:
+ * bt_solver_params::depth_min/max (they define which pixels enter the source list). */
+BT_API int bt_frame_cache_reserve(bt_ctx* ctx, int capacity, int H, int W, float image_downscale);
+BT_API int bt_frame_cache_store(bt_ctx* ctx, int n_frames, const int32_t* slots, const float* const* depth_dev, const float* const* normal_dev,
+                         int H, int W, float fx, float fy, float cx, float cy, float depth_min, float depth_max, void* stream);
 
 /* Small device-memory helpers so non-CUDA hosts (ctypes, cgo, JNI) can drive the library without another runtime. */
 BT_API int bt_dev_alloc(void** out, size_t bytes);

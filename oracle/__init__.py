@@ -182,6 +182,7 @@ def ref_lib():
         _ref = ctypes.CDLL(path)
         _ref.ref_optimize_frames.restype = ctypes.c_int
         _ref.ref_ransac_pairs.restype = ctypes.c_int
+        _ref.ref_frame_preprocess.restype = ctypes.c_int
     return _ref
 
 
@@ -207,3 +208,23 @@ def ref_optimize_frames(depth_ptrs, normal_ptrs, H, W, K, corr, poses, params=No
     if rc != 0:
         raise RuntimeError(f"ref_optimize_frames rc={rc}")
     return poses, pairs[: npairs.value].copy(), t_outer.value, t_solve.value
+
+
+def ref_frame_preprocess(depth_raw, K, dp=None):
+    """The reference's Frame front end (its own kernels, oracle/_ref) on the current CUDA device.
+    depth_raw [H,W] float32, K=(fx,fy,cx,cy), dp = dict(erode_radius, erode_diff, erode_ratio, bf_radius, sigma_D, sigma_R).
+    Returns (depth [H,W], xyz [H,W,4], normal [H,W,4], t_ms)."""
+    from . import frame_oracle
+    lib = ref_lib()
+    dp = dict(frame_oracle.DEFAULTS, **(dp or {}))
+    d = np.ascontiguousarray(depth_raw, np.float32)
+    H, W = d.shape
+    dout = np.zeros((H, W), np.float32); xyz = np.zeros((H, W, 4), np.float32); nrm = np.zeros((H, W, 4), np.float32)
+    t = ctypes.c_double(0)
+    rc = lib.ref_frame_preprocess(ctypes.c_int(H), ctypes.c_int(W), _fp(d), ctypes.c_float(K[0]), ctypes.c_float(K[1]), ctypes.c_float(K[2]), ctypes.c_float(K[3]),
+                                  ctypes.c_int(int(dp["erode_radius"])), ctypes.c_float(dp["erode_diff"]), ctypes.c_float(dp["erode_ratio"]),
+                                  ctypes.c_int(int(dp["bf_radius"])), ctypes.c_float(dp["sigma_D"]), ctypes.c_float(dp["sigma_R"]),
+                                  _fp(dout), _fp(xyz), _fp(nrm), ctypes.byref(t))
+    if rc != 0:
+        raise RuntimeError(f"ref_frame_preprocess failed: {rc}")
+    return dout, xyz, nrm, t.value

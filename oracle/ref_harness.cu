@@ -198,3 +198,40 @@ extern "C" int ref_ransac_pairs(int n_pairs, const float* const* h_ptsA /*[n][4]
 	}
 	return 0;
 }
+
+/* Frame::Frame -> updateDepthGPU, processDepth, depthToCloudAndNormals (/root/reference/src/Frame.cpp:62-81,107-127,152-233)
+ * with the reference's own kernels and its allocation pattern (cudaMalloc/cudaFree of the two temporaries per frame, the
+ * host round trips of the maps).  K^-1 as Eigen::Matrix3f::inverse() forms it (cofactors times 1/det, Frame.cpp:189). */
+extern "C" int ref_frame_preprocess(int H, int W, const float* h_depth_raw, float fx, float fy, float cx, float cy,
+                                    int erode_radius, float erode_diff, float erode_ratio, int bf_radius, float sigma_D, float sigma_R,
+                                    float* h_depth_out, float* h_xyz_out /*[H*W*4]*/, float* h_normal_out /*[H*W*4]*/, double* t_ms) {
+	CK(cudaDeviceSynchronize());
+	const double t0 = now_ms();
+	const int n = H * W;
+	float *d_depth, *d_tmp; float4 *d_normal, *d_xyz;
+	CK(cudaMalloc(&d_depth, sizeof(float) * n)); CK(cudaMalloc(&d_normal, sizeof(float4) * n));      /* Frame ctor, Frame.cpp:68-70 */
+	CK(cudaMemcpy(d_depth, h_depth_raw, sizeof(float) * n, cudaMemcpyHostToDevice));                 /* updateDepthGPU */
+	CK(cudaMalloc(&d_tmp, sizeof(float) * n));                                                       /* processDepth */
+	CUDAImageUtil::erodeDepthMap(d_tmp, d_depth, erode_radius, W, H, erode_diff, erode_ratio);
+	CUDAImageUtil::gaussFilterDepthMap(d_depth, d_tmp, bf_radius, sigma_D, sigma_R, W, H);
+	CUDAImageUtil::gaussFilterDepthMap(d_tmp, d_depth, bf_radius, sigma_D, sigma_R, W, H);
+	{ float* t = d_depth; d_depth = d_tmp; d_tmp = t; }
+	CK(cudaMemcpy(h_depth_out, d_depth, sizeof(float) * n, cudaMemcpyDeviceToHost));                 /* updateDepthCPU */
+	CK(cudaFree(d_tmp));
+	CK(cudaMalloc(&d_xyz, sizeof(float4) * n));                                                      /* depthToCloudAndNormals */
+	float4x4 Kinv; Kinv.setIdentity();
+	{
+		const float det = fx * fy, invdet = 1.0f / det;
+		Kinv(0,0) = fy * invdet; Kinv(0,1) = 0.0f; Kinv(0,2) = (0.0f * cy - cx * fy) * invdet;
+		Kinv(1,0) = 0.0f; Kinv(1,1) = fx * invdet; Kinv(1,2) = -(fx * cy - cx * 0.0f) * invdet;
+		Kinv(2,0) = 0.0f; Kinv(2,1) = 0.0f; Kinv(2,2) = 1.0f;
+	}
+	CUDAImageUtil::convertDepthFloatToCameraSpaceFloat4(d_xyz, d_depth, Kinv, W, H);
+	CUDAImageUtil::computeNormals(d_normal, d_xyz, W, H);
+	CK(cudaMemcpy(h_xyz_out, d_xyz, sizeof(float4) * n, cudaMemcpyDeviceToHost));
+	CK(cudaMemcpy(h_normal_out, d_normal, sizeof(float4) * n, cudaMemcpyDeviceToHost));
+	CK(cudaFree(d_xyz)); CK(cudaFree(d_depth)); CK(cudaFree(d_normal));
+	CK(cudaDeviceSynchronize());
+	if (t_ms) *t_ms = now_ms() - t0;
+	return 0;
+}

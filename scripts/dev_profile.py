@@ -32,6 +32,9 @@ for nw in nwin:
         for i, nm in enumerate(names):
             print(f"   {nm:14s} {d[:, i].mean():9.0f} {np.percentile(d[:, i], 50):9.0f} {np.percentile(d[:, i], 95):9.0f}")
         print(f"   total          {(tiles[:,7]-tiles[:,2]).mean():9.0f}")
+    pl = rec[kind == 3]
+    if len(pl):
+        print(' plan phases (cycles): counts, scan, pair prefix, tile records, tail:', np.diff(pl[0, 2:8]).tolist())
     ws = rec[kind == 2]
     if len(ws):
         px = ws[:, 1] >> 32

@@ -230,3 +230,37 @@ def test_matches_reference_kernels_live(opt, cuda_device):
         a = oracle.solve_window(w.depth, w.normal, w.K, w.corr, w.poses_init, pairs=pairs)   # pins Oracle A too
         r, t = synth.pose_errors(a, ref)
         assert r <= TOL and t <= TOL, (seed, r, t)
+
+
+def test_frame_cache_is_bit_identical(cuda_device):
+    """bt_frame_cache_store + bt_window::cache_slots (the quarter-res maps built once per keyframe) give exactly the poses of
+    the per-call rebuild, also when a window mixes slots in another order and after a slot is overwritten."""
+    from bundletrack_b200.optimizer import OptimizerGpu, SolveWindow
+    from bundletrack_b200 import _lib
+    o = OptimizerGpu(None, max_windows=4, max_frames=6, max_corr=2000)
+    wa = synth.make_window(50, n_frames=6, n_corr=900)
+    wb = synth.make_window(51, n_frames=4, n_corr=500)
+    da, na = _upload(wa, cuda_device)
+    db, nb = _upload(wb, cuda_device)
+    plain = o.optimizeWindows([SolveWindow(wa.corr, wa.H, wa.W, da, na, wa.poses_init, wa.K), SolveWindow(wb.corr, wb.H, wb.W, db, nb, wb.poses_init, wb.K)])
+    o.reserve_frame_cache(16)
+    o.store_frames([3, 4, 5, 6, 7, 8], da, na, wa.H, wa.W, wa.K)
+    o.store_frames([12, 0, 9, 1], db, nb, wb.H, wb.W, wb.K)
+    cached = o.optimizeWindows([SolveWindow(wa.corr, wa.H, wa.W, None, None, wa.poses_init, wa.K, cache_slots=[3, 4, 5, 6, 7, 8]),
+                                SolveWindow(wb.corr, wb.H, wb.W, None, None, wb.poses_init, wb.K, cache_slots=[12, 0, 9, 1])])
+    assert np.array_equal(plain[0], cached[0]) and np.array_equal(plain[1], cached[1])
+    # mixed batch: one window from the cache, one rebuilt per call
+    mixed = o.optimizeWindows([SolveWindow(wa.corr, wa.H, wa.W, da, na, wa.poses_init, wa.K), SolveWindow(wb.corr, wb.H, wb.W, None, None, wb.poses_init, wb.K, cache_slots=[12, 0, 9, 1])])
+    assert np.array_equal(plain[0], mixed[0]) and np.array_equal(plain[1], mixed[1])
+    # overwrite a slot with another frame: the window that uses it changes, then changes back
+    o.store_frames([0], [da[0]], [na[0]], wa.H, wa.W, wa.K)
+    other = o.optimizeWindows([SolveWindow(wb.corr, wb.H, wb.W, None, None, wb.poses_init, wb.K, cache_slots=[12, 0, 9, 1])])[0]
+    assert not np.array_equal(other, plain[1])
+    o.store_frames([0], [db[1]], [nb[1]], wb.H, wb.W, wb.K)
+    again = o.optimizeWindows([SolveWindow(wb.corr, wb.H, wb.W, None, None, wb.poses_init, wb.K, cache_slots=[12, 0, 9, 1])])[0]
+    assert np.array_equal(again, plain[1])
+    with pytest.raises(_lib.BtError):      # empty slot
+        o.optimizeWindows([SolveWindow(wb.corr, wb.H, wb.W, None, None, wb.poses_init, wb.K, cache_slots=[12, 0, 9, 15])])
+    with pytest.raises(_lib.BtError):      # stored with another K
+        o.optimizeWindows([SolveWindow(wb.corr, wb.H, wb.W, None, None, wb.poses_init, tuple(v * 1.01 for v in wb.K), cache_slots=[12, 0, 9, 1])])
+    o.close()
