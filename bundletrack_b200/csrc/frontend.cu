@@ -28,9 +28,55 @@ struct FrontArgs {
 
 __device__ __forceinline__ float4 to_camera(const FrontArgs& a, int x, int y, float d) {
 	// convertDepthFloatToCameraSpaceFloat4_Kernel (CUDAImageUtil.cu:310-326): K^-1 * (x d, y d, d, d), output (x, y, w=d, 1)
-	if (!((double)d >= 0.1)) return make_float4(0.f, 0.f, 0.f, 0.f);
+	if (!(d >= 0.1f)) return make_float4(0.f, 0.f, 0.f, 0.f);     // (double)d >= 0.1 <=> d >= 0.1f
 	const float xd = (float)x * d, yd = (float)y * d;
 	return make_float4(a.k00 * xd + 0.f * yd + a.k02 * d + 0.f * d, 0.f * xd + a.k11 * yd + a.k12 * d + 0.f * d, d, 1.0f);
+}
+
+// One output pixel of gaussFilterDepthMapDevice (CUDAImageUtil.cu:735-796) from the staged neighbourhood (see the kernel for
+// why no bounds tests are needed and how the weight table stays bit-identical to exp(a_tap - q)).  BR > 0: compile-time radius,
+// the (2BR+1)^2 taps are read once into registers and serve both loops; BR == 0: run-time radius `rbr`, taps re-read.
+template <int BR>
+__device__ __forceinline__ float filter_pixel(const float* __restrict__ Sc, int RW, const float* __restrict__ t_a, const float* __restrict__ t_w,
+                                              const float* __restrict__ t_q, float inv2sr, float num_total, int rbr = BR) {
+	constexpr int SIDE = 2 * BR + 1, NT = BR > 0 ? SIDE * SIDE : 1;
+	const int side = BR > 0 ? SIDE : 2 * rbr + 1, ntap = side * side, br = BR > 0 ? BR : rbr;
+	const float centre = Sc[0];
+	float v[NT];
+	float mean = 0.f; int nv = 0;
+	if (BR > 0) {
+#pragma unroll
+		for (int t = 0; t < NT; t++) {         // tap t: x offset outer, y offset inner (the reference's summation order)
+			v[t] = Sc[(t % SIDE - BR) * RW + (t / SIDE - BR)];
+			if (v[t] >= 0.1f) { nv++; mean += v[t]; }
+		}
+	} else {
+		for (int t = 0; t < ntap; t++) { const float d = Sc[(t % side - br) * RW + (t / side - br)]; if (d >= 0.1f) { nv++; mean += d; } }
+	}
+	if (nv == 0) return 0.f;
+	mean /= nv;
+	float s = 0.f, sw = 0.f;
+	if (BR > 0) {
+#pragma unroll
+		for (int t = 0; t < NT; t++) {
+			const float d = v[t];
+			if (d >= 0.1f && fabsf(d - mean) <= 0.01f) {
+				const float dd = (centre - d) * (centre - d);
+				const float wgt = (dd < t_q[t]) ? t_w[t] : expf(t_a[t] - dd / inv2sr);
+				sw += wgt; s += wgt * d;
+			}
+		}
+	} else {
+		for (int t = 0; t < ntap; t++) {
+			const float d = Sc[(t % side - br) * RW + (t / side - br)];
+			if (d >= 0.1f && fabsf(d - mean) <= 0.01f) {
+				const float dd = (centre - d) * (centre - d);
+				const float wgt = (dd < t_q[t]) ? t_w[t] : expf(t_a[t] - dd / inv2sr);
+				sw += wgt; s += wgt * d;
+			}
+		}
+	}
+	return (sw > 0.0f && (float)nv / num_total > 0) ? s / sw : 0.f;
 }
 
 __global__ void __launch_bounds__(FE_THREADS) k_frame_frontend(FrontArgs a) {
@@ -43,8 +89,7 @@ __global__ void __launch_bounds__(FE_THREADS) k_frame_frontend(FrontArgs a) {
 	const int x0 = blockIdx.x * FE_TW - halo, y0 = blockIdx.y * FE_TH - halo;   // image coordinates of region cell (0,0)
 	const int W = a.W, H = a.H;
 	const float* __restrict__ din = a.depth_in[f];
-	// ---- stage 0: raw depth of the region (cells outside the image are never read as neighbours: every stencil below
-	//      tests the image bounds exactly like the reference kernels do)
+	// ---- stage 0: raw depth of the region; cells outside the image hold 0 here and after every later stage
 	for (int c = threadIdx.x; c < RW * RH; c += FE_THREADS) {
 		const int cx = c % RW, cy = c / RW, x = x0 + cx, y = y0 + cy;
 		A[c] = (x >= 0 && x < W && y >= 0 && y < H) ? __ldg(din + (size_t)y * W + x) : 0.f;
@@ -75,10 +120,27 @@ __global__ void __launch_bounds__(FE_THREADS) k_frame_frontend(FrontArgs a) {
 		}
 	}
 	__syncthreads();
-	// ---- stages 2, 3: gaussFilterDepthMapDevice (CUDAImageUtil.cu:735-796), twice: B -> A (margin er+br), A -> B (margin er+2br)
+	// ---- stages 2, 3: gaussFilterDepthMapDevice (CUDAImageUtil.cu:735-796), twice: B -> A (margin er+br), A -> B (margin er+2br).
+	//      Cells outside the image hold 0 in every stage, and the filter ignores neighbours below 0.1 m, so the reference's
+	//      bounds tests on the neighbours are implied.  The weight exp(a_tap - q), a_tap = -(dx^2+dy^2)/(2 sigD^2), q =
+	//      (centre-d)^2/(2 sigR^2): whenever q is too small to change a_tap in float (always, with the shipped sigma_R = 1e5)
+	//      the sum rounds to a_tap and the weight IS the tabulated expf(a_tap) - same bits, no exp, no division.
+	//      The reference's double comparisons are replaced by their exact float equivalents: (double)x < 0.01 <=> x <= 0.01f
+	//      (0.01f is the largest float below 0.01), (double)x >= 0.1 <=> x >= 0.1f (0.1f is the smallest float above 0.1).
 	const float inv2sd = 2.0f * a.sigD * a.sigD;
 	const float inv2sr = 2 * a.sigR * a.sigR;
-	const float num_total = (float)((2 * br + 1) * (2 * br + 1));
+	const int side = 2 * br + 1, ntap = side * side;
+	float* t_a = B + RW * RH;            // [ntap] a_tap
+	float* t_w = t_a + ntap;             // [ntap] expf(a_tap)
+	float* t_q = t_w + ntap;             // [ntap] (centre-d)^2 below this leaves a_tap (and the weight) unchanged
+	for (int t = threadIdx.x; t < ntap; t += FE_THREADS) {
+		const int mm = t / side - br, nn = t % side - br;      // x offset outer, y offset inner: the reference's summation order
+		const float at = -(float)(mm * mm + nn * nn) / inv2sd;
+		t_a[t] = at; t_w[t] = expf(at);
+		t_q[t] = (at != 0.f) ? inv2sr * fabsf(at) * 1.4901161e-8f /* 2^-26 */ : inv2sr * 1.4901161e-8f;
+	}
+	__syncthreads();
+	const float num_total = (float)(side * side);
 	for (int pass = 0; pass < 2; pass++) {
 		const float* S = pass == 0 ? B : A;
 		float* D = pass == 0 ? A : B;
@@ -87,28 +149,10 @@ __global__ void __launch_bounds__(FE_THREADS) k_frame_frontend(FrontArgs a) {
 			const int cx = m + c % w, cy = m + c / w, x = x0 + cx, y = y0 + cy;
 			float out = 0.f;
 			if (x >= 0 && x < W && y >= 0 && y < H) {
-				const float centre = S[cy * RW + cx];
-				float mean = 0.f; int nv = 0;
-				for (int mm = -br; mm <= br; mm++)                 // the reference's order: x offset outer, y offset inner
-					for (int nn = -br; nn <= br; nn++)
-						if (x + mm >= 0 && y + nn >= 0 && x + mm < W && y + nn < H) {
-							const float d = S[(cy + nn) * RW + (cx + mm)];
-							if (d >= 0.1f) { nv++; mean += d; }
-						}
-				if (nv > 0) {
-					mean /= nv;
-					float s = 0.f, sw = 0.f;
-					for (int mm = -br; mm <= br; mm++)
-						for (int nn = -br; nn <= br; nn++)
-							if (x + mm >= 0 && y + nn >= 0 && x + mm < W && y + nn < H) {
-								const float d = S[(cy + nn) * RW + (cx + mm)];
-								if (d >= 0.1f && (double)fabsf(d - mean) < 0.01) {
-									const float wgt = expf(-(float)(mm * mm + nn * nn) / inv2sd - (centre - d) * (centre - d) / inv2sr);
-									sw += wgt; s += wgt * d;
-								}
-							}
-					if (sw > 0.0f && (float)nv / num_total > 0) out = s / sw;
-				}
+				const float* Sc = S + cy * RW + cx;
+				if (br == 2) out = filter_pixel<2>(Sc, RW, t_a, t_w, t_q, inv2sr, num_total);       // the shipped radius: taps and tables in registers
+				else if (br == 1) out = filter_pixel<1>(Sc, RW, t_a, t_w, t_q, inv2sr, num_total);
+				else out = filter_pixel<0>(Sc, RW, t_a, t_w, t_q, inv2sr, num_total, br);
 			}
 			D[cy * RW + cx] = out;
 		}
@@ -129,13 +173,13 @@ __global__ void __launch_bounds__(FE_THREADS) k_frame_frontend(FrontArgs a) {
 		const float4 CC = to_camera(a, x, y, d);
 		if (xout) xout[o] = CC;
 		float4 nrm = make_float4(0.f, 0.f, 0.f, 0.f);
-		if (x > 0 && x < W - 1 && y > 0 && y < H - 1 && !((double)CC.z < 0.1)) {
+		if (x > 0 && x < W - 1 && y > 0 && y < H - 1 && !(CC.z < 0.1f)) {
 			const float4 PC = to_camera(a, x, y + 1, B[(cy + 1) * RW + cx]);
 			const float4 CP = to_camera(a, x + 1, y, B[cy * RW + cx + 1]);
 			const float4 MC = to_camera(a, x, y - 1, B[(cy - 1) * RW + cx]);
 			const float4 CM = to_camera(a, x - 1, y, B[cy * RW + cx - 1]);
-			const bool pc = (double)PC.z >= 0.1 && fabsf(PC.z - CC.z) <= zth, mc = (double)MC.z >= 0.1 && fabsf(MC.z - CC.z) <= zth;
-			const bool cp = (double)CP.z >= 0.1 && fabsf(CP.z - CC.z) <= zth, cm = (double)CM.z >= 0.1 && fabsf(CM.z - CC.z) <= zth;
+			const bool pc = PC.z >= 0.1f && fabsf(PC.z - CC.z) <= zth, mc = MC.z >= 0.1f && fabsf(MC.z - CC.z) <= zth;
+			const bool cp = CP.z >= 0.1f && fabsf(CP.z - CC.z) <= zth, cm = CM.z >= 0.1f && fabsf(CM.z - CC.z) <= zth;
 			if ((pc || mc) && (cp || cm)) {
 				float ax, ay, az, bx, by, bz;      // "x_dir" (vertical difference) and "y_dir" (horizontal), as named in the reference
 				if (pc && mc) { ax = PC.x - MC.x; ay = PC.y - MC.y; az = PC.z - MC.z; }
@@ -220,7 +264,8 @@ extern "C" int bt_frames_preprocess(bt_ctx* ctx, int n_frames, const float* cons
 	a.er = prm->erode_radius; a.e_diff = prm->erode_diff; a.e_ratio = prm->erode_ratio;
 	a.br = prm->bf_radius; a.sigD = prm->sigma_D; a.sigR = prm->sigma_R;
 	const int halo = a.er + 2 * a.br + 1;
-	const size_t smem = sizeof(float) * 2 * (size_t)(FE_TW + 2 * halo) * (FE_TH + 2 * halo);
+	const int ntap = (2 * a.br + 1) * (2 * a.br + 1);
+	const size_t smem = sizeof(float) * (2 * (size_t)(FE_TW + 2 * halo) * (FE_TH + 2 * halo) + 3 * (size_t)ntap);
 	if (smem > 48 * 1024) BT_CUDA(cudaFuncSetAttribute(k_frame_frontend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	const dim3 grid((unsigned)((W + FE_TW - 1) / FE_TW), (unsigned)((H + FE_TH - 1) / FE_TH), (unsigned)n_frames);
 	k_frame_frontend<<<grid, FE_THREADS, smem, stream>>>(a);

@@ -15,11 +15,13 @@
 //                 group of 4 train columns to its minimum and push (min key | group index in the low 11 mantissa bits)
 //                 through a branch-free min/max insertion network that keeps the 12 smallest group minima per thread:
 //                 no data-dependent branch anywhere in the epilogue.
-//   k_knn_rerank  per query row: groups whose minimum could still reach the top k (interval test with the measured bf16
-//                 rounding error of both rows) are expanded to all 4 members and re-scored EXACTLY (float64 sum of
-//                 (a-b)^2 on the fp32 inputs, one lane per candidate); top k by (distance, index).  The same bound proves
-//                 that no train row outside the kept groups can enter the top k; rows where the proof fails go to
-//   k_knn_exact   exact brute force for those rows only (rare).
+//   k_knn_rerank  per query row, three filters with rigorous intervals: groups whose minimum could still reach the top k
+//                 (measured bf16 rounding error of both rows) -> their 4 members re-scored on the bf16 pool rows
+//                 (coalesced, fp32) -> the survivors re-scored EXACTLY (float64 sum of (a-b)^2 on the fp32 inputs); top k
+//                 by (distance, index).  The same bound proves that no train row outside the kept groups can enter the
+//                 top k; rows where the proof fails go to
+//   k_knn_exact   exact brute force for those rows only (rare; train set split over 16 CTAs per row + ticketed merge).
+//   (Sixteen epilogue warps with four shorter lists per row were measured: 5 % faster tensor pass, 17x more fallback rows.)
 // Result == exact brute-force kNN (float64 distances, ties -> lower train index), distances returned as
 // float(sqrt(d2)) like cv::NORM_L2.
 #include <algorithm>
@@ -387,10 +389,10 @@ static constexpr int RR_MAXC = RR_MAXG * GRP; // = 96 candidate train rows
 //       |d~ - d| <= errn[q] + errn[t], both measured by k_desc_prep)                           -> rows that can reach the k-th
 //   (3) exact float64 distance on the caller's fp32 rows for the survivors (typically k + 1..3 rows)
 // Traffic per query row: ~8 groups x 2 KB + ~7 x 1 KB instead of ~32 uncoalesced fp32 rows.
-__global__ void __launch_bounds__(256, 2) k_knn_rerank(const RerankJob* __restrict__ jobs, const int* __restrict__ job_row_start, int n_jobs, int total_rows,
+__global__ void __launch_bounds__(256, 3) k_knn_rerank(const RerankJob* __restrict__ jobs, const int* __restrict__ job_row_start, int n_jobs, int total_rows,
                                                      const float* __restrict__ cand, const __nv_bfloat16* __restrict__ pool, const float* __restrict__ norms,
                                                      const float* __restrict__ errn, const int* __restrict__ set_maxnorm2, const int* __restrict__ set_maxerr,
-                                                     int k, KnnOut out, int* fallback_rows, int* fallback_count) {
+                                                     int k, KnnOut out, int* fallback_rows, int* fallback_count, int force_fallback) {
 	__shared__ int s_g[8][RR_MAXG];
 	__shared__ float s_lo[8][RR_MAXC];
 	__shared__ float s_hi[8][RR_MAXC];
@@ -411,11 +413,15 @@ __global__ void __launch_bounds__(256, 2) k_knn_rerank(const RerankJob* __restri
 	// the fp32 accumulation in the tensor core; the index packing costs <= 2^-IDX_BITS relative on the key itself.
 	const float qn2 = __ldg(norms + jb.q_pool_row0 + r);
 	const float qerr = __ldg(errn + jb.q_pool_row0 + r);
-	const double qn = sqrt((double)qn2), tn = sqrt((double)__int_as_float(set_maxnorm2[jb.t_set]));
-	const double eps = (double)qerr + (double)__int_as_float(set_maxerr[jb.t_set]) + 1e-4 * (qn + tn) + 1e-6;
-	const double pk_rel = 1.0 / (double)(1 << IDX_BITS);
-	auto d_lo = [&](float key) -> double { const double v = (double)qn2 + (double)key - fabs((double)key) * pk_rel - 1e-6; return (v > 0.0 ? sqrt(v) : 0.0) - eps; };
-	auto d_hi = [&](float key) -> double { const double v = (double)qn2 + (double)key + fabs((double)key) * pk_rel + 1e-6; return (v > 0.0 ? sqrt(v) : 0.0) + eps; };
+	// All interval bounds are evaluated in fp32 and widened so that they stay conservative (B200 issues one FP64 warp instruction
+	// per ~16 cycles per scheduler: the float64 pipe is reserved for the exact distances below).  eps is rounded up by 1e-5
+	// relative, the radicand gets 3e-6 of absolute slack for its three roundings, sqrtf is correctly rounded and the factor
+	// (1 +- 1e-6) covers it and the final add.
+	const float qn = sqrtf(qn2), tn = sqrtf(__int_as_float(set_maxnorm2[jb.t_set]));
+	const float eps = (qerr + __int_as_float(set_maxerr[jb.t_set]) + 1e-4f * (qn + tn) + 1e-6f) * 1.00001f;
+	const float pk_rel = 1.0f / (float)(1 << IDX_BITS);
+	auto d_lo = [&](float key) -> float { const float v = qn2 + key - fabsf(key) * pk_rel - 4e-6f; return sqrtf(fmaxf(v, 0.f)) * (1.0f - 1e-6f) - eps; };
+	auto d_hi = [&](float key) -> float { const float v = qn2 + key + fabsf(key) * pk_rel + 4e-6f; return sqrtf(fmaxf(v, 0.f)) * (1.0f + 1e-6f) + eps; };
 	// ---- pass 1 over the list entries: k-th smallest key (d_hi is monotone in the key, and every entry IS a real train row, so
 	//      the exact k-th distance is <= D5 = d_hi(k-th key)); tau = smallest "list is full" threshold (rows of groups that
 	//      never made a list have key >= tau)
@@ -442,7 +448,7 @@ __global__ void __launch_bounds__(256, 2) k_knn_rerank(const RerankJob* __restri
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) tau = fminf(tau, __shfl_xor_sync(0xffffffffu, tau, o));
 	const float key_k = upk;
-	const double D5 = (kk > 0 && key_k < INF) ? d_hi(key_k) : 1e300;
+	const float D5 = (kk > 0 && key_k < INF) ? d_hi(key_k) : INF;
 	// ---- pass 2: every group whose lower bound can still reach D5
 	int ng = 0;
 	for (int e0 = 0; e0 < E; e0 += 32) {
@@ -558,10 +564,11 @@ __global__ void __launch_bounds__(256, 2) k_knn_rerank(const RerankJob* __restri
 			d = (double)qb.z - (double)b1.z; s += d * d; d = (double)qb.w - (double)b1.w; s += d * d;
 			return s;
 		};
-		auto insert = [&](double cd, int ci) {
+		auto insert = [&](double cd, int ci) {      // non-negative doubles order like their bit patterns: integer compares, no FP64 issue slots
 #pragma unroll
 			for (int j = 0; j < 8; j++) {
-				const bool lt = (cd < best_d[j]) || (cd == best_d[j] && ci < best_i[j]);
+				const long long a64 = __double_as_longlong(cd), b64 = __double_as_longlong(best_d[j]);
+				const bool lt = (a64 < b64) || (a64 == b64 && ci < best_i[j]);
 				if (lt) { const double td = best_d[j]; const int tix = best_i[j]; best_d[j] = cd; best_i[j] = ci; cd = td; ci = tix; }
 			}
 		};
@@ -576,68 +583,114 @@ __global__ void __launch_bounds__(256, 2) k_knn_rerank(const RerankJob* __restri
 			insert(sa, t0);
 			if (c + 1 < nsv) insert(sb, t1);
 		}
+	}
+	// ---- one FP64 square root per output slot, lane j takes slot j (a serial loop on lane 0 would cost k warp-wide FP64 sequences)
+	double mine_d = 1e300; int mine_i = 0x7fffffff;
+#pragma unroll
+	for (int j = 0; j < 8; j++) if (lane == j) { mine_d = best_d[j]; mine_i = best_i[j]; }
+	const bool have = lane < kk && mine_i != 0x7fffffff;
+	const float dist = have ? (float)sqrt(mine_d) : INF;
+	if (!overflow) {
 		// ---- proof for everything that never made a list: its key is >= tau
-		double bk = 1e300; int bi = 0x7fffffff;
-#pragma unroll
-		for (int j = 0; j < 8; j++) if (j == kk - 1) { bk = best_d[j]; bi = best_i[j]; }
-		if (kk > 0 && tau < INF) ok = (bi != 0x7fffffff) && (sqrt(bk) < d_lo(tau));
-		if (kk > 0 && bi == 0x7fffffff) ok = false;      // fewer than k survivors can only mean a broken bound: recompute exactly
+		const float dk = __shfl_sync(0xffffffffu, dist, max(kk - 1, 0));
+		const int ik = __shfl_sync(0xffffffffu, mine_i, max(kk - 1, 0));
+		if (kk > 0 && tau < INF) ok = (ik != 0x7fffffff) && (dk * (1.0f + 1e-6f) < d_lo(tau));
+		if (kk > 0 && ik == 0x7fffffff) ok = false;      // fewer than k survivors can only mean a broken bound: recompute exactly
 	}
-	if (lane == 0) {
-		int32_t* io = out.idx[jb.dir] + ((size_t)jb.out_off + r) * k;
-		float* dd = out.dist[jb.dir] + ((size_t)jb.out_off + r) * k;
-#pragma unroll
-		for (int j = 0; j < 8; j++) {
-			if (j < k) {
-				const bool have = j < kk && best_i[j] != 0x7fffffff;
-				io[j] = have ? best_i[j] : -1;
-				dd[j] = have ? (float)sqrt(best_d[j]) : INF;
-			}
-		}
-		if (!ok) { const int slot = atomicAdd(fallback_count, 1); fallback_rows[slot] = gw; }
+	if (lane < k) {
+		out.idx[jb.dir][((size_t)jb.out_off + r) * k + lane] = have ? mine_i : -1;
+		out.dist[jb.dir][((size_t)jb.out_off + r) * k + lane] = dist;
 	}
+	if (force_fallback > 0 && gw % force_fallback == 0) ok = false;
+	if (lane == 0 && !ok) { const int slot = atomicAdd(fallback_count, 1); fallback_rows[slot] = gw; }
 }
 
-// exact brute force for the rows the proof rejected: one CTA per row, persistent over the list
+// exact brute force for the rows the proof rejected.  Few rows (the normal case: ~1 per thousand): each row's train set is cut
+// into FB_SEG segments, one CTA per (row, segment), the last CTA of a row (ticket) merges the FB_SEG partial lists - a lone
+// CTA walking 2000 train rows took 0.17 ms, longer than the tensor pass of the whole batch.  Many rows: one CTA per row.
+static constexpr int FB_SEG = 16, FB_SPLIT_ROWS = 1024;
+
+__device__ __forceinline__ bool dist_less(double da, int ia, double db, int ib) {      // non-negative doubles order like their bit patterns
+	const long long a = __double_as_longlong(da), b = __double_as_longlong(db);
+	return a < b || (a == b && ia < ib);
+}
+
 __global__ void __launch_bounds__(256) k_knn_exact(const RerankJob* __restrict__ jobs, const int* __restrict__ job_row_start, int n_jobs,
-                                                    const int* __restrict__ fallback_rows, const int* __restrict__ fallback_count, int k, KnnOut out) {
+                                                    const int* __restrict__ fallback_rows, const int* __restrict__ fallback_count, int k, KnnOut out,
+                                                    double* part_d, int* part_i, int* tickets) {
 	__shared__ double s_d[8][8];
 	__shared__ int s_i[8][8];
+	__shared__ int s_last;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int n = *fallback_count;
-	for (int f = blockIdx.x; f < n; f += gridDim.x) {
+	const bool split = n <= FB_SPLIT_ROWS;
+	const int S = split ? FB_SEG : 1;
+	for (int w = blockIdx.x; w < n * S; w += gridDim.x) {
+		const int f = w / S, seg = w - f * S;
 		const int gw = fallback_rows[f];
 		const int ji = find_job(job_row_start, n_jobs, gw);
 		const RerankJob jb = jobs[ji];
 		const int r = gw - job_row_start[ji];
 		const float* qrow = (const float*)((const char*)jb.q + (size_t)r * jb.q_pitch);
+		const int len = (jb.nt + S - 1) / S, t0 = seg * len, t1 = min(jb.nt, t0 + len);
 		double best_d[8]; int best_i[8];
 #pragma unroll
 		for (int j = 0; j < 8; j++) { best_d[j] = 1e300; best_i[j] = 0x7fffffff; }
-		for (int ti = warp; ti < jb.nt; ti += 8) {
+		for (int ti = t0 + warp; ti < t1; ti += 8) {
 			const float* trow = (const float*)((const char*)jb.t + (size_t)ti * jb.t_pitch);
 			double cd = exact_d2(qrow, trow, lane); int ci = ti;
 #pragma unroll
 			for (int j = 0; j < 8; j++) {
-				const bool lt = (cd < best_d[j]) || (cd == best_d[j] && ci < best_i[j]);
-				if (lt) { const double td = best_d[j]; const int tix = best_i[j]; best_d[j] = cd; best_i[j] = ci; cd = td; ci = tix; }
+				if (dist_less(cd, ci, best_d[j], best_i[j])) { const double td = best_d[j]; const int tix = best_i[j]; best_d[j] = cd; best_i[j] = ci; cd = td; ci = tix; }
 			}
 		}
 		__syncthreads();
 		if (lane == 0) for (int j = 0; j < 8; j++) { s_d[warp][j] = best_d[j]; s_i[warp][j] = best_i[j]; }
 		__syncthreads();
-		if (threadIdx.x == 0) {   // 8-way merge of the per-warp sorted lists
+		int32_t* io = out.idx[jb.dir] + ((size_t)jb.out_off + r) * k;
+		float* dd = out.dist[jb.dir] + ((size_t)jb.out_off + r) * k;
+		if (threadIdx.x == 0) {   // 8-way merge of the per-warp sorted lists: the CTA's k best, sorted
 			int ptr[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-			int32_t* io = out.idx[jb.dir] + ((size_t)jb.out_off + r) * k;
-			float* dd = out.dist[jb.dir] + ((size_t)jb.out_off + r) * k;
-			for (int j = 0; j < k; j++) {
+			for (int j = 0; j < 8; j++) {
 				int bw = -1;
-				for (int w2 = 0; w2 < 8; w2++) {
-					if (ptr[w2] >= 8 || s_i[w2][ptr[w2]] == 0x7fffffff) continue;
-					if (bw < 0 || s_d[w2][ptr[w2]] < s_d[bw][ptr[bw]] || (s_d[w2][ptr[w2]] == s_d[bw][ptr[bw]] && s_i[w2][ptr[w2]] < s_i[bw][ptr[bw]])) bw = w2;
+				if (j < k) {
+					for (int w2 = 0; w2 < 8; w2++) {
+						if (ptr[w2] >= 8 || s_i[w2][ptr[w2]] == 0x7fffffff) continue;
+						if (bw < 0 || dist_less(s_d[w2][ptr[w2]], s_i[w2][ptr[w2]], s_d[bw][ptr[bw]], s_i[bw][ptr[bw]])) bw = w2;
+					}
 				}
-				if (bw < 0) { io[j] = -1; dd[j] = __int_as_float(0x7f800000); }
-				else { io[j] = s_i[bw][ptr[bw]]; dd[j] = (float)sqrt(s_d[bw][ptr[bw]]); ptr[bw]++; }
+				const double md = bw < 0 ? 1e300 : s_d[bw][ptr[bw]];
+				const int mi = bw < 0 ? 0x7fffffff : s_i[bw][ptr[bw]];
+				if (bw >= 0) ptr[bw]++;
+				if (!split) { if (j < k) { io[j] = bw < 0 ? -1 : mi; dd[j] = bw < 0 ? __int_as_float(0x7f800000) : (float)sqrt(md); } }
+				else { part_d[((size_t)f * FB_SEG + seg) * 8 + j] = md; part_i[((size_t)f * FB_SEG + seg) * 8 + j] = mi; }
+			}
+			s_last = 0;
+			if (split) { __threadfence(); s_last = (atomicAdd(tickets + f, 1) == FB_SEG - 1); }
+		}
+		__syncthreads();
+		if (split && s_last) {     // FB_SEG sorted lists -> the row's k best (staged in shared memory: 128 dependent L2 reads cost 30 us)
+			__shared__ double m_d[FB_SEG * 8];
+			__shared__ int m_i[FB_SEG * 8];
+			__threadfence();
+			if (threadIdx.x < FB_SEG * 8) {
+				m_d[threadIdx.x] = __ldcg(part_d + (size_t)f * FB_SEG * 8 + threadIdx.x);
+				m_i[threadIdx.x] = __ldcg(part_i + (size_t)f * FB_SEG * 8 + threadIdx.x);
+			}
+			__syncthreads();
+			if (threadIdx.x == 0) {
+				tickets[f] = 0;
+				int ptr[FB_SEG];
+				for (int q = 0; q < FB_SEG; q++) ptr[q] = 0;
+				for (int j = 0; j < k; j++) {
+					int bq = -1;
+					for (int q = 0; q < FB_SEG; q++) {
+						if (ptr[q] >= 8 || m_i[q * 8 + ptr[q]] == 0x7fffffff) continue;
+						if (bq < 0 || dist_less(m_d[q * 8 + ptr[q]], m_i[q * 8 + ptr[q]], m_d[bq * 8 + ptr[bq]], m_i[bq * 8 + ptr[bq]])) bq = q;
+					}
+					if (bq < 0) { io[j] = -1; dd[j] = __int_as_float(0x7f800000); }
+					else { io[j] = m_i[bq * 8 + ptr[bq]]; dd[j] = (float)sqrt(m_d[bq * 8 + ptr[bq]]); ptr[bq]++; }
+				}
 			}
 		}
 		__syncthreads();
@@ -651,7 +704,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 struct MatcherState {
 	int max_pairs = 0, max_feats = 0, dim = 0;
 	int pool_rows = 0;                      // capacity of the bf16 pool (rows)
-	DevBuf pool, norms, errn, sets, set_max, set_err, items, cand, jobs, job_rows, fb_rows, fb_count;
+	DevBuf pool, norms, errn, sets, set_max, set_err, items, cand, jobs, job_rows, fb_rows, fb_count, fb_part_d, fb_part_i, fb_tickets;
 	PinnedBuf h_stage, h_small;
 	PFN_encodeTiled encode = nullptr;
 	CUtensorMap tmap_q, tmap_t;
@@ -661,12 +714,13 @@ struct MatcherState {
 	int last_items = 0, last_rows = 0;
 	cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
 	bool timing = false;
+	int force_fallback = 0;     // test knob: every n-th query row is sent to the exact fallback regardless of the proof
 };
 
 void matcher_destroy(bt_ctx* ctx) {
 	MatcherState* m = ctx->matcher;
 	if (!m) return;
-	DevBuf* bufs[] = { &m->pool, &m->norms, &m->errn, &m->sets, &m->set_max, &m->set_err, &m->items, &m->cand, &m->jobs, &m->job_rows, &m->fb_rows, &m->fb_count };
+	DevBuf* bufs[] = { &m->pool, &m->norms, &m->errn, &m->sets, &m->set_max, &m->set_err, &m->items, &m->cand, &m->jobs, &m->job_rows, &m->fb_rows, &m->fb_count, &m->fb_part_d, &m->fb_part_i, &m->fb_tickets };
 	for (DevBuf* b : bufs) b->release();
 	m->h_stage.release(); m->h_small.release();
 	for (auto& e : m->ev) if (e) cudaEventDestroy(e);
@@ -726,12 +780,21 @@ extern "C" int bt_matcher_reserve(bt_ctx* ctx, int max_pairs, int max_feats, int
 	RES(job_rows, sizeof(int) * (m->max_jobs + 1));
 	RES(fb_rows, sizeof(int) * (size_t)m->max_rows_total);
 	RES(fb_count, 16);
+	RES(fb_part_d, sizeof(double) * (size_t)FB_SPLIT_ROWS * FB_SEG * 8); RES(fb_part_i, sizeof(int) * (size_t)FB_SPLIT_ROWS * FB_SEG * 8);
+	RES(fb_tickets, sizeof(int) * (size_t)FB_SPLIT_ROWS);
+	BT_CUDA(cudaMemset(m->fb_tickets.p, 0, sizeof(int) * (size_t)FB_SPLIT_ROWS));
 #undef RES
 	if ((rc = m->h_small.alloc(64)) != BT_OK) return rc;
 	if ((rc = make_tmap(m, &m->tmap_q, m->pool.p, (uint64_t)m->pool_rows, BM)) != BT_OK) return rc;
 	if ((rc = make_tmap(m, &m->tmap_t, m->pool.p, (uint64_t)m->pool_rows, BN)) != BT_OK) return rc;
 	m->maps_ready = true;
 	BT_CUDA(cudaFuncSetAttribute(k_knn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
+	return BT_OK;
+}
+
+extern "C" int bt_knn_debug_force_fallback(bt_ctx* ctx, int every_nth) {
+	BT_REQUIRE(ctx && ctx->matcher, BT_ERR_INVALID_ARG, "bt_knn_debug_force_fallback: call bt_matcher_reserve first");
+	ctx->matcher->force_fallback = every_nth > 0 ? every_nth : 0;
 	return BT_OK;
 }
 
@@ -881,9 +944,10 @@ extern "C" int bt_knn_match_pairs(bt_ctx* ctx, int n_pairs, const bt_desc_view* 
 	KnnOut out; out.idx[0] = idxAB; out.idx[1] = idxBA; out.dist[0] = distAB; out.dist[1] = distBA;
 	if (total_rows > 0) {
 		k_knn_rerank<<<(total_rows + 7) / 8, 256, 0, stream>>>(m->jobs.as<RerankJob>(), m->job_rows.as<int>(), (int)jobs.size(), total_rows, m->cand.as<float>(),
-		                                                     m->pool.as<__nv_bfloat16>(), m->norms.as<float>(), m->errn.as<float>(), m->set_max.as<int>(), m->set_err.as<int>(), k, out, m->fb_rows.as<int>(), m->fb_count.as<int>());
+		                                                     m->pool.as<__nv_bfloat16>(), m->norms.as<float>(), m->errn.as<float>(), m->set_max.as<int>(), m->set_err.as<int>(), k, out, m->fb_rows.as<int>(), m->fb_count.as<int>(), m->force_fallback);
 		if (m->timing) BT_CUDA(cudaEventRecord(m->ev[3], stream));
-		k_knn_exact<<<ctx->sm_count * 2, 256, 0, stream>>>(m->jobs.as<RerankJob>(), m->job_rows.as<int>(), (int)jobs.size(), m->fb_rows.as<int>(), m->fb_count.as<int>(), k, out);
+		k_knn_exact<<<ctx->sm_count * 2, 256, 0, stream>>>(m->jobs.as<RerankJob>(), m->job_rows.as<int>(), (int)jobs.size(), m->fb_rows.as<int>(), m->fb_count.as<int>(), k, out,
+		                                              m->fb_part_d.as<double>(), m->fb_part_i.as<int>(), m->fb_tickets.as<int>());
 	} else if (m->timing) BT_CUDA(cudaEventRecord(m->ev[3], stream));
 	if (m->timing) BT_CUDA(cudaEventRecord(m->ev[4], stream));
 	BT_CUDA(cudaGetLastError());

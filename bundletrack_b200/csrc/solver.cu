@@ -99,6 +99,7 @@ struct SolveArgs {
 	int* queue;           // [1]
 	long long* n_src_px;  // [1] stats
 	int chunk;
+	int grid_ctas;        // CTAs k_solve will be launched with (tile planning targets one wave for small batches)
 	bt_solver_params prm;
 	float* dbg_JtJ; float* dbg_Jtr; int dbg_stride;   // optional dense-system dump (last GN iteration)
 	float* dbg_cnt; int dbg_cnt_stride;               // optional per-pair #correspondences found (last GN iteration)
@@ -381,6 +382,28 @@ __device__ void plan_body(const SolveArgs& a, WinDesc* wins_rw) {
 	PROF_T(0);
 	if (tid == 0) { s_carry = 0; s_px = 0ull; *a.queue = 0; }
 	__syncthreads();
+	// Small batches: when one GN iteration has only slightly more tiles than k_solve has CTAs, the few CTAs that get two tiles
+	// put a whole extra tile on the critical path of every iteration.  Grow the chunk until an iteration fits one wave.
+	int chunk = a.chunk;
+	if (a.n_windows <= 1024) {
+		__shared__ int s_total;
+		const WinDesc wl0 = a.wins[a.n_windows - 1];
+		const int n_pairs_all = wl0.pair_off + wl0.n_pairs;
+		for (int attempt = 0; attempt < 4; attempt++) {
+			if (tid == 0) s_total = 0;
+			__syncthreads();
+			int mine = 0;
+			for (int q = tid; q < n_pairs_all; q += 1024) { int per; mine += chunks_for(a.nsrc[a.pair_src_slot[q]], chunk, per); }
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+			if ((tid & 31) == 0 && mine) atomicAdd(&s_total, mine);
+			__syncthreads();
+			const int total = s_total;
+			__syncthreads();
+			if (total <= a.grid_ctas || total > 2 * a.grid_ctas) break;
+			chunk = (int)(((long long)chunk * total / a.grid_ctas + 63) / 32 * 32);     // ~(total/grid) x larger, rounded up to warps
+		}
+	}
 	for (int base = 0; base < a.n_windows; base += 1024) {
 		const int nw = min(1024, a.n_windows - base);
 		s_cnt[tid] = 0;
@@ -394,7 +417,7 @@ __device__ void plan_body(const SolveArgs& a, WinDesc* wins_rw) {
 			const int lo = a.pair_win[q];
 			const int n = a.nsrc[a.pair_src_slot[q]];
 			int per;
-			const int nch = chunks_for(n, a.chunk, per);
+			const int nch = chunks_for(n, chunk, per);
 			a.pair_ntile[q] = nch;
 			atomicAdd(&s_cnt[lo - base], nch);
 			px += (unsigned long long)n;
@@ -459,7 +482,7 @@ __device__ void plan_body(const SolveArgs& a, WinDesc* wins_rw) {
 				const int n = a.nsrc[a.pair_src_slot[q]];
 				const int pair_off_w = a.wins[lo].pair_off;
 				int per;
-				const int nch = chunks_for(n, a.chunk, per);
+				const int nch = chunks_for(n, chunk, per);
 				int t = s_cnt[lo - base] + a.pair_tile0[q];
 				for (int c = 0; c < nch; c++) { Tile tl; tl.win = lo; tl.pair = q - pair_off_w; tl.start = c * per; tl.count = min(per, n - c * per); a.tiles[t++] = tl; }
 			}
@@ -1469,6 +1492,20 @@ extern "C" int bt_solve_stage(bt_ctx* ctx, int n_windows, const bt_window* windo
 	return stage_impl(ctx, n_windows, windows, params, poses_in, stream_, false);
 }
 
+static int ensure_occupancy(bt_ctx* ctx) {
+	SolverState* s = ctx->solver;
+	if (s->attr_bytes < s->smem_bytes || s->attr_bytes == 0) {      // per context (= per device), not per process
+		s->attr_bytes = std::max(s->smem_bytes, 48 * 1024);
+		BT_CUDA(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, s->attr_bytes));
+	}
+	if (s->occ_smem != s->smem_bytes) {
+		int occ_q = 1;
+		BT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_q, k_solve, kThreads, s->smem_bytes));
+		s->occ = std::max(occ_q, 1); s->occ_smem = s->smem_bytes;
+	}
+	return BT_OK;
+}
+
 static SolveArgs make_args(bt_ctx* ctx) {
 	SolverState* s = ctx->solver;
 	SolveArgs a;
@@ -1487,7 +1524,7 @@ static SolveArgs make_args(bt_ctx* ctx) {
 	a.pair_tile0 = s->pair_tile0.as<int>(); a.pair_ntile = s->pair_ntile.as<int>();
 	a.n_tiles_total = s->scalars.as<int>(); a.queue = s->scalars.as<int>() + 1; a.n_src_px = (long long*)(s->scalars.as<char>() + 16);
 	a.tiles_done = s->tiles_done.as<int>(); a.iter_done = s->iter_done.as<int>();
-	a.chunk = s->chunk; a.prm = s->prm;
+	a.chunk = s->chunk; a.prm = s->prm; a.grid_ctas = ctx->sm_count * s->occ;
 	if (s->prof_cap > 0) { a.prof = s->prof.as<long long>(); a.prof_cap = s->prof_cap; }
 	if (s->debug) { a.dbg_JtJ = s->dbgJ.as<float>(); a.dbg_Jtr = s->dbgR.as<float>(); a.dbg_stride = 6 * s->lim.max_frames; a.dbg_cnt = s->dbgC.as<float>(); a.dbg_cnt_stride = s->max_pairs; }
 	return a;
@@ -1495,6 +1532,8 @@ static SolveArgs make_args(bt_ctx* ctx) {
 
 static int launch_prep(bt_ctx* ctx, cudaStream_t stream) {
 	SolverState* s = ctx->solver;
+	int rco = ensure_occupancy(ctx);
+	if (rco != BT_OK) return rco;
 	SolveArgs a = make_args(ctx);
 	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[0], stream));
 	k_prep_frames<<<s->frames_total, 1024, 0, stream>>>(a, const_cast<WinDesc*>(a.wins), s->scalars.as<int>() + 8);
@@ -1509,6 +1548,7 @@ extern "C" int bt_solve_run(bt_ctx* ctx, void* stream_) {
 	SolverState* s = ctx->solver;
 	cudaStream_t stream = (cudaStream_t)stream_;
 	BT_CUDA(cudaSetDevice(ctx->device));
+	{ int rco = ensure_occupancy(ctx); if (rco != BT_OK) return rco; }
 	SolveArgs a = make_args(ctx);
 	if (s->debug) {
 		BT_CUDA(cudaMemsetAsync(s->dbgJ.p, 0, s->dbgJ.bytes, stream));
@@ -1518,15 +1558,6 @@ extern "C" int bt_solve_run(bt_ctx* ctx, void* stream_) {
 	if (!s->prep_launched) { int rcp = launch_prep(ctx, stream); if (rcp != BT_OK) return rcp; }
 	s->prep_launched = false;       // a second bt_solve_run on the same staged batch prepares again (poses restart from the staged input)
 	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[2], stream));
-	if (s->attr_bytes < s->smem_bytes || s->attr_bytes == 0) {      // per context (= per device), not per process
-		s->attr_bytes = std::max(s->smem_bytes, 48 * 1024);
-		BT_CUDA(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, s->attr_bytes));
-	}
-	if (s->occ_smem != s->smem_bytes) {
-		int occ_q = 1;
-		BT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_q, k_solve, kThreads, s->smem_bytes));
-		s->occ = std::max(occ_q, 1); s->occ_smem = s->smem_bytes;
-	}
 	const int occ = s->occ;
 	const int grid = ctx->sm_count * occ;
 	k_solve<<<grid, kThreads, s->smem_bytes, stream>>>(a);

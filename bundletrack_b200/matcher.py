@@ -63,6 +63,10 @@ class KnnMatcher:
             ib += b.shape[0]
         return [x[0] for x in oAB], [x[1] for x in oAB], [x[0] for x in oBA], [x[1] for x in oBA]
 
+    def force_fallback(self, every_nth: int):
+        """Test knob: every n-th query row goes through the exact brute-force kernel (0 = off)."""
+        _lib.check(self.lib.bt_knn_debug_force_fallback(self.ctx, ctypes.c_int(every_nth)), "bt_knn_debug_force_fallback")
+
     def enable_timing(self, on=True):
         _lib.check(self.lib.bt_knn_enable_timing(self.ctx, ctypes.c_int(1 if on else 0)), "bt_knn_enable_timing")
 

@@ -168,6 +168,8 @@ BT_API int bt_knn_match_pairs(bt_ctx* ctx, int n_pairs, const bt_desc_view* A, c
 /* Device time of the last bt_knn_match_pairs: ms4 = {bf16 conversion, tensor-core pass, exact re-rank, exact fallback},
  * info3 = {work items, query rows, rows that needed the exact fallback}. */
 BT_API int bt_knn_enable_timing(bt_ctx* ctx, int on);
+/* Test knob: send every n-th query row through the exact brute-force fallback (0 = off).  Results do not change. */
+BT_API int bt_knn_debug_force_fallback(bt_ctx* ctx, int every_nth);
 BT_API int bt_knn_get_timing(bt_ctx* ctx, float* ms4, int* info3);
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -43,6 +43,22 @@ def test_knn_equals_exact_brute_force(matcher, cuda_device, na, nb):
     _check(matcher, cuda_device, a, b)
 
 
+@pytest.mark.parametrize("every,na,nb", [(7, 900, 1300), (1, 40, 33), (1, 1500, 2100)])
+def test_knn_exact_fallback_paths(matcher, cuda_device, every, na, nb):
+    """The brute-force fallback in both of its shapes (few rows: train set split over 16 CTAs + ticketed merge; many rows: one
+    CTA per row) returns exactly what the tensor-core path + proof returns."""
+    a, b, _, _ = synth.make_descriptors(na + nb, na, nb)
+    b[5] = b[6] = a[3]                      # ties across segment boundaries resolve to the lower index
+    matcher.force_fallback(every)
+    matcher.enable_timing(True)
+    try:
+        _check(matcher, cuda_device, a, b)
+        assert matcher.timing()["fallback_rows"] >= (na + nb) // every - 1
+    finally:
+        matcher.force_fallback(0)
+        matcher.enable_timing(False)
+
+
 def test_knn_cfg5_5000x5000(matcher, cuda_device):
     a, b, _, _ = synth.make_descriptors(55, 5000, 5000)
     _check(matcher, cuda_device, a, b)
