@@ -413,10 +413,10 @@ __global__ void __launch_bounds__(256, 3) k_knn_rerank(const RerankJob* __restri
 	// the fp32 accumulation in the tensor core; the index packing costs <= 2^-IDX_BITS relative on the key itself.
 	const float qn2 = __ldg(norms + jb.q_pool_row0 + r);
 	const float qerr = __ldg(errn + jb.q_pool_row0 + r);
-	// All interval bounds are evaluated in fp32 and widened so that they stay conservative (B200 issues one FP64 warp instruction
-	// per ~16 cycles per scheduler: the float64 pipe is reserved for the exact distances below).  eps is rounded up by 1e-5
-	// relative, the radicand gets 3e-6 of absolute slack for its three roundings, sqrtf is correctly rounded and the factor
-	// (1 +- 1e-6) covers it and the final add.
+	// All interval bounds are evaluated in fp32 and widened so that they stay conservative: the float64 square-root and compare
+	// sequences they replaced were a third of this kernel's instructions; float64 is kept for the exact distances only.
+	// eps is rounded up by 1e-5 relative, the radicand gets 4e-6 of absolute slack for its three roundings, sqrtf is correctly
+	// rounded and the factor (1 +- 1e-6) covers it and the final add.
 	const float qn = sqrtf(qn2), tn = sqrtf(__int_as_float(set_maxnorm2[jb.t_set]));
 	const float eps = (qerr + __int_as_float(set_maxerr[jb.t_set]) + 1e-4f * (qn + tn) + 1e-6f) * 1.00001f;
 	const float pk_rel = 1.0f / (float)(1 << IDX_BITS);
@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(256, 3) k_knn_rerank(const RerankJob* __restri
 			d = (double)qb.z - (double)b1.z; s += d * d; d = (double)qb.w - (double)b1.w; s += d * d;
 			return s;
 		};
-		auto insert = [&](double cd, int ci) {      // non-negative doubles order like their bit patterns: integer compares, no FP64 issue slots
+		auto insert = [&](double cd, int ci) {      // non-negative doubles order like their bit patterns: integer compares
 #pragma unroll
 			for (int j = 0; j < 8; j++) {
 				const long long a64 = __double_as_longlong(cd), b64 = __double_as_longlong(best_d[j]);
@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(256, 3) k_knn_rerank(const RerankJob* __restri
 			if (c + 1 < nsv) insert(sb, t1);
 		}
 	}
-	// ---- one FP64 square root per output slot, lane j takes slot j (a serial loop on lane 0 would cost k warp-wide FP64 sequences)
+	// ---- one FP64 square root per output slot, lane j takes slot j (a serial loop on lane 0 would run k square-root sequences back to back)
 	double mine_d = 1e300; int mine_i = 0x7fffffff;
 #pragma unroll
 	for (int j = 0; j < 8; j++) if (lane == j) { mine_d = best_d[j]; mine_i = best_i[j]; }

@@ -19,6 +19,7 @@
 #include <curand_kernel.h>
 #include <algorithm>
 #include <vector>
+#include <math.h>
 #include "bt_common.cuh"
 
 namespace bt {
@@ -110,48 +111,49 @@ __global__ void __launch_bounds__(256) k_ransac_model(const RansacPair* __restri
 	good[(size_t)pair * n_trials + t] = 1;
 }
 
-static constexpr int kEvalPts = 1024;   // points staged per shared-memory chunk (2 x 12 KB)
+static constexpr int kEvalPts = 1024;   // points staged per shared-memory chunk (2 x 16 KB)
+static constexpr int kEvalCheck = 128;   // points between two looks at the best count found so far
 
+// Counts the inliers of every trial (one thread per trial, the points broadcast from shared memory).  Two things keep the
+// instruction count down - the kernel is issue-bound, ~2000 trials x ~1500 points x 45 pairs:
+//  * `sqrtf(d2) <= thresh` is evaluated as `d2 <= d2_max` with d2_max the largest float whose correctly rounded square root
+//    is <= thresh (computed on the host): same truth value for every float, no square root;
+//  * a trial stops as soon as it can no longer reach the best count any trial of this pair has finished with so far
+//    (count + points left < best): it cannot win and it cannot tie, so the winner (max count, then lowest trial) is unchanged.
 __global__ void __launch_bounds__(256) k_ransac_eval(const RansacPair* __restrict__ pairs, int n_trials, const float* __restrict__ poses, const int* __restrict__ good,
-                                                      float thresh, unsigned long long* __restrict__ best) {
-	__shared__ float sA[kEvalPts * 3];
-	__shared__ float sB[kEvalPts * 3];
-	__shared__ unsigned long long s_best[8];
+                                                      float d2_max, unsigned long long* __restrict__ best) {
+	__shared__ float4 sA[kEvalPts];
+	__shared__ float4 sB[kEvalPts];
 	const int pair = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
 	const RansacPair pr = pairs[pair];
 	const bool live = t < n_trials && good[(size_t)pair * n_trials + t] != 0;
 	float P[12];
 	if (live) { const float* Pg = poses + ((size_t)pair * n_trials + t) * 12; for (int k = 0; k < 12; k++) P[k] = Pg[k]; }
 	else for (int k = 0; k < 12; k++) P[k] = 0.f;
-	const float th2 = thresh;
 	int count = 0;
+	bool running = live;
 	for (int base = 0; base < pr.n; base += kEvalPts) {
 		const int m = min(kEvalPts, pr.n - base);
 		__syncthreads();
-		for (int k = threadIdx.x; k < m; k += blockDim.x) {
-			const float4 a = __ldg(pr.A + base + k), b = __ldg(pr.B + base + k);
-			sA[3 * k] = a.x; sA[3 * k + 1] = a.y; sA[3 * k + 2] = a.z; sB[3 * k] = b.x; sB[3 * k + 1] = b.y; sB[3 * k + 2] = b.z;
-		}
+		for (int k = threadIdx.x; k < m; k += blockDim.x) { sA[k] = __ldg(pr.A + base + k); sB[k] = __ldg(pr.B + base + k); }
 		__syncthreads();
-		if (live) {
+		for (int k0 = 0; k0 < m && running; k0 += kEvalCheck) {
+			const int k1 = min(m, k0 + kEvalCheck);
 #pragma unroll 4
-			for (int k = 0; k < m; k++) {
-				const float ax = sA[3 * k], ay = sA[3 * k + 1], az = sA[3 * k + 2];
-				const float dx = sB[3 * k] - (P[0] * ax + P[1] * ay + P[2] * az + P[3]);
-				const float dy = sB[3 * k + 1] - (P[4] * ax + P[5] * ay + P[6] * az + P[7]);
-				const float dz = sB[3 * k + 2] - (P[8] * ax + P[9] * ay + P[10] * az + P[11]);
-				count += (sqrtf(dx * dx + dy * dy + dz * dz) <= th2) ? 1 : 0;
+			for (int k = k0; k < k1; k++) {
+				const float4 pa = sA[k], pb = sB[k];
+				const float dx = pb.x - (P[0] * pa.x + P[1] * pa.y + P[2] * pa.z + P[3]);
+				const float dy = pb.y - (P[4] * pa.x + P[5] * pa.y + P[6] * pa.z + P[7]);
+				const float dz = pb.z - (P[8] * pa.x + P[9] * pa.y + P[10] * pa.z + P[11]);
+				count += (dx * dx + dy * dy + dz * dz <= d2_max) ? 1 : 0;
 			}
+			// best[pair] only ever holds counts of trials that have seen ALL points
+			const int best_cnt = (int)(__ldcg(best + pair) >> 32);
+			if (count + (pr.n - base - k1) < best_cnt) running = false;
 		}
-	}
-	unsigned long long key = live ? (((unsigned long long)(unsigned)count << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)t)) : 0ull;
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o); key = other > key ? other : key; }
-	if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = key;
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		for (int k = 1; k < (int)(blockDim.x >> 5); k++) key = s_best[k] > key ? s_best[k] : key;
-		if (key) atomicMax(best + pair, key);
+		if (running && base + m >= pr.n) {     // finished: publish (count, lowest trial) right away so that slower trials can stop early
+			atomicMax(best + pair, ((unsigned long long)(unsigned)count << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)t));
+		}
 	}
 }
 
@@ -223,9 +225,16 @@ int ransac_run_device(bt_ctx* ctx, const RansacPair* d_pairs, int n_pairs, int n
 		r->table_seed = seed; r->table_trials = r->max_trials;
 	}
 	BT_CUDA(cudaMemsetAsync(r->best.p, 0, sizeof(unsigned long long) * n_pairs, stream));
+	// largest float d2 with sqrtf(d2) <= dist_thresh (both correctly rounded, host and device): lets the kernel compare squares
+	float d2_max = -1.0f;
+	if (dist_thresh >= 0.f) {
+		d2_max = dist_thresh * dist_thresh;
+		while (d2_max > 0.f && sqrtf(d2_max) > dist_thresh) d2_max = nextafterf(d2_max, 0.f);
+		while (sqrtf(nextafterf(d2_max, INFINITY)) <= dist_thresh) d2_max = nextafterf(d2_max, INFINITY);
+	}
 	const dim3 grid((n_trials + 255) / 256, n_pairs);
 	k_ransac_model<<<grid, 256, 0, stream>>>(d_pairs, n_trials, r->table.as<float>(), r->poses.as<float>(), r->good.as<int>());
-	k_ransac_eval<<<grid, 256, 0, stream>>>(d_pairs, n_trials, r->poses.as<float>(), r->good.as<int>(), dist_thresh, r->best.as<unsigned long long>());
+	k_ransac_eval<<<grid, 256, 0, stream>>>(d_pairs, n_trials, r->poses.as<float>(), r->good.as<int>(), d2_max, r->best.as<unsigned long long>());
 	k_ransac_inliers<<<n_pairs, 256, 0, stream>>>(d_pairs, n_trials, r->poses.as<float>(), dist_thresh, r->best.as<unsigned long long>(), inlier_ids_out, n_inliers_out, r->best_trial.as<int32_t>());
 	BT_CUDA(cudaGetLastError());
 	return BT_OK;
