@@ -61,10 +61,15 @@ struct WinDesc {
 	int pad[3];
 };
 
+// The correspondence-side fields of a window, uploaded AFTER the frame preparation has been launched (the host scans the
+// correspondences while the GPU already works); window_tail reads them from here, the copies inside WinDesc are unused.
+struct WinSparse { int n_corr, n_groups, corr_off, grp_off, mem_off, unique_blocks, pad0, pad1; };
+
 struct Tile { int win; int pair; int start; int count; };  // pair < 0 => dummy tile (window without dense work)
 
 struct SolveArgs {
 	const WinDesc* wins;
+	const WinSparse* wsp;
 	int n_windows;
 	// frame slots
 	const float* const* depth_ptr;
@@ -642,7 +647,9 @@ __device__ __forceinline__ void unpack_sym(int e, int& r, int& c) {
 	c = r + e;
 }
 
-__device__ void window_tail(const SolveArgs& a, const WinDesc& wd, int w, int it, float* smem_base) {
+__device__ void window_tail(const SolveArgs& a, const WinDesc& wd_in, int w, int it, float* smem_base) {
+	WinDesc wd = wd_in;
+	{ const WinSparse ws = a.wsp[w]; wd.n_corr = ws.n_corr; wd.n_groups = ws.n_groups; wd.corr_off = ws.corr_off; wd.grp_off = ws.grp_off; wd.mem_off = ws.mem_off; wd.unique_blocks = ws.unique_blocks; }
 	const int tid = threadIdx.x, lane = tid & 31;
 	const int N = wd.n_frames, P = wd.n_pairs, G = wd.n_groups;
 	TailSmem s;
@@ -1123,7 +1130,7 @@ __global__ void __launch_bounds__(kThreads, BT_SOLVE_MIN_CTAS) k_solve(SolveArgs
 // single H2D copy: the small tables first (carved for the worst case of this window count), the correspondences last so
 // that the copy length follows the actual number of entries.
 struct StageLayout {
-	size_t wins, dp, np, fw, texp, srcp, nsrcp, pose, gi, gj, gs, pairs, pwin, psrc, mem, corr, total;
+	size_t wins, dp, np, fw, texp, srcp, nsrcp, pose, pairs, pwin, psrc, late, wsp, gi, gj, gs, mem, corr, total;   // [0,late): needed by k_prep_frames
 };
 static StageLayout stage_layout(int n_windows, size_t F, size_t C, int max_frames, size_t maxG, size_t maxP) {
 	StageLayout L;
@@ -1132,9 +1139,10 @@ static StageLayout stage_layout(int n_windows, size_t F, size_t C, int max_frame
 	const size_t nw = (size_t)n_windows;
 	L.wins = carve(sizeof(WinDesc) * nw); L.dp = carve(sizeof(void*) * F); L.np = carve(sizeof(void*) * F); L.fw = carve(sizeof(int) * F);
 	L.texp = carve(sizeof(void*) * F); L.srcp = carve(sizeof(void*) * F); L.nsrcp = carve(sizeof(void*) * F);
-	L.pose = carve(sizeof(float) * 16 * F); L.gi = carve(sizeof(int) * maxG * nw); L.gj = carve(sizeof(int) * maxG * nw);
-	L.gs = carve(sizeof(int) * (maxG + 1) * nw); L.pairs = carve(sizeof(uint2) * maxP * nw); L.pwin = carve(sizeof(int) * maxP * nw);
-	L.psrc = carve(sizeof(int) * maxP * nw); L.mem = carve(sizeof(int) * (2 * ((size_t)max_frames + 1) + 2 * maxG + 2 * maxP) * nw);
+	L.pose = carve(sizeof(float) * 16 * F); L.pairs = carve(sizeof(uint2) * maxP * nw); L.pwin = carve(sizeof(int) * maxP * nw); L.psrc = carve(sizeof(int) * maxP * nw);
+	L.late = off;
+	L.wsp = carve(sizeof(WinSparse) * nw); L.gi = carve(sizeof(int) * maxG * nw); L.gj = carve(sizeof(int) * maxG * nw); L.gs = carve(sizeof(int) * (maxG + 1) * nw);
+	L.mem = carve(sizeof(int) * (2 * ((size_t)max_frames + 1) + 2 * maxG + 2 * maxP) * nw);
 	L.corr = carve(sizeof(bt_entryj) * C + 32);
 	L.total = off;
 	return L;
@@ -1162,7 +1170,7 @@ struct SolverState {
 	std::vector<int> n_frames;
 	bool staged = false, debug = false, timing = false;
 	int launches = 0;
-	int attr_bytes = 0, occ = 1, occ_smem = -1;
+	int attr_bytes = 0, occ = BT_SOLVE_MIN_CTAS, occ_smem = -1;
 	bool prep_launched = false;
 	cudaStream_t copy_stream = nullptr;
 	cudaEvent_t ev_prev = nullptr, ev_corr = nullptr, ev_h2d = nullptr;
@@ -1284,27 +1292,24 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 		BT_REQUIRE(params->w_dense <= 0.f || bw.cache_slots || (bw.depth_dev && bw.normal_dev), BT_ERR_INVALID_ARG, "window %d: depth/normal pointers are NULL and no cache slots given", w);
 		F += bw.n_frames; C += bw.n_corr;
 	}
-	// ---- host staging: one pinned block, one H2D per array
+	// ---- host staging: one pinned block mirrored by one device block
 	const size_t maxP = (size_t)s->max_pairs, maxG = (size_t)s->max_groups;
 	const StageLayout L = stage_layout(n_windows, F, C, s->lim.max_frames, maxG, maxP);
 	BT_REQUIRE(L.total <= s->stage_dev.bytes, BT_ERR_CAPACITY, "bt_solve_stage: staging block %zu > reserved %zu bytes", L.total, s->stage_dev.bytes);
-	const size_t o_wins = L.wins, o_dp = L.dp, o_np = L.np, o_fw = L.fw, o_pose = L.pose, o_corr = L.corr, o_gi = L.gi, o_gj = L.gj, o_gs = L.gs, o_pairs = L.pairs,
-	             o_pwin = L.pwin, o_psrc = L.psrc, o_mem = L.mem;
 	int rc = s->h_stage.alloc(L.total);
 	if (rc != BT_OK) return rc;
 	char* hb = s->h_stage.as<char>();
-	WinDesc* hw = (WinDesc*)(hb + o_wins);
-	const void** hdp = (const void**)(hb + o_dp); const void** hnp = (const void**)(hb + o_np);
+	WinDesc* hw = (WinDesc*)(hb + L.wins);
+	const void** hdp = (const void**)(hb + L.dp); const void** hnp = (const void**)(hb + L.np);
 	const void** htex = (const void**)(hb + L.texp); const void** hsrc = (const void**)(hb + L.srcp); const void** hnsrc = (const void**)(hb + L.nsrcp);
-	int* hfw = (int*)(hb + o_fw); float* hpose = (float*)(hb + o_pose); bt_entryj* hcorr = (bt_entryj*)(hb + o_corr);
-	int* hgi = (int*)(hb + o_gi); int* hgj = (int*)(hb + o_gj); int* hgs = (int*)(hb + o_gs); uint2* hpairs = (uint2*)(hb + o_pairs);
-	int* hpwin = (int*)(hb + o_pwin); int* hpsrc = (int*)(hb + o_psrc); int* hmem = (int*)(hb + o_mem);
-	size_t m_off = 0;
+	int* hfw = (int*)(hb + L.fw); float* hpose = (float*)(hb + L.pose); bt_entryj* hcorr = (bt_entryj*)(hb + L.corr);
+	WinSparse* hws = (WinSparse*)(hb + L.wsp);
+	int* hgi = (int*)(hb + L.gi); int* hgj = (int*)(hb + L.gj); int* hgs = (int*)(hb + L.gs); uint2* hpairs = (uint2*)(hb + L.pairs);
+	int* hpwin = (int*)(hb + L.pwin); int* hpsrc = (int*)(hb + L.psrc); int* hmem = (int*)(hb + L.mem);
 	s->frame_off.assign(n_windows, 0); s->n_frames.assign(n_windows, 0);
-	size_t f_off = 0, c_off = 0, g_off = 0, p_off = 0, smem_need = 0;
-	struct CorrJob { const bt_entryj* src; int n_in; size_t dst; int N; std::vector<int> bin; };   // bin non-empty => stable counting sort
-	std::vector<CorrJob> jobs;
-	jobs.reserve(n_windows);
+
+	// ==== phase 1: what the frame preparation needs - geometry, frame tables, poses, dense pair tables (no look at the correspondences)
+	size_t f_off = 0, p_off = 0;
 	for (int w = 0; w < n_windows; w++) {
 		const bt_window& bw = windows[w];
 		const int N = bw.n_frames;
@@ -1317,7 +1322,7 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 		d.ifx = 1.0f / bw.fx; d.ify = 1.0f / bw.fy; d.icx = -bw.cx / bw.fx; d.icy = -bw.cy / bw.fy;
 		d.scaleW = (float)(bw.W - 1) / (float)(d.w - 1); d.scaleH = (float)(bw.H - 1) / (float)(d.h - 1);
 		d.compat_flip = bw.compat_flip;
-		d.frame_off = (int)f_off; d.corr_off = (int)c_off; d.grp_off = (int)g_off; d.pair_off = (int)p_off;
+		d.frame_off = (int)f_off; d.pair_off = (int)p_off;
 		s->frame_off[w] = (int)f_off; s->n_frames[w] = N;
 		for (int f = 0; f < N; f++) {
 			const size_t fs = f_off + f;
@@ -1337,9 +1342,57 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 				htex[fs] = s->texel.as<float4>() + fs * 2 * (size_t)s->npix_max; hsrc[fs] = s->src.as<float4>() + fs * 2 * (size_t)s->npix_max;
 				hnsrc[fs] = nullptr;
 			}
-			hfw[f_off + f] = w;
-			memcpy(hpose + (f_off + f) * 16, poses_in + (f_off + f) * 16, sizeof(float) * 16);
+			hfw[fs] = w;
+			memcpy(hpose + fs * 16, poses_in + fs * 16, sizeof(float) * 16);
 		}
+		int np = 0;
+		if (params->w_dense > 0.f) {
+			if (bw.dense_pairs) {
+				BT_REQUIRE(bw.n_dense_pairs >= 0 && bw.n_dense_pairs <= s->max_pairs, BT_ERR_CAPACITY, "window %d: %d dense pairs > %d", w, bw.n_dense_pairs, s->max_pairs);
+				for (int p = 0; p < bw.n_dense_pairs; p++) {
+					const uint32_t ti = bw.dense_pairs[2 * p], sj = bw.dense_pairs[2 * p + 1];
+					BT_REQUIRE(ti < (uint32_t)N && sj < (uint32_t)N && ti != sj, BT_ERR_INVALID_ARG, "window %d: dense pair %d = (%u,%u) invalid", w, p, ti, sj);
+					hpairs[p_off + np++] = make_uint2(ti, sj);
+				}
+			} else {
+				for (int i = 0; i < N; i++) for (int j = 0; j < i; j++) hpairs[p_off + np++] = make_uint2((unsigned)i, (unsigned)j);
+			}
+		}
+		d.n_pairs = np;
+		for (int p = 0; p < np; p++) { hpwin[p_off + p] = w; hpsrc[p_off + p] = (int)f_off + (int)hpairs[p_off + p].y; }
+		f_off += N; p_off += np;
+	}
+	s->n_windows = n_windows; s->frames_total = (int)f_off; s->prm = *params;
+	// chunk: aim for >= 4 tiles per SM-resident CTA over the batch, between 256 and 2048 source pixels
+	{
+		const long long est_px = (long long)p_off * (s->npix_max / 8);   // ~12 % valid
+		long long c = est_px / ((long long)ctx->sm_count * 2 * 4);
+		c = std::max(256LL, std::min(2048LL, c));
+		s->chunk = (int)((c + 255) / 256 * 256);
+	}
+	s->layout = L;
+	if (!s->copy_stream) {
+		BT_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+		BT_CUDA(cudaEventCreateWithFlags(&s->ev_prev, cudaEventDisableTiming));
+		BT_CUDA(cudaEventCreateWithFlags(&s->ev_corr, cudaEventDisableTiming));
+		BT_CUDA(cudaEventCreateWithFlags(&s->ev_h2d, cudaEventDisableTiming));
+	}
+	// early tables, in stream order behind whatever the caller's stream still runs on the previous batch; then (fused call) the frame prep
+	BT_CUDA(cudaMemcpyAsync(s->stage_dev.p, hb, L.late, cudaMemcpyHostToDevice, stream));
+	BT_CUDA(cudaEventRecord(s->ev_prev, stream));
+	BT_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_prev, 0));
+	if (early_prep) { if ((rc = launch_prep(ctx, stream)) != BT_OK) return rc; }
+
+	// ==== phase 2 (the GPU is already busy in the fused call): correspondences -> groups, membership CSR, pinned copy, chunked upload
+	size_t c_off = 0, g_off = 0, m_off = 0, smem_need = 0, sent = 0;
+	std::vector<int> bin;
+	std::vector<char> seen;
+	p_off = 0;
+	for (int w = 0; w < n_windows; w++) {
+		const bt_window& bw = windows[w];
+		const int N = bw.n_frames, np = hw[w].n_pairs;
+		const size_t f_off_w = (size_t)hw[w].frame_off;
+		(void)f_off_w;
 		// correspondences: stable counting sort by (i,j) so each pair's entries are contiguous (Bundler::optimizeGPU
 		// already emits them that way, /root/reference/src/Bundler.cpp:298-324); invalid entries are dropped.
 		int n_valid = 0, ng = 0;
@@ -1354,13 +1407,12 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 				if (key != prev) { hgi[g_off + ng] = (int)e.imgIdx_i; hgj[g_off + ng] = (int)e.imgIdx_j; hgs[g_off + w + ng] = c; ng++; prev = key; }
 			}
 		}
-		CorrJob job; job.src = bw.corr; job.n_in = bw.n_corr; job.dst = c_off; job.N = N;
 		if (grouped) {
 			n_valid = bw.n_corr;
 			hgs[g_off + w + ng] = n_valid;
+			if (n_valid) memcpy(hcorr + c_off, bw.corr, sizeof(bt_entryj) * (size_t)n_valid);      // the window's entries are still in cache from the scan
 		} else {
 			ng = 0;
-			std::vector<int>& bin = job.bin;
 			bin.assign((size_t)N * N + 1, 0);
 			for (int c = 0; c < bw.n_corr; c++) {
 				const bt_entryj& e = bw.corr[c];
@@ -1378,35 +1430,24 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 				for (size_t b = 0; b < (size_t)N * N; b++) if (bin[b + 1] > bin[b]) hgs[g_off + w + gg++] = bin[b];
 				hgs[g_off + w + ng] = n_valid;
 			}
-		}
-		jobs.push_back(std::move(job));
-		d.n_corr = n_valid; d.n_groups = ng;
-		// dense pairs
-		int np = 0;
-		if (params->w_dense > 0.f) {
-			if (bw.dense_pairs) {
-				BT_REQUIRE(bw.n_dense_pairs >= 0 && bw.n_dense_pairs <= s->max_pairs, BT_ERR_CAPACITY, "window %d: %d dense pairs > %d", w, bw.n_dense_pairs, s->max_pairs);
-				for (int p = 0; p < bw.n_dense_pairs; p++) {
-					const uint32_t ti = bw.dense_pairs[2 * p], sj = bw.dense_pairs[2 * p + 1];
-					BT_REQUIRE(ti < (uint32_t)N && sj < (uint32_t)N && ti != sj, BT_ERR_INVALID_ARG, "window %d: dense pair %d = (%u,%u) invalid", w, p, ti, sj);
-					hpairs[p_off + np++] = make_uint2(ti, sj);
-				}
-			} else {
-				for (int i = 0; i < N; i++) for (int j = 0; j < i; j++) hpairs[p_off + np++] = make_uint2((unsigned)i, (unsigned)j);
+			for (int c = 0; c < bw.n_corr; c++) {
+				const bt_entryj& e = bw.corr[c];
+				if (e.imgIdx_i == 0xFFFFFFFFu) continue;
+				hcorr[c_off + bin[(size_t)e.imgIdx_i * N + e.imgIdx_j]++] = e;
 			}
 		}
-		d.n_pairs = np;
+		WinSparse& ws = hws[w];
+		memset(&ws, 0, sizeof ws);
+		ws.n_corr = n_valid; ws.n_groups = ng; ws.corr_off = (int)c_off; ws.grp_off = (int)g_off; ws.mem_off = (int)m_off;
 		{   // cross blocks are written without atomics when every unordered frame pair occurs at most once per table
-			std::vector<char> seen((size_t)N * N, 0);
+			seen.assign((size_t)N * N, 0);
 			bool uq = true;
 			for (int g = 0; g < ng && uq; g++) { const int a2 = std::min(hgi[g_off + g], hgj[g_off + g]), b2 = std::max(hgi[g_off + g], hgj[g_off + g]); if (seen[(size_t)a2 * N + b2]) uq = false; seen[(size_t)a2 * N + b2] = 1; }
 			std::fill(seen.begin(), seen.end(), 0);
 			for (int p = 0; p < np && uq; p++) { const int a2 = (int)std::min(hpairs[p_off + p].x, hpairs[p_off + p].y), b2 = (int)std::max(hpairs[p_off + p].x, hpairs[p_off + p].y); if (seen[(size_t)a2 * N + b2]) uq = false; seen[(size_t)a2 * N + b2] = 1; }
-			d.unique_blocks = uq ? 1 : 0;
+			ws.unique_blocks = uq ? 1 : 0;
 		}
-		for (int p = 0; p < np; p++) { hpwin[p_off + p] = w; hpsrc[p_off + p] = (int)f_off + (int)hpairs[p_off + p].y; }
 		{   // per-frame membership CSR: groups then pairs touching each frame, in increasing index order (fixed summation order)
-			d.mem_off = (int)m_off;
 			int* fg_start = hmem + m_off; int* fp_start = fg_start + (N + 1); int* fg_items = fp_start + (N + 1); int* fp_items = fg_items + 2 * ng;
 			int q = 0;
 			for (int f = 0; f < N; f++) {
@@ -1429,51 +1470,16 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 			m_off += (size_t)(2 * (N + 1) + 2 * ng + 2 * np);
 		}
 		smem_need = std::max(smem_need, tail_smem_floats(N, np, ng) * sizeof(float));
-		f_off += N; c_off += n_valid; g_off += ng; p_off += np;
-	}
-	BT_REQUIRE(smem_need <= 200 * 1024, BT_ERR_CAPACITY, "bt_solve_stage: window needs %zu bytes of shared memory (> 200 KB)", smem_need);
-	s->n_windows = n_windows; s->frames_total = (int)f_off; s->smem_bytes = (int)smem_need; s->prm = *params;
-	// chunk: aim for >= 4 tiles per SM-resident CTA over the batch, between 256 and 2048 source pixels
-	{
-		const long long est_px = (long long)p_off * (s->npix_max / 8);   // ~12 % valid
-		long long c = est_px / ((long long)ctx->sm_count * 2 * 4);
-		c = std::max(256LL, std::min(2048LL, c));
-		s->chunk = (int)((c + 255) / 256 * 256);
-	}
-	(void)p_off; (void)g_off; (void)m_off;
-	s->layout = L;
-	if (!s->copy_stream) {
-		BT_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
-		BT_CUDA(cudaEventCreateWithFlags(&s->ev_prev, cudaEventDisableTiming));
-		BT_CUDA(cudaEventCreateWithFlags(&s->ev_corr, cudaEventDisableTiming));
-		BT_CUDA(cudaEventCreateWithFlags(&s->ev_h2d, cudaEventDisableTiming));
-	}
-	// (1) tables, in stream order behind whatever the caller's stream still runs on the previous batch
-	BT_CUDA(cudaMemcpyAsync(s->stage_dev.p, hb, o_corr, cudaMemcpyHostToDevice, stream));
-	BT_CUDA(cudaEventRecord(s->ev_prev, stream));
-	BT_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_prev, 0));
-	if (early_prep) { if ((rc = launch_prep(ctx, stream)) != BT_OK) return rc; }
-	// (2) correspondences: pinned copy (or stable counting sort) per window, uploaded in chunks of >= 256 KB on the copy stream
-	{
-		size_t sent = 0;      // entries already handed to the copy engine
-		for (size_t j = 0; j < jobs.size(); j++) {
-			CorrJob& jb = jobs[j];
-			if (jb.bin.empty()) {
-				if (jb.n_in) memcpy(hcorr + jb.dst, jb.src, sizeof(bt_entryj) * (size_t)jb.n_in);
-			} else {
-				for (int c = 0; c < jb.n_in; c++) {
-					const bt_entryj& e = jb.src[c];
-					if (e.imgIdx_i == 0xFFFFFFFFu) continue;
-					hcorr[jb.dst + jb.bin[(size_t)e.imgIdx_i * jb.N + e.imgIdx_j]++] = e;
-				}
-			}
-			const size_t done = (j + 1 < jobs.size()) ? jobs[j + 1].dst : c_off;
-			if ((done - sent) * sizeof(bt_entryj) >= 256 * 1024 || (j + 1 == jobs.size() && done > sent)) {
-				BT_CUDA(cudaMemcpyAsync(s->stage_dev.as<char>() + o_corr + sent * sizeof(bt_entryj), hcorr + sent, (done - sent) * sizeof(bt_entryj), cudaMemcpyHostToDevice, s->copy_stream));
-				sent = done;
-			}
+		c_off += n_valid; g_off += ng; p_off += np;
+		// upload what has accumulated once it is worth a copy (>= 256 KB), and whatever is left after the last window
+		if ((c_off - sent) * sizeof(bt_entryj) >= 256 * 1024 || (w + 1 == n_windows && c_off > sent)) {
+			BT_CUDA(cudaMemcpyAsync(s->stage_dev.as<char>() + L.corr + sent * sizeof(bt_entryj), hcorr + sent, (c_off - sent) * sizeof(bt_entryj), cudaMemcpyHostToDevice, s->copy_stream));
+			sent = c_off;
 		}
 	}
+	BT_REQUIRE(smem_need <= 200 * 1024, BT_ERR_CAPACITY, "bt_solve_stage: window needs %zu bytes of shared memory (> 200 KB)", smem_need);
+	s->smem_bytes = (int)smem_need;
+	BT_CUDA(cudaMemcpyAsync(s->stage_dev.as<char>() + L.late, hb + L.late, L.corr - L.late, cudaMemcpyHostToDevice, s->copy_stream));      // group tables, CSR, WinSparse
 	BT_CUDA(cudaEventRecord(s->ev_corr, s->copy_stream));
 	BT_CUDA(cudaEventRecord(s->ev_h2d, s->copy_stream));
 	BT_CUDA(cudaStreamWaitEvent(stream, s->ev_corr, 0));     // everything later on the caller's stream sees the correspondences
@@ -1512,7 +1518,7 @@ static SolveArgs make_args(bt_ctx* ctx) {
 	memset(&a, 0, sizeof a);
 	char* sd = s->stage_dev.as<char>();
 	const StageLayout& L = s->layout;
-	a.wins = (WinDesc*)(sd + L.wins); a.n_windows = s->n_windows;
+	a.wins = (WinDesc*)(sd + L.wins); a.wsp = (const WinSparse*)(sd + L.wsp); a.n_windows = s->n_windows;
 	a.depth_ptr = (const float**)(sd + L.dp); a.normal_ptr = (const float4**)(sd + L.np); a.frame_win = (int*)(sd + L.fw);
 	a.texel = s->texel.as<float4>(); a.src = s->src.as<float4>(); a.nsrc = s->nsrc.as<int>();
 	a.texel_tab = (const float4* const*)(sd + L.texp); a.src_tab = (const float4* const*)(sd + L.srcp); a.nsrc_cached = (const int* const*)(sd + L.nsrcp);
@@ -1532,8 +1538,7 @@ static SolveArgs make_args(bt_ctx* ctx) {
 
 static int launch_prep(bt_ctx* ctx, cudaStream_t stream) {
 	SolverState* s = ctx->solver;
-	int rco = ensure_occupancy(ctx);
-	if (rco != BT_OK) return rco;
+	// (in the fused call the tail's shared-memory size is not known yet: the tile plan then aims at the occupancy of the last batch)
 	SolveArgs a = make_args(ctx);
 	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[0], stream));
 	k_prep_frames<<<s->frames_total, 1024, 0, stream>>>(a, const_cast<WinDesc*>(a.wins), s->scalars.as<int>() + 8);
