@@ -257,8 +257,9 @@ def ncu_traffic(kernel):
         return None
 
 
-def cpu_baseline(host, n_windows):
-    """Oracle A (float build) on the host cores: threads over windows (the C call releases the GIL)."""
+def cpu_baseline(host, n_windows, check_against=None):
+    """Oracle A (float build) on the host cores: threads over windows (the C call releases the GIL).  `check_against`: the GPU
+    poses of window 0 - the oracle's own result for that window doubles as the parity check of this very run."""
     import oracle
     from concurrent.futures import ThreadPoolExecutor
     cores = os.cpu_count() or 1
@@ -271,10 +272,15 @@ def cpu_baseline(host, n_windows):
     run(jobs[0])
     t0 = time.perf_counter()
     with ThreadPoolExecutor(max_workers=cores) as ex:
-        list(ex.map(run, jobs))
+        res = list(ex.map(run, jobs))
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "windows/s", "cores": cores, "kind": "port",
-            "sample": f"{n} windows of the bench workload, oracle/solver_oracle.c (fp32), {cores} threads, {dt:.1f} s"}
+    out = {"value": n / dt, "unit": "windows/s", "cores": cores, "kind": "port",
+           "sample": f"{n} windows of the bench workload, oracle/solver_oracle.c (fp32), {cores} threads, {dt:.1f} s"}
+    if check_against is not None:
+        from bundletrack_b200 import synth
+        r, t = synth.pose_errors(check_against, res[0])
+        out["gpu_vs_port_window0"] = {"rot_rad": r, "trans_m": t}
+    return out
 
 
 def main():
@@ -404,17 +410,12 @@ def main():
         peak, peak_src = hbm_peak()
         alg_bytes = args.windows * (7 * (N * npix * 32 + C * 32) + 2 * N * 64)
         ach = alg_bytes / (tm["solve"] * 1e-3) / 1e9
-        cb = cpu_baseline(host, args.cpu_windows)
-        from bundletrack_b200 import synth
-        import oracle
-        sc, p0 = host[0]
-        chk = synth.pose_errors(out_poses[0], oracle.solve_window(sc.depth, sc.normal, sc.K, sc.corr, p0))
+        cb = cpu_baseline(host, args.cpu_windows, check_against=out_poses[0])
         out = dict(base, value=value, ms_per_step=ms_step, gpu_launches=int(stats["n_kernel_launches"]) * args.steps,
                    e2e={"value": e2e_val, "unit": "windows/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                    roofline={"bound": "hbm", "kernel": "k_solve", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic("k_solve"),
                              "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": tm},
                    cpu_baseline=cb, clocks=clocks,
-                   parity={"window0_vs_oracle_rot_rad": chk[0], "window0_vs_oracle_trans_m": chk[1]},
                    matcher=matcher, **extras,
                    solver_stats=stats)
         print(json.dumps(out))

@@ -49,6 +49,12 @@ class Window(ctypes.Structure):
         ("n_dense_pairs", ctypes.c_int),
         ("compat_flip", ctypes.c_int),
         ("cache_slots", ctypes.c_void_p),
+        ("corr_dev", ctypes.c_void_p),
+        ("n_blocks", ctypes.c_int),
+        ("block_off", ctypes.c_void_p),
+        ("block_n", ctypes.c_void_p),
+        ("block_i", ctypes.c_void_p),
+        ("block_j", ctypes.c_void_p),
     ]
 
 

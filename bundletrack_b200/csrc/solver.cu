@@ -1285,12 +1285,24 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 	for (int w = 0; w < n_windows; w++) {
 		const bt_window& bw = windows[w];
 		BT_REQUIRE(bw.n_frames >= 2 && bw.n_frames <= s->lim.max_frames, BT_ERR_CAPACITY, "window %d: n_frames %d outside [2,%d]", w, bw.n_frames, s->lim.max_frames);
-		BT_REQUIRE(bw.n_corr >= 0 && bw.n_corr <= s->lim.max_corr, BT_ERR_CAPACITY, "window %d: n_corr %d > reserved %d", w, bw.n_corr, s->lim.max_corr);
+		long long nc = bw.n_corr;
+		if (bw.corr_dev) {     // device-resident blocks: validate the host-side description
+			BT_REQUIRE(bw.n_blocks >= 0 && (bw.n_blocks == 0 || (bw.block_off && bw.block_n && bw.block_i && bw.block_j)), BT_ERR_INVALID_ARG, "window %d: corr_dev given without block arrays", w);
+			nc = 0;
+			for (int b = 0; b < bw.n_blocks; b++) {
+				BT_REQUIRE(bw.block_n[b] >= 0 && bw.block_off[b] >= 0 && (b == 0 || bw.block_off[b] == bw.block_off[b - 1] + bw.block_n[b - 1]), BT_ERR_INVALID_ARG,
+				           "window %d: correspondence block %d is not back to back with its predecessor", w, b);
+				BT_REQUIRE(bw.block_n[b] == 0 || (bw.block_i[b] < (uint32_t)bw.n_frames && bw.block_j[b] < (uint32_t)bw.n_frames), BT_ERR_INVALID_ARG,
+				           "window %d: correspondence block %d references a frame outside [0,%d)", w, b, bw.n_frames);
+				nc += bw.block_n[b];
+			}
+		}
+		BT_REQUIRE(nc >= 0 && nc <= s->lim.max_corr, BT_ERR_CAPACITY, "window %d: n_corr %lld > reserved %d", w, nc, s->lim.max_corr);
 		BT_REQUIRE(bw.H > 0 && bw.W > 0 && bw.H <= s->lim.H && bw.W <= s->lim.W, BT_ERR_CAPACITY, "window %d: image %dx%d larger than reserved", w, bw.W, bw.H);
 		BT_REQUIRE((int)(bw.W / params->image_downscale) >= 2 && (int)(bw.H / params->image_downscale) >= 2, BT_ERR_INVALID_ARG, "window %d: image too small", w);
-		BT_REQUIRE(bw.n_corr == 0 || bw.corr, BT_ERR_INVALID_ARG, "window %d: corr is NULL", w);
+		BT_REQUIRE(bw.corr_dev || bw.n_corr == 0 || bw.corr, BT_ERR_INVALID_ARG, "window %d: corr is NULL", w);
 		BT_REQUIRE(params->w_dense <= 0.f || bw.cache_slots || (bw.depth_dev && bw.normal_dev), BT_ERR_INVALID_ARG, "window %d: depth/normal pointers are NULL and no cache slots given", w);
-		F += bw.n_frames; C += bw.n_corr;
+		F += bw.n_frames; C += (size_t)nc;
 	}
 	// ---- host staging: one pinned block mirrored by one device block
 	const size_t maxP = (size_t)s->max_pairs, maxG = (size_t)s->max_groups;
@@ -1397,7 +1409,22 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 		// already emits them that way, /root/reference/src/Bundler.cpp:298-324); invalid entries are dropped.
 		int n_valid = 0, ng = 0;
 		bool grouped = true;    // fast path: keys (i*N+j) non-decreasing and no invalid entries => groups are runs, plain copy
-		{
+		if (bw.corr_dev) {      // blocks produced on the device: every non-empty block is a group, the entries move device -> device
+			for (int b = 0; b < bw.n_blocks; b++) {
+				if (bw.block_n[b] == 0) continue;
+				hgi[g_off + ng] = (int)bw.block_i[b]; hgj[g_off + ng] = (int)bw.block_j[b]; hgs[g_off + w + ng] = n_valid; ng++;
+				n_valid += bw.block_n[b];
+			}
+			hgs[g_off + w + ng] = n_valid;
+			if (n_valid) {
+				if (c_off > sent) {     // flush what the host path has staged so far: the pinned block has a hole where this window's entries would be
+					BT_CUDA(cudaMemcpyAsync(s->stage_dev.as<char>() + L.corr + sent * sizeof(bt_entryj), hcorr + sent, (c_off - sent) * sizeof(bt_entryj), cudaMemcpyHostToDevice, s->copy_stream));
+				}
+				BT_CUDA(cudaMemcpyAsync(s->stage_dev.as<char>() + L.corr + c_off * sizeof(bt_entryj), bw.corr_dev + bw.block_off[0], (size_t)n_valid * sizeof(bt_entryj),
+				                        cudaMemcpyDeviceToDevice, s->copy_stream));
+				sent = c_off + n_valid;
+			}
+		} else {
 			long long prev = -1;
 			for (int c = 0; c < bw.n_corr; c++) {
 				const bt_entryj& e = bw.corr[c];
@@ -1407,7 +1434,9 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 				if (key != prev) { hgi[g_off + ng] = (int)e.imgIdx_i; hgj[g_off + ng] = (int)e.imgIdx_j; hgs[g_off + w + ng] = c; ng++; prev = key; }
 			}
 		}
-		if (grouped) {
+		if (bw.corr_dev) {
+			// nothing to copy on the host
+		} else if (grouped) {
 			n_valid = bw.n_corr;
 			hgs[g_off + w + ng] = n_valid;
 			if (n_valid) memcpy(hcorr + c_off, bw.corr, sizeof(bt_entryj) * (size_t)n_valid);      // the window's entries are still in cache from the scan

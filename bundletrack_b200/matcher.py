@@ -195,9 +195,10 @@ class MatchPipeline:
             o += fa["kpts"].shape[0] + fb["kpts"].shape[0]
         return out
 
-    def match_pairs(self, pairs, H, W, K, seed: int = 0, capacity: int = 0):
-        """Fused pipeline.  Returns (entries [total] EntryJ structured numpy array, n_entry [n_pairs], entry_off [n_pairs]) —
-        device tensors are also kept in self.last for a zero-copy hand-off to the solver."""
+    def match_pairs(self, pairs, H, W, K, seed: int = 0, capacity: int = 0, keep_on_device: bool = False):
+        """Fused pipeline.  Returns (entries [total] EntryJ structured numpy array, n_entry [n_pairs], entry_off [n_pairs]).
+        keep_on_device=True: the entries stay on the GPU - returns (device int32 tensor [cap, 8], n_entry, entry_off) and only the
+        two small count arrays are read back; hand them to SolveWindow(corr_dev=..., blocks=...) (see `solver_blocks`)."""
         import numpy as np
         import torch
         from .synth import ENTRYJ_DTYPE
@@ -215,6 +216,18 @@ class MatchPipeline:
                                            ctypes.c_void_p(ent.data_ptr()), ctypes.c_int(cap), ctypes.c_void_p(n_ent.data_ptr()), ctypes.c_void_p(off.data_ptr()),
                                            ctypes.c_void_p(tot.data_ptr()), self.stream), "bt_match_pairs")
         self.last = (ent, n_ent, off, tot)
+        if keep_on_device:
+            cnt = torch.stack([n_ent, off]).cpu().numpy()      # one small D2H (2 x n_pairs ints), no entry leaves the device
+            return ent, cnt[0], cnt[1]
         total = int(tot[0].item())
         host = ent[:total].cpu().numpy().view(np.uint8).reshape(-1).view(ENTRYJ_DTYPE)
         return host, n_ent.cpu().numpy(), off.cpu().numpy()
+
+    @staticmethod
+    def solver_blocks(pairs, n_entry, entry_off):
+        """blocks=(off, n, i, j) for SolveWindow from match_pairs(keep_on_device=True): block p carries (imgIdx_i, imgIdx_j) =
+        (older frame B's window index, newer frame A's), exactly what k_emit_entryj writes into the entries."""
+        import numpy as np
+        bi = np.array([fb["window_index"] for _, fb in pairs], np.uint32)
+        bj = np.array([fa["window_index"] for fa, _ in pairs], np.uint32)
+        return np.asarray(entry_off, np.int32), np.asarray(n_entry, np.int32), bi, bj

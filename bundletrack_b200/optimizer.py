@@ -29,8 +29,12 @@ class SolveWindow:
     """One window's inputs: device frame maps + host correspondences/poses (the reference's argument list)."""
 
     def __init__(self, corr: np.ndarray, H: int, W: int, depths_gpu: Sequence, normals_gpu: Sequence, poses: np.ndarray, K,
-                 dense_pairs: Optional[np.ndarray] = None, compat_flip: bool = True, cache_slots: Optional[Sequence[int]] = None):
-        self.corr = np.ascontiguousarray(corr, dtype=ENTRYJ_DTYPE)
+                 dense_pairs: Optional[np.ndarray] = None, compat_flip: bool = True, cache_slots: Optional[Sequence[int]] = None,
+                 corr_dev=None, blocks=None):
+        self.corr = np.ascontiguousarray(corr if corr is not None else np.zeros(0, ENTRYJ_DTYPE), dtype=ENTRYJ_DTYPE)
+        # device-resident correspondences (bt_match_pairs output): corr_dev = device EntryJ buffer, blocks = (off, n, i, j) host arrays
+        self.corr_dev = corr_dev
+        self.blocks = None if blocks is None else tuple(np.ascontiguousarray(b, t) for b, t in zip(blocks, (np.int32, np.int32, np.uint32, np.uint32)))
         self.H, self.W = int(H), int(W)
         self.depths = [_ptr(d) for d in (depths_gpu or [])]
         self.normals = [_ptr(n) for n in (normals_gpu or [])]
@@ -42,7 +46,7 @@ class SolveWindow:
         self.cache_slots = None if cache_slots is None else np.ascontiguousarray(cache_slots, np.int32)
         self._keep = (depths_gpu, normals_gpu)
 
-    _MARSHALLED = frozenset(("corr", "H", "W", "depths", "normals", "poses", "K", "dense_pairs", "compat_flip", "cache_slots"))
+    _MARSHALLED = frozenset(("corr", "H", "W", "depths", "normals", "poses", "K", "dense_pairs", "compat_flip", "cache_slots", "corr_dev", "blocks"))
 
     def __setattr__(self, name, value):
         if name in SolveWindow._MARSHALLED:
@@ -66,6 +70,11 @@ class SolveWindow:
                 if len(self.cache_slots) != N:
                     raise ValueError("cache_slots needs one slot per frame")
                 cw.cache_slots = self.cache_slots.ctypes.data
+            if self.corr_dev is not None:
+                off, nb, bi, bj = self.blocks
+                cw.corr_dev = _ptr(self.corr_dev)
+                cw.n_blocks = len(off)
+                cw.block_off, cw.block_n, cw.block_i, cw.block_j = off.ctypes.data, nb.ctypes.data, bi.ctypes.data, bj.ctypes.data
             cw.fx, cw.fy, cw.cx, cw.cy = self.K
             zero = None
             if self.dense_pairs is not None:
@@ -76,7 +85,7 @@ class SolveWindow:
                 cw.dense_pairs, cw.n_dense_pairs = None, 0
             cw.compat_flip = 1 if self.compat_flip else 0
             self.__dict__["_cwin"] = cw
-            self.__dict__["_cwin_keep"] = (dp, nq, zero, self.corr, self.dense_pairs, self.cache_slots)
+            self.__dict__["_cwin_keep"] = (dp, nq, zero, self.corr, self.dense_pairs, self.cache_slots, self.corr_dev, self.blocks)
         return cw
 
     @property
@@ -155,8 +164,9 @@ class OptimizerGpu:
     @staticmethod
     def _split(windows, poses):
         out, o = [], 0
+        p4 = poses.reshape(-1, 4, 4)          # `poses` is a fresh array owned by this call: per-window views, no copies
         for w in windows:
-            out.append(poses[o:o + w.n_frames].reshape(-1, 4, 4).copy())
+            out.append(p4[o:o + w.n_frames])
             o += w.n_frames
         return out
 

@@ -89,6 +89,17 @@ typedef struct {
 	 * read: the quarter-resolution maps CUDACache::storeFrame (CUDACache.cpp:76-88) would rebuild for this call were built
 	 * once per keyframe.  Results are bit-identical either way. */
 	const int32_t* cache_slots;
+	/* Optional: correspondences that are ALREADY ON THE DEVICE, as bt_match_pairs leaves them: no entry
+	 * crosses the PCIe bus.  corr_dev: DEVICE EntryJ array holding n_blocks blocks back to back; block b has block_n[b]
+	 * entries that all carry (imgIdx_i, imgIdx_j) = (block_i[b], block_j[b]) and starts at block_off[b] (entries), with
+	 * block_off[b+1] == block_off[b] + block_n[b].  block_* are HOST arrays - bt_match_pairs' n_entry_out / entry_off_out read
+	 * back (a few dozen ints) and the pair list the caller gave it.  When corr_dev is non-NULL, corr / n_corr are ignored. */
+	const bt_entryj* corr_dev;
+	int n_blocks;
+	const int32_t* block_off;
+	const int32_t* block_n;
+	const uint32_t* block_i;
+	const uint32_t* block_j;
 } bt_window;
 
 typedef struct {

@@ -33,6 +33,19 @@ def test_struct_layouts_match_reference_types():
     assert ENTRYJ_DTYPE.fields["pos_i"][1] == 8 and ENTRYJ_DTYPE.fields["pos_j"][1] == 20
 
 
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """sizeof of every struct the Python mirror passes by pointer, measured by compiling the C header with gcc."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "bundletrack_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(bt_window), sizeof(bt_depth_params), '
+                   'sizeof(bt_solver_params), sizeof(bt_solver_limits), sizeof(bt_entryj));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert got == [ctypes.sizeof(_lib.Window), ctypes.sizeof(_lib.DepthParams), ctypes.sizeof(_lib.SolverParams), ctypes.sizeof(_lib.SolverLimits), 32]
+
+
 def test_no_gpu_fails_loudly():
     """Without a CUDA device the library must refuse (BT_ERR_NO_DEVICE), never fall back to a CPU path."""
     import torch

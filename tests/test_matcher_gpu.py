@@ -249,3 +249,42 @@ def test_fused_pipeline_matches_oracle_and_feeds_solver(cuda_device):
     r, t = synth.pose_errors(out, ref)
     assert r <= 2e-3 and t <= 1e-3, (r, t)      # RANSAC winners may differ by a borderline inlier; the solve must agree closely
     opt.close(); mp.close()
+
+
+def test_device_resident_handoff_equals_host_path(cuda_device):
+    """bt_match_pairs' EntryJ list consumed by the solver straight from device memory (bt_window::corr_dev + block arrays: only
+    2 x n_pairs ints come back to the host) gives the poses of the host round trip, bit for bit - also next to a host-fed window."""
+    from bundletrack_b200.matcher import MatchPipeline
+    from bundletrack_b200.optimizer import OptimizerGpu, SolveWindow
+    from bundletrack_b200 import _lib
+    w, host, devf = _feature_window(8, 5, 600, cuda_device)
+    mp = MatchPipeline(None, max_pairs=16, max_feats=640)
+    pairs_idx = [(j, i) for i in range(5) for j in range(i + 1, 5)]
+    prs = [(devf[a], devf[b]) for a, b in pairs_idx]
+    ent_h, n_h, off_h = mp.match_pairs(prs, w.H, w.W, w.K)
+    ent_d, n_d, off_d = mp.match_pairs(prs, w.H, w.W, w.K, keep_on_device=True)
+    assert np.array_equal(n_h, n_d) and np.array_equal(off_h, off_d) and n_d.sum() >= 20
+    depth = [f["depth"] for f in devf]; normal = [f["normal"] for f in devf]
+    opt = OptimizerGpu(None, max_windows=2, max_frames=8, max_corr=8192)
+    via_host = opt.optimizeWindows([SolveWindow(ent_h, w.H, w.W, depth, normal, w.poses_init, w.K)])[0]
+    blocks = MatchPipeline.solver_blocks(prs, n_d, off_d)
+    wd = SolveWindow(None, w.H, w.W, depth, normal, w.poses_init, w.K, corr_dev=ent_d, blocks=blocks)
+    via_dev = opt.optimizeWindows([wd])[0]
+    assert np.array_equal(via_host, via_dev)
+    w2 = synth.make_window(9, n_frames=4, n_corr=300)
+    d2 = [torch_from(x, cuda_device) for x in w2.depth]; n2 = [torch_from(x, cuda_device) for x in w2.normal]
+    alone = opt.optimizeWindows([SolveWindow(w2.corr, w2.H, w2.W, d2, n2, w2.poses_init, w2.K)])[0]
+    for order in ((0, 1), (1, 0)):      # host-fed and device-fed windows in one batch, either order
+        ws = [SolveWindow(w2.corr, w2.H, w2.W, d2, n2, w2.poses_init, w2.K), wd]
+        out = opt.optimizeWindows([ws[k] for k in order])
+        assert np.array_equal(out[order.index(0)], alone) and np.array_equal(out[order.index(1)], via_dev)
+    bad = (blocks[0].copy(), blocks[1], blocks[2], blocks[3]); bad[0][1] += 1       # not back to back
+    if len(bad[0]) > 1:
+        with pytest.raises(_lib.BtError):
+            opt.optimizeWindows([SolveWindow(None, w.H, w.W, depth, normal, w.poses_init, w.K, corr_dev=ent_d, blocks=bad)])
+    opt.close(); mp.close()
+
+
+def torch_from(x, dev):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
