@@ -50,7 +50,7 @@ static constexpr float kEps = 0.000001f;      // FLOAT_EPSILON, /root/reference/
 struct WinDesc {
 	int n_frames, n_corr, n_groups, n_pairs;
 	int corr_off, grp_off, pair_off, frame_off;
-	int tile_off, n_tiles;            // per GN iteration; written by k_plan
+	int tile_off, n_tiles;            // per GN iteration; written by the tile plan (last CTA of k_prep_frames)
 	int H, W, w, h;                   // full / quarter resolution
 	float fx, fy, cx, cy;             // quarter-res intrinsics (CUDACache.cpp:20-24)
 	float ifx, ify, icx, icy;         // inverse full-res intrinsics (m_inputIntrinsicsInv)
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(1024, 2) k_frame_cache_store(CacheStoreArgs c)
 	if (threadIdx.x == 0) c.nsrc[slot] = n;
 }
 
-// ------------------------------------------------------------------------------------------------ k_plan
+// ------------------------------------------------------------------------------------------------ tile plan
 __device__ __forceinline__ int chunks_for(int n, int chunk, int& per) {
 	if (n <= 0) { per = 0; return 0; }
 	const int nch = (n + chunk - 1) / chunk;
@@ -1251,7 +1251,7 @@ extern "C" int bt_solve_enable_timing(bt_ctx* ctx, int on) {
 	return BT_OK;
 }
 
-// Device time of the three kernels of the LAST bt_solve_run (prep, plan, solve), from CUDA events recorded on the
+// Device time of the LAST bt_solve_run as (prep incl. the tile plan, gap, solve), from CUDA events recorded on the
 // launching stream.  Synchronises on the last event.
 extern "C" int bt_solve_get_timing(bt_ctx* ctx, float* ms3) {
 	BT_REQUIRE(ctx && ctx->solver && ctx->solver->timing && ms3, BT_ERR_INVALID_ARG, "bt_solve_get_timing: timing not enabled");
