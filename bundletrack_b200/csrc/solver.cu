@@ -4,15 +4,18 @@
 // (/root/reference/src/cuda/LossGPU.cu:53-139) -> CUDACache::storeFrame (CUDACache.cpp:76-88) -> SBA::align
 // (SBA.cpp:81-139) -> CUDASolverBundling::solve (Solver/CUDASolverBundling.cpp:190-288) -> solveBundlingStub
 // (Solver/SolverBundling.cu:931-1003): ~260 kernel launches, ~75 memsets, 7 blocking copies and ~110 cudaMalloc per
-// window there; TWO launches per BATCH here, none of them allocating:
+// window there; THREE launches per BATCH here, none of them allocating:
 //
-//   k_prep_frames  one CTA per (window, frame): quarter-res cache (camera-space point + normal interleaved in one
+//   k_prep_count   one CTA per 1024 quarter-res pixels of a (window, frame): number of valid pixels of the block.
+//   k_prep_frames  same grid: quarter-res cache (camera-space point + normal interleaved in one
 //                  32-byte texel so a bilinear tap is a single sector) + an order-preserving COMPACTED list of the
 //                  valid source pixels (the object mask leaves ~10 % of the image valid), + se(3) of the input pose.
+//                  Each block's offset in the ordered list = the counts of the blocks before it.
 //   (plan)         the LAST CTA of k_prep_frames to finish: per-window tile counts -> exclusive scan -> flat tile list.
 //   k_solve        persistent, dynamically scheduled: tiles are (GN iteration, window, pair, pixel chunk); a tile
 //                  evaluates point-to-plane residuals/Jacobians for its chunk and reduces a 6x6 system in the TARGET
-//                  camera frame; the CTA that retires a window's last tile of an iteration runs that window's "tail":
+//                  camera frame; the FIRST CTA to retire a tile of (window, iteration) also computes the window's sparse
+//                  moment sums (they only need the poses), the one that retires the LAST ticket runs the window's "tail":
 //                  assembles the (6(N-1))^2 normal equations in shared memory (dense blocks + explicit sparse
 //                  blocks from per-pair moment sums), runs the PCG steps, updates the poses and releases the
 //                  window's next iteration.  Tiles of iteration k+1 wait on a per-window flag, so all GN iterations
@@ -78,6 +81,7 @@ struct SolveArgs {
 	float4* texel;        // [F][2*npix_max]  the context's own maps (frames prepared by this call)
 	float4* src;          // [F][2*npix_max]
 	int* nsrc;            // [F]
+	float* grp_sums;      // [groups of the batch][kGrpVals] sparse moment sums of the current GN iteration (written by the first CTA that retires a tile of the window)
 	const float4* const* texel_tab;   // [F] where each frame slot's texel map / source list lives: the arrays above, or a
 	const float4* const* src_tab;     //     frame-cache slot built earlier by bt_frame_cache_store
 	const int* const* nsrc_cached;    // [F] cached frame: address of its source count, else nullptr
@@ -316,22 +320,90 @@ __device__ int build_frame_maps(const FrameGeom& g, const float* __restrict__ de
 	return base;
 }
 
-__global__ void __launch_bounds__(1024, 2) k_prep_frames(SolveArgs a, WinDesc* wins_rw, int* prep_ticket) {
-	const int fs = blockIdx.x;
+// Frame preparation, one CTA per 1024 quarter-res pixels of a frame (two launches): k_prep_count counts the valid pixels of
+// every block, k_prep_frames turns the counts of the blocks before it into its offset in the frame's ordered source list and
+// writes its slice of the texel map and of the list.  (One CTA per frame walked 19 rounds serially: 50 us for a lone window.)
+__device__ __forceinline__ bool prep_sample(const WinDesc& wd, int idx, unsigned& xi, unsigned& yi) {
+	// nearest-neighbour sample position of quarter-res pixel idx in the full-res maps (resampleFloat4, CUDAImageUtil.cu:82-99)
+	const int x = idx % wd.w, y = idx / wd.w;
+	xi = (unsigned)((float)x * wd.scaleW + 0.5f); yi = (unsigned)((float)y * wd.scaleH + 0.5f);
+	return xi < (unsigned)wd.W && yi < (unsigned)wd.H;
+}
+
+__global__ void __launch_bounds__(1024, 2) k_prep_count(SolveArgs a, int* __restrict__ blk_cnt) {
+	const int fs = blockIdx.y, b = blockIdx.x;
+	if (a.nsrc_cached[fs] || !(a.prm.w_dense > 0.0f)) return;
 	const WinDesc wd = a.wins[a.frame_win[fs]];
-	__shared__ int s_cnt[kPrepRounds * 32];
-	__shared__ int s_wt[32];
-	const int tid = threadIdx.x;
-	int base = 0;
-	const int* cached = a.nsrc_cached[fs];
-	if (cached) base = *cached;                      // maps and source list were built by bt_frame_cache_store
-	else if (a.prm.w_dense > 0.0f) {
-		FrameGeom g; g.W = wd.W; g.H = wd.H; g.w = wd.w; g.h = wd.h; g.ifx = wd.ifx; g.ify = wd.ify; g.icx = wd.icx; g.icy = wd.icy; g.scaleW = wd.scaleW; g.scaleH = wd.scaleH;
-		base = build_frame_maps(g, a.depth_ptr[fs], a.normal_ptr[fs], a.texel + (size_t)fs * 2 * a.npix_max, a.src + (size_t)fs * 2 * a.npix_max,
-		                        a.prm.depth_min, a.prm.depth_max, s_cnt, s_wt);
+	const int npix = wd.w * wd.h, idx = b * 1024 + threadIdx.x;
+	__shared__ int s_w[32];
+	bool valid = false;
+	if (idx < npix) {       // must agree bit for bit with k_prep_frames: z = 0 for a missing / too-near sample
+		unsigned xi, yi;
+		float z = 0.f;
+		if (prep_sample(wd, idx, xi, yi)) { const float d = __ldg(a.depth_ptr[fs] + (size_t)yi * wd.W + xi); if (d >= 0.1f) z = d; }
+		valid = (z > a.prm.depth_min && z < a.prm.depth_max);
 	}
-	if (tid == 0) a.nsrc[fs] = base;
-	if (tid == 1023) {      // pose -> (rot, trans) -> T of iteration 0, off the critical path of the sweeps (last warp, one lane)
+	const unsigned bal = __ballot_sync(0xffffffffu, valid);
+	if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = __popc(bal);
+	__syncthreads();
+	if (threadIdx.x < 32) {
+		int t = s_w[threadIdx.x];
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+		if (threadIdx.x == 0) blk_cnt[fs * gridDim.x + b] = t;
+	}
+}
+
+__global__ void __launch_bounds__(1024, 2) k_prep_frames(SolveArgs a, WinDesc* wins_rw, int* prep_ticket, const int* __restrict__ blk_cnt) {
+	const int fs = blockIdx.y, b = blockIdx.x;
+	const WinDesc wd = a.wins[a.frame_win[fs]];
+	__shared__ int s_w[32];
+	__shared__ int s_base;
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const int* cached = a.nsrc_cached[fs];
+	const int npix = wd.w * wd.h;
+	if (cached) { if (b == 0 && tid == 0) a.nsrc[fs] = *cached; }      // maps and source list were built by bt_frame_cache_store
+	else if (!(a.prm.w_dense > 0.0f)) { if (b == 0 && tid == 0) a.nsrc[fs] = 0; }
+	else if (b * 1024 < npix) {
+		if (wid == 0) {      // offset of this block = valid pixels of the blocks before it (at most a few dozen)
+			int t = 0;
+			for (int q = lane; q < b; q += 32) t += blk_cnt[fs * gridDim.x + q];
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+			if (lane == 0) s_base = t;
+		}
+		const float dmin = a.prm.depth_min, dmax = a.prm.depth_max;
+		float4* texel = a.texel + (size_t)fs * 2 * a.npix_max;
+		float4* src = a.src + (size_t)fs * 2 * a.npix_max;
+		const int idx = b * 1024 + tid;
+		float4 cp = make_float4(0.f, 0.f, 0.f, 0.f), nr = make_float4(0.f, 0.f, 0.f, 0.f);
+		bool valid = false;
+		if (idx < npix) {
+			unsigned xi, yi;
+			if (prep_sample(wd, idx, xi, yi)) {
+				const size_t sidx = (size_t)yi * wd.W + xi;
+				const float d = __ldg(a.depth_ptr[fs] + sidx);
+				nr = __ldg(a.normal_ptr[fs] + sidx);
+				if (d >= 0.1f) cp = make_float4(wd.ifx * ((float)xi * d) + wd.icx * d, wd.ify * ((float)yi * d) + wd.icy * d, d, 1.0f);
+			}
+			texel[2 * idx] = make_float4(cp.x, cp.y, cp.z, nr.x);      // 32-byte texel: point xyz + normal xyz (+ pad)
+			texel[2 * idx + 1] = make_float4(nr.y, nr.z, 0.f, 0.f);
+			valid = (cp.z > dmin && cp.z < dmax);
+		}
+		const unsigned bal = __ballot_sync(0xffffffffu, valid);
+		if (lane == 0) s_w[wid] = __popc(bal);
+		__syncthreads();
+		int off = (lane < wid) ? s_w[lane] : 0;       // exclusive prefix over the warps of this block
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) off += __shfl_xor_sync(0xffffffffu, off, o);
+		if (valid) {
+			const int o = s_base + off + __popc(bal & ((1u << lane) - 1u));
+			src[2 * o] = make_float4(cp.x, cp.y, cp.z, nr.x);
+			src[2 * o + 1] = make_float4(nr.y, nr.z, nr.w, 0.f);
+		}
+		if ((b + 1) * 1024 >= npix && tid == 1023) a.nsrc[fs] = s_base + off + __popc(bal);     // last block of the frame, last warp: the total
+	}
+	if (b == 0 && tid == 1023) {      // pose -> (rot, trans) -> T of iteration 0 (one lane of the frame's first block)
 		float Tm[12];
 		const float* P = a.pose_in + (size_t)fs * 16;
 		for (int k = 0; k < 12; k++) Tm[k] = P[k];
@@ -347,7 +419,7 @@ __global__ void __launch_bounds__(1024, 2) k_prep_frames(SolveArgs a, WinDesc* w
 	__shared__ int s_last;
 	__threadfence();
 	__syncthreads();
-	if (tid == 0) { const int t = atomicAdd(prep_ticket, 1); s_last = (t == (int)gridDim.x - 1); if (s_last) { *prep_ticket = 0; __threadfence(); } }
+	if (tid == 0) { const int t = atomicAdd(prep_ticket, 1); s_last = (t == (int)(gridDim.x * gridDim.y) - 1); if (s_last) { *prep_ticket = 0; __threadfence(); } }
 	__syncthreads();
 	if (s_last) plan_body(a, wins_rw);
 }
@@ -647,6 +719,65 @@ __device__ __forceinline__ void unpack_sym(int e, int& r, int& c) {
 	c = r + e;
 }
 
+// Sparse moment sums of one window for the CURRENT poses: 8 lanes per (i,j) group of correspondences, loads one iteration
+// ahead; 44 sums per group go to a.grp_sums.  Runs on the first CTA that retires a dense tile of (window, iteration), while the
+// other tiles of the window are still in flight, so the window's tail no longer waits for it.
+__device__ void sparse_sums(const SolveArgs& a, int w) {
+	const WinDesc wd0 = a.wins[w];
+	const WinSparse ws = a.wsp[w];
+	const int G = ws.n_groups, tid = threadIdx.x;
+	const int sub = tid >> 3, sl = tid & 7, nsub = kThreads >> 3;
+	for (int g0 = 0; g0 < G; g0 += nsub) {
+		const int g = g0 + sub;
+		float m[kGrpVals];
+#pragma unroll
+		for (int k = 0; k < kGrpVals; k++) m[k] = 0.f;
+		if (g < G) {
+			const int c0 = a.grp_start[ws.grp_off + w + g], c1 = a.grp_start[ws.grp_off + w + g + 1];
+			const float* Ti = a.T + (size_t)(wd0.frame_off + a.grp_i[ws.grp_off + g]) * 12; const float* Tj = a.T + (size_t)(wd0.frame_off + a.grp_j[ws.grp_off + g]) * 12;
+			const float t00 = __ldcg(Ti + 0), t01 = __ldcg(Ti + 1), t02 = __ldcg(Ti + 2), t03 = __ldcg(Ti + 3), t10 = __ldcg(Ti + 4), t11 = __ldcg(Ti + 5), t12 = __ldcg(Ti + 6), t13 = __ldcg(Ti + 7),
+			            t20 = __ldcg(Ti + 8), t21 = __ldcg(Ti + 9), t22 = __ldcg(Ti + 10), t23 = __ldcg(Ti + 11);
+			const float u00 = __ldcg(Tj + 0), u01 = __ldcg(Tj + 1), u02 = __ldcg(Tj + 2), u03 = __ldcg(Tj + 3), u10 = __ldcg(Tj + 4), u11 = __ldcg(Tj + 5), u12 = __ldcg(Tj + 6), u13 = __ldcg(Tj + 7),
+			            u20 = __ldcg(Tj + 8), u21 = __ldcg(Tj + 9), u22 = __ldcg(Tj + 10), u23 = __ldcg(Tj + 11);
+			int c = c0 + sl;
+			float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+			if (c < c1) { const float4* e4 = reinterpret_cast<const float4*>(a.corr + ws.corr_off + c); lo = __ldg(e4); hi = __ldg(e4 + 1); }
+			while (c < c1) {
+				const int cn = c + 8;
+				float4 lo_n = lo, hi_n = hi;
+				if (cn < c1) { const float4* e4 = reinterpret_cast<const float4*>(a.corr + ws.corr_off + cn); lo_n = __ldg(e4); hi_n = __ldg(e4 + 1); }
+				const float pix = lo.z, piy = lo.w, piz = hi.x, pjx = hi.y, pjy = hi.z, pjz = hi.w;   // {i, j, pi.x, pi.y}, {pi.z, pj.x, pj.y, pj.z}
+				const V3 q = mk(t00 * pix + t01 * piy + t02 * piz + t03, t10 * pix + t11 * piy + t12 * piz + t13, t20 * pix + t21 * piy + t22 * piz + t23);
+				const V3 sp = mk(u00 * pjx + u01 * pjy + u02 * pjz + u03, u10 * pjx + u11 * pjy + u12 * pjz + u13, u20 * pjx + u21 * pjy + u22 * pjz + u23);
+				const V3 rr = q - sp;
+				const float rho = huber_w(dot(rr, rr), a.prm.robust_delta);
+				m[0] += 1.f;
+				m[1] += q.x; m[2] += q.y; m[3] += q.z;
+				m[4] += sp.x; m[5] += sp.y; m[6] += sp.z;
+				m[7] += q.x * q.x; m[8] += q.x * q.y; m[9] += q.x * q.z; m[10] += q.y * q.y; m[11] += q.y * q.z; m[12] += q.z * q.z;
+				m[13] += sp.x * sp.x; m[14] += sp.x * sp.y; m[15] += sp.x * sp.z; m[16] += sp.y * sp.y; m[17] += sp.y * sp.z; m[18] += sp.z * sp.z;
+				m[19] += sp.x * q.x; m[20] += sp.x * q.y; m[21] += sp.x * q.z;      // Qsq[a][b] = sum s_a q_b
+				m[22] += sp.y * q.x; m[23] += sp.y * q.y; m[24] += sp.y * q.z;
+				m[25] += sp.z * q.x; m[26] += sp.z * q.y; m[27] += sp.z * q.z;
+				const V3 gq = cross(q, rr), gs = cross(sp, rr);
+				m[28] += rho * gq.x; m[29] += rho * gq.y; m[30] += rho * gq.z;
+				m[31] += rho * gs.x; m[32] += rho * gs.y; m[33] += rho * gs.z;
+				m[34] += rho * rr.x; m[35] += rho * rr.y; m[36] += rho * rr.z;
+				m[37] += rho * q.x * q.x; m[38] += rho * q.y * q.y; m[39] += rho * q.z * q.z;
+				m[40] += rho * sp.x * sp.x; m[41] += rho * sp.y * sp.y; m[42] += rho * sp.z * sp.z;
+				m[43] += rho;
+				lo = lo_n; hi = hi_n; c = cn;
+			}
+		}
+#pragma unroll
+		for (int k = 0; k < kGrpVals; k++) {
+			float v = m[k];
+			v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 1);
+			if (g < G && sl == 0) __stcg(a.grp_sums + (size_t)(ws.grp_off + g) * kGrpVals + k, v);
+		}
+	}
+}
+
 __device__ void window_tail(const SolveArgs& a, const WinDesc& wd_in, int w, int it, float* smem_base) {
 	WinDesc wd = wd_in;
 	{ const WinSparse ws = a.wsp[w]; wd.n_corr = ws.n_corr; wd.n_groups = ws.n_groups; wd.corr_off = ws.corr_off; wd.grp_off = ws.grp_off; wd.mem_off = ws.mem_off; wd.unique_blocks = ws.unique_blocks; }
@@ -678,57 +809,9 @@ __device__ void window_tail(const SolveArgs& a, const WinDesc& wd_in, int w, int
 	__syncthreads();
 	PROF_T(1);
 
-	// ---- P1: sparse moment sums, 8 lanes per (i,j) group of correspondences, loads one iteration ahead
-	{
-		const int sub = tid >> 3, sl = tid & 7, nsub = kThreads >> 3;
-		for (int g0 = 0; g0 < G; g0 += nsub) {
-			const int g = g0 + sub;
-			float m[kGrpVals];
-#pragma unroll
-			for (int k = 0; k < kGrpVals; k++) m[k] = 0.f;
-			if (g < G) {
-				const int c1 = s.gstart[g + 1];
-				const float* Ti = s.T + s.gi[g] * 12; const float* Tj = s.T + s.gj[g] * 12;
-				const float t00 = Ti[0], t01 = Ti[1], t02 = Ti[2], t03 = Ti[3], t10 = Ti[4], t11 = Ti[5], t12 = Ti[6], t13 = Ti[7], t20 = Ti[8], t21 = Ti[9], t22 = Ti[10], t23 = Ti[11];
-				const float u00 = Tj[0], u01 = Tj[1], u02 = Tj[2], u03 = Tj[3], u10 = Tj[4], u11 = Tj[5], u12 = Tj[6], u13 = Tj[7], u20 = Tj[8], u21 = Tj[9], u22 = Tj[10], u23 = Tj[11];
-				int c = s.gstart[g] + sl;
-				float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
-				if (c < c1) { const float4* e4 = reinterpret_cast<const float4*>(a.corr + wd.corr_off + c); lo = __ldg(e4); hi = __ldg(e4 + 1); }
-				while (c < c1) {
-					const int cn = c + 8;
-					float4 lo_n = lo, hi_n = hi;
-					if (cn < c1) { const float4* e4 = reinterpret_cast<const float4*>(a.corr + wd.corr_off + cn); lo_n = __ldg(e4); hi_n = __ldg(e4 + 1); }
-					const float pix = lo.z, piy = lo.w, piz = hi.x, pjx = hi.y, pjy = hi.z, pjz = hi.w;   // {i, j, pi.x, pi.y}, {pi.z, pj.x, pj.y, pj.z}
-					const V3 q = mk(t00 * pix + t01 * piy + t02 * piz + t03, t10 * pix + t11 * piy + t12 * piz + t13, t20 * pix + t21 * piy + t22 * piz + t23);
-					const V3 sp = mk(u00 * pjx + u01 * pjy + u02 * pjz + u03, u10 * pjx + u11 * pjy + u12 * pjz + u13, u20 * pjx + u21 * pjy + u22 * pjz + u23);
-					const V3 rr = q - sp;
-					const float rho = huber_w(dot(rr, rr), a.prm.robust_delta);
-					m[0] += 1.f;
-					m[1] += q.x; m[2] += q.y; m[3] += q.z;
-					m[4] += sp.x; m[5] += sp.y; m[6] += sp.z;
-					m[7] += q.x * q.x; m[8] += q.x * q.y; m[9] += q.x * q.z; m[10] += q.y * q.y; m[11] += q.y * q.z; m[12] += q.z * q.z;
-					m[13] += sp.x * sp.x; m[14] += sp.x * sp.y; m[15] += sp.x * sp.z; m[16] += sp.y * sp.y; m[17] += sp.y * sp.z; m[18] += sp.z * sp.z;
-					m[19] += sp.x * q.x; m[20] += sp.x * q.y; m[21] += sp.x * q.z;      // Qsq[a][b] = sum s_a q_b
-					m[22] += sp.y * q.x; m[23] += sp.y * q.y; m[24] += sp.y * q.z;
-					m[25] += sp.z * q.x; m[26] += sp.z * q.y; m[27] += sp.z * q.z;
-					const V3 gq = cross(q, rr), gs = cross(sp, rr);
-					m[28] += rho * gq.x; m[29] += rho * gq.y; m[30] += rho * gq.z;
-					m[31] += rho * gs.x; m[32] += rho * gs.y; m[33] += rho * gs.z;
-					m[34] += rho * rr.x; m[35] += rho * rr.y; m[36] += rho * rr.z;
-					m[37] += rho * q.x * q.x; m[38] += rho * q.y * q.y; m[39] += rho * q.z * q.z;
-					m[40] += rho * sp.x * sp.x; m[41] += rho * sp.y * sp.y; m[42] += rho * sp.z * sp.z;
-					m[43] += rho;
-					lo = lo_n; hi = hi_n; c = cn;
-				}
-			}
-#pragma unroll
-			for (int k = 0; k < kGrpVals; k++) {
-				float v = m[k];
-				v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 1);
-				if (g < G && sl == 0) s.grp[g * kGrpVals + k] = v;
-			}
-		}
-	}
+	// ---- P1: the sparse moment sums were computed by sparse_sums() while the window's dense tiles were still running
+	for (int k = tid; k < G * kGrpVals; k += kThreads) s.grp[k] = __ldcg(a.grp_sums + (size_t)wd.grp_off * kGrpVals + k);
+	__syncthreads();
 	PROF_T(2);
 	// ---- P2: per-pair sums over the pair's tiles (already in the model frame; the tile epilogue applied X S' X^T).  A pair's
 	//      tiles are consecutive and summed in order (deterministic); RI items per thread keep RI loads in flight.
@@ -998,7 +1081,7 @@ __global__ void __launch_bounds__(kThreads, BT_SOLVE_MIN_CTAS) k_solve(SolveArgs
 	__shared__ float s_X[36];
 	__shared__ float s_red[kTileVals];
 	__shared__ float s_part[kWarps][kTileVals];
-	__shared__ int s_is_last;
+	__shared__ int s_is_last, s_is_first;
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const int total = *a.n_tiles_total;
 	if (total <= 0) return;
@@ -1105,9 +1188,10 @@ __global__ void __launch_bounds__(kThreads, BT_SOLVE_MIN_CTAS) k_solve(SolveArgs
 				__threadfence();      // the writers order their store before the ticket below
 			}
 			__syncwarp();
-			if (lane == 0) {
+			if (lane == 0) {     // n_tiles + 1 tickets per (window, iteration): the dense tiles and the sparse sums
 				const int done = atomicAdd(a.tiles_done + tl.win, 1) + 1;
-				s_is_last = (done == (it + 1) * wd.n_tiles);
+				s_is_first = (done == it * (wd.n_tiles + 1) + 1);
+				s_is_last = (done == (it + 1) * (wd.n_tiles + 1));
 				if (s_is_last) __threadfence();
 			}
 		}
@@ -1115,6 +1199,17 @@ __global__ void __launch_bounds__(kThreads, BT_SOLVE_MIN_CTAS) k_solve(SolveArgs
 		__syncthreads();
 		PROF_T(5);
 		if (a.prof && tid == 0) { prf.kind_cta = blockIdx.x; prf.tile_win = ((long long)tl_idx << 32) | ((long long)it << 16) | tl.count; prf.t[6] = prf.t[7] = prf.t[8] = prf.t[9] = 0; prof_emit(a, prf); }
+		if (s_is_first) {     // CTA-uniform: the first tile of this (window, iteration) to retire also does the window's sparse sums
+			sparse_sums(a, tl.win);
+			__threadfence();
+			__syncthreads();
+			if (tid == 0) {
+				const int done = atomicAdd(a.tiles_done + tl.win, 1) + 1;
+				s_is_last = (done == (it + 1) * (wd.n_tiles + 1));
+				if (s_is_last) __threadfence();
+			}
+			__syncthreads();
+		}
 		if (s_is_last) {
 			window_tail(a, wd, tl.win, it, dyn_smem);
 			__threadfence();
@@ -1151,7 +1246,7 @@ static StageLayout stage_layout(int n_windows, size_t F, size_t C, int max_frame
 struct SolverState {
 	bt_solver_limits lim{};
 	int npix_max = 0, max_pairs = 0, max_frames_total = 0, max_tiles = 0, max_groups = 0;
-	DevBuf stage_dev, texel, src, nsrc, x, T, pose_out, tiles, scalars, partial, tiles_done, iter_done, pair_tile0, pair_ntile, dbgJ, dbgR, dbgC, prof;
+	DevBuf blk_cnt, grp_sums, stage_dev, texel, src, nsrc, x, T, pose_out, tiles, scalars, partial, tiles_done, iter_done, pair_tile0, pair_ntile, dbgJ, dbgR, dbgC, prof;
 	StageLayout layout{};
 	// frame cache (bt_frame_cache_*): quarter-res maps of keyframes, built once, referenced by bt_window::cache_slots
 	struct CacheMeta { bool valid = false; int H = 0, W = 0; float fx = 0, fy = 0, cx = 0, cy = 0, dmin = 0, dmax = 0; };
@@ -1171,7 +1266,7 @@ struct SolverState {
 	bool staged = false, debug = false, timing = false;
 	int launches = 0;
 	int attr_bytes = 0, occ = BT_SOLVE_MIN_CTAS, occ_smem = -1;
-	bool prep_launched = false;
+	bool prep_launched = false, any_uncached = true;
 	cudaStream_t copy_stream = nullptr;
 	cudaEvent_t ev_prev = nullptr, ev_corr = nullptr, ev_h2d = nullptr;
 	cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
@@ -1180,7 +1275,7 @@ struct SolverState {
 void solver_destroy(bt_ctx* ctx) {
 	SolverState* s = ctx->solver;
 	if (!s) return;
-	DevBuf* bufs[] = { &s->c_texel, &s->c_src, &s->c_nsrc, &s->c_tables, &s->stage_dev, &s->texel, &s->src, &s->nsrc, &s->x, &s->T, &s->pose_out, &s->tiles, &s->scalars, &s->partial,
+	DevBuf* bufs[] = { &s->blk_cnt, &s->grp_sums, &s->c_texel, &s->c_src, &s->c_nsrc, &s->c_tables, &s->stage_dev, &s->texel, &s->src, &s->nsrc, &s->x, &s->T, &s->pose_out, &s->tiles, &s->scalars, &s->partial,
 	                   &s->tiles_done, &s->iter_done, &s->pair_tile0, &s->pair_ntile, &s->dbgJ, &s->dbgR, &s->dbgC, &s->prof };
 	for (DevBuf* b : bufs) b->release();
 	s->h_stage.release(); s->h_poses.release(); s->c_htables.release();
@@ -1215,6 +1310,8 @@ static int reserve_impl(bt_ctx* ctx, const bt_solver_limits* lim) {
 	RES(texel, sizeof(float4) * 2 * (size_t)s->npix_max * F);
 	RES(src, sizeof(float4) * 2 * (size_t)s->npix_max * F);
 	RES(nsrc, sizeof(int) * F);
+	RES(grp_sums, sizeof(float) * kGrpVals * (size_t)s->max_groups * lim->max_windows);
+	RES(blk_cnt, sizeof(int) * (size_t)F * ((s->npix_max + 1023) / 1024));
 	RES(x, sizeof(float) * 6 * F); RES(T, sizeof(float) * 12 * F); RES(pose_out, sizeof(float) * 16 * F);
 	RES(pair_tile0, sizeof(int) * (size_t)s->max_pairs * lim->max_windows);
 	RES(pair_ntile, sizeof(int) * (size_t)s->max_pairs * lim->max_windows);
@@ -1320,6 +1417,7 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 	int* hpwin = (int*)(hb + L.pwin); int* hpsrc = (int*)(hb + L.psrc); int* hmem = (int*)(hb + L.mem);
 	s->frame_off.assign(n_windows, 0); s->n_frames.assign(n_windows, 0);
 
+	s->any_uncached = false;
 	// ==== phase 1: what the frame preparation needs - geometry, frame tables, poses, dense pair tables (no look at the correspondences)
 	size_t f_off = 0, p_off = 0;
 	for (int w = 0; w < n_windows; w++) {
@@ -1353,6 +1451,7 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 				hnp[fs] = (params->w_dense > 0.f) ? bw.normal_dev[f] : nullptr;
 				htex[fs] = s->texel.as<float4>() + fs * 2 * (size_t)s->npix_max; hsrc[fs] = s->src.as<float4>() + fs * 2 * (size_t)s->npix_max;
 				hnsrc[fs] = nullptr;
+				if (params->w_dense > 0.f) s->any_uncached = true;
 			}
 			hfw[fs] = w;
 			memcpy(hpose + fs * 16, poses_in + fs * 16, sizeof(float) * 16);
@@ -1549,7 +1648,7 @@ static SolveArgs make_args(bt_ctx* ctx) {
 	const StageLayout& L = s->layout;
 	a.wins = (WinDesc*)(sd + L.wins); a.wsp = (const WinSparse*)(sd + L.wsp); a.n_windows = s->n_windows;
 	a.depth_ptr = (const float**)(sd + L.dp); a.normal_ptr = (const float4**)(sd + L.np); a.frame_win = (int*)(sd + L.fw);
-	a.texel = s->texel.as<float4>(); a.src = s->src.as<float4>(); a.nsrc = s->nsrc.as<int>();
+	a.texel = s->texel.as<float4>(); a.src = s->src.as<float4>(); a.nsrc = s->nsrc.as<int>(); a.grp_sums = s->grp_sums.as<float>();
 	a.texel_tab = (const float4* const*)(sd + L.texp); a.src_tab = (const float4* const*)(sd + L.srcp); a.nsrc_cached = (const int* const*)(sd + L.nsrcp);
 	a.pose_in = (float*)(sd + L.pose); a.x = s->x.as<float>(); a.T = s->T.as<float>(); a.pose_out = s->pose_out.as<float>();
 	a.npix_max = s->npix_max;
@@ -1570,7 +1669,10 @@ static int launch_prep(bt_ctx* ctx, cudaStream_t stream) {
 	// (in the fused call the tail's shared-memory size is not known yet: the tile plan then aims at the occupancy of the last batch)
 	SolveArgs a = make_args(ctx);
 	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[0], stream));
-	k_prep_frames<<<s->frames_total, 1024, 0, stream>>>(a, const_cast<WinDesc*>(a.wins), s->scalars.as<int>() + 8);
+	// frames whose maps come from the frame cache need one block each (source count + pose); a batch of cached frames only skips the count kernel
+	const dim3 pgrid(s->any_uncached ? (unsigned)((s->npix_max + 1023) / 1024) : 1u, (unsigned)s->frames_total);
+	if (s->any_uncached) k_prep_count<<<pgrid, 1024, 0, stream>>>(a, s->blk_cnt.as<int>());
+	k_prep_frames<<<pgrid, 1024, 0, stream>>>(a, const_cast<WinDesc*>(a.wins), s->scalars.as<int>() + 8, s->blk_cnt.as<int>());
 	BT_CUDA(cudaGetLastError());
 	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[1], stream));
 	s->prep_launched = true;
@@ -1597,7 +1699,7 @@ extern "C" int bt_solve_run(bt_ctx* ctx, void* stream_) {
 	k_solve<<<grid, kThreads, s->smem_bytes, stream>>>(a);
 	BT_CUDA(cudaGetLastError());
 	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[3], stream));
-	s->launches = 2;
+	s->launches = s->any_uncached ? 3 : 2;
 	return BT_OK;
 }
 
