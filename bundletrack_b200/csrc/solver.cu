@@ -814,7 +814,7 @@ __device__ void window_tail(const SolveArgs& a, const WinDesc& wd_in, int w, int
 	__syncthreads();
 	PROF_T(2);
 	// ---- P2: per-pair sums over the pair's tiles (already in the model frame; the tile epilogue applied X S' X^T).  A pair's
-	//      tiles are consecutive and summed in order (deterministic); RI items per thread keep RI loads in flight.
+	//      tiles are consecutive and summed in order (deterministic); 4 tiles x RI items per thread are in flight at a time.
 	if (use_dense) {
 		constexpr int RI = 5;
 		for (int k0 = tid; k0 < P * kTileVals; k0 += kThreads * RI) {
@@ -825,9 +825,18 @@ __device__ void window_tail(const SolveArgs& a, const WinDesc& wd_in, int w, int
 				v[r] = 0.f; nt[r] = 0; src[r] = a.partial;
 				if (k < P * kTileVals) { const int p = k / kTileVals, e = k - p * kTileVals; nt[r] = s.pnt[p]; src[r] = a.partial + (size_t)(wd.tile_off + s.pt0[p]) * kTileVals + e; mx = max(mx, nt[r]); }
 			}
-			for (int c = 0; c < mx; c++) {
+			for (int c = 0; c < mx; c += 4) {      // four tiles x RI items in flight per thread; the adds keep the tile order (x + 0.f == x)
+				float t[4][RI];
 #pragma unroll
-				for (int r = 0; r < RI; r++) if (c < nt[r]) v[r] += __ldcg(src[r] + (size_t)c * kTileVals);
+				for (int u = 0; u < 4; u++) {
+#pragma unroll
+					for (int r = 0; r < RI; r++) t[u][r] = (c + u < nt[r]) ? __ldcg(src[r] + (size_t)(c + u) * kTileVals) : 0.f;
+				}
+#pragma unroll
+				for (int u = 0; u < 4; u++) {
+#pragma unroll
+					for (int r = 0; r < RI; r++) v[r] += t[u][r];
+				}
 			}
 #pragma unroll
 			for (int r = 0; r < RI; r++) {
