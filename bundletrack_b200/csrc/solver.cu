@@ -14,8 +14,9 @@
 //   (plan)         the LAST CTA of k_prep_frames to finish: per-window tile counts -> exclusive scan -> flat tile list.
 //   k_solve        persistent, dynamically scheduled: tiles are (GN iteration, window, pair, pixel chunk); a tile
 //                  evaluates point-to-plane residuals/Jacobians for its chunk and reduces a 6x6 system in the TARGET
-//                  camera frame; the FIRST CTA to retire a tile of (window, iteration) also computes the window's sparse
-//                  moment sums (they only need the poses), the one that retires the LAST ticket runs the window's "tail":
+//                  camera frame; every window also has one SPARSE tile per iteration (the moment sums of its
+//                  correspondences: they only need the poses, so they run next to the dense tiles); the CTA that retires
+//                  a window's last tile of an iteration runs that window's "tail":
 //                  assembles the (6(N-1))^2 normal equations in shared memory (dense blocks + explicit sparse
 //                  blocks from per-pair moment sums), runs the PCG steps, updates the poses and releases the
 //                  window's next iteration.  Tiles of iteration k+1 wait on a per-window flag, so all GN iterations
@@ -68,7 +69,7 @@ struct WinDesc {
 // correspondences while the GPU already works); window_tail reads them from here, the copies inside WinDesc are unused.
 struct WinSparse { int n_corr, n_groups, corr_off, grp_off, mem_off, unique_blocks, pad0, pad1; };
 
-struct Tile { int win; int pair; int start; int count; };  // pair < 0 => dummy tile (window without dense work)
+struct Tile { int win; int pair; int start; int count; };  // pair == -2 => the window's sparse tile (moment sums of its correspondences)
 
 struct SolveArgs {
 	const WinDesc* wins;
@@ -81,7 +82,7 @@ struct SolveArgs {
 	float4* texel;        // [F][2*npix_max]  the context's own maps (frames prepared by this call)
 	float4* src;          // [F][2*npix_max]
 	int* nsrc;            // [F]
-	float* grp_sums;      // [groups of the batch][kGrpVals] sparse moment sums of the current GN iteration (written by the first CTA that retires a tile of the window)
+	float* grp_sums;      // [groups of the batch][kGrpVals] sparse moment sums of the current GN iteration (written by the window's sparse tile)
 	const float4* const* texel_tab;   // [F] where each frame slot's texel map / source list lives: the arrays above, or a
 	const float4* const* src_tab;     //     frame-cache slot built earlier by bt_frame_cache_store
 	const int* const* nsrc_cached;    // [F] cached frame: address of its source count, else nullptr
@@ -475,7 +476,7 @@ __device__ void plan_body(const SolveArgs& a, WinDesc* wins_rw) {
 			for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
 			if ((tid & 31) == 0 && mine) atomicAdd(&s_total, mine);
 			__syncthreads();
-			const int total = s_total;
+			const int total = s_total + a.n_windows;      // + one sparse tile per window
 			__syncthreads();
 			if (total <= a.grid_ctas || total > 2 * a.grid_ctas) break;
 			chunk = (int)(((long long)chunk * total / a.grid_ctas + 63) / 32 * 32);     // ~(total/grid) x larger, rounded up to warps
@@ -505,9 +506,9 @@ __device__ void plan_body(const SolveArgs& a, WinDesc* wins_rw) {
 		if ((tid & 31) == 0 && px) atomicAdd(&s_px, px);
 		__syncthreads();
 		PROF_T(1);
-		// (2) exclusive scan of the per-window tile counts (a window without dense work still gets one dummy tile)
+		// (2) exclusive scan of the per-window tile counts: the dense tiles plus ONE sparse tile (the window's moment sums), first in line
 		int cnt = 0;
-		if (tid < nw) { cnt = s_cnt[tid]; if (cnt == 0) cnt = 1; a.tiles_done[base + tid] = 0; a.iter_done[base + tid] = 0; }
+		if (tid < nw) { cnt = s_cnt[tid] + 1; a.tiles_done[base + tid] = 0; a.iter_done[base + tid] = 0; }
 		{   // inclusive scan over the 1024 per-window counts: warp shuffles + one pass over the 32 warp totals
 			__shared__ int s_wtot[32];
 			int incl = cnt;
@@ -545,10 +546,10 @@ __device__ void plan_body(const SolveArgs& a, WinDesc* wins_rw) {
 				int incl = v;
 #pragma unroll
 				for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-				if (p < np) a.pair_tile0[poff + p] = carry + incl - v;
+				if (p < np) a.pair_tile0[poff + p] = 1 + carry + incl - v;      // slot 0 of the window is its sparse tile
 				carry += __shfl_sync(0xffffffffu, incl, 31);
 			}
-			if (lane == 0 && carry == 0 && fits) { Tile tl; tl.win = w; tl.pair = -1; tl.start = 0; tl.count = 0; a.tiles[s_cnt[wl]] = tl; }
+			if (lane == 0 && fits) { Tile tl; tl.win = w; tl.pair = -2; tl.start = 0; tl.count = 0; a.tiles[s_cnt[wl]] = tl; }
 		}
 		__syncthreads();
 		PROF_T(3);
@@ -720,8 +721,8 @@ __device__ __forceinline__ void unpack_sym(int e, int& r, int& c) {
 }
 
 // Sparse moment sums of one window for the CURRENT poses: 8 lanes per (i,j) group of correspondences, loads one iteration
-// ahead; 44 sums per group go to a.grp_sums.  Runs on the first CTA that retires a dense tile of (window, iteration), while the
-// other tiles of the window are still in flight, so the window's tail no longer waits for it.
+// ahead; 44 sums per group go to a.grp_sums.  This is the window's SPARSE tile: first in the window's slice of the queue, it runs
+// on whichever CTA claims it while the dense tiles are in flight, so the window's tail does not wait for it.
 __device__ void sparse_sums(const SolveArgs& a, int w) {
 	const WinDesc wd0 = a.wins[w];
 	const WinSparse ws = a.wsp[w];
@@ -1090,7 +1091,7 @@ __global__ void __launch_bounds__(kThreads, BT_SOLVE_MIN_CTAS) k_solve(SolveArgs
 	__shared__ float s_X[36];
 	__shared__ float s_red[kTileVals];
 	__shared__ float s_part[kWarps][kTileVals];
-	__shared__ int s_is_last, s_is_first;
+	__shared__ int s_is_last;
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const int total = *a.n_tiles_total;
 	if (total <= 0) return;
@@ -1113,6 +1114,20 @@ __global__ void __launch_bounds__(kThreads, BT_SOLVE_MIN_CTAS) k_solve(SolveArgs
 			__syncthreads();
 		}
 		PROF_T(1);
+		if (tl.pair == -2) {     // the window's sparse tile: moment sums of all its (i,j) groups for the current poses (CTA-uniform branch)
+			PROF_T(2);
+			sparse_sums(a, tl.win);
+			PROF_T(3);
+			__threadfence();
+			__syncthreads();
+			if (tid == 0) {
+				const int done = atomicAdd(a.tiles_done + tl.win, 1) + 1;
+				s_is_last = (done == (it + 1) * wd.n_tiles);
+				if (s_is_last) __threadfence();
+			}
+			PROF_T(4);
+			__syncthreads();
+		} else {
 		TileAcc acc;
 #pragma unroll
 		for (int k = 0; k < kTileVals; k++) acc.v[k] = 0.f;
@@ -1197,28 +1212,17 @@ __global__ void __launch_bounds__(kThreads, BT_SOLVE_MIN_CTAS) k_solve(SolveArgs
 				__threadfence();      // the writers order their store before the ticket below
 			}
 			__syncwarp();
-			if (lane == 0) {     // n_tiles + 1 tickets per (window, iteration): the dense tiles and the sparse sums
+			if (lane == 0) {
 				const int done = atomicAdd(a.tiles_done + tl.win, 1) + 1;
-				s_is_first = (done == it * (wd.n_tiles + 1) + 1);
-				s_is_last = (done == (it + 1) * (wd.n_tiles + 1));
+				s_is_last = (done == (it + 1) * wd.n_tiles);
 				if (s_is_last) __threadfence();
 			}
 		}
 		PROF_T(4);
 		__syncthreads();
+		}      // dense tile
 		PROF_T(5);
 		if (a.prof && tid == 0) { prf.kind_cta = blockIdx.x; prf.tile_win = ((long long)tl_idx << 32) | ((long long)it << 16) | tl.count; prf.t[6] = prf.t[7] = prf.t[8] = prf.t[9] = 0; prof_emit(a, prf); }
-		if (s_is_first) {     // CTA-uniform: the first tile of this (window, iteration) to retire also does the window's sparse sums
-			sparse_sums(a, tl.win);
-			__threadfence();
-			__syncthreads();
-			if (tid == 0) {
-				const int done = atomicAdd(a.tiles_done + tl.win, 1) + 1;
-				s_is_last = (done == (it + 1) * (wd.n_tiles + 1));
-				if (s_is_last) __threadfence();
-			}
-			__syncthreads();
-		}
 		if (s_is_last) {
 			window_tail(a, wd, tl.win, it, dyn_smem);
 			__threadfence();
@@ -1309,7 +1313,7 @@ static int reserve_impl(bt_ctx* ctx, const bt_solver_limits* lim) {
 	s->max_pairs = lim->max_frames * (lim->max_frames - 1);   // both directions allowed in custom lists
 	s->max_groups = lim->max_frames * lim->max_frames;
 	const int min_chunk = 256;   // worst case: every pixel valid at the smallest chunk the scheduler ever picks
-	s->max_tiles = lim->max_windows * (lim->max_frames * (lim->max_frames - 1) / 2) * ((s->npix_max + min_chunk - 1) / min_chunk + 1);
+	s->max_tiles = lim->max_windows * (lim->max_frames * (lim->max_frames - 1) / 2) * ((s->npix_max + min_chunk - 1) / min_chunk + 1) + lim->max_windows;
 	int rc;
 #define RES(buf, bytes) if ((rc = s->buf.alloc(bytes)) != BT_OK) return rc
 	{   // worst case over every window count <= max_windows (the table offsets grow with the count, so the maximum is at max_windows)
