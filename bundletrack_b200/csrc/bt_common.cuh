@@ -60,6 +60,7 @@ struct SolverState;   // solver.cu
 struct MatcherState;  // knn.cu
 struct RansacState;   // ransac.cu
 struct FrontState;    // frontend.cu
+struct PruneState;    // prune.cu
 
 }  // namespace bt
 
@@ -71,6 +72,7 @@ struct bt_ctx {
 	bt::MatcherState* matcher = nullptr;
 	bt::RansacState* ransac = nullptr;
 	bt::FrontState* front = nullptr;
+	bt::PruneState* prune = nullptr;
 };
 
 namespace bt {

@@ -170,20 +170,17 @@ static PruneState* g_prune_of(bt_ctx* ctx);
 
 using namespace bt;
 
-// The prune state hangs off the matcher slot of the context through a side table (keeps bt_ctx unchanged).
-#include <map>
-static std::map<bt_ctx*, PruneState*> g_prune;
+// The prune state is owned by the context like the solver / matcher / RANSAC / front-end states.
 namespace bt {
-static PruneState* g_prune_of(bt_ctx* ctx) { auto it = g_prune.find(ctx); return it == g_prune.end() ? nullptr : it->second; }
+static PruneState* g_prune_of(bt_ctx* ctx) { return ctx->prune; }
 void prune_destroy(bt_ctx* ctx) {
-	auto it = g_prune.find(ctx);
-	if (it == g_prune.end()) return;
-	PruneState* s = it->second;
+	PruneState* s = ctx->prune;
+	if (!s) return;
 	DevBuf* bufs[] = { &s->pairs, &s->corr, &s->PA, &s->PB, &s->n_corr, &s->rpairs, &s->inl, &s->n_inl, &s->idxAB, &s->distAB, &s->idxBA, &s->distBA, &s->entry_off, &s->total };
 	for (DevBuf* b : bufs) b->release();
 	s->h_pairs.release();
 	delete s;
-	g_prune.erase(it);
+	ctx->prune = nullptr;
 }
 }
 
@@ -194,7 +191,7 @@ extern "C" int bt_pipeline_reserve(bt_ctx* ctx, int max_pairs, int max_feats, in
 	rc = bt_ransac_reserve(ctx, max_pairs, 2 * max_feats, max_trials);
 	if (rc != BT_OK) return rc;
 	PruneState* s = g_prune_of(ctx);
-	if (!s) { s = new PruneState(); g_prune[ctx] = s; }
+	if (!s) { s = new PruneState(); ctx->prune = s; }
 	s->max_pairs = max_pairs; s->max_feats = max_feats;
 	const size_t cap = (size_t)2 * max_feats * max_pairs;
 #define RES(buf, bytes) if ((rc = s->buf.alloc(bytes)) != BT_OK) return rc
