@@ -37,6 +37,7 @@
 //     Solver/LieDerivUtil.h:126-194,276-282.
 #include <algorithm>
 #include <math.h>
+#include <stddef.h>
 #include "bt_common.cuh"
 
 namespace bt {
@@ -1537,13 +1538,21 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 				sent = c_off + n_valid;
 			}
 		} else {
-			long long prev = -1;
+			// one 8-byte compare per entry (imgIdx_i | imgIdx_j << 32, little endian); range and order are only checked where a run ends
+			static_assert(offsetof(bt_entryj, imgIdx_i) == 0 && offsetof(bt_entryj, imgIdx_j) == 4, "EntryJ header layout");
+			unsigned long long prev_raw = 0ull;
+			bool have_prev = false;
+			long long prev_key = -1;
 			for (int c = 0; c < bw.n_corr; c++) {
-				const bt_entryj& e = bw.corr[c];
-				if (e.imgIdx_i >= (uint32_t)N || e.imgIdx_j >= (uint32_t)N) { grouped = false; break; }
-				const long long key = (long long)e.imgIdx_i * N + e.imgIdx_j;
-				if (key < prev) { grouped = false; break; }
-				if (key != prev) { hgi[g_off + ng] = (int)e.imgIdx_i; hgj[g_off + ng] = (int)e.imgIdx_j; hgs[g_off + w + ng] = c; ng++; prev = key; }
+				unsigned long long raw;
+				memcpy(&raw, &bw.corr[c], sizeof raw);
+				if (have_prev && raw == prev_raw) continue;
+				const uint32_t ei = (uint32_t)raw, ej = (uint32_t)(raw >> 32);
+				if (ei >= (uint32_t)N || ej >= (uint32_t)N) { grouped = false; break; }
+				const long long key = (long long)ei * N + ej;
+				if (key < prev_key) { grouped = false; break; }
+				hgi[g_off + ng] = (int)ei; hgj[g_off + ng] = (int)ej; hgs[g_off + w + ng] = c; ng++;
+				prev_raw = raw; prev_key = key; have_prev = true;
 			}
 		}
 		if (bw.corr_dev) {
