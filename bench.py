@@ -102,15 +102,25 @@ def make_batch(args, rank, dev):
     from bundletrack_b200.optimizer import SolveWindow
     scenes = [synth.make_window(1000 * rank + s, n_frames=args.frames, n_corr=args.corr) for s in range(min(args.scenes, args.windows))]
     wins, host = [], []
+    # every window's correspondences live in ONE page-locked host block (the contract's "inputs from pinned host memory"): the
+    # library then lets the copy engine read them in place instead of staging them through its own pinned buffer
+    n_ent = sum(len(scenes[k % len(scenes)].corr) for k in range(args.windows))
+    pinned = torch.empty(max(n_ent, 1) * 32, dtype=torch.uint8).pin_memory()
+    corr_all = pinned.numpy().view(synth.ENTRYJ_DTYPE)
+    make_batch.keep = pinned
+    c0 = 0
     for k in range(args.windows):
         sc = scenes[k % len(scenes)]
+        corr_k = corr_all[c0:c0 + len(sc.corr)]
+        corr_k[:] = sc.corr
+        c0 += len(sc.corr)
         rng = np.random.default_rng(77 + 1000 * rank + k)
         poses = sc.poses_gt.copy()
         for f in range(1, sc.n_frames):
             poses[f] = sc.poses_gt[f] @ synth.se3(synth.so3_exp(rng.normal(0, np.deg2rad(1.0), 3)), rng.normal(0, 0.003, 3))
         depth = [torch.from_numpy(sc.depth[f]).to(dev) for f in range(sc.n_frames)]
         normal = [torch.from_numpy(sc.normal[f]).to(dev) for f in range(sc.n_frames)]
-        wins.append(SolveWindow(sc.corr, sc.H, sc.W, depth, normal, poses.astype(np.float32), sc.K))
+        wins.append(SolveWindow(corr_k, sc.H, sc.W, depth, normal, poses.astype(np.float32), sc.K))
         host.append((sc, poses.astype(np.float32)))
     return wins, host
 

@@ -1510,6 +1510,7 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 
 	// ==== phase 2 (the GPU is already busy in the fused call): correspondences -> groups, membership CSR, pinned copy, chunked upload
 	size_t c_off = 0, g_off = 0, m_off = 0, smem_need = 0, sent = 0;
+	const bt_entryj* run_src = nullptr; size_t run_dst = 0, run_n = 0;      // pending in-place transfer from page-locked caller memory
 	std::vector<int> bin;
 	std::vector<char> seen;
 	p_off = 0;
@@ -1560,7 +1561,25 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 		} else if (grouped) {
 			n_valid = bw.n_corr;
 			hgs[g_off + w + ng] = n_valid;
-			if (n_valid) memcpy(hcorr + c_off, bw.corr, sizeof(bt_entryj) * (size_t)n_valid);      // the window's entries are still in cache from the scan
+			if (n_valid) {
+				// Caller's buffer page-locked (cudaHostAlloc / cudaHostRegister / bt_host_alloc_pinned)?  Then the copy engine reads it in
+				// place - no staging copy - and windows whose buffers follow each other in memory share one transfer.
+				cudaPointerAttributes pa;
+				const bool pinned_src = cudaPointerGetAttributes(&pa, bw.corr) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+				if (pinned_src) {
+					if (c_off > sent) {      // flush what was staged so far: the staging block has a hole where this window's entries would be
+						BT_CUDA(cudaMemcpyAsync(s->stage_dev.as<char>() + L.corr + sent * sizeof(bt_entryj), hcorr + sent, (c_off - sent) * sizeof(bt_entryj), cudaMemcpyHostToDevice, s->copy_stream));
+					}
+					if (run_n && run_src + run_n == bw.corr && run_dst + run_n == c_off) run_n += (size_t)n_valid;      // extends the pending run
+					else {
+						if (run_n) BT_CUDA(cudaMemcpyAsync(s->stage_dev.as<char>() + L.corr + run_dst * sizeof(bt_entryj), run_src, run_n * sizeof(bt_entryj), cudaMemcpyHostToDevice, s->copy_stream));
+						run_src = bw.corr; run_dst = c_off; run_n = (size_t)n_valid;
+					}
+					sent = c_off + n_valid;
+				} else {
+					memcpy(hcorr + c_off, bw.corr, sizeof(bt_entryj) * (size_t)n_valid);      // the window's entries are still in cache from the scan
+				}
+			}
 		} else {
 			ng = 0;
 			bin.assign((size_t)N * N + 1, 0);
@@ -1627,6 +1646,7 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 			sent = c_off;
 		}
 	}
+	if (run_n) BT_CUDA(cudaMemcpyAsync(s->stage_dev.as<char>() + L.corr + run_dst * sizeof(bt_entryj), run_src, run_n * sizeof(bt_entryj), cudaMemcpyHostToDevice, s->copy_stream));
 	BT_REQUIRE(smem_need <= 200 * 1024, BT_ERR_CAPACITY, "bt_solve_stage: window needs %zu bytes of shared memory (> 200 KB)", smem_need);
 	s->smem_bytes = (int)smem_need;
 	BT_CUDA(cudaMemcpyAsync(s->stage_dev.as<char>() + L.late, hb + L.late, L.corr - L.late, cudaMemcpyHostToDevice, s->copy_stream));      // group tables, CSR, WinSparse

@@ -72,7 +72,11 @@ typedef struct {
 	int n_frames;                     /* N, frame 0 is the gauge (never moves) */
 	int H, W;                         /* full-resolution image size */
 	int n_corr;
-	const bt_entryj* corr;            /* HOST pointer, n_corr entries (std::vector<EntryJ>::data()) */
+	const bt_entryj* corr;            /* HOST pointer, n_corr entries (std::vector<EntryJ>::data()).  Pageable memory is copied
+	                                   * during the call.  PAGE-LOCKED memory (cudaHostAlloc / cudaHostRegister /
+	                                   * bt_host_alloc_pinned) is read in place by the copy engine - windows whose buffers follow
+	                                   * each other share one transfer - and must stay unchanged until bt_solve_windows returns
+	                                   * (split API: until bt_solve_fetch). */
 	const float* const* depth_dev;    /* HOST array of N DEVICE pointers: Frame::_depth_gpu, float[H*W], metres, 0 = invalid */
 	const float* const* normal_dev;   /* HOST array of N DEVICE pointers: Frame::_normal_gpu, float4[H*W], (nx,ny,nz,0) */
 	float fx, fy, cx, cy;             /* K at full resolution */

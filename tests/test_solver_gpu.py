@@ -264,3 +264,31 @@ def test_frame_cache_is_bit_identical(cuda_device):
     with pytest.raises(_lib.BtError):      # stored with another K
         o.optimizeWindows([SolveWindow(wb.corr, wb.H, wb.W, None, None, wb.poses_init, tuple(v * 1.01 for v in wb.K), cache_slots=[12, 0, 9, 1])])
     o.close()
+
+
+def test_pinned_correspondences_are_read_in_place(opt, cuda_device):
+    """Correspondences in page-locked host memory (one block for consecutive windows, or one window alone) skip the library's
+    staging copy; the poses equal the pageable-memory path bit for bit, also when pinned and pageable windows alternate."""
+    import torch
+    from bundletrack_b200.optimizer import SolveWindow
+    ws = [synth.make_window(70 + k, n_frames=4, n_corr=300 + 40 * k) for k in range(4)]
+    maps = [_upload(w, cuda_device) for w in ws]
+    plain = opt.optimizeWindows([SolveWindow(w.corr, w.H, w.W, d, n, w.poses_init, w.K) for w, (d, n) in zip(ws, maps)])
+    total = sum(len(w.corr) for w in ws)
+    block = torch.empty(total * 32, dtype=torch.uint8).pin_memory()
+    arr = block.numpy().view(synth.ENTRYJ_DTYPE)
+    views, o = [], 0
+    for w in ws:
+        arr[o:o + len(w.corr)] = w.corr
+        views.append(arr[o:o + len(w.corr)]); o += len(w.corr)
+    for mask in ((1, 1, 1, 1), (1, 0, 1, 0), (0, 1, 1, 0)):
+        batch = [SolveWindow(views[k] if mask[k] else ws[k].corr, ws[k].H, ws[k].W, maps[k][0], maps[k][1], ws[k].poses_init, ws[k].K) for k in range(4)]
+        got = opt.optimizeWindows(batch)
+        for a, b in zip(got, plain):
+            assert np.array_equal(a, b)
+    # shuffled (ungrouped) entries in pinned memory still go through the sorting path
+    perm = np.random.default_rng(1).permutation(len(ws[0].corr))
+    arr[:len(ws[0].corr)] = ws[0].corr[perm]
+    s1 = opt.optimizeWindows([SolveWindow(views[0], ws[0].H, ws[0].W, maps[0][0], maps[0][1], ws[0].poses_init, ws[0].K)])[0]
+    s0 = opt.optimizeWindows([SolveWindow(ws[0].corr[perm], ws[0].H, ws[0].W, maps[0][0], maps[0][1], ws[0].poses_init, ws[0].K)])[0]
+    assert np.array_equal(s1, s0)
