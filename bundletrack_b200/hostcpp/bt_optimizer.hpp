@@ -1,10 +1,13 @@
 // bt_optimizer.hpp — C++ host shim with the REFERENCE'S signatures on top of the C-ABI (include/bundletrack_b200.h).
 //
-// Drop-in for the two classes BundleTrack's host code talks to on the hot path:
+// Drop-in for what BundleTrack's host code talks to on the hot path:
 //   * OptimizerGpu::optimizeFrames      (/root/reference/src/cuda/LossGPU.h:50, called from Bundler::optimizeGPU,
 //                                        /root/reference/src/Bundler.cpp:350-351)
 //   * ransacMultiPairGPU                (/root/reference/src/cuda/cuda_ransac.h:50, called from
 //                                        SiftManager::runRansacMultiPairGPU, /root/reference/src/FeatureManager.cpp:713)
+//   * knnMatchBothDirections            (the two cv::cuda::DescriptorMatcher::knnMatch calls of SiftManager::findCorresbyNN,
+//                                        /root/reference/src/FeatureManager.cpp:271-273)
+//   * processDepthAndNormals            (Frame::processDepth + Frame::depthToCloudAndNormals, /root/reference/src/Frame.cpp:152-233)
 // Header-only, no Eigen/yaml-cpp/OpenCV dependency of its own: the pose and intrinsics types are template parameters
 // that only need operator()(row, col) (Eigen::Matrix4f / Matrix3f satisfy it), and the yml values arrive through
 // BtSolverConfig, which the caller fills from the UNCHANGED config_*.yml keys (see INTEGRATION.md for the 6-line
@@ -108,4 +111,53 @@ inline void ransacMultiPairGPU(bt_ctx* ctx, const std::vector<Float4T*>& ptsA, c
 	int off = 0;
 	for (int p = 0; p < n; p++) { inlier_ids[p].assign(ids.begin() + off, ids.begin() + off + cnt[p]); off += n_pts[p]; }
 	bt_dev_free(d_ids); bt_dev_free(d_cnt);
+}
+
+// ---- Frame::processDepth + Frame::depthToCloudAndNormals (/root/reference/src/Frame.cpp:152-233) ----------------------------------
+struct BtDepthConfig {            // depth_processing.* of config_nocs.yml, same names
+	float erode_radius = 1, erode_diff = 0.001f, erode_ratio = 0.8f;
+	int bf_radius = 2; float sigma_D = 2.f, sigma_R = 100000.f;
+	bt_depth_params to_params() const { bt_depth_params p; p.erode_radius = (int)erode_radius; p.erode_diff = erode_diff; p.erode_ratio = erode_ratio;
+		p.bf_radius = bf_radius; p.sigma_D = sigma_D; p.sigma_R = sigma_R; return p; }
+};
+// raw depth (device, metres) -> Frame::_depth_gpu, Frame::_normal_gpu and, if wanted, the camera-space point map that the
+// reference copies to the host for its PCL cloud (xyz_gpu may be nullptr).  One fused kernel; depth_gpu != depth_raw_gpu.
+template <class Float4T, class Mat3>
+inline void processDepthAndNormals(bt_ctx* ctx, const float* depth_raw_gpu, float* depth_gpu, Float4T* normal_gpu, Float4T* xyz_gpu, int H, int W, const Mat3& K,
+                                   const BtDepthConfig& cfg, void* stream = nullptr) {
+	const bt_depth_params prm = cfg.to_params();
+	const float* in[1] = { depth_raw_gpu }; float* out[1] = { depth_gpu };
+	float* nrm[1] = { reinterpret_cast<float*>(normal_gpu) }; float* xyz[1] = { reinterpret_cast<float*>(xyz_gpu) };
+	if (bt_frames_preprocess(ctx, 1, in, H, W, K(0, 0), K(1, 1), K(0, 2), K(1, 2), &prm, out, xyz_gpu ? xyz : nullptr, nrm, stream) != BT_OK)
+		throw std::runtime_error(std::string("bt_frames_preprocess: ") + bt_last_error());
+}
+
+// ---- the two knnMatch calls of SiftManager::findCorresbyNN (/root/reference/src/FeatureManager.cpp:271-273) in one call --------
+// desA/desB: device CV_32F descriptor matrices (GpuMat::data, rows, step).  DMatchT needs queryIdx, trainIdx, distance (cv::DMatch).
+template <class DMatchT>
+inline void knnMatchBothDirections(bt_ctx* ctx, const float* desA, int nA, size_t stepA, const float* desB, int nB, size_t stepB, int dim, int k,
+                                   std::vector<std::vector<DMatchT>>& matchesAB, std::vector<std::vector<DMatchT>>& matchesBA, void* stream = nullptr) {
+	auto check = [](int rc, const char* what) { if (rc != BT_OK) throw std::runtime_error(std::string(what) + ": " + bt_last_error()); };
+	check(bt_matcher_reserve(ctx, 1, nA > nB ? nA : nB, dim), "bt_matcher_reserve");
+	bt_desc_view A{}; A.dev = desA; A.n = nA; A.dim = dim; A.pitch_bytes = stepA;
+	bt_desc_view B{}; B.dev = desB; B.n = nB; B.dim = dim; B.pitch_bytes = stepB;
+	void *iab = nullptr, *dab = nullptr, *iba = nullptr, *dba = nullptr;
+	const size_t ea = (size_t)(nA > 0 ? nA : 1) * k, eb = (size_t)(nB > 0 ? nB : 1) * k;
+	check(bt_dev_alloc(&iab, 4 * ea), "bt_dev_alloc"); check(bt_dev_alloc(&dab, 4 * ea), "bt_dev_alloc");
+	check(bt_dev_alloc(&iba, 4 * eb), "bt_dev_alloc"); check(bt_dev_alloc(&dba, 4 * eb), "bt_dev_alloc");
+	check(bt_knn_match_pairs(ctx, 1, &A, &B, k, (int32_t*)iab, (float*)dab, (int32_t*)iba, (float*)dba, stream), "bt_knn_match_pairs");
+	std::vector<int32_t> hiab(ea), hiba(eb); std::vector<float> hdab(ea), hdba(eb);
+	check(bt_memcpy_d2h(hiab.data(), iab, 4 * ea, stream), "bt_memcpy_d2h"); check(bt_memcpy_d2h(hdab.data(), dab, 4 * ea, stream), "bt_memcpy_d2h");
+	check(bt_memcpy_d2h(hiba.data(), iba, 4 * eb, stream), "bt_memcpy_d2h"); check(bt_memcpy_d2h(hdba.data(), dba, 4 * eb, stream), "bt_memcpy_d2h");
+	auto fill = [k](int n, const std::vector<int32_t>& idx, const std::vector<float>& dist, std::vector<std::vector<DMatchT>>& out) {
+		out.assign(n, {});
+		for (int q = 0; q < n; q++)
+			for (int j = 0; j < k; j++) {
+				if (idx[(size_t)q * k + j] < 0) break;          // fewer than k train rows
+				DMatchT m{}; m.queryIdx = q; m.trainIdx = idx[(size_t)q * k + j]; m.distance = dist[(size_t)q * k + j];
+				out[q].push_back(m);
+			}
+	};
+	fill(nA, hiab, hdab, matchesAB); fill(nB, hiba, hdba, matchesBA);
+	bt_dev_free(iab); bt_dev_free(dab); bt_dev_free(iba); bt_dev_free(dba);
 }

@@ -1,4 +1,4 @@
-"""The C++ host shim (reference-shaped OptimizerGpu::optimizeFrames / ransacMultiPairGPU on top of the C-ABI) must compile
+"""The C++ host shim (reference-shaped OptimizerGpu::optimizeFrames / ransacMultiPairGPU / knnMatch / depth front end on top of the C-ABI) must compile
 against a minimal Eigen-like matrix type and link with the in-tree library."""
 import os
 import subprocess
@@ -22,6 +22,13 @@ def test_cpp_shim_compiles_and_links(tmp_path):
                 OptimizerGpu opt(cfg);            // throws without a GPU: the product has no CPU fallback
                 std::vector<EntryJ> corr; std::vector<int> nm; std::vector<float*> d; std::vector<uchar4_*> c; std::vector<float4_*> n; std::vector<Mat4> poses; Mat3 K{};
                 opt.optimizeFrames(corr, nm, 0, 480, 640, d, c, n, poses, K);
+                // the other two call sites of the path and the frame front end instantiate too
+                struct DMatch { int queryIdx, trainIdx; float distance; };
+                std::vector<std::vector<DMatch>> ab, ba;
+                knnMatchBothDirections(opt.ctx(), (const float*)nullptr, 0, 1024, (const float*)nullptr, 0, 1024, 256, 5, ab, ba);
+                std::vector<float4_*> pa, pb; std::vector<int> np; std::vector<std::vector<int>> inl;
+                ransacMultiPairGPU(opt.ctx(), pa, pb, np, 2000, 0.005f, inl);
+                processDepthAndNormals(opt.ctx(), (const float*)nullptr, (float*)nullptr, (float4_*)nullptr, (float4_*)nullptr, 480, 640, K, BtDepthConfig());
             } catch (const std::exception& e) { std::printf("caught: %s\n", e.what()); return 0; }
             return 0;
         }
