@@ -127,6 +127,7 @@ EXPORTS = [
     "bt_matcher_reserve", "bt_knn_match_pairs", "bt_knn_enable_timing", "bt_knn_get_timing", "bt_knn_debug_force_fallback", "bt_ransac_reserve", "bt_ransac_pairs", "bt_ransac_debug",
     "bt_pipeline_reserve", "bt_prune_mutual_pairs", "bt_match_pairs", "bt_frames_preprocess",
     "bt_frame_cache_reserve", "bt_frame_cache_store",
+    "bt_rotation_geodesic", "bt_keyframe_check", "bt_select_keyframes", "bt_rigid_transform",
     "bt_dev_alloc", "bt_dev_free", "bt_memcpy_h2d", "bt_memcpy_d2h", "bt_host_alloc_pinned", "bt_host_free_pinned",
     "bt_stream_sync",
 ]
@@ -148,9 +149,10 @@ def load() -> ctypes.CDLL:
     lib.bt_last_error.restype = ctypes.c_char_p
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("bt_last_error", "bt_ctx_destroy"):
+        if name not in ("bt_last_error", "bt_ctx_destroy", "bt_rotation_geodesic"):
             fn.restype = ctypes.c_int
     lib.bt_ctx_destroy.restype = None
+    lib.bt_rotation_geodesic.restype = ctypes.c_float
     _lib = lib
     return lib
 

@@ -1,0 +1,156 @@
+// policy.cu — the host-side policy around the hot path: keyframe admission, keyframe subset selection for
+// one bundle adjustment, and the closed-form initial pose.  Scalar O(K^2) work on 4x4 matrices: plain host code, no kernels, no
+// CUDA calls (these entry points work without a GPU).  Restated from
+//   Utils::rotationGeodesicDistance          /root/reference/src/Utils.cpp:42-47
+//   Bundler::checkAndAddKeyframe             /root/reference/src/Bundler.cpp:185-221
+//   Bundler::selectKeyFramesForBA            /root/reference/src/Bundler.cpp:224-274   ("greedy_rot")
+//   Utils::solveRigidTransformBetweenPoints  /root/reference/src/Utils.cpp:180-214      (used by SiftManager::procrustesByCorrespondence)
+// Poses are row-major 4x4 cam->model like everywhere in this ABI.
+#include <math.h>
+#include <algorithm>
+#include <limits>
+#include <vector>
+#include "bt_common.cuh"
+
+namespace {
+
+// acos((trace(R1 R2^T) - 1) / 2), clamped, in float like the reference
+float geodesic(const float* A, const float* B) {
+	float tr = 0.f;
+	for (int r = 0; r < 3; r++)
+		for (int c = 0; c < 3; c++) tr += A[r * 4 + c] * B[r * 4 + c];      // trace(R1 R2^T) = sum_rc R1(r,c) R2(r,c)
+	float t = (tr - 1.f) / 2.0f;
+	t = std::max(std::min(1.0f, t), -1.0f);
+	return acosf(t);
+}
+
+// one-sided Jacobi SVD of a 3x3 (double): M = U diag(s) V^T, singular values sorted descending
+void svd3(const double M[9], double U[9], double S[3], double V[9]) {
+	double A[9];
+	for (int i = 0; i < 9; i++) { A[i] = M[i]; V[i] = (i % 4 == 0) ? 1.0 : 0.0; }
+	for (int sweep = 0; sweep < 60; sweep++) {
+		double off = 0.0;
+		for (int p = 0; p < 2; p++)
+			for (int q = p + 1; q < 3; q++) {
+				double a = 0, b = 0, g = 0;      // columns p, q of A
+				for (int r = 0; r < 3; r++) { a += A[r * 3 + p] * A[r * 3 + p]; b += A[r * 3 + q] * A[r * 3 + q]; g += A[r * 3 + p] * A[r * 3 + q]; }
+				off = std::max(off, fabs(g) / (sqrt(a * b) + 1e-300));
+				if (fabs(g) < 1e-300) continue;
+				const double zeta = (b - a) / (2.0 * g);
+				const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+				const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+				for (int r = 0; r < 3; r++) {
+					const double ap = A[r * 3 + p], aq = A[r * 3 + q];
+					A[r * 3 + p] = c * ap - s * aq; A[r * 3 + q] = s * ap + c * aq;
+					const double vp = V[r * 3 + p], vq = V[r * 3 + q];
+					V[r * 3 + p] = c * vp - s * vq; V[r * 3 + q] = s * vp + c * vq;
+				}
+			}
+		if (off < 1e-15) break;
+	}
+	int order[3] = { 0, 1, 2 };
+	double n[3];
+	for (int j = 0; j < 3; j++) n[j] = sqrt(A[j] * A[j] + A[3 + j] * A[3 + j] + A[6 + j] * A[6 + j]);
+	std::sort(order, order + 3, [&](int x, int y) { return n[x] > n[y]; });
+	double Vs[9];
+	for (int j = 0; j < 3; j++) {
+		const int o = order[j];
+		S[j] = n[o];
+		for (int r = 0; r < 3; r++) { U[r * 3 + j] = n[o] > 1e-300 ? A[r * 3 + o] / n[o] : 0.0; Vs[r * 3 + j] = V[r * 3 + o]; }
+	}
+	for (int i = 0; i < 9; i++) V[i] = Vs[i];
+	// complete U to an orthonormal basis when M is rank deficient (Eigen's thin U is full for a 3x3 as well)
+	for (int j = 0; j < 3; j++) {
+		if (S[j] > 1e-300) continue;
+		const int a = (j + 1) % 3, b = (j + 2) % 3;
+		U[0 * 3 + j] = U[1 * 3 + a] * U[2 * 3 + b] - U[2 * 3 + a] * U[1 * 3 + b];
+		U[1 * 3 + j] = U[2 * 3 + a] * U[0 * 3 + b] - U[0 * 3 + a] * U[2 * 3 + b];
+		U[2 * 3 + j] = U[0 * 3 + a] * U[1 * 3 + b] - U[1 * 3 + a] * U[0 * 3 + b];
+	}
+}
+
+}  // namespace
+
+extern "C" float bt_rotation_geodesic(const float* pose_a, const float* pose_b) {
+	if (!pose_a || !pose_b) return std::numeric_limits<float>::quiet_NaN();
+	return geodesic(pose_a, pose_b);
+}
+
+extern "C" int bt_keyframe_check(const float* pose_new, int frame_id, int n_keypts, const float* keyframe_poses, int n_keyframes, int min_feat_num, float min_rot_deg) {
+	if (frame_id == 0) return 1;                         // the first frame always becomes a keyframe
+	if (!pose_new || (n_keyframes > 0 && !keyframe_poses)) return 0;
+	if (n_keypts < min_feat_num) return 0;
+	for (int i = 0; i < n_keyframes; i++) {
+		const float rot_deg = geodesic(pose_new, keyframe_poses + 16 * (size_t)i) * 180 / (float)M_PI;
+		if (rot_deg < min_rot_deg) return 0;             // too close in rotation to an existing keyframe
+	}
+	return 1;
+}
+
+extern "C" int bt_select_keyframes(const float* pose_new, const float* keyframe_poses, int n_keyframes, int max_BA_frames, int32_t* chosen_out, int* n_chosen_out) {
+	BT_REQUIRE(pose_new && chosen_out && n_chosen_out && n_keyframes >= 0 && (n_keyframes == 0 || keyframe_poses) && max_BA_frames >= 1, BT_ERR_INVALID_ARG,
+	           "bt_select_keyframes: bad arguments");
+	std::vector<char> in(n_keyframes, 0);
+	int n_in = 1;                                        // the new frame is always part of the window
+	if (n_keyframes + 1 <= max_BA_frames) {
+		for (int i = 0; i < n_keyframes; i++) in[i] = 1;
+	} else {
+		in[0] = 1; n_in = 2;                             // keyframe 0 anchors the model frame
+		// greedy_rot: repeatedly add the keyframe with the smallest summed rotation distance to the frames chosen so far.  The
+		// reference walks a std::set of shared_ptr (pointer order); here the chosen set is walked new frame first, then keyframes in
+		// index order, and ties go to the lower index.
+		while (n_in < max_BA_frames) {
+			float best = std::numeric_limits<float>::max();
+			int best_i = -1;
+			for (int i = 0; i < n_keyframes; i++) {
+				if (in[i]) continue;
+				const float* kf = keyframe_poses + 16 * (size_t)i;
+				float cum = geodesic(kf, pose_new);
+				for (int j = 0; j < n_keyframes; j++) if (in[j]) cum += geodesic(kf, keyframe_poses + 16 * (size_t)j);
+				if (cum < best) { best = cum; best_i = i; }
+			}
+			if (best_i < 0) break;                       // every distance was NaN / nothing left
+			in[best_i] = 1; n_in++;
+		}
+	}
+	int n = 0;
+	for (int i = 0; i < n_keyframes; i++) if (in[i]) chosen_out[n++] = i;
+	*n_chosen_out = n;
+	return BT_OK;
+}
+
+extern "C" int bt_rigid_transform(const float* pts1, const float* pts2, int n, float* pose_out) {
+	BT_REQUIRE(pts1 && pts2 && pose_out && n >= 3, BT_ERR_INVALID_ARG, "bt_rigid_transform: needs two arrays of >= 3 points");
+	float* T = pose_out;
+	for (int i = 0; i < 16; i++) T[i] = (i % 5 == 0) ? 1.f : 0.f;
+	double m1[3] = { 0, 0, 0 }, m2[3] = { 0, 0, 0 };
+	for (int i = 0; i < n; i++) for (int k = 0; k < 3; k++) { m1[k] += pts1[3 * i + k]; m2[k] += pts2[3 * i + k]; }
+	for (int k = 0; k < 3; k++) { m1[k] /= n; m2[k] /= n; }
+	double S[9] = { 0 };                                 // S = P^T Q with P, Q the centred point sets
+	for (int i = 0; i < n; i++)
+		for (int r = 0; r < 3; r++)
+			for (int c = 0; c < 3; c++) S[r * 3 + c] += ((double)pts1[3 * i + r] - m1[r]) * ((double)pts2[3 * i + c] - m2[c]);
+	double U[9], sv[3], V[9];
+	svd3(S, U, sv, V);
+	auto vut = [&](double R[9]) { for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { R[r * 3 + c] = 0; for (int k = 0; k < 3; k++) R[r * 3 + c] += V[r * 3 + k] * U[c * 3 + k]; } };
+	double R[9];
+	vut(R);                                              // R = V U^T
+	for (int r = 0; r < 3; r++)                          // R^T R must be the identity (isApprox, Utils.cpp:196), else the pose stays identity
+		for (int c = 0; c < 3; c++) {
+			double d = 0;
+			for (int k = 0; k < 3; k++) d += R[k * 3 + r] * R[k * 3 + c];
+			if (!(fabs(d - (r == c ? 1.0 : 0.0)) <= 1e-5)) return BT_OK;
+		}
+	const double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
+	if (det < 0) { for (int r = 0; r < 3; r++) V[r * 3 + 2] = -V[r * 3 + 2]; vut(R); }      // reflection: flip the last right singular vector
+	float out[16] = { 0 };
+	out[15] = 1.f;
+	for (int r = 0; r < 3; r++) {
+		double t = m2[r];
+		for (int c = 0; c < 3; c++) { out[r * 4 + c] = (float)R[r * 3 + c]; t -= R[r * 3 + c] * m1[c]; }
+		out[r * 4 + 3] = (float)t;
+	}
+	for (int i = 0; i < 16; i++) if (!isfinite(out[i])) return BT_OK;      // isMatrixFinite, Utils.cpp:209
+	for (int i = 0; i < 16; i++) T[i] = out[i];
+	return BT_OK;
+}

@@ -1,0 +1,42 @@
+"""Host-side mirror of the policy functions around the hot path (`Bundler::checkAndAddKeyframe`, `Bundler::selectKeyFramesForBA`,
+`Utils::solveRigidTransformBetweenPoints`; /root/reference/src/Bundler.cpp:185-274, Utils.cpp:42-47,180-214) on top of the C-ABI.
+These entry points are plain host code in the library: they work without a GPU."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def rotation_geodesic(pose_a, pose_b) -> float:
+    a, b = np.ascontiguousarray(pose_a, np.float32), np.ascontiguousarray(pose_b, np.float32)
+    return float(_lib.load().bt_rotation_geodesic(_p(a), _p(b)))
+
+
+def keyframe_check(pose_new, frame_id: int, n_keypts: int, keyframe_poses, min_feat_num: int = 0, min_rot_deg: float = 10.0) -> bool:
+    kp = np.ascontiguousarray(keyframe_poses, np.float32).reshape(-1, 4, 4)
+    pn = np.ascontiguousarray(pose_new, np.float32)
+    return bool(_lib.load().bt_keyframe_check(_p(pn), ctypes.c_int(frame_id), ctypes.c_int(n_keypts), _p(kp), ctypes.c_int(len(kp)), ctypes.c_int(min_feat_num),
+                                              ctypes.c_float(min_rot_deg)))
+
+
+def select_keyframes(pose_new, keyframe_poses, max_BA_frames: int = 15) -> np.ndarray:
+    kp = np.ascontiguousarray(keyframe_poses, np.float32).reshape(-1, 4, 4)
+    pn = np.ascontiguousarray(pose_new, np.float32)
+    out = np.zeros(max(len(kp), 1), np.int32)
+    n = ctypes.c_int(0)
+    _lib.check(_lib.load().bt_select_keyframes(_p(pn), _p(kp), ctypes.c_int(len(kp)), ctypes.c_int(max_BA_frames), _p(out), ctypes.byref(n)), "bt_select_keyframes")
+    return out[:n.value].copy()
+
+
+def rigid_transform(pts1, pts2) -> np.ndarray:
+    a, b = np.ascontiguousarray(pts1, np.float32).reshape(-1, 3), np.ascontiguousarray(pts2, np.float32).reshape(-1, 3)
+    out = np.zeros((4, 4), np.float32)
+    _lib.check(_lib.load().bt_rigid_transform(_p(a), _p(b), ctypes.c_int(len(a)), _p(out)), "bt_rigid_transform")
+    return out

@@ -269,6 +269,24 @@ BT_API int bt_frame_cache_reserve(bt_ctx* ctx, int capacity, int H, int W, float
 BT_API int bt_frame_cache_store(bt_ctx* ctx, int n_frames, const int32_t* slots, const float* const* depth_dev, const float* const* normal_dev,
                          int H, int W, float fx, float fy, float cx, float cy, float depth_min, float depth_max, void* stream);
 
+/* ---- host-side policy around the path: plain host code, callable without a GPU -----------------------------
+ * Poses are row-major 4x4 cam->model.  keyframe_poses: n_keyframes consecutive 4x4 matrices. */
+/* Utils::rotationGeodesicDistance (/root/reference/src/Utils.cpp:42-47): angle between the two rotations, radians. */
+BT_API float bt_rotation_geodesic(const float* pose_a, const float* pose_b);
+/* Bundler::checkAndAddKeyframe (/root/reference/src/Bundler.cpp:185-221): 1 = the frame becomes a keyframe (frame 0 always; otherwise
+ * enough keypoints and at least min_rot_deg degrees away from EVERY existing keyframe), 0 = not.  The caller applies the
+ * reference's `_status == OTHER` test. */
+BT_API int bt_keyframe_check(const float* pose_new, int frame_id, int n_keypts, const float* keyframe_poses, int n_keyframes,
+                      int min_feat_num, float min_rot_deg);
+/* Bundler::selectKeyFramesForBA, method "greedy_rot" (Bundler.cpp:224-274): indices (ascending) of the keyframes that join the new
+ * frame in the window; at most max_BA_frames - 1 of them.  chosen_out needs room for n_keyframes entries. */
+BT_API int bt_select_keyframes(const float* pose_new, const float* keyframe_poses, int n_keyframes, int max_BA_frames,
+                        int32_t* chosen_out, int* n_chosen_out);
+/* Utils::solveRigidTransformBetweenPoints (Utils.cpp:180-214), the closed form behind SiftManager::procrustesByCorrespondence
+ * (FeatureManager.cpp:523-557): pose_out (row-major 4x4) maps pts1 onto pts2 (n x 3 each) in the least-squares sense; identity when
+ * the fit degenerates, as in the reference. */
+BT_API int bt_rigid_transform(const float* pts1, const float* pts2, int n, float* pose_out);
+
 /* Small device-memory helpers so non-CUDA hosts (ctypes, cgo, JNI) can drive the library without another runtime. */
 BT_API int bt_dev_alloc(void** out, size_t bytes);
 BT_API int bt_dev_free(void* p);

@@ -1,0 +1,78 @@
+"""CPU tests (no GPU needed: these entry points are host code inside the library) of the policy functions around the hot path
+against the numpy restatement in oracle/policy_oracle.py and against properties the reference's functions have by construction."""
+import numpy as np
+import pytest
+
+from bundletrack_b200 import policy, synth
+from oracle import policy_oracle as po
+
+
+def _poses(seed, n, max_deg=60.0):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        ax = rng.normal(size=3); ax /= np.linalg.norm(ax)
+        R = synth.so3_exp(ax * np.deg2rad(rng.uniform(0, max_deg)))
+        out.append(synth.se3(R, rng.normal(0, 0.05, 3)).astype(np.float32))
+    return np.stack(out)
+
+
+def test_rotation_geodesic():
+    P = _poses(0, 12)
+    for a in range(0, 12, 3):
+        for b in range(12):
+            want = po.rotation_geodesic(P[a], P[b])
+            if want > 0.05:            # acos is ill-conditioned near 0 (d angle = d trace / (2 sin angle)); identical poses are checked below
+                assert abs(policy.rotation_geodesic(P[a], P[b]) - want) <= 1e-5
+    assert policy.rotation_geodesic(P[3], P[3]) <= 1e-3            # acos near 1 is ill-conditioned in float, like the reference
+    R = synth.so3_exp(np.array([0, 0, np.pi]))                     # 180 degrees: the clamp keeps acos defined
+    assert abs(policy.rotation_geodesic(synth.se3(R, np.zeros(3)), np.eye(4)) - np.pi) <= 1e-3
+
+
+def test_keyframe_check_rules():
+    P = _poses(1, 6, max_deg=90)
+    new = _poses(2, 1, max_deg=90)[0]
+    for min_rot in (1.0, 10.0, 30.0, 80.0):
+        assert policy.keyframe_check(new, 7, 500, P, 0, min_rot) == po.keyframe_check(new, 7, 500, P, 0, min_rot)
+    assert policy.keyframe_check(new, 0, 0, P, 100, 180.0)         # frame 0 always
+    assert not policy.keyframe_check(new, 7, 50, P, 100, 0.0)      # too few keypoints
+    assert not policy.keyframe_check(P[2], 7, 500, P, 0, 10.0)     # identical to an existing keyframe
+    assert policy.keyframe_check(new, 7, 500, P[:0], 0, 10.0)      # no keyframes yet
+
+
+@pytest.mark.parametrize("seed,K,maxf", [(3, 8, 15), (4, 20, 15), (5, 40, 10), (6, 16, 16), (7, 16, 17), (8, 30, 2), (9, 5, 1)])
+def test_select_keyframes_matches_oracle(seed, K, maxf):
+    P = _poses(seed, K, max_deg=120)
+    new = _poses(100 + seed, 1, max_deg=120)[0]
+    got = policy.select_keyframes(new, P, maxf)
+    want = po.select_keyframes(new, P, maxf)
+    assert np.array_equal(got, want)
+    assert len(got) == min(K, max(maxf - 1, 0)) or (K + 1 > maxf and len(got) == max(maxf - 1, 1))
+    if K + 1 > maxf:
+        assert got[0] == 0                                         # keyframe 0 anchors the model frame
+    assert np.all(np.diff(got) > 0)
+
+
+def test_rigid_transform():
+    rng = np.random.default_rng(11)
+    for n in (3, 5, 40, 500):
+        a = rng.normal(0, 0.1, (n, 3)).astype(np.float32)
+        T = synth.se3(synth.so3_exp(rng.normal(0, 1.0, 3)), rng.normal(0, 0.3, 3))
+        b = (a @ T[:3, :3].T + T[:3, 3]).astype(np.float32)
+        got = policy.rigid_transform(a, b)
+        assert np.abs(got - T).max() <= 2e-5
+        noisy = b + rng.normal(0, 0.002, b.shape).astype(np.float32)
+        assert np.abs(policy.rigid_transform(a, noisy) - po.rigid_transform(a, noisy)).max() <= 2e-5
+    # a mirrored target has no proper rotation that fits: the closed form still returns a rotation (det +1), the best one
+    a = rng.normal(0, 0.1, (30, 3)).astype(np.float32)
+    m = a * np.array([1, 1, -1], np.float32)
+    got = policy.rigid_transform(a, m)
+    assert abs(np.linalg.det(got[:3, :3].astype(np.float64)) - 1) <= 1e-5
+    assert np.abs(got - po.rigid_transform(a, m)).max() <= 1e-4
+    # coplanar / collinear input is rank deficient but still yields an orthonormal frame or the identity, never NaN
+    line = np.outer(np.linspace(0, 1, 10), [1, 2, 3]).astype(np.float32)
+    out = policy.rigid_transform(line, line + np.float32(0.5))
+    assert np.isfinite(out).all() and np.allclose(out[:3, :3].T @ out[:3, :3], np.eye(3), atol=1e-4)
+    from bundletrack_b200 import _lib
+    with pytest.raises(_lib.BtError):
+        policy.rigid_transform(a[:2], a[:2])
