@@ -154,3 +154,39 @@ extern "C" int bt_rigid_transform(const float* pts1, const float* pts2, int n, f
 	for (int i = 0; i < 16; i++) T[i] = out[i];
 	return BT_OK;
 }
+
+// ---- LF-Net reply: Lfnet::detectFeature, /root/reference/src/FeatureManager.cpp:876-907, for rot_deg = 0 (the only
+// value Bundler::processNewFrame passes, /root/reference/src/Bundler.cpp:104-107).  Wire format of the server's reply
+// (lf-net-release/run_server.py:171-177): part 0 = int32 (n, dim), part 1 = float32 n x 2 keypoints (x, y) in the 400 x 400 network input,
+// part 2 = float32 n x dim descriptors (row-major: exactly the matrix bt_knn_match_pairs takes, no repacking).  Keypoints go back to
+// image pixels through forward^-1, forward = scale(400/side) * translate(-umin, -vmin), side = max(roi height, roi width).
+extern "C" int bt_lfnet_parse_reply(const void* info, size_t info_bytes, const void* kpts, size_t kpts_bytes, size_t desc_bytes, const int* roi,
+                                    float* kpts_out, int kpts_capacity, int* n_out, int* dim_out) {
+	BT_REQUIRE(info && roi && n_out && dim_out, BT_ERR_INVALID_ARG, "bt_lfnet_parse_reply: NULL argument");
+	BT_REQUIRE(info_bytes == 2 * sizeof(int32_t), BT_ERR_INVALID_ARG, "bt_lfnet_parse_reply: the first part must be 2 x int32 (n, dim), got %zu bytes", info_bytes);
+	int32_t nd[2];
+	memcpy(nd, info, sizeof nd);
+	const int n = nd[0], dim = nd[1];
+	BT_REQUIRE(n >= 0 && dim > 0, BT_ERR_INVALID_ARG, "bt_lfnet_parse_reply: bad header (n=%d, dim=%d)", n, dim);
+	BT_REQUIRE(kpts_bytes == sizeof(float) * 2 * (size_t)n, BT_ERR_INVALID_ARG, "bt_lfnet_parse_reply: keypoint part has %zu bytes, %d keypoints need %zu", kpts_bytes, n, sizeof(float) * 2 * (size_t)n);
+	BT_REQUIRE(desc_bytes == sizeof(float) * (size_t)n * dim, BT_ERR_INVALID_ARG, "bt_lfnet_parse_reply: descriptor part has %zu bytes, %d x %d floats need %zu", desc_bytes, n, dim, sizeof(float) * (size_t)n * dim);
+	BT_REQUIRE(n == 0 || (kpts && kpts_out), BT_ERR_INVALID_ARG, "bt_lfnet_parse_reply: NULL keypoint buffer");
+	BT_REQUIRE(n <= kpts_capacity, BT_ERR_CAPACITY, "bt_lfnet_parse_reply: %d keypoints > capacity %d", n, kpts_capacity);
+	const int W = roi[1] - roi[0], H = roi[3] - roi[2];
+	BT_REQUIRE(W > 0 && H > 0, BT_ERR_INVALID_ARG, "bt_lfnet_parse_reply: empty roi");
+	const int side = std::max(H, W);
+	// forward = [[a, 0, a*(-umin)], [0, b, b*(-vmin)], [0, 0, 1]]; its inverse as Eigen's 3x3 inverse forms it (cofactors times 1/det, float)
+	const float a = 400 / float(side), b = 400 / float(side);
+	const float f02 = a * (float)(-roi[0]), f12 = b * (float)(-roi[2]);
+	const float invdet = 1.0f / (a * b);
+	const float i00 = b * invdet, i11 = a * invdet, i02 = (0.f * f12 - f02 * b) * invdet, i12 = -(a * f12 - f02 * 0.f) * invdet;
+	const float* k = (const float*)kpts;
+	for (int i = 0; i < n; i++) {
+		float xy[2];
+		memcpy(xy, k + 2 * (size_t)i, sizeof xy);        // the message buffer need not be aligned
+		kpts_out[2 * (size_t)i] = i00 * xy[0] + 0.f * xy[1] + i02 * 1.f;
+		kpts_out[2 * (size_t)i + 1] = 0.f * xy[0] + i11 * xy[1] + i12 * 1.f;
+	}
+	*n_out = n; *dim_out = dim;
+	return BT_OK;
+}

@@ -40,3 +40,16 @@ def rigid_transform(pts1, pts2) -> np.ndarray:
     out = np.zeros((4, 4), np.float32)
     _lib.check(_lib.load().bt_rigid_transform(_p(a), _p(b), ctypes.c_int(len(a)), _p(out)), "bt_rigid_transform")
     return out
+
+
+def lfnet_parse_reply(parts, roi):
+    """parts: the three byte strings of the LF-Net server's reply; roi = (umin, umax, vmin, vmax).  Returns (kpts [n,2] float32 in image
+    pixels, desc [n,dim] float32 view of part 2)."""
+    info, kp, desc = (bytes(p) for p in parts)
+    n_guess = max(len(kp) // 8, 1)
+    out = np.zeros((n_guess, 2), np.float32)
+    n, dim = ctypes.c_int(0), ctypes.c_int(0)
+    r = (ctypes.c_int * 4)(*[int(v) for v in roi])
+    _lib.check(_lib.load().bt_lfnet_parse_reply(info, ctypes.c_size_t(len(info)), kp, ctypes.c_size_t(len(kp)), ctypes.c_size_t(len(desc)), r, _p(out),
+                                                ctypes.c_int(n_guess), ctypes.byref(n), ctypes.byref(dim)), "bt_lfnet_parse_reply")
+    return out[:n.value], np.frombuffer(desc, np.float32).reshape(n.value, dim.value)

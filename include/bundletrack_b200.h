@@ -287,6 +287,14 @@ BT_API int bt_select_keyframes(const float* pose_new, const float* keyframe_pose
  * the fit degenerates, as in the reference. */
 BT_API int bt_rigid_transform(const float* pts1, const float* pts2, int n, float* pose_out);
 
+/* Lfnet::detectFeature's reply handling (/root/reference/src/FeatureManager.cpp:876-907; rot_deg = 0, the only value the tracker uses):
+ * validates the three message parts of the LF-Net server's reply (int32 (n, dim) | float32 n x 2 keypoints in the 400 x 400 network
+ * input | float32 n x dim descriptors) and maps the keypoints back to image pixels through the crop / pad-to-square / resize
+ * transform of `roi` = Frame::_roi (umin, umax, vmin, vmax).  kpts_out: n x 2 floats (x, y).  The descriptor part is already the
+ * row-major matrix bt_knn_match_pairs takes: upload it as it is (bt_memcpy_h2d). */
+BT_API int bt_lfnet_parse_reply(const void* info, size_t info_bytes, const void* kpts, size_t kpts_bytes, size_t desc_bytes, const int* roi,
+                         float* kpts_out, int kpts_capacity, int* n_out, int* dim_out);
+
 /* Small device-memory helpers so non-CUDA hosts (ctypes, cgo, JNI) can drive the library without another runtime. */
 BT_API int bt_dev_alloc(void** out, size_t bytes);
 BT_API int bt_dev_free(void* p);

@@ -59,3 +59,15 @@ def rigid_transform(p1, p2):
     T[:3, :3] = R
     T[:3, 3] = m2 - R @ m1
     return T.astype(np.float32) if np.isfinite(T).all() else np.eye(4, dtype=np.float32)
+
+
+def lfnet_keypoints_to_image(kpts, roi):
+    """Lfnet::detectFeature (FeatureManager.cpp:811-907, rot_deg = 0): forward = scale(400/side) @ translate(-umin, -vmin); keypoints
+    come back through its inverse."""
+    umin, umax, vmin, vmax = roi
+    side = max(vmax - vmin, umax - umin)
+    T = np.eye(3, dtype=np.float32); T[0, 2] = -umin; T[1, 2] = -vmin
+    S = np.eye(3, dtype=np.float32); S[0, 0] = np.float32(400) / np.float32(side); S[1, 1] = np.float32(400) / np.float32(side)
+    back = np.linalg.inv((S @ T).astype(np.float64))
+    p = np.concatenate([np.asarray(kpts, np.float64), np.ones((len(kpts), 1))], 1) @ back.T
+    return p[:, :2].astype(np.float32)

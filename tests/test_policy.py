@@ -76,3 +76,27 @@ def test_rigid_transform():
     from bundletrack_b200 import _lib
     with pytest.raises(_lib.BtError):
         policy.rigid_transform(a[:2], a[:2])
+
+
+def test_lfnet_reply_parsing():
+    rng = np.random.default_rng(21)
+    n, dim = 137, 256
+    kp = rng.uniform(0, 400, (n, 2)).astype(np.float32)
+    desc = rng.normal(size=(n, dim)).astype(np.float32)
+    parts = [np.array([n, dim], np.int32).tobytes(), kp.tobytes(), desc.tobytes()]
+    for roi in ((100, 420, 60, 300), (0, 640, 0, 480), (311, 352, 200, 333)):
+        got_k, got_d = policy.lfnet_parse_reply(parts, roi)
+        assert np.array_equal(got_d, desc)
+        assert np.abs(got_k - po.lfnet_keypoints_to_image(kp, roi)).max() <= 2e-4
+        side = max(roi[1] - roi[0], roi[3] - roi[2])
+        assert got_k[:, 0].min() >= roi[0] - 1e-3 and got_k[:, 0].max() <= roi[0] + side + 1e-3      # inside the padded square of the roi
+    empty = [np.array([0, dim], np.int32).tobytes(), b"", b""]
+    k0, d0 = policy.lfnet_parse_reply(empty, (0, 10, 0, 10))
+    assert k0.shape == (0, 2) and d0.shape == (0, dim)
+    from bundletrack_b200 import _lib
+    with pytest.raises(_lib.BtError):
+        policy.lfnet_parse_reply([parts[0], parts[1][:-4], parts[2]], (0, 640, 0, 480))             # truncated keypoint part
+    with pytest.raises(_lib.BtError):
+        policy.lfnet_parse_reply([parts[0], parts[1], parts[2] + b"0000"], (0, 640, 0, 480))         # descriptor part too long
+    with pytest.raises(_lib.BtError):
+        policy.lfnet_parse_reply(parts, (5, 5, 0, 10))                                              # empty roi
