@@ -128,6 +128,7 @@ EXPORTS = [
     "bt_pipeline_reserve", "bt_prune_mutual_pairs", "bt_match_pairs", "bt_frames_preprocess",
     "bt_frame_cache_reserve", "bt_frame_cache_store",
     "bt_rotation_geodesic", "bt_keyframe_check", "bt_select_keyframes", "bt_rigid_transform", "bt_lfnet_parse_reply",
+    "bt_tracks_create", "bt_tracks_destroy", "bt_tracks_update_pair", "bt_tracks_propagate", "bt_tracks_forget_frame", "bt_tracks_stats",
     "bt_dev_alloc", "bt_dev_free", "bt_memcpy_h2d", "bt_memcpy_d2h", "bt_host_alloc_pinned", "bt_host_free_pinned",
     "bt_stream_sync",
 ]
@@ -149,10 +150,11 @@ def load() -> ctypes.CDLL:
     lib.bt_last_error.restype = ctypes.c_char_p
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("bt_last_error", "bt_ctx_destroy", "bt_rotation_geodesic"):
+        if name not in ("bt_last_error", "bt_ctx_destroy", "bt_rotation_geodesic", "bt_tracks_destroy"):
             fn.restype = ctypes.c_int
     lib.bt_ctx_destroy.restype = None
     lib.bt_rotation_geodesic.restype = ctypes.c_float
+    lib.bt_tracks_destroy.restype = None
     _lib = lib
     return lib
 

@@ -53,3 +53,45 @@ def lfnet_parse_reply(parts, roi):
     _lib.check(_lib.load().bt_lfnet_parse_reply(info, ctypes.c_size_t(len(info)), kp, ctypes.c_size_t(len(kp)), ctypes.c_size_t(len(desc)), r, _p(out),
                                                 ctypes.c_int(n_guess), ctypes.byref(n), ctypes.byref(dim)), "bt_lfnet_parse_reply")
     return out[:n.value], np.frombuffer(desc, np.float32).reshape(n.value, dim.value)
+
+
+class Tracks:
+    """Map-point bookkeeping (`SiftManager::updateFramePairMapPoints` / `findCorresByMapPoints`, FeatureManager.cpp:448-520)."""
+
+    def __init__(self):
+        self.lib = _lib.load()
+        self.h = ctypes.c_void_p()
+        _lib.check(self.lib.bt_tracks_create(ctypes.byref(self.h)), "bt_tracks_create")
+
+    def close(self):
+        if self.h:
+            self.lib.bt_tracks_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def update_pair(self, frame_a: int, frame_b: int, uv, is_inlier=None):
+        uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 4)
+        inl = None if is_inlier is None else np.ascontiguousarray(is_inlier, np.uint8)
+        _lib.check(self.lib.bt_tracks_update_pair(self.h, ctypes.c_int(frame_a), ctypes.c_int(frame_b), _p(uv), None if inl is None else _p(inl), ctypes.c_int(len(uv))),
+                   "bt_tracks_update_pair")
+
+    def propagate(self, frame_a: int, frame_b: int, existing_uv, capacity: int = 65536) -> np.ndarray:
+        ex = np.ascontiguousarray(existing_uv, np.float32).reshape(-1, 4)
+        out = np.zeros((capacity, 4), np.float32)
+        n = ctypes.c_int(0)
+        _lib.check(self.lib.bt_tracks_propagate(self.h, ctypes.c_int(frame_a), ctypes.c_int(frame_b), _p(ex), ctypes.c_int(len(ex)), _p(out), ctypes.c_int(capacity),
+                                                ctypes.byref(n)), "bt_tracks_propagate")
+        return out[:n.value].copy()
+
+    def forget_frame(self, frame: int):
+        _lib.check(self.lib.bt_tracks_forget_frame(self.h, ctypes.c_int(frame)), "bt_tracks_forget_frame")
+
+    def stats(self):
+        a, b = ctypes.c_int(0), ctypes.c_int(0)
+        _lib.check(self.lib.bt_tracks_stats(self.h, ctypes.byref(a), ctypes.byref(b)), "bt_tracks_stats")
+        return a.value, b.value

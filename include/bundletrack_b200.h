@@ -295,6 +295,21 @@ BT_API int bt_rigid_transform(const float* pts1, const float* pts2, int n, float
 BT_API int bt_lfnet_parse_reply(const void* info, size_t info_bytes, const void* kpts, size_t kpts_bytes, size_t desc_bytes, const int* roi,
                          float* kpts_out, int kpts_capacity, int* n_out, int* dim_out);
 
+/* Map-point bookkeeping between matching and RANSAC (host code, no GPU):
+ * SiftManager::updateFramePairMapPoints / findCorresByMapPoints / the map-point part of forgetFrame
+ * (/root/reference/src/FeatureManager.cpp:448-520,163-169).  Frames are named by Frame::_id; uv arrays hold (uA, vA, uB, vB) per
+ * match, A = the newer frame.  bt_tracks_propagate returns the matches findCorresByMapPoints would APPEND for the pair (map points
+ * seen in both frames whose (uA,vA) and (uB,vB) are not matched yet), in the reference's order; the caller looks the 3-D points up
+ * at round(u), round(v) of its point maps exactly as the reference does and hands them to RANSAC with the rest. */
+typedef struct bt_tracks bt_tracks;
+BT_API int bt_tracks_create(bt_tracks** out);
+BT_API void bt_tracks_destroy(bt_tracks* t);
+BT_API int bt_tracks_update_pair(bt_tracks* t, int frame_a, int frame_b, const float* uv, const unsigned char* is_inlier, int n);
+BT_API int bt_tracks_propagate(bt_tracks* t, int frame_a, int frame_b, const float* existing_uv, int n_existing,
+                        float* out_uv, int capacity, int* n_out);
+BT_API int bt_tracks_forget_frame(bt_tracks* t, int frame);
+BT_API int bt_tracks_stats(const bt_tracks* t, int* n_points, int* n_observations);
+
 /* Small device-memory helpers so non-CUDA hosts (ctypes, cgo, JNI) can drive the library without another runtime. */
 BT_API int bt_dev_alloc(void** out, size_t bytes);
 BT_API int bt_dev_free(void* p);

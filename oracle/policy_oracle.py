@@ -71,3 +71,51 @@ def lfnet_keypoints_to_image(kpts, roi):
     back = np.linalg.inv((S @ T).astype(np.float64))
     p = np.concatenate([np.asarray(kpts, np.float64), np.ones((len(kpts), 1))], 1) @ back.T
     return p[:, :2].astype(np.float32)
+
+
+class Tracks:
+    """SiftManager::updateFramePairMapPoints / findCorresByMapPoints / forgetFrame (FeatureManager.cpp:448-520,163-169) with Python
+    containers: `frame_map[frame]` is the std::map<(u,v), MapPoint> of the frame (walked in sorted key order), a map point is a dict
+    frame -> (u, v)."""
+
+    def __init__(self):
+        self.points = []
+        self.frame_map = {}
+
+    def update_pair(self, fa, fb, uv, is_inlier=None):
+        A, B = self.frame_map.setdefault(fa, {}), self.frame_map.setdefault(fb, {})
+        for i, (uA, vA, uB, vB) in enumerate(np.asarray(uv, np.float32).reshape(-1, 4)):
+            if is_inlier is not None and not is_inlier[i]:
+                continue
+            kA, kB = (float(uA), float(vA)), (float(uB), float(vB))
+            if kA in A and kB in B:
+                continue
+            if kB not in B:
+                mp = {fb: kB}
+                self.points.append(mp)
+                B[kB] = mp
+            else:
+                mp = B[kB]
+            mp[fa] = kA
+            A[kA] = mp
+
+    def propagate(self, fa, fb, existing_uv):
+        matches = [tuple(float(x) for x in r) for r in np.asarray(existing_uv, np.float32).reshape(-1, 4)]
+        n0 = len(matches)
+        for kA in sorted(self.frame_map.get(fa, {})):
+            mp = self.frame_map[fa][kA]
+            if fb not in mp:
+                continue
+            kB = mp[fb]
+            if any((m[0], m[1]) == kA or (m[2], m[3]) == kB for m in matches):
+                continue
+            matches.append((kA[0], kA[1], kB[0], kB[1]))
+        return np.array(matches[n0:], np.float32).reshape(-1, 4)
+
+    def forget_frame(self, f):
+        for mp in self.points:
+            mp.pop(f, None)
+        self.frame_map.pop(f, None)
+
+    def stats(self):
+        return len(self.points), sum(len(mp) for mp in self.points)

@@ -100,3 +100,47 @@ def test_lfnet_reply_parsing():
         policy.lfnet_parse_reply([parts[0], parts[1], parts[2] + b"0000"], (0, 640, 0, 480))         # descriptor part too long
     with pytest.raises(_lib.BtError):
         policy.lfnet_parse_reply(parts, (5, 5, 0, 10))                                              # empty roi
+
+
+def test_map_point_tracks_match_the_restatement():
+    """A random stream of frame pairs (inlier matches with repeated keypoints, overwritten observations, forgotten frames) through the
+    library's map-point bookkeeping and through the Python restatement: same propagated matches in the same order, same statistics."""
+    rng = np.random.default_rng(33)
+    n_frames = 9
+    kps = [np.round(rng.uniform(0, 640, (60, 2)), 1).astype(np.float32) for _ in range(n_frames)]     # keypoints recur across pairs
+    got, want = policy.Tracks(), po.Tracks()
+    for step in range(60):
+        a = int(rng.integers(1, n_frames)); b = int(rng.integers(0, a))
+        n = int(rng.integers(0, 25))
+        ia, ib = rng.integers(0, 60, n), rng.integers(0, 60, n)
+        uv = np.concatenate([kps[a][ia], kps[b][ib]], 1).astype(np.float32)
+        ex_n = int(rng.integers(0, 10))
+        existing = np.concatenate([kps[a][rng.integers(0, 60, ex_n)], kps[b][rng.integers(0, 60, ex_n)]], 1).astype(np.float32)
+        pg, pw = got.propagate(a, b, existing), want.propagate(a, b, existing)
+        assert np.array_equal(pg, pw), (step, a, b)
+        inl = rng.random(n) < 0.7
+        got.update_pair(a, b, uv, inl); want.update_pair(a, b, uv, inl)
+        assert got.stats() == want.stats()
+        if step % 17 == 16:
+            f = int(rng.integers(0, n_frames))
+            got.forget_frame(f); want.forget_frame(f)
+            assert got.stats() == want.stats()
+    assert got.stats()[0] > 50
+    # the documented rules, one by one
+    t = policy.Tracks()
+    t.update_pair(1, 0, [[10, 10, 20, 20]])
+    assert t.stats() == (1, 2)
+    t.update_pair(2, 1, [[30, 30, 10, 10]])                      # frame 1's keypoint already belongs to the point: frame 2 joins it
+    assert t.stats() == (1, 3)
+    assert np.array_equal(t.propagate(2, 0, np.zeros((0, 4))), [[30, 30, 20, 20]])      # seen in 2 and 0 through the shared point
+    assert len(t.propagate(2, 0, [[30, 30, 5, 5]])) == 0          # (uA, vA) already matched
+    assert len(t.propagate(2, 0, [[7, 7, 20, 20]])) == 0          # (uB, vB) already matched
+    t.forget_frame(0)
+    assert len(t.propagate(2, 0, np.zeros((0, 4)))) == 0 and t.stats() == (1, 2)
+    from bundletrack_b200 import _lib
+    with pytest.raises(_lib.BtError):
+        t.update_pair(0, 1, [[1, 1, 2, 2]])                       # A must be the newer frame
+    assert np.array_equal(t.propagate(2, 1, np.zeros((0, 4))), [[30, 30, 10, 10]])
+    with pytest.raises(_lib.BtError):
+        t.propagate(2, 1, np.zeros((0, 4)), capacity=0)           # more matches than the caller made room for
+    t.close(); got.close()
