@@ -58,14 +58,23 @@ void svd3(const double M[9], double U[9], double S[3], double V[9]) {
 		S[j] = n[o];
 		for (int r = 0; r < 3; r++) { U[r * 3 + j] = n[o] > 1e-300 ? A[r * 3 + o] / n[o] : 0.0; Vs[r * 3 + j] = V[r * 3 + o]; }
 	}
+	// A singular value that is rounding noise next to the largest one (coplanar points: one column of M V is ~1e-18) carries no
+	// direction: normalising that column would give a U that is not orthogonal.  Treat it as zero and complete U below.
+	for (int j = 1; j < 3; j++) if (S[j] <= 1e-12 * S[0]) S[j] = 0.0;
 	for (int i = 0; i < 9; i++) V[i] = Vs[i];
 	// complete U to an orthonormal basis when M is rank deficient (Eigen's thin U is full for a 3x3 as well)
-	for (int j = 0; j < 3; j++) {
-		if (S[j] > 1e-300) continue;
-		const int a = (j + 1) % 3, b = (j + 2) % 3;
-		U[0 * 3 + j] = U[1 * 3 + a] * U[2 * 3 + b] - U[2 * 3 + a] * U[1 * 3 + b];
-		U[1 * 3 + j] = U[2 * 3 + a] * U[0 * 3 + b] - U[0 * 3 + a] * U[2 * 3 + b];
-		U[2 * 3 + j] = U[0 * 3 + a] * U[1 * 3 + b] - U[1 * 3 + a] * U[0 * 3 + b];
+	if (!(S[0] > 1e-300)) { for (int i = 0; i < 9; i++) U[i] = (i % 4 == 0) ? 1.0 : 0.0; return; }      // M = 0
+	if (!(S[1] > 1e-300)) {      // rank 1: any unit vector orthogonal to column 0
+		const int m = fabs(U[0]) < fabs(U[3]) ? (fabs(U[0]) < fabs(U[6]) ? 0 : 2) : (fabs(U[3]) < fabs(U[6]) ? 1 : 2);
+		double e[3] = { 0, 0, 0 }; e[m] = 1.0;
+		const double c[3] = { U[3] * e[2] - U[6] * e[1], U[6] * e[0] - U[0] * e[2], U[0] * e[1] - U[3] * e[0] };
+		const double cn = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+		for (int r = 0; r < 3; r++) U[r * 3 + 1] = c[r] / cn;
+	}
+	if (!(S[2] > 1e-300)) {      // rank <= 2: column 2 = column 0 x column 1
+		U[2] = U[3] * U[7] - U[6] * U[4];
+		U[5] = U[6] * U[1] - U[0] * U[7];
+		U[8] = U[0] * U[4] - U[3] * U[1];
 	}
 }
 

@@ -134,13 +134,17 @@ __global__ void __launch_bounds__(1024) k_emit_entryj(const PrunePair* __restric
 		s_scan[tid] = cnt;
 		__syncthreads();
 		for (int o = 1; o < 1024; o <<= 1) { const int v = (tid >= o) ? s_scan[tid - o] : 0; __syncthreads(); s_scan[tid] += v; __syncthreads(); }
-		const int excl = s_scan[tid] - cnt + s_carry;
+		int excl = s_scan[tid] - cnt + s_carry;
+		// never describe more than the caller's buffer holds: a pair that does not fit is cut (or dropped), so the (offset, count)
+		// arrays a caller hands on as bt_window::block_off / block_n always stay inside entry_out
+		if (excl > capacity) excl = capacity;
+		if (excl + cnt > capacity) cnt = capacity - excl;
 		if (p < n_pairs) { n_entry_out[p] = cnt; entry_off_out[p] = excl; }
 		__syncthreads();
 		if (tid == 1023) s_carry += s_scan[1023];
 		__syncthreads();
 	}
-	if (tid == 0) *total_out = s_carry;
+	if (tid == 0) *total_out = min(s_carry, capacity);
 }
 
 // one CTA per pair: its EntryJ block (a lone CTA filling all pairs took 0.1 ms for 20 k entries)
@@ -163,6 +167,7 @@ struct PruneState {
 	int max_pairs = 0, max_feats = 0;
 	DevBuf pairs, corr, PA, PB, n_corr, rpairs, inl, n_inl, idxAB, distAB, idxBA, distBA, entry_off, total;
 	PinnedBuf h_pairs;
+	cudaEvent_t ev_up = nullptr;      // recorded behind the upload of h_pairs (the calls are asynchronous: see fill_pairs)
 };
 static PruneState* g_prune_of(bt_ctx* ctx);
 
@@ -179,6 +184,7 @@ void prune_destroy(bt_ctx* ctx) {
 	DevBuf* bufs[] = { &s->pairs, &s->corr, &s->PA, &s->PB, &s->n_corr, &s->rpairs, &s->inl, &s->n_inl, &s->idxAB, &s->distAB, &s->idxBA, &s->distBA, &s->entry_off, &s->total };
 	for (DevBuf* b : bufs) b->release();
 	s->h_pairs.release();
+	if (s->ev_up) cudaEventDestroy(s->ev_up);
 	delete s;
 	ctx->prune = nullptr;
 }
@@ -209,6 +215,9 @@ extern "C" int bt_pipeline_reserve(bt_ctx* ctx, int max_pairs, int max_feats, in
 }
 
 static int fill_pairs(PruneState* s, int n_pairs, const bt_match_frame* A, const bt_match_frame* B, cudaStream_t stream) {
+	// an earlier asynchronous call's upload may still be reading the pinned table: wait for it before rewriting the block
+	if (!s->ev_up) BT_CUDA(cudaEventCreateWithFlags(&s->ev_up, cudaEventDisableTiming));
+	else BT_CUDA(cudaEventSynchronize(s->ev_up));
 	PrunePair* hp = s->h_pairs.as<PrunePair>();
 	int offA = 0, offB = 0, out = 0;
 	for (int p = 0; p < n_pairs; p++) {
@@ -226,6 +235,7 @@ static int fill_pairs(PruneState* s, int n_pairs, const bt_match_frame* A, const
 		offA += A[p].n; offB += B[p].n; out += A[p].n + B[p].n;
 	}
 	BT_CUDA(cudaMemcpyAsync(s->pairs.p, hp, sizeof(PrunePair) * n_pairs, cudaMemcpyHostToDevice, stream));
+	BT_CUDA(cudaEventRecord(s->ev_up, stream));
 	return BT_OK;
 }
 

@@ -200,6 +200,7 @@ struct RansacState {
 	int max_pairs = 0, max_pts = 0, max_trials = 0;
 	DevBuf pairs, table, poses, good, best, best_trial;
 	PinnedBuf h_pairs;
+	cudaEvent_t ev_up = nullptr;      // recorded behind the upload of h_pairs: the next call waits on it before rewriting the pinned block
 	unsigned long long table_seed = ~0ull;
 	int table_trials = 0;
 };
@@ -210,6 +211,7 @@ void ransac_destroy(bt_ctx* ctx) {
 	DevBuf* bufs[] = { &r->pairs, &r->table, &r->poses, &r->good, &r->best, &r->best_trial };
 	for (DevBuf* b : bufs) b->release();
 	r->h_pairs.release();
+	if (r->ev_up) cudaEventDestroy(r->ev_up);
 	delete r;
 	ctx->ransac = nullptr;
 }
@@ -272,6 +274,9 @@ extern "C" int bt_ransac_pairs(bt_ctx* ctx, int n_pairs, const float* const* pts
 	cudaStream_t stream = (cudaStream_t)stream_;
 	BT_CUDA(cudaSetDevice(ctx->device));
 	BT_REQUIRE(n_pairs <= r->max_pairs, BT_ERR_CAPACITY, "bt_ransac_pairs: %d pairs > reserved %d", n_pairs, r->max_pairs);
+	// the entry points are asynchronous: an earlier call's upload may still be reading the pinned table
+	if (!r->ev_up) BT_CUDA(cudaEventCreateWithFlags(&r->ev_up, cudaEventDisableTiming));
+	else BT_CUDA(cudaEventSynchronize(r->ev_up));
 	RansacPair* hp = r->h_pairs.as<RansacPair>();
 	int off = 0;
 	for (int p = 0; p < n_pairs; p++) {
@@ -280,6 +285,7 @@ extern "C" int bt_ransac_pairs(bt_ctx* ctx, int n_pairs, const float* const* pts
 		off += n_pts[p];
 	}
 	BT_CUDA(cudaMemcpyAsync(r->pairs.p, hp, sizeof(RansacPair) * n_pairs, cudaMemcpyHostToDevice, stream));
+	BT_CUDA(cudaEventRecord(r->ev_up, stream));
 	return ransac_run_device(ctx, r->pairs.as<RansacPair>(), n_pairs, n_trials, dist_thresh, seed, inlier_ids_out, n_inliers_out, stream);
 }
 

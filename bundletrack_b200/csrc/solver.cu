@@ -1670,8 +1670,8 @@ extern "C" int bt_solve_stage(bt_ctx* ctx, int n_windows, const bt_window* windo
 
 static int ensure_occupancy(bt_ctx* ctx) {
 	SolverState* s = ctx->solver;
-	if (s->attr_bytes < s->smem_bytes || s->attr_bytes == 0) {      // per context (= per device), not per process
-		s->attr_bytes = std::max(s->smem_bytes, 48 * 1024);
+	if (s->attr_bytes == 0) {      // the attribute belongs to (function, device), not to the context: set it to the ceiling stage_impl enforces, once,
+		s->attr_bytes = 200 * 1024;   // so that a second context on the same device can never lower what another context's next launch needs
 		BT_CUDA(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, s->attr_bytes));
 	}
 	if (s->occ_smem != s->smem_bytes) {

@@ -42,10 +42,11 @@ static_assert(sizeof(bt_entryj) == 32, "EntryJ layout");
 
 class OptimizerGpu {
 public:
-	explicit OptimizerGpu(const BtSolverConfig& cfg, int device = 0, int max_frames = 15, int max_corr = 1 << 16, int H = 480, int W = 640)
+	// max_windows > 1 lets optimizeWindows() solve several independent windows in ONE call (one launch sequence for the batch).
+	explicit OptimizerGpu(const BtSolverConfig& cfg, int device = 0, int max_frames = 15, int max_corr = 1 << 16, int H = 480, int W = 640, int max_windows = 1)
 	    : cfg_(cfg) {
 		check(bt_ctx_create(&ctx_, device), "bt_ctx_create");
-		bt_solver_limits lim = { 1, max_frames, max_corr, H, W, cfg.image_downscale };
+		bt_solver_limits lim = { max_windows, max_frames, max_corr, H, W, cfg.image_downscale };
 		check(bt_solver_reserve(ctx_, &lim), "bt_solver_reserve");
 	}
 	~OptimizerGpu() { bt_ctx_destroy(ctx_); }
@@ -78,6 +79,44 @@ public:
 		for (int f = 0; f < n_frames; f++)
 			for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) poses[f](r, c) = flat[16 * f + 4 * r + c];
 	}
+	// Batched form: the windows of several tracked objects (or several frames' worth of work) in one call.  Every element of `windows`
+	// carries what one optimizeFrames call takes; poses[w] is in-out like above.
+	template <class EntryJT, class Float4T, class Mat4, class Alloc, class Mat3>
+	struct WindowArgs {
+		const std::vector<EntryJT>* global_corres; int n_frames, H, W;
+		const std::vector<float*>* depths_gpu; const std::vector<Float4T*>* normals_gpu;
+		std::vector<Mat4, Alloc>* poses; const Mat3* K;
+	};
+	template <class EntryJT, class Float4T, class Mat4, class Alloc, class Mat3>
+	void optimizeWindows(const std::vector<WindowArgs<EntryJT, Float4T, Mat4, Alloc, Mat3>>& windows, void* stream = nullptr) {
+		static_assert(sizeof(EntryJT) == sizeof(bt_entryj), "EntryJ must be the 32-byte reference struct");
+		const size_t nw = windows.size();
+		if (nw == 0) return;
+		std::vector<bt_window> wins(nw);
+		std::vector<std::vector<const float*>> dptr(nw), nptr(nw);
+		std::vector<float> flat;
+		for (size_t w = 0; w < nw; w++) {
+			const auto& a = windows[w];
+			dptr[w].resize(a.n_frames); nptr[w].resize(a.n_frames);
+			for (int f = 0; f < a.n_frames; f++) {
+				dptr[w][f] = (*a.depths_gpu)[f]; nptr[w][f] = reinterpret_cast<const float*>((*a.normals_gpu)[f]);
+				for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) flat.push_back((*a.poses)[f](r, c));
+			}
+			bt_window win{};
+			win.n_frames = a.n_frames; win.H = a.H; win.W = a.W;
+			win.n_corr = (int)a.global_corres->size(); win.corr = reinterpret_cast<const bt_entryj*>(a.global_corres->data());
+			win.depth_dev = dptr[w].data(); win.normal_dev = nptr[w].data();
+			win.fx = (*a.K)(0, 0); win.fy = (*a.K)(1, 1); win.cx = (*a.K)(0, 2); win.cy = (*a.K)(1, 2);
+			win.compat_flip = 1;
+			wins[w] = win;
+		}
+		const bt_solver_params prm = cfg_.to_params();
+		check(bt_solve_windows(ctx_, (int)nw, wins.data(), &prm, flat.data(), stream), "bt_solve_windows");
+		size_t o = 0;
+		for (size_t w = 0; w < nw; w++)
+			for (int f = 0; f < windows[w].n_frames; f++, o += 16)
+				for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) (*windows[w].poses)[f](r, c) = flat[o + 4 * r + c];
+	}
 	bt_ctx* ctx() { return ctx_; }
 
 private:
@@ -88,29 +127,55 @@ private:
 	bt_ctx* ctx_ = nullptr;
 };
 
-// ransacMultiPairGPU with the reference's argument list (device float4 arrays per pair, host result vectors).
+// ransacMultiPairGPU with the reference's argument list (device float4 arrays per pair, host result vectors).  The device result
+// buffers and the library's scratch belong to the object: nothing is allocated per call (the reference allocates six arrays and a
+// stream per pair per call, cuda_ransac.cu:1240-1275).
+class RansacGpu {
+public:
+	RansacGpu(bt_ctx* ctx, int max_pairs, int max_pts_per_pair, int max_trials) : ctx_(ctx), max_pairs_(max_pairs), max_total_((size_t)max_pairs * max_pts_per_pair) {
+		check(bt_ransac_reserve(ctx, max_pairs, max_pts_per_pair, max_trials), "bt_ransac_reserve");
+		check(bt_dev_alloc(&d_ids_, sizeof(int32_t) * max_total_), "bt_dev_alloc");
+		check(bt_dev_alloc(&d_cnt_, sizeof(int32_t) * (size_t)max_pairs), "bt_dev_alloc");
+		ids_.resize(max_total_); cnt_.resize(max_pairs);
+	}
+	~RansacGpu() { bt_dev_free(d_ids_); bt_dev_free(d_cnt_); }
+	RansacGpu(const RansacGpu&) = delete;
+	RansacGpu& operator=(const RansacGpu&) = delete;
+	template <class Float4T>
+	void ransacMultiPairGPU(const std::vector<Float4T*>& ptsA, const std::vector<Float4T*>& ptsB, const std::vector<int>& n_pts,
+	                        int n_trials, float dist_thres, std::vector<std::vector<int>>& inlier_ids, void* stream = nullptr) {
+		const int n = (int)ptsA.size();
+		inlier_ids.assign(n, {});
+		if (n == 0) return;
+		size_t total = 0;
+		for (int v : n_pts) total += (size_t)v;
+		if (n > max_pairs_ || total > max_total_) throw std::runtime_error("RansacGpu: more pairs / points than the object was created for");
+		a_.resize(n); b_.resize(n);
+		for (int p = 0; p < n; p++) { a_[p] = reinterpret_cast<const float*>(ptsA[p]); b_[p] = reinterpret_cast<const float*>(ptsB[p]); }
+		check(bt_ransac_pairs(ctx_, n, a_.data(), b_.data(), n_pts.data(), n_trials, dist_thres, 0, (int32_t*)d_ids_, (int32_t*)d_cnt_, stream), "bt_ransac_pairs");
+		check(bt_memcpy_d2h(cnt_.data(), d_cnt_, sizeof(int32_t) * n, stream), "bt_memcpy_d2h");
+		if (total) check(bt_memcpy_d2h(ids_.data(), d_ids_, sizeof(int32_t) * total, stream), "bt_memcpy_d2h");
+		size_t off = 0;
+		for (int p = 0; p < n; p++) { inlier_ids[p].assign(ids_.begin() + off, ids_.begin() + off + cnt_[p]); off += (size_t)n_pts[p]; }
+	}
+private:
+	static void check(int rc, const char* what) { if (rc != BT_OK) throw std::runtime_error(std::string(what) + ": " + bt_last_error()); }
+	bt_ctx* ctx_; int max_pairs_; size_t max_total_;
+	void *d_ids_ = nullptr, *d_cnt_ = nullptr;
+	std::vector<int32_t> ids_, cnt_;
+	std::vector<const float*> a_, b_;
+};
+// Free-function form with exactly the reference's name: creates a RansacGpu sized for this call (convenient, but it allocates - hold
+// a RansacGpu in SiftManager instead).
 template <class Float4T>
 inline void ransacMultiPairGPU(bt_ctx* ctx, const std::vector<Float4T*>& ptsA, const std::vector<Float4T*>& ptsB, const std::vector<int>& n_pts,
                                int n_trials, float dist_thres, std::vector<std::vector<int>>& inlier_ids, void* stream = nullptr) {
-	const int n = (int)ptsA.size();
-	inlier_ids.assign(n, {});
-	if (n == 0) return;
-	int total = 0, maxp = 1;
-	for (int v : n_pts) { total += v; if (v > maxp) maxp = v; }
-	auto check = [](int rc, const char* what) { if (rc != BT_OK) throw std::runtime_error(std::string(what) + ": " + bt_last_error()); };
-	check(bt_ransac_reserve(ctx, n, maxp, n_trials), "bt_ransac_reserve");
-	std::vector<const float*> a(n), b(n);
-	for (int p = 0; p < n; p++) { a[p] = reinterpret_cast<const float*>(ptsA[p]); b[p] = reinterpret_cast<const float*>(ptsB[p]); }
-	void *d_ids = nullptr, *d_cnt = nullptr;
-	check(bt_dev_alloc(&d_ids, sizeof(int32_t) * (size_t)(total > 0 ? total : 1)), "bt_dev_alloc");
-	check(bt_dev_alloc(&d_cnt, sizeof(int32_t) * n), "bt_dev_alloc");
-	check(bt_ransac_pairs(ctx, n, a.data(), b.data(), n_pts.data(), n_trials, dist_thres, 0, (int32_t*)d_ids, (int32_t*)d_cnt, stream), "bt_ransac_pairs");
-	std::vector<int32_t> ids((size_t)(total > 0 ? total : 1)), cnt(n);
-	check(bt_memcpy_d2h(cnt.data(), d_cnt, sizeof(int32_t) * n, stream), "bt_memcpy_d2h");
-	check(bt_memcpy_d2h(ids.data(), d_ids, sizeof(int32_t) * ids.size(), stream), "bt_memcpy_d2h");
-	int off = 0;
-	for (int p = 0; p < n; p++) { inlier_ids[p].assign(ids.begin() + off, ids.begin() + off + cnt[p]); off += n_pts[p]; }
-	bt_dev_free(d_ids); bt_dev_free(d_cnt);
+	inlier_ids.assign(ptsA.size(), {});
+	if (ptsA.empty()) return;
+	int maxp = 1;
+	for (int v : n_pts) if (v > maxp) maxp = v;
+	RansacGpu r(ctx, (int)ptsA.size(), maxp, n_trials);
+	r.ransacMultiPairGPU(ptsA, ptsB, n_pts, n_trials, dist_thres, inlier_ids, stream);
 }
 
 // ---- Frame::processDepth + Frame::depthToCloudAndNormals (/root/reference/src/Frame.cpp:152-233) ----------------------------------
@@ -134,30 +199,50 @@ inline void processDepthAndNormals(bt_ctx* ctx, const float* depth_raw_gpu, floa
 
 // ---- the two knnMatch calls of SiftManager::findCorresbyNN (/root/reference/src/FeatureManager.cpp:271-273) in one call --------
 // desA/desB: device CV_32F descriptor matrices (GpuMat::data, rows, step).  DMatchT needs queryIdx, trainIdx, distance (cv::DMatch).
+// The device result buffers belong to the object (sized once for max_feats x k), nothing is allocated per call.
+class KnnMatcherGpu {
+public:
+	KnnMatcherGpu(bt_ctx* ctx, int max_feats, int dim = 256, int k = 5) : ctx_(ctx), max_feats_(max_feats), dim_(dim), k_(k) {
+		check(bt_matcher_reserve(ctx, 1, max_feats, dim), "bt_matcher_reserve");
+		const size_t e = (size_t)max_feats * k;
+		check(bt_dev_alloc(&iab_, 4 * e), "bt_dev_alloc"); check(bt_dev_alloc(&dab_, 4 * e), "bt_dev_alloc");
+		check(bt_dev_alloc(&iba_, 4 * e), "bt_dev_alloc"); check(bt_dev_alloc(&dba_, 4 * e), "bt_dev_alloc");
+		hi_[0].resize(e); hi_[1].resize(e); hd_[0].resize(e); hd_[1].resize(e);
+	}
+	~KnnMatcherGpu() { bt_dev_free(iab_); bt_dev_free(dab_); bt_dev_free(iba_); bt_dev_free(dba_); }
+	KnnMatcherGpu(const KnnMatcherGpu&) = delete;
+	KnnMatcherGpu& operator=(const KnnMatcherGpu&) = delete;
+	template <class DMatchT>
+	void knnMatchBothDirections(const float* desA, int nA, size_t stepA, const float* desB, int nB, size_t stepB,
+	                            std::vector<std::vector<DMatchT>>& matchesAB, std::vector<std::vector<DMatchT>>& matchesBA, void* stream = nullptr) {
+		if (nA > max_feats_ || nB > max_feats_) throw std::runtime_error("KnnMatcherGpu: more features than the object was created for");
+		bt_desc_view A{}; A.dev = desA; A.n = nA; A.dim = dim_; A.pitch_bytes = stepA;
+		bt_desc_view B{}; B.dev = desB; B.n = nB; B.dim = dim_; B.pitch_bytes = stepB;
+		check(bt_knn_match_pairs(ctx_, 1, &A, &B, k_, (int32_t*)iab_, (float*)dab_, (int32_t*)iba_, (float*)dba_, stream), "bt_knn_match_pairs");
+		if (nA) { check(bt_memcpy_d2h(hi_[0].data(), iab_, 4 * (size_t)nA * k_, stream), "bt_memcpy_d2h"); check(bt_memcpy_d2h(hd_[0].data(), dab_, 4 * (size_t)nA * k_, stream), "bt_memcpy_d2h"); }
+		if (nB) { check(bt_memcpy_d2h(hi_[1].data(), iba_, 4 * (size_t)nB * k_, stream), "bt_memcpy_d2h"); check(bt_memcpy_d2h(hd_[1].data(), dba_, 4 * (size_t)nB * k_, stream), "bt_memcpy_d2h"); }
+		fill(nA, hi_[0], hd_[0], matchesAB); fill(nB, hi_[1], hd_[1], matchesBA);
+	}
+private:
+	static void check(int rc, const char* what) { if (rc != BT_OK) throw std::runtime_error(std::string(what) + ": " + bt_last_error()); }
+	template <class DMatchT>
+	void fill(int n, const std::vector<int32_t>& idx, const std::vector<float>& dist, std::vector<std::vector<DMatchT>>& out) const {
+		out.assign(n, {});
+		for (int q = 0; q < n; q++)
+			for (int j = 0; j < k_; j++) {
+				if (idx[(size_t)q * k_ + j] < 0) break;          // fewer than k train rows
+				DMatchT m{}; m.queryIdx = q; m.trainIdx = idx[(size_t)q * k_ + j]; m.distance = dist[(size_t)q * k_ + j];
+				out[q].push_back(m);
+			}
+	}
+	bt_ctx* ctx_; int max_feats_, dim_, k_;
+	void *iab_ = nullptr, *dab_ = nullptr, *iba_ = nullptr, *dba_ = nullptr;
+	std::vector<int32_t> hi_[2]; std::vector<float> hd_[2];
+};
+// Free-function form: creates a KnnMatcherGpu sized for this call (it allocates - hold a KnnMatcherGpu in SiftManager instead).
 template <class DMatchT>
 inline void knnMatchBothDirections(bt_ctx* ctx, const float* desA, int nA, size_t stepA, const float* desB, int nB, size_t stepB, int dim, int k,
                                    std::vector<std::vector<DMatchT>>& matchesAB, std::vector<std::vector<DMatchT>>& matchesBA, void* stream = nullptr) {
-	auto check = [](int rc, const char* what) { if (rc != BT_OK) throw std::runtime_error(std::string(what) + ": " + bt_last_error()); };
-	check(bt_matcher_reserve(ctx, 1, nA > nB ? nA : nB, dim), "bt_matcher_reserve");
-	bt_desc_view A{}; A.dev = desA; A.n = nA; A.dim = dim; A.pitch_bytes = stepA;
-	bt_desc_view B{}; B.dev = desB; B.n = nB; B.dim = dim; B.pitch_bytes = stepB;
-	void *iab = nullptr, *dab = nullptr, *iba = nullptr, *dba = nullptr;
-	const size_t ea = (size_t)(nA > 0 ? nA : 1) * k, eb = (size_t)(nB > 0 ? nB : 1) * k;
-	check(bt_dev_alloc(&iab, 4 * ea), "bt_dev_alloc"); check(bt_dev_alloc(&dab, 4 * ea), "bt_dev_alloc");
-	check(bt_dev_alloc(&iba, 4 * eb), "bt_dev_alloc"); check(bt_dev_alloc(&dba, 4 * eb), "bt_dev_alloc");
-	check(bt_knn_match_pairs(ctx, 1, &A, &B, k, (int32_t*)iab, (float*)dab, (int32_t*)iba, (float*)dba, stream), "bt_knn_match_pairs");
-	std::vector<int32_t> hiab(ea), hiba(eb); std::vector<float> hdab(ea), hdba(eb);
-	check(bt_memcpy_d2h(hiab.data(), iab, 4 * ea, stream), "bt_memcpy_d2h"); check(bt_memcpy_d2h(hdab.data(), dab, 4 * ea, stream), "bt_memcpy_d2h");
-	check(bt_memcpy_d2h(hiba.data(), iba, 4 * eb, stream), "bt_memcpy_d2h"); check(bt_memcpy_d2h(hdba.data(), dba, 4 * eb, stream), "bt_memcpy_d2h");
-	auto fill = [k](int n, const std::vector<int32_t>& idx, const std::vector<float>& dist, std::vector<std::vector<DMatchT>>& out) {
-		out.assign(n, {});
-		for (int q = 0; q < n; q++)
-			for (int j = 0; j < k; j++) {
-				if (idx[(size_t)q * k + j] < 0) break;          // fewer than k train rows
-				DMatchT m{}; m.queryIdx = q; m.trainIdx = idx[(size_t)q * k + j]; m.distance = dist[(size_t)q * k + j];
-				out[q].push_back(m);
-			}
-	};
-	fill(nA, hiab, hdab, matchesAB); fill(nB, hiba, hdba, matchesBA);
-	bt_dev_free(iab); bt_dev_free(dab); bt_dev_free(iba); bt_dev_free(dba);
+	KnnMatcherGpu m(ctx, (nA > nB ? nA : nB) > 0 ? (nA > nB ? nA : nB) : 1, dim, k);
+	m.knnMatchBothDirections(desA, nA, stepA, desB, nB, stepB, matchesAB, matchesBA, stream);
 }

@@ -306,3 +306,17 @@ def make_raw_depth(seed: int, H: int = 480, W: int = 640, K=None, noise: float =
     raw = raw + fly * rng.uniform(0.02, 0.06, d.shape).astype(np.float32) * rng.choice([-1.0, 1.0], d.shape).astype(np.float32)
     raw[rng.random(d.shape) < hole_frac] = 0.0
     return raw.astype(np.float32), K
+
+
+def make_ransac_case(seed: int, n: int, inlier_frac: float = 0.7, noise: float = 0.0005):
+    """Model-frame point pairs as SiftManager::runRansacMultiPairGPU uploads them (/root/reference/src/FeatureManager.cpp:676-706):
+    B = T A + noise for the inliers, the rest displaced by centimetres.  Returns (A [n,4], B [n,4] float32 with w = 1, inlier mask)."""
+    rng = np.random.default_rng(seed)
+    A = rng.uniform(-0.1, 0.1, (n, 3)) + [0, 0, 0.7]
+    R = so3_exp(rng.normal(0, 0.3, 3)); t = rng.normal(0, 0.05, 3)
+    B = A @ R.T + t + rng.normal(0, noise, (n, 3))
+    out = rng.uniform(size=n) > inlier_frac
+    B[out] += rng.normal(0, 1, (int(out.sum()), 3)) * 0.02 + 0.03
+    A4 = np.concatenate([A, np.ones((n, 1))], 1).astype(np.float32)
+    B4 = np.concatenate([B, np.ones((n, 1))], 1).astype(np.float32)
+    return A4, B4, ~out

@@ -228,3 +228,28 @@ def ref_frame_preprocess(depth_raw, K, dp=None):
     if rc != 0:
         raise RuntimeError(f"ref_frame_preprocess failed: {rc}")
     return dout, xyz, nrm, t.value
+
+
+def ref_ransac_pairs(ptsA, ptsB, n_trials=2000, dist_thresh=0.005):
+    """The reference's ransacMultiPairGPU (/root/reference/src/cuda/cuda_ransac.cu:1228-1323, its own kernels in oracle/_ref) on the
+    current CUDA device, behind the upload SiftManager::runRansacMultiPairGPU does (FeatureManager.cpp:701-717).
+    ptsA[p], ptsB[p]: [n_p, 4] float32 model-frame points (w = 1).  Returns (list of int32 inlier-id arrays, t_ms)."""
+    lib = ref_lib()
+    n = len(ptsA)
+    A = [np.ascontiguousarray(a, np.float32) for a in ptsA]
+    B = [np.ascontiguousarray(b, np.float32) for b in ptsB]
+    cnt = (ctypes.c_int * n)(*[a.shape[0] for a in A])
+    pa = (ctypes.c_void_p * n)(*[a.ctypes.data for a in A])
+    pb = (ctypes.c_void_p * n)(*[b.ctypes.data for b in B])
+    total = sum(a.shape[0] for a in A)
+    ids = np.zeros(max(total, 1), np.int32)
+    nin = np.zeros(n, np.int32)
+    t = ctypes.c_double(0)
+    rc = lib.ref_ransac_pairs(ctypes.c_int(n), pa, pb, cnt, ctypes.c_int(n_trials), ctypes.c_float(dist_thresh), _fp(ids), _fp(nin), ctypes.byref(t))
+    if rc != 0:
+        raise RuntimeError(f"ref_ransac_pairs rc={rc}")
+    out, o = [], 0
+    for p in range(n):
+        out.append(ids[o:o + int(nin[p])].copy())
+        o += int(nin[p])
+    return out, t.value

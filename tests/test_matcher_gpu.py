@@ -107,15 +107,33 @@ def test_knn_matches_opencv(matcher, cuda_device):
 
 # ------------------------------------------------------------------------------------------------------------ RANSAC
 def _ransac_case(seed, n, inlier_frac=0.7, noise=0.0005, big=False):
-    rng = np.random.default_rng(seed)
-    A = rng.uniform(-0.1, 0.1, (n, 3)) + [0, 0, 0.7]
-    R = synth.so3_exp(rng.normal(0, 0.3, 3)); t = rng.normal(0, 0.05, 3)
-    B = A @ R.T + t + rng.normal(0, noise, (n, 3))
-    out = rng.uniform(size=n) > inlier_frac
-    B[out] += rng.normal(0, 1, (int(out.sum()), 3)) * 0.02 + 0.03
-    A4 = np.concatenate([A, np.ones((n, 1))], 1).astype(np.float32)
-    B4 = np.concatenate([B, np.ones((n, 1))], 1).astype(np.float32)
-    return A4, B4, ~out
+    return synth.make_ransac_case(seed, n, inlier_frac, noise)
+
+
+def _ransac_vs_reference(A4, B4, got, ref, u3, best_trial, thresh):
+    """How bt_ransac_pairs' inlier set relates to the one the reference's ransacMultiPairGPU returned for the same points.
+    'identical': same ids.  'better': another trial won here with at least as many inliers - the reference's McAdams-SVD fit is
+    approximate and its arg-max is racy, so among near-tied trials either may win.  'borderline': same winner, the
+    sets differ only in points whose distance under the winning model is within 5e-6 m of the threshold (the two fits of the same
+    three points differ by ~1e-6).  Anything else is a failure."""
+    if np.array_equal(got, ref):
+        return "identical"
+    A = A4[:, :3].astype(np.float64); B = B4[:, :3].astype(np.float64)
+    n = len(A)
+    ids = np.floor(u3[best_trial].astype(np.float32) * np.float32(n - 1) + np.float32(0.5)).astype(np.int64)
+    s, d = A[ids], B[ids]
+    sm, dm = s.mean(0), d.mean(0)
+    U, _, Vt = np.linalg.svd((s - sm).T @ (d - dm))
+    R = Vt.T @ U.T
+    if np.linalg.det(R) < 0:
+        Vt[2] *= -1; R = Vt.T @ U.T
+    dist = np.linalg.norm(B - (A @ R.T + (dm - R @ sm)), axis=1)
+    diff = np.setxor1d(got, ref)
+    if np.all(np.abs(dist[diff] - thresh) <= 5e-6):
+        return "borderline"
+    if len(got) >= len(ref):
+        return "better"
+    return "worse"
 
 
 def test_ransac_sampler_is_curand_xorwow(cuda_device):
@@ -166,6 +184,58 @@ def test_ransac_edge_cases(cuda_device):
     ids = r.ransac_pairs([torch.from_numpy(A4).to(cuda_device)], [torch.from_numpy(B4).to(cuda_device)], 500, 0.0005)
     assert len(ids[0]) <= 6
     r.close()
+
+
+def _ransac_reference_check(cuda_device, A, B, ref_ids, thresh, label):
+    """bt_ransac_pairs (seed 0 = the reference's XORWOW sequence) against the reference's own ransacMultiPairGPU outputs."""
+    from bundletrack_b200.matcher import Ransac
+    import torch
+    r = Ransac(max_pairs=max(len(A), 1), max_pts=4096, max_trials=2000)
+    ids = r.ransac_pairs([torch.from_numpy(a).to(cuda_device) for a in A], [torch.from_numpy(b).to(cuda_device) for b in B], 2000, thresh)
+    u3, best = r.debug(2000, len(A))
+    r.close()
+    verdicts = []
+    for p in range(len(A)):
+        got = ids[p].cpu().numpy()
+        v = _ransac_vs_reference(A[p], B[p], got, ref_ids[p], u3, best[p], thresh)
+        verdicts.append(v)
+        assert v != "worse", (label, p, len(got), len(ref_ids[p]))
+        # whichever trial won on either side, the two inlier sets describe the same rigid motion: they overlap almost entirely
+        inter = len(np.intersect1d(got, ref_ids[p]))
+        assert inter >= min(len(got), len(ref_ids[p])) - max(2, len(ref_ids[p]) // 100), (label, p, inter, len(got), len(ref_ids[p]))
+    return verdicts
+
+
+def test_ransac_matches_reference_golden(cuda_device):
+    """tests/golden/ref_ransac.npz: inputs + the inlier ids the reference's ransacMultiPairGPU (cuda_ransac.cu:1228-1323, compiled
+    verbatim into oracle/_ref) returned on a B200 (scripts/make_golden_ransac.py)."""
+    path = os.path.join(GOLD, "ref_ransac.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/ref_ransac.npz not generated yet")
+    g = np.load(path)
+    verdicts = []
+    for k in range(int(g["n_cases"])):
+        verdicts += _ransac_reference_check(cuda_device, [g[f"A{k}"]], [g[f"B{k}"]], [g[f"ref{k}"]], float(g["thresh"][k]), f"golden{k}")
+    assert verdicts.count("identical") >= (len(verdicts) + 1) // 2, verdicts
+
+
+def test_ransac_matches_reference_live(cuda_device):
+    """The reference's own kernels run live on this GPU (oracle/_ref): n = 8 ... 3000 points, and the 45 pairs of a 10-keyframe
+    window at cfg2 sizes in one call.  Identical inlier sets are the rule; a pair may differ only as _ransac_vs_reference allows."""
+    import oracle
+    if not os.path.exists(os.path.join(os.path.dirname(oracle.__file__), "_ref", "libbt_ref.so")):
+        pytest.skip("oracle/_ref not built")
+    verdicts = []
+    for n, thresh in ((8, 0.005), (60, 0.005), (300, 0.01), (1000, 0.005), (3000, 0.005)):
+        cases = [_ransac_case(7000 + 10 * n + k, n, inlier_frac=0.5 + 0.1 * k) for k in range(3)]
+        ref, _ = oracle.ref_ransac_pairs([c[0] for c in cases], [c[1] for c in cases], 2000, thresh)
+        verdicts += _ransac_reference_check(cuda_device, [c[0] for c in cases], [c[1] for c in cases], ref, thresh, f"n{n}")
+    rng = np.random.default_rng(5)
+    cases = [_ransac_case(8000 + p, int(rng.integers(300, 1600)), inlier_frac=float(rng.uniform(0.3, 0.9))) for p in range(45)]
+    ref, _ = oracle.ref_ransac_pairs([c[0] for c in cases], [c[1] for c in cases], 2000, 0.005)
+    verdicts += _ransac_reference_check(cuda_device, [c[0] for c in cases], [c[1] for c in cases], ref, 0.005, "cfg2")
+    print("RANSAC vs reference:", {v: verdicts.count(v) for v in sorted(set(verdicts))})
+    assert verdicts.count("identical") >= int(0.6 * len(verdicts)), verdicts
 
 
 # ------------------------------------------------------------------------------------------------- prune / fused pipeline

@@ -33,3 +33,23 @@ def test_knn_ties_go_to_lower_index_and_padding():
     assert e_i.shape == (0, 5)
     z_i, z_d = mo.knn(a, b[:0])
     assert (z_i == -1).all() and np.isinf(z_d).all()
+
+
+def test_ransac_oracle_against_reference_golden():
+    """Pins mo.ransac_pair (float64 Kabsch fit, deterministic arg-max) to the reference's own ransacMultiPairGPU: on the committed
+    inputs its winner has at least the reference's inlier count up to borderline points, and the two sets describe the same motion."""
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    path = os.path.join(gold, "ref_ransac.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/ref_ransac.npz not generated yet")
+    g = np.load(path)
+    u3 = np.load(os.path.join(gold, "curand_xorwow_seed0.npy"))[: int(g["n_trials"])]
+    same = 0
+    for k in range(int(g["n_cases"])):
+        A, B, ref, thr = g[f"A{k}"], g[f"B{k}"], g[f"ref{k}"], float(g["thresh"][k])
+        ids, best, counts = mo.ransac_pair(A, B, u3, thr)
+        assert len(ids) >= len(ref) - max(2, len(ref) // 100), (k, len(ids), len(ref))
+        assert len(np.intersect1d(ids, ref)) >= min(len(ids), len(ref)) - max(2, len(ref) // 100)
+        same += int(np.array_equal(ids, ref))
+    assert same >= 1

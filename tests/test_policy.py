@@ -73,6 +73,13 @@ def test_rigid_transform():
     line = np.outer(np.linspace(0, 1, 10), [1, 2, 3]).astype(np.float32)
     out = policy.rigid_transform(line, line + np.float32(0.5))
     assert np.isfinite(out).all() and np.allclose(out[:3, :3].T @ out[:3, :3], np.eye(3), atol=1e-4)
+    # exactly coplanar points (one coordinate identically 0): S has an exactly zero singular value; Eigen's JacobiSVD still returns an
+    # orthogonal U and the reference recovers the rotation (Utils.cpp:192-207) - so must this closed form, every time
+    for trial in range(200):
+        flat = rng.normal(0, 0.1, (12, 3)).astype(np.float32); flat[:, 2] = 0
+        T = synth.se3(synth.so3_exp(rng.normal(0, 1.0, 3)), rng.normal(0, 0.3, 3))
+        got = policy.rigid_transform(flat, (flat @ T[:3, :3].T + T[:3, 3]).astype(np.float32))
+        assert np.abs(got - T).max() <= 5e-5, trial
     from bundletrack_b200 import _lib
     with pytest.raises(_lib.BtError):
         policy.rigid_transform(a[:2], a[:2])
