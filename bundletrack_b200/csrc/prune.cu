@@ -257,16 +257,17 @@ extern "C" int bt_prune_mutual_pairs(bt_ctx* ctx, int n_pairs, const bt_match_fr
 
 // The whole matcher half of the hot path for a batch of frame pairs, device-resident end to end:
 // kNN (both directions) -> prune -> mutual union -> RANSAC -> EntryJ.  Pair p's entries are contiguous in entry_out.
-extern "C" int bt_match_pairs(bt_ctx* ctx, int n_pairs, const bt_match_frame* A, const bt_match_frame* B, const bt_desc_view* dA, const bt_desc_view* dB,
-                              int H, int W, float fx, float fy, float cx, float cy, const bt_prune_params* prune, int ransac_trials, float ransac_inlier_dist,
-                              uint64_t ransac_seed, bt_entryj* entry_out, int entry_capacity, int32_t* n_entry_out, int32_t* entry_off_out, int32_t* total_out, void* stream_) {
+static int match_pairs_impl(bt_ctx* ctx, int n_pairs, const bt_match_frame* A, const bt_match_frame* B, const bt_desc_view* dA, const bt_desc_view* dB,
+                            const int32_t* slotA, const int32_t* slotB, int H, int W, float fx, float fy, float cx, float cy, const bt_prune_params* prune, int ransac_trials,
+                            float ransac_inlier_dist, uint64_t ransac_seed, bt_entryj* entry_out, int entry_capacity, int32_t* n_entry_out, int32_t* entry_off_out, int32_t* total_out, void* stream_) {
 	PruneState* s = ctx ? g_prune_of(ctx) : nullptr;
 	BT_REQUIRE(s, BT_ERR_INVALID_ARG, "bt_match_pairs: call bt_pipeline_reserve first");
-	BT_REQUIRE(A && B && dA && dB && prune && entry_out && n_entry_out && entry_off_out && total_out && n_pairs > 0 && n_pairs <= s->max_pairs, BT_ERR_INVALID_ARG, "bt_match_pairs: bad argument");
+	BT_REQUIRE(A && B && ((dA && dB) || (slotA && slotB)) && prune && entry_out && n_entry_out && entry_off_out && total_out && n_pairs > 0 && n_pairs <= s->max_pairs, BT_ERR_INVALID_ARG, "bt_match_pairs: bad argument");
 	cudaStream_t stream = (cudaStream_t)stream_;
 	BT_CUDA(cudaSetDevice(ctx->device));
 	const int k = 5;   // k_near, FeatureManager.cpp:264
-	int rc = bt_knn_match_pairs(ctx, n_pairs, dA, dB, k, s->idxAB.as<int32_t>(), s->distAB.as<float>(), s->idxBA.as<int32_t>(), s->distBA.as<float>(), stream_);
+	int rc = dA ? bt_knn_match_pairs(ctx, n_pairs, dA, dB, k, s->idxAB.as<int32_t>(), s->distAB.as<float>(), s->idxBA.as<int32_t>(), s->distBA.as<float>(), stream_)
+	            : bt_knn_match_slots(ctx, n_pairs, slotA, slotB, k, s->idxAB.as<int32_t>(), s->distAB.as<float>(), s->idxBA.as<int32_t>(), s->distBA.as<float>(), stream_);
 	if (rc != BT_OK) return rc;
 	rc = bt_prune_mutual_pairs(ctx, n_pairs, A, B, H, W, fx, fy, cx, cy, s->idxAB.as<int32_t>(), s->idxBA.as<int32_t>(), k, prune, s->corr.as<bt_correspondence>(), s->n_corr.as<int32_t>(), stream_);
 	if (rc != BT_OK) return rc;
@@ -277,4 +278,18 @@ extern "C" int bt_match_pairs(bt_ctx* ctx, int n_pairs, const bt_match_frame* A,
 	k_emit_fill<<<n_pairs, 256, 0, stream>>>(s->pairs.as<PrunePair>(), s->corr.as<bt_correspondence>(), s->inl.as<int32_t>(), n_entry_out, entry_off_out, entry_out, entry_capacity);
 	BT_CUDA(cudaGetLastError());
 	return BT_OK;
+}
+
+extern "C" int bt_match_pairs(bt_ctx* ctx, int n_pairs, const bt_match_frame* A, const bt_match_frame* B, const bt_desc_view* dA, const bt_desc_view* dB,
+                              int H, int W, float fx, float fy, float cx, float cy, const bt_prune_params* prune, int ransac_trials, float ransac_inlier_dist,
+                              uint64_t ransac_seed, bt_entryj* entry_out, int entry_capacity, int32_t* n_entry_out, int32_t* entry_off_out, int32_t* total_out, void* stream_) {
+	BT_REQUIRE(dA && dB, BT_ERR_INVALID_ARG, "bt_match_pairs: NULL descriptor views");
+	return match_pairs_impl(ctx, n_pairs, A, B, dA, dB, nullptr, nullptr, H, W, fx, fy, cx, cy, prune, ransac_trials, ransac_inlier_dist, ransac_seed, entry_out, entry_capacity, n_entry_out, entry_off_out, total_out, stream_);
+}
+
+extern "C" int bt_match_pairs_pool(bt_ctx* ctx, int n_pairs, const bt_match_frame* A, const bt_match_frame* B, const int32_t* slotA, const int32_t* slotB,
+                                   int H, int W, float fx, float fy, float cx, float cy, const bt_prune_params* prune, int ransac_trials, float ransac_inlier_dist,
+                                   uint64_t ransac_seed, bt_entryj* entry_out, int entry_capacity, int32_t* n_entry_out, int32_t* entry_off_out, int32_t* total_out, void* stream_) {
+	BT_REQUIRE(slotA && slotB, BT_ERR_INVALID_ARG, "bt_match_pairs_pool: NULL slot arrays");
+	return match_pairs_impl(ctx, n_pairs, A, B, nullptr, nullptr, slotA, slotB, H, W, fx, fy, cx, cy, prune, ransac_trials, ransac_inlier_dist, ransac_seed, entry_out, entry_capacity, n_entry_out, entry_off_out, total_out, stream_);
 }

@@ -9,7 +9,7 @@ from . import _lib
 
 
 class KnnMatcher:
-    """knnMatch(query, train, k) for many (A, B) pairs at once, both directions from one tensor-core pass per direction."""
+    """knnMatch(query, train, k) for many (A, B) pairs at once; ONE tensor-core contraction per pair serves both directions."""
 
     def __init__(self, device: int = 0, max_pairs: int = 64, max_feats: int = 4096, dim: int = 256, stream: int = 0, ctx=None):
         self.lib = _lib.load()
@@ -63,6 +63,33 @@ class KnnMatcher:
             ib += b.shape[0]
         return [x[0] for x in oAB], [x[1] for x in oAB], [x[0] for x in oBA], [x[1] for x in oBA]
 
+    # ---- persistent descriptor pool: a frame's descriptors are converted once (Lfnet::detectFeature, FeatureManager.cpp:907) ----
+    def pool_reserve(self, n_slots: int):
+        _lib.check(self.lib.bt_desc_pool_reserve(self.ctx, ctypes.c_int(n_slots)), "bt_desc_pool_reserve")
+
+    def pool_store(self, slot: int, desc: "torch.Tensor"):
+        v = _lib.DescView()
+        v.dev, v.n, v.dim, v.pitch_bytes = desc.data_ptr(), desc.shape[0], desc.shape[1], (desc.stride(0) * 4 if desc.shape[0] > 1 else desc.shape[1] * 4)
+        _lib.check(self.lib.bt_desc_pool_store(self.ctx, ctypes.c_int(slot), ctypes.byref(v), self.stream), "bt_desc_pool_store")
+
+    def knn_match_slots(self, slot_pairs: Sequence[Tuple[int, int]], sizes: Sequence[Tuple[int, int]], k: int = 5, device=None):
+        """slot_pairs: (slotA, slotB) per pair; sizes: (nA, nB) per pair (what was stored).  Same outputs as knn_match_pairs."""
+        import torch
+        n = len(slot_pairs)
+        sa = (ctypes.c_int32 * n)(*[int(a) for a, _ in slot_pairs])
+        sb = (ctypes.c_int32 * n)(*[int(b) for _, b in slot_pairs])
+        na, nb = sum(a for a, _ in sizes), sum(b for _, b in sizes)
+        dev = device or torch.device("cuda", torch.cuda.current_device())
+        idxAB = torch.empty((max(na, 1), k), dtype=torch.int32, device=dev); distAB = torch.empty((max(na, 1), k), dtype=torch.float32, device=dev)
+        idxBA = torch.empty((max(nb, 1), k), dtype=torch.int32, device=dev); distBA = torch.empty((max(nb, 1), k), dtype=torch.float32, device=dev)
+        _lib.check(self.lib.bt_knn_match_slots(self.ctx, ctypes.c_int(n), sa, sb, ctypes.c_int(k), ctypes.c_void_p(idxAB.data_ptr()), ctypes.c_void_p(distAB.data_ptr()),
+                                               ctypes.c_void_p(idxBA.data_ptr()), ctypes.c_void_p(distBA.data_ptr()), self.stream), "bt_knn_match_slots")
+        oAB, oBA, ia, ib = [], [], 0, 0
+        for a, b in sizes:
+            oAB.append((idxAB[ia:ia + a], distAB[ia:ia + a])); oBA.append((idxBA[ib:ib + b], distBA[ib:ib + b]))
+            ia += a; ib += b
+        return [x[0] for x in oAB], [x[1] for x in oAB], [x[0] for x in oBA], [x[1] for x in oBA]
+
     def force_fallback(self, every_nth: int):
         """Test knob: every n-th query row goes through the exact brute-force kernel (0 = off)."""
         _lib.check(self.lib.bt_knn_debug_force_fallback(self.ctx, ctypes.c_int(every_nth)), "bt_knn_debug_force_fallback")
@@ -74,7 +101,7 @@ class KnnMatcher:
         ms = (ctypes.c_float * 4)()
         info = (ctypes.c_int * 3)()
         _lib.check(self.lib.bt_knn_get_timing(self.ctx, ms, info), "bt_knn_get_timing")
-        return {"prep_ms": ms[0], "tc_ms": ms[1], "rerank_ms": ms[2], "fallback_ms": ms[3], "items": info[0], "rows": info[1], "fallback_rows": info[2]}
+        return {"prep_ms": ms[0], "tc_ms": ms[1], "rerank_ms": ms[2], "fallback_ms": ms[3], "units": info[0], "rows": info[1], "fallback_rows": info[2]}
 
 
 class Ransac:
@@ -195,8 +222,17 @@ class MatchPipeline:
             o += fa["kpts"].shape[0] + fb["kpts"].shape[0]
         return out
 
-    def match_pairs(self, pairs, H, W, K, seed: int = 0, capacity: int = 0, keep_on_device: bool = False):
-        """Fused pipeline.  Returns (entries [total] EntryJ structured numpy array, n_entry [n_pairs], entry_off [n_pairs]).
+    def pool_reserve(self, n_slots: int):
+        _lib.check(self.lib.bt_desc_pool_reserve(self.ctx, ctypes.c_int(n_slots)), "bt_desc_pool_reserve")
+
+    def pool_store(self, slot: int, desc: "torch.Tensor"):
+        v = _lib.DescView()
+        v.dev, v.n, v.dim, v.pitch_bytes = desc.data_ptr(), desc.shape[0], desc.shape[1], (desc.stride(0) * 4 if desc.shape[0] > 1 else desc.shape[1] * 4)
+        _lib.check(self.lib.bt_desc_pool_store(self.ctx, ctypes.c_int(slot), ctypes.byref(v), self.stream), "bt_desc_pool_store")
+
+    def match_pairs(self, pairs, H, W, K, seed: int = 0, capacity: int = 0, keep_on_device: bool = False, slots=None):
+        """Fused pipeline.  slots: optional list of (slotA, slotB) naming descriptor sets stored with pool_store (the frames' "desc" entries
+        are then not read).  Returns (entries [total] EntryJ structured numpy array, n_entry [n_pairs], entry_off [n_pairs]).
         keep_on_device=True: the entries stay on the GPU - returns (device int32 tensor [cap, 8], n_entry, entry_off) and only the
         two small count arrays are read back; hand them to SolveWindow(corr_dev=..., blocks=...) (see `solver_blocks`)."""
         import numpy as np
@@ -210,11 +246,15 @@ class MatchPipeline:
         n_ent = torch.empty(n, dtype=torch.int32, device=dev)
         off = torch.empty(n, dtype=torch.int32, device=dev)
         tot = torch.zeros(4, dtype=torch.int32, device=dev)
-        _lib.check(self.lib.bt_match_pairs(self.ctx, ctypes.c_int(n), A, B, dA, dB, ctypes.c_int(H), ctypes.c_int(W),
-                                           ctypes.c_float(K[0]), ctypes.c_float(K[1]), ctypes.c_float(K[2]), ctypes.c_float(K[3]),
-                                           ctypes.byref(self.prune), ctypes.c_int(self.ransac_trials), ctypes.c_float(self.ransac_inlier_dist), ctypes.c_uint64(seed),
-                                           ctypes.c_void_p(ent.data_ptr()), ctypes.c_int(cap), ctypes.c_void_p(n_ent.data_ptr()), ctypes.c_void_p(off.data_ptr()),
-                                           ctypes.c_void_p(tot.data_ptr()), self.stream), "bt_match_pairs")
+        tail = (ctypes.c_int(H), ctypes.c_int(W), ctypes.c_float(K[0]), ctypes.c_float(K[1]), ctypes.c_float(K[2]), ctypes.c_float(K[3]),
+                ctypes.byref(self.prune), ctypes.c_int(self.ransac_trials), ctypes.c_float(self.ransac_inlier_dist), ctypes.c_uint64(seed),
+                ctypes.c_void_p(ent.data_ptr()), ctypes.c_int(cap), ctypes.c_void_p(n_ent.data_ptr()), ctypes.c_void_p(off.data_ptr()),
+                ctypes.c_void_p(tot.data_ptr()), self.stream)
+        if slots is None:
+            _lib.check(self.lib.bt_match_pairs(self.ctx, ctypes.c_int(n), A, B, dA, dB, *tail), "bt_match_pairs")
+        else:
+            sa = (ctypes.c_int32 * n)(*[int(a) for a, _ in slots]); sb = (ctypes.c_int32 * n)(*[int(b) for _, b in slots])
+            _lib.check(self.lib.bt_match_pairs_pool(self.ctx, ctypes.c_int(n), A, B, sa, sb, *tail), "bt_match_pairs_pool")
         self.last = (ent, n_ent, off, tot)
         if keep_on_device:
             cnt = torch.stack([n_ent, off]).cpu().numpy()      # one small D2H (2 x n_pairs ints), no entry leaves the device

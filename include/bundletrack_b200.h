@@ -176,12 +176,22 @@ typedef struct {
 
 BT_API int bt_matcher_reserve(bt_ctx* ctx, int max_pairs, int max_feats, int dim);
 /* idxAB/distAB: DEVICE [sum_p nA_p * k] results for queries in A against train B; idxBA/distBA the reverse
- * direction, computed from the same tensor-core pass.  Pair p's block starts at k * (sum of nA over pairs < p)
- * (resp. nB).  Rows with fewer than k candidates are padded with idx -1 / dist +inf. */
+ * direction.  ONE tensor-core contraction per pair serves both directions (rows of its accumulator tile are reduced for
+ * A->B, columns for B->A).  Pair p's block starts at k * (sum of nA over pairs < p) (resp. nB).  Rows with fewer than k
+ * candidates are padded with idx -1 / dist +inf. */
 BT_API int bt_knn_match_pairs(bt_ctx* ctx, int n_pairs, const bt_desc_view* A, const bt_desc_view* B, int k,
                        int32_t* idxAB, float* distAB, int32_t* idxBA, float* distBA, void* stream);
-/* Device time of the last bt_knn_match_pairs: ms4 = {bf16 conversion, tensor-core pass, exact re-rank, exact fallback},
- * info3 = {work items, query rows, rows that needed the exact fallback}. */
+/* Persistent descriptor pool.  Lfnet::detectFeature uploads a frame's descriptors once
+ * (/root/reference/src/FeatureManager.cpp:876-908); bt_desc_pool_store converts them ONCE into pool slot `slot` (fp16 rows for the
+ * tensor pass, fp32 copy for the exact stage, norms, measured rounding errors - the caller's buffer is not referenced afterwards) and
+ * bt_knn_match_slots / bt_match_pairs_pool then name slots: no per-call conversion.  Slots stay valid until overwritten or until
+ * bt_matcher_reserve / bt_desc_pool_reserve re-size the pool. */
+BT_API int bt_desc_pool_reserve(bt_ctx* ctx, int n_slots);
+BT_API int bt_desc_pool_store(bt_ctx* ctx, int slot, const bt_desc_view* desc, void* stream);
+BT_API int bt_knn_match_slots(bt_ctx* ctx, int n_pairs, const int32_t* slotA, const int32_t* slotB, int k,
+                       int32_t* idxAB, float* distAB, int32_t* idxBA, float* distBA, void* stream);
+/* Device time of the last kNN call: ms4 = {descriptor conversion, tensor-core pass, candidate selection + exact re-rank, exact
+ * fallback}, info3 = {tensor-pass units (128 x 256 tiles), query rows, rows that needed the exact fallback}. */
 BT_API int bt_knn_enable_timing(bt_ctx* ctx, int on);
 /* Test knob: send every n-th query row through the exact brute-force fallback (0 = off).  Results do not change. */
 BT_API int bt_knn_debug_force_fallback(bt_ctx* ctx, int every_nth);
@@ -235,12 +245,20 @@ BT_API int bt_prune_mutual_pairs(bt_ctx* ctx, int n_pairs, const bt_match_frame*
                           const bt_prune_params* prm, bt_correspondence* corr_out, int32_t* n_corr_out, void* stream);
 /* kNN -> prune -> mutual -> RANSAC -> EntryJ without leaving the device.  entry_out: DEVICE, pairs back to back
  * (entry_off_out[p], n_entry_out[p]; *total_out entries in all).  Pairs with <= 5 pruned matches or < 5 RANSAC
- * inliers contribute nothing (FeatureManager.cpp:575-579,233-241). */
+ * inliers contribute nothing (FeatureManager.cpp:575-579,233-241).  The list never exceeds entry_capacity: a pair that does not
+ * fit is cut and (offset, count) describe what was written, so they can be handed on as bt_window::block_off / block_n as they
+ * are; entry_capacity = sum over pairs of (nA + nB) can never truncate. */
 BT_API int bt_match_pairs(bt_ctx* ctx, int n_pairs, const bt_match_frame* A, const bt_match_frame* B,
                    const bt_desc_view* dA, const bt_desc_view* dB, int H, int W, float fx, float fy, float cx, float cy,
                    const bt_prune_params* prune, int ransac_trials, float ransac_inlier_dist, uint64_t ransac_seed,
                    bt_entryj* entry_out, int entry_capacity, int32_t* n_entry_out, int32_t* entry_off_out,
                    int32_t* total_out, void* stream);
+/* The same chain on descriptor sets stored with bt_desc_pool_store (slotA[p] / slotB[p] instead of descriptor views). */
+BT_API int bt_match_pairs_pool(bt_ctx* ctx, int n_pairs, const bt_match_frame* A, const bt_match_frame* B,
+                        const int32_t* slotA, const int32_t* slotB, int H, int W, float fx, float fy, float cx, float cy,
+                        const bt_prune_params* prune, int ransac_trials, float ransac_inlier_dist, uint64_t ransac_seed,
+                        bt_entryj* entry_out, int entry_capacity, int32_t* n_entry_out, int32_t* entry_off_out,
+                        int32_t* total_out, void* stream);
 
 /* ---- frame front end: Frame::processDepth + Frame::depthToCloudAndNormals -------------------------
  * /root/reference/src/Frame.cpp:152-233 -> CUDAImageUtil::erodeDepthMap, gaussFilterDepthMap x2,

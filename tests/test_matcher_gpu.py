@@ -95,6 +95,34 @@ def test_knn_pitched_rows_and_batch(matcher, cuda_device):
             p += 1
 
 
+def test_knn_descriptor_pool_slots(matcher, cuda_device):
+    """bt_desc_pool_store once per frame + bt_knn_match_slots == bt_knn_match_pairs on the raw views, bit for bit; a slot can be
+    overwritten; an empty slot is an error; steady-state calls launch no descriptor conversion."""
+    import torch
+    from bundletrack_b200 import _lib
+    descs = [synth.make_descriptors(300 + f, 500 + 130 * f, 8)[0] for f in range(4)]
+    dev = [torch.from_numpy(d).to(cuda_device) for d in descs]
+    matcher.pool_reserve(6)
+    for f in range(4):
+        matcher.pool_store(f, dev[f])
+    idx = [(j, i) for i in range(4) for j in range(i + 1, 4)]
+    want = matcher.knn_match_pairs([(dev[a], dev[b]) for a, b in idx])
+    got = matcher.knn_match_slots(idx, [(len(descs[a]), len(descs[b])) for a, b in idx], device=cuda_device)
+    for w4, g4 in zip(want, got):
+        for w, g in zip(w4, g4):
+            assert torch.equal(w, g)
+    matcher.enable_timing(True)
+    matcher.knn_match_slots(idx, [(len(descs[a]), len(descs[b])) for a, b in idx], device=cuda_device)
+    assert matcher.timing()["prep_ms"] < 0.005            # nothing between the two events: no conversion kernel in steady state
+    matcher.enable_timing(False)
+    matcher.pool_store(1, dev[3])                          # overwrite: slot 1 now holds frame 3's descriptors
+    iAB, _, iBA, _ = matcher.knn_match_slots([(1, 0)], [(len(descs[3]), len(descs[0]))], device=cuda_device)
+    assert np.array_equal(iAB[0].cpu().numpy(), mo.knn(descs[3], descs[0])[0])
+    assert np.array_equal(iBA[0].cpu().numpy(), mo.knn(descs[0], descs[3])[0])
+    with pytest.raises(_lib.BtError):
+        matcher.knn_match_slots([(5, 0)], [(10, 10)], device=cuda_device)
+
+
 def test_knn_matches_opencv(matcher, cuda_device):
     pytest.importorskip("cv2")
     import torch
