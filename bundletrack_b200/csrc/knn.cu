@@ -563,27 +563,20 @@ __global__ void __launch_bounds__(256) k_knn_rerank(const SelJob* __restrict__ j
 	const float INF = __int_as_float(0x7f800000);
 	const int nc = (jb.pconst >= 0) ? cand_cnt[gw] : 0;
 	bool ok = nc >= kk;      // fewer candidates than neighbours can only mean an overflow (-1) or a broken bound: recompute exactly
-	double best_d[8]; int best_i[8];
-#pragma unroll
-	for (int j = 0; j < 8; j++) { best_d[j] = 1e300; best_i[j] = 0x7fffffff; }
+	double my_d = 1e300; int my_i = 0x7fffffff;      // lane c keeps candidate c
 	if (ok && nc > 0) {
 		const int myc = (lane < nc) ? cand[(size_t)gw * SEL_MAXC + lane] : 0;
 		const float* qrow = pool_f + (size_t)(jb.q_pool_row0 + r) * KD;
 		const float* tbase = pool_f + (size_t)jb.t_pool_row0 * KD;
 		const float4 qa = __ldg(reinterpret_cast<const float4*>(qrow) + lane * 2), qb = __ldg(reinterpret_cast<const float4*>(qrow) + lane * 2 + 1);
+		const double q0 = qa.x, q1 = qa.y, q2 = qa.z, q3 = qa.w, q4 = qb.x, q5 = qb.y, q6 = qb.z, q7 = qb.w;
 		auto d2_exact = [&](const float4& b0, const float4& b1) -> double {
 			double s = 0.0, d;
-			d = (double)qa.x - (double)b0.x; s += d * d; d = (double)qa.y - (double)b0.y; s += d * d;
-			d = (double)qa.z - (double)b0.z; s += d * d; d = (double)qa.w - (double)b0.w; s += d * d;
-			d = (double)qb.x - (double)b1.x; s += d * d; d = (double)qb.y - (double)b1.y; s += d * d;
-			d = (double)qb.z - (double)b1.z; s += d * d; d = (double)qb.w - (double)b1.w; s += d * d;
+			d = q0 - (double)b0.x; s += d * d; d = q1 - (double)b0.y; s += d * d;
+			d = q2 - (double)b0.z; s += d * d; d = q3 - (double)b0.w; s += d * d;
+			d = q4 - (double)b1.x; s += d * d; d = q5 - (double)b1.y; s += d * d;
+			d = q6 - (double)b1.z; s += d * d; d = q7 - (double)b1.w; s += d * d;
 			return s;
-		};
-		auto insert = [&](double cd, int ci) {
-#pragma unroll
-			for (int j = 0; j < 8; j++) {
-				if (dist_less(cd, ci, best_d[j], best_i[j])) { const double td = best_d[j]; const int tix = best_i[j]; best_d[j] = cd; best_i[j] = ci; cd = td; ci = tix; }
-			}
 		};
 		for (int c = 0; c < nc; c += 2) {
 			const int t0 = __shfl_sync(0xffffffffu, myc, c), t1 = __shfl_sync(0xffffffffu, myc, min(c + 1, nc - 1));
@@ -593,19 +586,22 @@ __global__ void __launch_bounds__(256) k_knn_rerank(const SelJob* __restrict__ j
 			double sa = d2_exact(x0, x1), sb = d2_exact(y0, y1);
 #pragma unroll
 			for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
-			insert(sa, t0);
-			if (c + 1 < nc) insert(sb, t1);
+			if (lane == c) { my_d = sa; my_i = t0; }
+			if (lane == c + 1 && c + 1 < nc) { my_d = sb; my_i = t1; }
 		}
 	}
-	// ---- one FP64 square root per output slot, lane j takes slot j
-	double mine_d = 1e300; int mine_i = 0x7fffffff;
-#pragma unroll
-	for (int j = 0; j < 8; j++) if (lane == j) { mine_d = best_d[j]; mine_i = best_i[j]; }
-	const bool have = lane < kk && mine_i != 0x7fffffff;
-	if (lane < k) {
-		out.idx[jb.dir][((size_t)jb.out_off + r) * k + lane] = have ? mine_i : -1;
-		out.dist[jb.dir][((size_t)jb.out_off + r) * k + lane] = have ? (float)sqrt(mine_d) : INF;
+	// ---- rank by counting: lane c's output slot = number of candidates that order before it by (distance, index); the indices are
+	//      distinct, so the ranks are a permutation (a sorted insertion of doubles cost five times the distance evaluation)
+	int rank = 0;
+	for (int j = 0; j < nc; j++) {
+		const double dj = __shfl_sync(0xffffffffu, my_d, j);
+		const int ij = __shfl_sync(0xffffffffu, my_i, j);
+		rank += dist_less(dj, ij, my_d, my_i) ? 1 : 0;
 	}
+	int32_t* io = out.idx[jb.dir] + ((size_t)jb.out_off + r) * k;
+	float* dd = out.dist[jb.dir] + ((size_t)jb.out_off + r) * k;
+	if (ok && lane < nc && rank < kk) { io[rank] = my_i; dd[rank] = (float)sqrt(my_d); }
+	if (lane < k && (!ok || lane >= kk)) { io[lane] = -1; dd[lane] = INF; }      // rows with fewer than k train rows are padded; a row that goes to the fallback is rewritten there
 	if (force_fallback > 0 && gw % force_fallback == 0) ok = false;
 	if (jb.nt == 0) ok = true;      // nothing to find
 	if (lane == 0 && !ok) { const int slot = atomicAdd(fallback_count, 1); fallback_rows[slot] = gw; }
@@ -844,6 +840,7 @@ static int knn_run(bt_ctx* ctx, int n_pairs, const PoolSetRef* A, const PoolSetR
 	BT_CUDA(cudaMemcpyAsync(m->q_start.p, h0 + b_pairs + b_jobs + b_int, b_int, cudaMemcpyHostToDevice, stream));
 	BT_CUDA(cudaEventRecord(m->ev_up, stream));
 	BT_CUDA(cudaMemsetAsync(m->fb_count.p, 0, 16, stream));
+	if (m->timing) BT_CUDA(cudaEventRecord(m->ev[1], stream));      // [ev0, ev1) = descriptor conversion + table upload
 	// ---- kernels
 	if (n_live > 0) {
 		k_knn_pairconst<<<(n_live + 127) / 128, 128, 0, stream>>>(m->pairs.as<KnnPair>(), n_live, m->slot_meta.as<int>(), m->pconst.as<PairConst>());
@@ -971,7 +968,7 @@ extern "C" int bt_knn_match_slots(bt_ctx* ctx, int n_pairs, const int32_t* slotA
 	}
 	BT_CUDA(cudaEventSynchronize(m->ev_up));
 	cudaStream_t stream = (cudaStream_t)stream_;
-	if (m->timing) { BT_CUDA(cudaEventRecord(m->ev[0], stream)); BT_CUDA(cudaEventRecord(m->ev[1], stream)); }
+	if (m->timing) BT_CUDA(cudaEventRecord(m->ev[0], stream));
 	return knn_run(ctx, n_pairs, A.data(), B.data(), k, idxAB, distAB, idxBA, distBA, m->h_stage.as<char>(), 0, stream);
 }
 
@@ -1039,6 +1036,5 @@ extern "C" int bt_knn_match_pairs(bt_ctx* ctx, int n_pairs, const bt_desc_view* 
 	size_t hoff = 0;
 	int rc = launch_prep(ctx, sets, m->h_stage.as<char>(), hoff, stream);
 	if (rc != BT_OK) return rc;
-	if (m->timing) BT_CUDA(cudaEventRecord(m->ev[1], stream));
 	return knn_run(ctx, n_pairs, sa.data(), sb.data(), k, idxAB, distAB, idxBA, distBA, m->h_stage.as<char>(), hoff, stream);
 }
