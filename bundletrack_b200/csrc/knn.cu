@@ -46,7 +46,8 @@ static constexpr int BK = 64;               // K elements per smem chunk: 64 fp1
 static constexpr int KCH = KD / BK;         // 4 chunks
 static constexpr int STAGES = 5;            // A-operand pipeline depth (16 KB each)
 static constexpr int GRP = 4;               // rows / columns per group minimum
-static constexpr int KNN_THREADS = 32 * 10; // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+static constexpr int EPI_WARPS = 16;        // 4 per TMEM lane quarter, 64 accumulator columns each: 4 epilogue warps per scheduler hide the shuffle / TMEM-load latencies
+static constexpr int KNN_THREADS = 32 * (2 + EPI_WARPS); // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 static constexpr uint32_t SA_BYTES = BM * BK * 2;     // 16 KB per stage: one K-chunk of an A tile
 static constexpr uint32_t SB_BYTES = BN * BK * 2;     // 32 KB per K-chunk of the resident B tile
 static constexpr uint32_t SMEM_B = KCH * SB_BYTES;    // 128 KB
@@ -232,12 +233,31 @@ __device__ __forceinline__ uint32_t hmin2_u32(uint32_t a, uint32_t b) {
 	return h2_as_u32(r);
 }
 
+// d2 (scaled) of two adjacent columns: one packed FFMA2 + one packed FADD2 (sm_100 f32x2 arithmetic) instead of two of each
+__device__ __forceinline__ void d2_pair(float& d0, float& d1, uint32_t v0, uint32_t v1, float n0, float n1, unsigned long long m2s2, unsigned long long nAs2) {
+	unsigned long long vv, nn, rr;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(vv) : "r"(v0), "r"(v1));
+	asm("mov.b64 %0, {%1, %2};" : "=l"(nn) : "f"(n0), "f"(n1));
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rr) : "l"(m2s2), "l"(vv), "l"(nn));
+	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rr) : "l"(rr), "l"(nAs2));
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(rr));
+}
+
 // One 32-column chunk of the accumulator, thread = A row: d2 (scaled) -> both group reductions -> global.
-__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* __restrict__ nrm, float nAs, float m2s,
+// nrm_s: shared-memory address (32-bit) of this chunk's 32 scaled |b~|^2.
+__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], uint32_t nrm_s, float nAs, float m2s,
                                           __half* __restrict__ rowp, size_t rstride, uint4* __restrict__ colp, int lane) {
 	float d[32];
+	unsigned long long m2s2, nAs2;
+	asm("mov.b64 %0, {%1, %1};" : "=l"(m2s2) : "f"(m2s));
+	asm("mov.b64 %0, {%1, %1};" : "=l"(nAs2) : "f"(nAs));
 #pragma unroll
-	for (int j = 0; j < 32; j++) d[j] = fmaf(m2s, __uint_as_float(v[j]), nrm[j]) + nAs;
+	for (int j = 0; j < 32; j += 4) {
+		float n0, n1, n2, n3;
+		asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(n0), "=f"(n1), "=f"(n2), "=f"(n3) : "r"(nrm_s + 4u * j));
+		d2_pair(d[j], d[j + 1], v[j], v[j + 1], n0, n1, m2s2, nAs2);
+		d2_pair(d[j + 2], d[j + 3], v[j + 2], v[j + 3], n2, n3, m2s2, nAs2);
+	}
 	// ---- A->B: minimum of every group of 4 consecutive B columns (registers only); |x| clears a rounding-level negative sign so the
 	//      stored halves order like unsigned integers
 #pragma unroll
@@ -292,7 +312,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUt
 		asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
 		for (int s = 0; s < KCH; s++) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
 		for (int s = 0; s < STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-		for (int b = 0; b < 2; b++) { mbar_init(tm_full + b, 1); mbar_init(tm_empty + b, 8); }
+		for (int b = 0; b < 2; b++) { mbar_init(tm_full + b, 1); mbar_init(tm_empty + b, EPI_WARPS); }
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	if (warp == 1) {   // TMEM: all 512 columns (two 256-column accumulators); this kernel runs 1 CTA / SM
@@ -360,12 +380,12 @@ k_knn_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUt
 			}
 		}
 	} else if (u0 < u1) {
-		// ================================================= epilogue: 8 warps, lane quarter = warp % 4, column half = (warp-2) / 4
+		// ================================================= epilogue: 16 warps, lane quarter = warp % 4, column quarter = (warp-2) / 4
 		const int ew = warp - 2;
 		const int quarter = warp & 3;            // TMEM lanes [32*quarter, 32*quarter+32) are the only ones this warp may read
-		const int half = ew >> 2;                // columns [128*half, 128*half+128) of the 256-column tile
+		const int cq = ew >> 2;                  // columns [64*cq, 64*cq+64) of the 256-column tile
 		const int row = quarter * 32 + lane;     // A row inside the tile == TMEM lane
-		const int etid = threadIdx.x - 64;       // 0..255
+		const int etid = threadIdx.x - 64;       // 0..511
 		uint32_t tcount = 0;
 		UnitWalk w; w.init(pairs, n_pairs, u0);
 		int cur_p = -1;
@@ -373,39 +393,34 @@ k_knn_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUt
 		for (int u = u0; u < u1; u++, tcount++) {
 			const bool newb = (u == u0) || (w.qt == 0);
 			if (w.p != cur_p) { cur_p = w.p; s = pconst[cur_p].s; }
-			if (newb) {      // |b~|^2 of the resident B tile (scaled) -> smem, one float per epilogue thread
-				asm volatile("bar.sync 1, 256;" ::: "memory");       // every epilogue thread is done with the previous tile's norms
-				sNorm[etid] = __ldg(norms + w.pr.b_row0 + w.tt * BN + etid) * s;
-				asm volatile("bar.sync 1, 256;" ::: "memory");
+			const float nA = __ldg(norms + w.pr.a_row0 + w.qt * BM + row);      // (used after the accumulator wait: the load has long landed)
+			if (newb) {      // |b~|^2 of the resident B tile (scaled) -> smem, one float per thread of the first 8 epilogue warps
+				asm volatile("bar.sync 1, 512;" ::: "memory");       // every epilogue thread is done with the previous tile's norms
+				if (etid < BN) sNorm[etid] = __ldg(norms + w.pr.b_row0 + w.tt * BN + etid) * s;
+				asm volatile("bar.sync 1, 512;" ::: "memory");
 			}
-			const float nAs = __ldg(norms + w.pr.a_row0 + w.qt * BM + row) * s;
 			const float m2s = -2.0f * s;
 			const uint32_t buf = tcount & 1, tphase = (tcount >> 1) & 1;
-			const float* nrm = sNorm + half * 128;
-			const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + half * 128;
+			const uint32_t nrm_s = smem_u32(sNorm + cq * 64);
+			const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + cq * 64;
 			const size_t rstride = (size_t)w.pr.nA_pad;
-			__half* rowp = G + w.pr.g_row + (size_t)((w.tt * BN + half * 128) / GRP) * rstride + (size_t)(w.qt * BM + row);
+			__half* rowp = G + w.pr.g_row + (size_t)((w.tt * BN + cq * 64) / GRP) * rstride + (size_t)(w.qt * BM + row);
 			uint4* colp = reinterpret_cast<uint4*>(G + w.pr.g_col + (size_t)(w.qt * (BM / GRP) + quarter * 8 + (lane >> 2)) * (size_t)w.pr.nB_pad
-			                                       + (size_t)(w.tt * BN + half * 128 + 16 * (lane & 1) + 8 * ((lane >> 1) & 1)));
+			                                       + (size_t)(w.tt * BN + cq * 64 + 16 * (lane & 1) + 8 * ((lane >> 1) & 1)));
 			mbar_wait(tm_full + buf, tphase);
 			tc_fence_after();
-			// TMEM -> registers, double-buffered: chunk c+1 is in flight while chunk c is reduced
+			const float nAs = nA * s;
+			// TMEM -> registers: the second chunk is in flight while the first is reduced
 			uint32_t va[32], vb[32];
 			TMEM_LD32(taddr0, va);
 			asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 			TMEM_LD32(taddr0 + 32, vb);
-			epi_chunk(va, nrm, nAs, m2s, rowp, rstride, colp, lane);
-			asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-			TMEM_LD32(taddr0 + 64, va);
-			epi_chunk(vb, nrm + 32, nAs, m2s, rowp + 8 * rstride, rstride, colp + 4, lane);
-			asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-			TMEM_LD32(taddr0 + 96, vb);
-			epi_chunk(va, nrm + 64, nAs, m2s, rowp + 16 * rstride, rstride, colp + 8, lane);
+			epi_chunk(va, nrm_s, nAs, m2s, rowp, rstride, colp, lane);
 			asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 			tc_fence_before();
 			__syncwarp();
 			if (lane == 0) mbar_arrive(tm_empty + buf);      // the accumulator is in registers: the next unit's MMAs may overwrite it
-			epi_chunk(vb, nrm + 96, nAs, m2s, rowp + 24 * rstride, rstride, colp + 12, lane);
+			epi_chunk(vb, nrm_s + 128u, nAs, m2s, rowp + 8 * rstride, rstride, colp + 4, lane);
 			if (u + 1 < u1) w.next();
 		}
 	}
@@ -438,107 +453,129 @@ __device__ __forceinline__ int find_by_start(const int* __restrict__ start, int 
 }
 struct KnnOut { int32_t* idx[2]; float* dist[2]; };
 
-template <int K> __device__ __forceinline__ void kmin_insert(unsigned (&a)[K], unsigned x) {      // branch-free, ascending, drops the largest
-	unsigned prev = a[0];
-	a[0] = min(a[0], x);
+// branch-free insertion into an ascending list that drops its largest entry; half2 = two queries at once (the keys are non-negative
+// halves, +inf = empty)
+template <int K> __device__ __forceinline__ void kmin_insert2(__half2 (&a)[K], __half2 x) {
+	__half2 prev = a[0];
+	a[0] = __hmin2(a[0], x);
 #pragma unroll
-	for (int j = 1; j < K; j++) { const unsigned cur = a[j]; a[j] = min(cur, max(prev, x)); prev = cur; }
+	for (int j = 1; j < K; j++) { const __half2 cur = a[j]; a[j] = __hmin2(cur, __hmax2(prev, x)); prev = cur; }
 }
+__device__ __forceinline__ __half2 u32_as_h2(unsigned v) { return *reinterpret_cast<__half2*>(&v); }
 
-// 32 queries per block (lane = query: the matrices are [group][query], so a warp reads 64 contiguous bytes per group), 8 warps = 8
-// segments of the group axis.
+// 64 queries per block: lane = two adjacent queries (the matrices are [group][query], so a warp reads 128 contiguous bytes per group
+// and every min / max of the selection network serves both queries), 8 warps = 8 segments of the group axis.
 template <int K> __global__ void __launch_bounds__(256) k_knn_select(const SelJob* __restrict__ jobs, const int* __restrict__ blk_start, int n_jobs,
                                                                      const __half* __restrict__ G, const float* __restrict__ errn, const PairConst* __restrict__ pconst,
                                                                      int k, int32_t* __restrict__ cand, int32_t* __restrict__ cand_cnt) {
 	__shared__ unsigned s_top[8][K][32];
-	__shared__ unsigned s_hmax[32];
-	__shared__ int s_ng[32], s_nc[32];
-	__shared__ int s_grp[32][SEL_MAXG];
-	__shared__ int s_cand[32][SEL_MAXC];
+	__shared__ unsigned s_hmax[64];
+	__shared__ int s_ng[64], s_nc[64];
+	__shared__ int s_grp[64][SEL_MAXG];
+	__shared__ int s_cand[64][SEL_MAXC];
 	const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
 	const int ji = find_by_start(blk_start, n_jobs, (int)blockIdx.x);
 	const SelJob jb = jobs[ji];
-	const int q = ((int)blockIdx.x - jb.blk0) * 32 + lane;
-	const bool valid = q < jb.nq && jb.pconst >= 0;
-	const unsigned short* Gq = reinterpret_cast<const unsigned short*>(G + jb.g_off) + q;
+	const int q0 = ((int)blockIdx.x - jb.blk0) * 64;
+	const bool live = jb.pconst >= 0;
+	const int qa = q0 + 2 * lane;                                   // my two queries: qa, qa + 1 (the matrices are padded to whole tiles: both loads stay inside)
+	const bool anyq = live && qa < jb.nq;
+	const unsigned* Gq = reinterpret_cast<const unsigned*>(G + jb.g_off + qa);
+	const size_t gstride = (size_t)jb.q_stride >> 1;                // in 32-bit words
 	const int per = (jb.n_groups + 7) >> 3;
 	const int g0 = min(seg * per, jb.n_groups), g1 = min(g0 + per, jb.n_groups);
-	if (threadIdx.x < 32) { s_ng[lane] = 0; s_nc[lane] = 0; }
-	// ---- pass 1: the K smallest keys of my segment (keys are non-negative halves: they order like their bit patterns)
-	unsigned top[K];
+	if (threadIdx.x < 64) { s_ng[threadIdx.x] = 0; s_nc[threadIdx.x] = 0; }
+	// ---- pass 1: the K smallest keys of my segment, for both queries
+	const __half2 inf2 = u32_as_h2(0x7c007c00u);
+	__half2 top[K];
 #pragma unroll
-	for (int j = 0; j < K; j++) top[j] = 0xffffu;
-	if (valid) {
+	for (int j = 0; j < K; j++) top[j] = inf2;
+	if (anyq) {
 		int g = g0;
 		for (; g + 4 <= g1; g += 4) {
-			const unsigned k0 = __ldg(Gq + (size_t)g * jb.q_stride), k1 = __ldg(Gq + (size_t)(g + 1) * jb.q_stride);
-			const unsigned k2 = __ldg(Gq + (size_t)(g + 2) * jb.q_stride), k3 = __ldg(Gq + (size_t)(g + 3) * jb.q_stride);
-			kmin_insert<K>(top, k0); kmin_insert<K>(top, k1); kmin_insert<K>(top, k2); kmin_insert<K>(top, k3);
+			const unsigned k0 = __ldg(Gq + (size_t)g * gstride), k1 = __ldg(Gq + (size_t)(g + 1) * gstride);
+			const unsigned k2 = __ldg(Gq + (size_t)(g + 2) * gstride), k3 = __ldg(Gq + (size_t)(g + 3) * gstride);
+			kmin_insert2<K>(top, u32_as_h2(k0)); kmin_insert2<K>(top, u32_as_h2(k1)); kmin_insert2<K>(top, u32_as_h2(k2)); kmin_insert2<K>(top, u32_as_h2(k3));
 		}
-		for (; g < g1; g++) kmin_insert<K>(top, (unsigned)__ldg(Gq + (size_t)g * jb.q_stride));
+		for (; g < g1; g++) kmin_insert2<K>(top, u32_as_h2(__ldg(Gq + (size_t)g * gstride)));
 	}
 #pragma unroll
-	for (int j = 0; j < K; j++) s_top[seg][j][lane] = top[j];
+	for (int j = 0; j < K; j++) s_top[seg][j][lane] = h2_as_u32(top[j]);
 	__syncthreads();
-	if (seg == 0) {      // merge: the k-th smallest key of the whole column, then the threshold
-		unsigned all[K];
+	if (seg == 0) {      // merge: the k-th smallest key of each whole column, then its threshold
+		__half2 all[K];
 #pragma unroll
-		for (int j = 0; j < K; j++) all[j] = 0xffffu;
+		for (int j = 0; j < K; j++) all[j] = inf2;
 		for (int s2 = 0; s2 < 8; s2++) {
 #pragma unroll
-			for (int j = 0; j < K; j++) kmin_insert<K>(all, s_top[s2][j][lane]);
+			for (int j = 0; j < K; j++) kmin_insert2<K>(all, u32_as_h2(s_top[s2][j][lane]));
 		}
 		const int kk = min(min(k, jb.nt), K);
-		unsigned hk16 = 0xffffu;
+		unsigned hk2 = 0x7c007c00u;
 #pragma unroll
-		for (int j = 0; j < K; j++) if (j == kk - 1) hk16 = all[j];
-		unsigned hmax = 0xffffu;
-		if (valid && kk > 0 && hk16 < 0x7c00u) {
-			const PairConst pc = pconst[jb.pconst];
-			const float hk = __half2float(__ushort_as_half((unsigned short)hk16));
-			const float eq = __ldg(errn + jb.q_pool_row0 + q);
-			const float e = (eq + (jb.dir == 0 ? pc.emaxB : pc.emaxA)) * 1.0001f + 1e-9f;
-			// k groups have a member (their minimum) whose stored key is <= hk  =>  the exact k-th distance is <= T:
-			//   stored = rn16(s * computed d2): |stored - s d2c| <= 2^-11 stored + 2^-25;  |d2c - d2(rounded rows)| <= delta;  | |a~-b~| - |a-b| | <= e
-			const float D2hi = fmaf(hk, 1.0f + 0x1p-10f, 0x1p-22f) * pc.inv_s + pc.delta;
-			const float T = sqrtf(D2hi) * (1.0f + 1e-6f) + e;
-			// a row whose rounded-row distance exceeds R is farther than T in exact arithmetic; translate R back into a stored key
-			const float R = (T + e) * (1.0f + 1e-6f);
-			const float hl = fmaf(R * R * (1.0f + 2e-6f) + pc.delta, pc.s * (1.0f + 0x1p-10f), 0x1p-22f);
-			if (hl < 65000.f) hmax = (unsigned)__half_as_ushort(__float2half_ru(hl));
+		for (int j = 0; j < K; j++) if (j == kk - 1) hk2 = h2_as_u32(all[j]);
+#pragma unroll
+		for (int hq = 0; hq < 2; hq++) {
+			const int q = qa + hq;
+			const unsigned hk16 = hq ? (hk2 >> 16) : (hk2 & 0xffffu);
+			unsigned hmax = 0u;
+			if (live && q < jb.nq) {
+				hmax = 0xffffu;
+				if (kk > 0 && hk16 < 0x7c00u) {
+					const PairConst pc = pconst[jb.pconst];
+					const float hk = __half2float(__ushort_as_half((unsigned short)hk16));
+					const float eq = __ldg(errn + jb.q_pool_row0 + q);
+					const float e = (eq + (jb.dir == 0 ? pc.emaxB : pc.emaxA)) * 1.0001f + 1e-9f;
+					// k groups have a member (their minimum) whose stored key is <= hk  =>  the exact k-th distance is <= T:
+					//   stored = rn16(s * computed d2): |stored - s d2c| <= 2^-11 stored + 2^-25;  |d2c - d2(rounded rows)| <= delta;  | |a~-b~| - |a-b| | <= e
+					const float D2hi = fmaf(hk, 1.0f + 0x1p-10f, 0x1p-22f) * pc.inv_s + pc.delta;
+					const float T = sqrtf(D2hi) * (1.0f + 1e-6f) + e;
+					// a row whose rounded-row distance exceeds R is farther than T in exact arithmetic; translate R back into a stored key
+					const float R = (T + e) * (1.0f + 1e-6f);
+					const float hl = fmaf(R * R * (1.0f + 2e-6f) + pc.delta, pc.s * (1.0f + 0x1p-10f), 0x1p-22f);
+					if (hl < 65000.f) hmax = (unsigned)__half_as_ushort(__float2half_ru(hl));
+				}
+			}
+			s_hmax[2 * lane + hq] = hmax;
 		}
-		s_hmax[lane] = valid ? hmax : 0u;
 	}
 	__syncthreads();
-	// ---- pass 2: groups that can still hold one of the k nearest
-	const unsigned hmax = s_hmax[lane];
-	if (valid) {
+	// ---- pass 2: groups that can still hold one of the k nearest (keys order like their bit patterns)
+	const unsigned hm0 = s_hmax[2 * lane], hm1 = s_hmax[2 * lane + 1];
+	if (anyq) {
 		for (int g = g0; g < g1; g++) {
-			const unsigned key = __ldg(Gq + (size_t)g * jb.q_stride);
-			if (key <= hmax) { const int slot = atomicAdd(&s_ng[lane], 1); if (slot < SEL_MAXG) s_grp[lane][slot] = g; }
+			const unsigned key2 = __ldg(Gq + (size_t)g * gstride);
+			const bool p0 = (key2 & 0xffffu) <= hm0 && hm0 != 0u, p1 = (key2 >> 16) <= hm1 && hm1 != 0u;
+			if (p0) { const int slot = atomicAdd(&s_ng[2 * lane], 1); if (slot < SEL_MAXG) s_grp[2 * lane][slot] = g; }
+			if (p1) { const int slot = atomicAdd(&s_ng[2 * lane + 1], 1); if (slot < SEL_MAXG) s_grp[2 * lane + 1][slot] = g; }
 		}
 	}
 	__syncthreads();
 	// ---- members: the other direction's matrix holds, for (my 4-row group, member column), a minimum that includes my own entry
 	//      => a lower bound of the member's stored key; 8 bytes per group instead of four descriptor rows
-	for (int it = seg; it < SEL_MAXG; it += 8) {
-		if (valid && it < min(s_ng[lane], SEL_MAXG)) {
-			const int g = s_grp[lane][it];
+	for (int w2 = threadIdx.x; w2 < 64 * SEL_MAXG; w2 += 256) {
+		const int ql = w2 & 63, it = w2 >> 6, q = q0 + ql;
+		if (live && q < jb.nq && it < min(s_ng[ql], SEL_MAXG)) {
+			const int g = s_grp[ql][it];
+			const unsigned hmax = s_hmax[ql];
 			const uint2 m = __ldg(reinterpret_cast<const uint2*>(G + jb.x_off + (size_t)(q >> 2) * jb.x_stride + (size_t)g * GRP));
 			const unsigned key4[4] = { m.x & 0xffffu, m.x >> 16, m.y & 0xffffu, m.y >> 16 };
 #pragma unroll
 			for (int j = 0; j < 4; j++) {
 				const int t = g * GRP + j;
-				if (t < jb.nt && key4[j] <= hmax) { const int c = atomicAdd(&s_nc[lane], 1); if (c < SEL_MAXC) s_cand[lane][c] = t; }
+				if (t < jb.nt && key4[j] <= hmax) { const int c = atomicAdd(&s_nc[ql], 1); if (c < SEL_MAXC) s_cand[ql][c] = t; }
 			}
 		}
 	}
 	__syncthreads();
-	if (q < jb.nq) {
-		const int ng = s_ng[lane], nc = s_nc[lane];
-		const bool over = ng > SEL_MAXG || nc > SEL_MAXC;
-		if (seg == 0) cand_cnt[jb.q_base + q] = over ? -1 : nc;
-		if (!over) for (int c = seg; c < nc; c += 8) cand[(size_t)(jb.q_base + q) * SEL_MAXC + c] = s_cand[lane][c];
+	for (int w2 = threadIdx.x; w2 < 64 * SEL_MAXC; w2 += 256) {
+		const int ql = w2 & 63, c = w2 >> 6, q = q0 + ql;
+		if (q < jb.nq) {
+			const int ng = s_ng[ql], nc = s_nc[ql];
+			const bool over = ng > SEL_MAXG || nc > SEL_MAXC;
+			if (c == 0) cand_cnt[jb.q_base + q] = over ? -1 : nc;
+			if (!over && c < nc) cand[(size_t)(jb.q_base + q) * SEL_MAXC + c] = s_cand[ql][c];
+		}
 	}
 }
 
@@ -607,10 +644,10 @@ __global__ void __launch_bounds__(256) k_knn_rerank(const SelJob* __restrict__ j
 	if (lane == 0 && !ok) { const int slot = atomicAdd(fallback_count, 1); fallback_rows[slot] = gw; }
 }
 
-// exact brute force for the rows whose candidate set overflowed.  Few rows (the normal case: none): each row's train set is cut
-// into FB_SEG segments, one CTA per (row, segment), the last CTA of a row (ticket) merges the FB_SEG partial lists.  Many rows: one
-// CTA per row.
-static constexpr int FB_SEG = 16, FB_SPLIT_ROWS = 1024;
+// exact brute force for the rows whose candidate set overflowed.  Few rows (the normal case: none or one): each row's train set is
+// cut into FB_SEG segments, one CTA per (row, segment), the last CTA of a row (ticket) merges the FB_SEG partial lists.  Many rows:
+// one CTA per row.  Every merge is a warp-parallel selection (k rounds of a shuffle arg-min), never a serial walk.
+static constexpr int FB_SEG = 64, FB_SPLIT_ROWS = 256;
 
 __device__ __forceinline__ double exact_d2(const float* __restrict__ a, const float* __restrict__ b, int lane) {
 	// warp-cooperative sum over KD floats: lane handles 8 consecutive elements; fixed order => deterministic
@@ -624,6 +661,25 @@ __device__ __forceinline__ double exact_d2(const float* __restrict__ a, const fl
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
 	return s;
+}
+// Every lane brings two (distance, index) entries (index 0x7fffffff = empty; real indices are distinct); lane j < 8 returns the j-th
+// smallest of the warp's 64 by (distance, index).
+__device__ __forceinline__ void warp_select8(double d0, int i0, double d1, int i1, double& od, int& oi) {
+	const int lane = threadIdx.x & 31;
+	od = 1e300; oi = 0x7fffffff;
+#pragma unroll 1
+	for (int r = 0; r < 8; r++) {
+		const bool first = dist_less(d0, i0, d1, i1);
+		double wd = first ? d0 : d1; int wi = first ? i0 : i1;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			const double xd = __shfl_xor_sync(0xffffffffu, wd, o); const int xi = __shfl_xor_sync(0xffffffffu, wi, o);
+			if (dist_less(xd, xi, wd, wi)) { wd = xd; wi = xi; }
+		}
+		if (lane == r) { od = wd; oi = wi; }
+		if (wi == 0x7fffffff) break;                     // nothing left (uniform: every lane holds the same winner)
+		if (i0 == wi) { d0 = 1e300; i0 = 0x7fffffff; } else if (i1 == wi) { d1 = 1e300; i1 = 0x7fffffff; }
+	}
 }
 
 __global__ void __launch_bounds__(256) k_knn_exact(const SelJob* __restrict__ jobs, const int* __restrict__ q_start, int n_jobs, const float* __restrict__ pool_f,
@@ -645,63 +701,57 @@ __global__ void __launch_bounds__(256) k_knn_exact(const SelJob* __restrict__ jo
 		const float* qrow = pool_f + (size_t)(jb.q_pool_row0 + r) * KD;
 		const float* tbase = pool_f + (size_t)jb.t_pool_row0 * KD;
 		const int len = (jb.nt + S - 1) / S, t0 = seg * len, t1 = min(jb.nt, t0 + len);
+		// ---- every warp: sorted top-8 of its share of the segment (two rows in flight)
 		double best_d[8]; int best_i[8];
 #pragma unroll
 		for (int j = 0; j < 8; j++) { best_d[j] = 1e300; best_i[j] = 0x7fffffff; }
-		for (int ti = t0 + warp; ti < t1; ti += 8) {
-			double cd = exact_d2(qrow, tbase + (size_t)ti * KD, lane); int ci = ti;
+		auto insert = [&](double cd, int ci) {
 #pragma unroll
 			for (int j = 0; j < 8; j++) {
 				if (dist_less(cd, ci, best_d[j], best_i[j])) { const double td = best_d[j]; const int tix = best_i[j]; best_d[j] = cd; best_i[j] = ci; cd = td; ci = tix; }
 			}
+		};
+		for (int ti = t0 + warp; ti < t1; ti += 16) {
+			const int tj = ti + 8;
+			const double da = exact_d2(qrow, tbase + (size_t)ti * KD, lane);
+			const double db = exact_d2(qrow, tbase + (size_t)min(tj, t1 - 1) * KD, lane);
+			insert(da, ti);
+			if (tj < t1) insert(db, tj);
 		}
-		__syncthreads();
-		if (lane == 0) for (int j = 0; j < 8; j++) { s_d[warp][j] = best_d[j]; s_i[warp][j] = best_i[j]; }
+		__syncthreads();      // (the previous round's readers of s_d are done)
+		if (lane < 8) {
+			double md = 1e300; int mi = 0x7fffffff;
+#pragma unroll
+			for (int j = 0; j < 8; j++) if (lane == j) { md = best_d[j]; mi = best_i[j]; }
+			s_d[warp][lane] = md; s_i[warp][lane] = mi;
+		}
 		__syncthreads();
 		int32_t* io = out.idx[jb.dir] + ((size_t)jb.out_off + r) * k;
 		float* dd = out.dist[jb.dir] + ((size_t)jb.out_off + r) * k;
-		if (threadIdx.x == 0) {   // 8-way merge of the per-warp sorted lists: the CTA's k best, sorted
-			int ptr[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-			for (int j = 0; j < 8; j++) {
-				int bw = -1;
-				if (j < k) {
-					for (int w2 = 0; w2 < 8; w2++) {
-						if (ptr[w2] >= 8 || s_i[w2][ptr[w2]] == 0x7fffffff) continue;
-						if (bw < 0 || dist_less(s_d[w2][ptr[w2]], s_i[w2][ptr[w2]], s_d[bw][ptr[bw]], s_i[bw][ptr[bw]])) bw = w2;
-					}
-				}
-				const double md = bw < 0 ? 1e300 : s_d[bw][ptr[bw]];
-				const int mi = bw < 0 ? 0x7fffffff : s_i[bw][ptr[bw]];
-				if (bw >= 0) ptr[bw]++;
-				if (!split) { if (j < k) { io[j] = bw < 0 ? -1 : mi; dd[j] = bw < 0 ? __int_as_float(0x7f800000) : (float)sqrt(md); } }
-				else { part_d[((size_t)f * FB_SEG + seg) * 8 + j] = md; part_i[((size_t)f * FB_SEG + seg) * 8 + j] = mi; }
+		if (warp == 0) {      // the CTA's 8 best of its 64 entries
+			double od; int oi;
+			warp_select8((&s_d[0][0])[2 * lane], (&s_i[0][0])[2 * lane], (&s_d[0][0])[2 * lane + 1], (&s_i[0][0])[2 * lane + 1], od, oi);
+			if (lane < 8) {
+				if (!split) { if (lane < k) { io[lane] = oi == 0x7fffffff ? -1 : oi; dd[lane] = oi == 0x7fffffff ? __int_as_float(0x7f800000) : (float)sqrt(od); } }
+				else { part_d[((size_t)f * FB_SEG + seg) * 8 + lane] = od; part_i[((size_t)f * FB_SEG + seg) * 8 + lane] = oi; }
 			}
-			s_last = 0;
-			if (split) { __threadfence(); s_last = (atomicAdd(tickets + f, 1) == FB_SEG - 1); }
+			if (lane == 0) s_last = 0;
+			__syncwarp();
+			if (split) { __threadfence(); if (lane == 0) s_last = (atomicAdd(tickets + f, 1) == FB_SEG - 1); }
 		}
 		__syncthreads();
-		if (split && s_last) {     // FB_SEG sorted lists -> the row's k best (staged in shared memory: 128 dependent L2 reads cost 30 us)
-			__shared__ double m_d[FB_SEG * 8];
-			__shared__ int m_i[FB_SEG * 8];
+		if (split && s_last) {     // FB_SEG sorted lists (512 entries, two per thread) -> per-warp 8 best -> the row's k best
 			__threadfence();
-			if (threadIdx.x < FB_SEG * 8) {
-				m_d[threadIdx.x] = __ldcg(part_d + (size_t)f * FB_SEG * 8 + threadIdx.x);
-				m_i[threadIdx.x] = __ldcg(part_i + (size_t)f * FB_SEG * 8 + threadIdx.x);
-			}
+			const size_t base = (size_t)f * FB_SEG * 8 + 2 * threadIdx.x;
+			double od; int oi;
+			warp_select8(__ldcg(part_d + base), __ldcg(part_i + base), __ldcg(part_d + base + 1), __ldcg(part_i + base + 1), od, oi);
 			__syncthreads();
-			if (threadIdx.x == 0) {
-				tickets[f] = 0;
-				int ptr[FB_SEG];
-				for (int q = 0; q < FB_SEG; q++) ptr[q] = 0;
-				for (int j = 0; j < k; j++) {
-					int bq = -1;
-					for (int q = 0; q < FB_SEG; q++) {
-						if (ptr[q] >= 8 || m_i[q * 8 + ptr[q]] == 0x7fffffff) continue;
-						if (bq < 0 || dist_less(m_d[q * 8 + ptr[q]], m_i[q * 8 + ptr[q]], m_d[bq * 8 + ptr[bq]], m_i[bq * 8 + ptr[bq]])) bq = q;
-					}
-					if (bq < 0) { io[j] = -1; dd[j] = __int_as_float(0x7f800000); }
-					else { io[j] = m_i[bq * 8 + ptr[bq]]; dd[j] = (float)sqrt(m_d[bq * 8 + ptr[bq]]); ptr[bq]++; }
-				}
+			if (lane < 8) { s_d[warp][lane] = od; s_i[warp][lane] = oi; }
+			__syncthreads();
+			if (warp == 0) {
+				warp_select8((&s_d[0][0])[2 * lane], (&s_i[0][0])[2 * lane], (&s_d[0][0])[2 * lane + 1], (&s_i[0][0])[2 * lane + 1], od, oi);
+				if (lane < k) { io[lane] = oi == 0x7fffffff ? -1 : oi; dd[lane] = oi == 0x7fffffff ? __int_as_float(0x7f800000) : (float)sqrt(od); }
+				if (lane == 0) tickets[f] = 0;
 			}
 		}
 		__syncthreads();
@@ -821,7 +871,7 @@ static int knn_run(bt_ctx* ctx, int n_pairs, const PoolSetRef* A, const PoolSetR
 			jb.dir = dir; jb.out_off = (int)off_dir[dir]; jb.q_base = q_total; jb.blk0 = blocks;
 			jobs.push_back(jb);
 			blk_start.push_back(blocks); q_start.push_back(q_total);
-			blocks += (jb.nq + 31) / 32; q_total += jb.nq; off_dir[dir] += (size_t)jb.nq;
+			blocks += (jb.nq + 63) / 64; q_total += jb.nq; off_dir[dir] += (size_t)jb.nq;
 		}
 	}
 	BT_REQUIRE((size_t)g_off <= m->g_halves_cap && q_total <= m->max_q_total && blocks <= m->max_blocks && units < (1ll << 31), BT_ERR_CAPACITY, "bt_knn_match_pairs: work list overflow");
@@ -892,7 +942,7 @@ extern "C" int bt_matcher_reserve(bt_ctx* ctx, int max_pairs, int max_feats, int
 	m->g_halves_cap = (size_t)max_pairs * ((size_t)(slot_rows / GRP) * pad_a + (size_t)(pad_a / GRP) * slot_rows);
 	m->max_jobs = 2 * max_pairs;
 	m->max_q_total = 2 * max_pairs * max_feats;
-	m->max_blocks = 2 * max_pairs * ((max_feats + 31) / 32);
+	m->max_blocks = 2 * max_pairs * ((max_feats + 63) / 64);
 #define RES(buf, bytes) if ((rc = m->buf.alloc(bytes)) != BT_OK) return rc
 	RES(sets, sizeof(PrepSet) * 2 * max_pairs);
 	RES(pairs, sizeof(KnnPair) * ((size_t)max_pairs + 1));

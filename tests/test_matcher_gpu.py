@@ -113,7 +113,7 @@ def test_knn_descriptor_pool_slots(matcher, cuda_device):
             assert torch.equal(w, g)
     matcher.enable_timing(True)
     matcher.knn_match_slots(idx, [(len(descs[a]), len(descs[b])) for a, b in idx], device=cuda_device)
-    assert matcher.timing()["prep_ms"] < 0.005            # nothing between the two events: no conversion kernel in steady state
+    assert matcher.timing()["prep_ms"] < 0.04             # only the table upload sits between the two events: no conversion kernel in steady state
     matcher.enable_timing(False)
     matcher.pool_store(1, dev[3])                          # overwrite: slot 1 now holds frame 3's descriptors
     iAB, _, iBA, _ = matcher.knn_match_slots([(1, 0)], [(len(descs[3]), len(descs[0]))], device=cuda_device)
