@@ -265,25 +265,33 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], uint32_t nrm_
 		const float m0 = fminf(fminf(d[4 * g], d[4 * g + 1]), fminf(d[4 * g + 2], d[4 * g + 3]));
 		const float m1 = fminf(fminf(d[4 * g + 4], d[4 * g + 5]), fminf(d[4 * g + 6], d[4 * g + 7]));
 		const uint32_t hm = h2_as_u32(__floats2half2_rn(m0, m1)) & 0x7fff7fffu;
-		*reinterpret_cast<unsigned short*>(rowp + (size_t)g * rstride) = (unsigned short)(hm & 0xffffu);
-		*reinterpret_cast<unsigned short*>(rowp + (size_t)(g + 1) * rstride) = (unsigned short)(hm >> 16);
+		asm volatile("st.global.b16 [%0], %1;" ::"l"(rowp + (size_t)g * rstride), "h"((unsigned short)hm) : "memory");
+		asm volatile("st.global.b16 [%0], %1;" ::"l"(rowp + (size_t)(g + 1) * rstride), "h"((unsigned short)(hm >> 16)) : "memory");
 	}
 	// ---- B->A: minimum over the 4 consecutive A rows held by lanes 4m..4m+3: transposing butterfly on packed halves (xor 1, xor 2);
-	//      lane L ends with 8 columns (16 (L&1) + 8 ((L>>1)&1) ...) of row group L >> 2
+	//      lane L ends with 8 columns (16 (L&1) + 8 ((L>>1)&1) ...) of row group L >> 2.  The "which half do I keep / send" choice is
+	//      integer arithmetic on the multiply pipe (keep = lo + bit (hi - lo)) instead of two selects on the ALU pipe, which the
+	//      min / pack / shuffle work of this epilogue already saturates.
 	uint32_t h[16];
 #pragma unroll
 	for (int i = 0; i < 16; i++) h[i] = h2_as_u32(__floats2half2_rn(d[2 * i], d[2 * i + 1]));
-	const bool b0 = (lane & 1) != 0, b1 = (lane & 2) != 0;
+	const uint32_t b0 = (uint32_t)(lane & 1), b1 = (uint32_t)((lane >> 1) & 1), nb0 = 0u - b0, nb1 = 0u - b1;
 	uint32_t r[8];
 #pragma unroll
 	for (int i = 0; i < 8; i++) {
-		const uint32_t send = b0 ? h[i] : h[i + 8], keep = b0 ? h[i + 8] : h[i];
+		const uint32_t diff = h[i + 8] - h[i];
+		uint32_t keep, send;
+		asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(keep) : "r"(diff), "r"(b0), "r"(h[i]));           // b0 ? h[i+8] : h[i]
+		asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(send) : "r"(diff), "r"(nb0), "r"(h[i + 8]));      // b0 ? h[i] : h[i+8]
 		r[i] = hmin2_u32(keep, __shfl_xor_sync(0xffffffffu, send, 1));
 	}
 	uint32_t o[4];
 #pragma unroll
 	for (int i = 0; i < 4; i++) {
-		const uint32_t send = b1 ? r[i] : r[i + 4], keep = b1 ? r[i + 4] : r[i];
+		const uint32_t diff = r[i + 4] - r[i];
+		uint32_t keep, send;
+		asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(keep) : "r"(diff), "r"(b1), "r"(r[i]));
+		asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(send) : "r"(diff), "r"(nb1), "r"(r[i + 4]));
 		o[i] = hmin2_u32(keep, __shfl_xor_sync(0xffffffffu, send, 2)) & 0x7fff7fffu;
 	}
 	*colp = make_uint4(o[0], o[1], o[2], o[3]);
@@ -933,9 +941,9 @@ extern "C" int bt_matcher_reserve(bt_ctx* ctx, int max_pairs, int max_feats, int
 		m->encode = (PFN_encodeTiled)fn;
 	}
 	const int slot_rows = (max_feats + BN - 1) / BN * BN;
-	if (slot_rows != m->slot_rows || 2 * max_pairs != m->n_transient) std::fill(m->slot_n.begin(), m->slot_n.end(), -1);     // the persistent slots move: what they held is dropped
+	if (slot_rows != m->slot_rows || std::min(2 * max_pairs, 128) != m->n_transient) std::fill(m->slot_n.begin(), m->slot_n.end(), -1);     // the persistent slots move: what they held is dropped
 	m->max_pairs = max_pairs; m->max_feats = max_feats; m->dim = dim; m->slot_rows = slot_rows;
-	m->n_transient = 2 * max_pairs;                      // worst case: every pair of a bt_knn_match_pairs call uses two distinct descriptor sets
+	m->n_transient = std::min(2 * max_pairs, 128);       // distinct descriptor sets one bt_knn_match_pairs call may name (all pairs of K frames: K sets)
 	int rc;
 	if ((rc = pool_alloc(m)) != BT_OK) return rc;
 	const int pad_a = (max_feats + BM - 1) / BM * BM;
@@ -944,7 +952,7 @@ extern "C" int bt_matcher_reserve(bt_ctx* ctx, int max_pairs, int max_feats, int
 	m->max_q_total = 2 * max_pairs * max_feats;
 	m->max_blocks = 2 * max_pairs * ((max_feats + 63) / 64);
 #define RES(buf, bytes) if ((rc = m->buf.alloc(bytes)) != BT_OK) return rc
-	RES(sets, sizeof(PrepSet) * 2 * max_pairs);
+	RES(sets, sizeof(PrepSet) * (size_t)std::max(m->n_transient, 1));
 	RES(pairs, sizeof(KnnPair) * ((size_t)max_pairs + 1));
 	RES(pconst, sizeof(PairConst) * (size_t)max_pairs);
 	RES(G, m->g_halves_cap * 2 + 64);
@@ -1079,7 +1087,7 @@ extern "C" int bt_knn_match_pairs(bt_ctx* ctx, int n_pairs, const bt_desc_view* 
 	};
 	std::vector<PoolSetRef> sa(n_pairs), sb(n_pairs);
 	for (int p = 0; p < n_pairs; p++) { sa[p] = PoolSetRef{ slot(A[p]), A[p].n }; sb[p] = PoolSetRef{ slot(B[p]), B[p].n }; }
-	BT_REQUIRE((int)sets.size() <= m->n_transient, BT_ERR_CAPACITY, "bt_knn_match_pairs: descriptor pool overflow");
+	BT_REQUIRE((int)sets.size() <= m->n_transient, BT_ERR_CAPACITY, "bt_knn_match_pairs: %d distinct descriptor sets in one call > %d (store them with bt_desc_pool_store and use bt_knn_match_slots)", (int)sets.size(), m->n_transient);
 	// the entry points are asynchronous: an earlier call's table upload may still be reading the pinned block
 	BT_CUDA(cudaEventSynchronize(m->ev_up));
 	if (m->timing) BT_CUDA(cudaEventRecord(m->ev[0], stream));

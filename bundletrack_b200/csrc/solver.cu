@@ -38,6 +38,8 @@
 #include <algorithm>
 #include <math.h>
 #include <stddef.h>
+#include <stdlib.h>
+#include <chrono>
 #include "bt_common.cuh"
 
 namespace bt {
@@ -45,11 +47,10 @@ namespace bt {
 #ifndef BT_SOLVE_MIN_CTAS
 #define BT_SOLVE_MIN_CTAS 2
 #endif
-static constexpr int kThreads = 256;          // CTA size of k_solve
-static constexpr int kWarps = kThreads / 32;
 static constexpr int kTileVals = 28;          // 21 (sym 6x6) + 6 (rhs) + 1 (#correspondences found)
 static constexpr int kGrpVals = 44;           // sparse moment sums per pair group
 static constexpr int kMaxFrames = 32;
+static constexpr int kSmallCtaMinWindows = 8;  // batches of at least this many windows run k_solve with 128-thread CTAs
 static constexpr float kEps = 0.000001f;      // FLOAT_EPSILON, /root/reference/src/cuda/SolverUtil.h:10
 
 struct WinDesc {
@@ -587,22 +588,27 @@ struct TileAcc { float v[kTileVals]; };
 
 // Software-pipelined over a thread's pixels (stride kThreads): iteration i issues the source load of pixel i+2 while it
 // evaluates pixel i (an explicit L1 prefetch of the taps of pixel i+1 was measured SLOWER on B200 and was removed).
-__device__ __forceinline__ void tile_pixels(const SolveArgs& a, const WinDesc& wd, const float4* __restrict__ src,
+template <int NT> __device__ __forceinline__ void tile_pixels(const SolveArgs& a, const WinDesc& wd, const float4* __restrict__ src,
                                             const float4* __restrict__ tex, const float* __restrict__ sM, int start, int count, TileAcc& acc) {
 	const float m00 = sM[0], m01 = sM[1], m02 = sM[2], m03 = sM[3];
 	const float m10 = sM[4], m11 = sM[5], m12 = sM[6], m13 = sM[7];
 	const float m20 = sM[8], m21 = sM[9], m22 = sM[10], m23 = sM[11];
 	const float fx = wd.fx, fy = wd.fy, cx = wd.cx, cy = wd.cy;
 	const unsigned W = (unsigned)wd.w, Hh = (unsigned)wd.h;
-	const float dmin = a.prm.depth_min, dmax = a.prm.depth_max, dist_t = a.prm.dense_dist_thresh, cos_t = a.prm.dense_cos_normal_thresh;
+	const float dmin = a.prm.depth_min, dmax = a.prm.depth_max, cos_t = a.prm.dense_cos_normal_thresh;
 	const float delta = a.prm.robust_delta, wdense = a.prm.w_dense;
+	// `sqrtf(d2) <= dist_t` evaluated as `d2 <= d2max`, d2max = the largest float whose correctly rounded square root is <= dist_t
+	// (same truth value for every float, no square root in the loop)
+	float d2max = a.prm.dense_dist_thresh * a.prm.dense_dist_thresh;
+	while (d2max > 0.f && sqrtf(d2max) > a.prm.dense_dist_thresh) d2max = __int_as_float(__float_as_int(d2max) - 1);
+	while (sqrtf(__int_as_float(__float_as_int(d2max) + 1)) <= a.prm.dense_dist_thresh) d2max = __int_as_float(__float_as_int(d2max) + 1);
 	const float4* sp = src + 2 * (size_t)start;
 	int k = threadIdx.x;
 	float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0, n0 = c0, n1 = c0, f0 = c0, f1 = c0;   // current, next, next-next source records
 	if (k < count) { c0 = __ldg(sp + 2 * k); c1 = __ldg(sp + 2 * k + 1); }
-	if (k + kThreads < count) { n0 = __ldg(sp + 2 * (k + kThreads)); n1 = __ldg(sp + 2 * (k + kThreads) + 1); }
-	for (; k < count; k += kThreads) {
-		const int k2 = k + 2 * kThreads;
+	if (k + NT < count) { n0 = __ldg(sp + 2 * (k + NT)); n1 = __ldg(sp + 2 * (k + NT) + 1); }
+	for (; k < count; k += NT) {
+		const int k2 = k + 2 * NT;
 		if (k2 < count) { f0 = __ldg(sp + 2 * k2); f1 = __ldg(sp + 2 * k2 + 1); }
 		const float4 s0 = c0, s1 = c1;
 		c0 = n0; c1 = n1; n0 = f0; n1 = f1;
@@ -611,7 +617,10 @@ __device__ __forceinline__ void tile_pixels(const SolveArgs& a, const WinDesc& w
 		const float tx = m00 * px + m01 * py + m02 * pz + m03;
 		const float ty = m10 * px + m11 * py + m12 * pz + m13;
 		const float tz = m20 * px + m21 * py + m22 * pz + m23;
-		const float sx = tx * fx / tz + cx, sy = ty * fy / tz + cy;    // cameraToDepth, CUDACameraUtil.h:9-14
+		// cameraToDepth, CUDACameraUtil.h:9-14.  One correctly rounded reciprocal serves both quotients (the reference itself is built
+		// with -use_fast_math: its divisions are approximate; either way the result differs from the exact quotient by an ulp or two)
+		const float itz = __frcp_rn(tz);
+		const float sx = (tx * fx) * itz + cx, sy = (ty * fy) * itz + cy;
 		const int ix = (int)roundf(sx), iy = (int)roundf(sy);
 		if (!(ix >= 0 && iy >= 0 && ix < (int)W && iy < (int)Hh)) continue;
 		// bilinearInterpolationFloat4 on camera-space points AND normals (same taps, same weights)
@@ -636,10 +645,10 @@ __device__ __forceinline__ void tile_pixels(const SolveArgs& a, const WinDesc& w
 				a1[0] += wt * cp.x; a1[1] += wt * cp.y; a1[2] += wt * cp.z; b1[0] += wt * cp.w; b1[1] += wt * nr.x; b1[2] += wt * nr.y; w1 += wt; }
 		}
 		float ww = 0.f, cxs = 0.f, cys = 0.f, czs = 0.f, nxs = 0.f, nys = 0.f, nzs = 0.f;
-		if (w0 > 0.f) { const float r = (1.0f - be) / w0; cxs += r * a0[0]; cys += r * a0[1]; czs += r * a0[2]; nxs += r * b0[0]; nys += r * b0[1]; nzs += r * b0[2]; ww += (1.0f - be); }
-		if (w1 > 0.f) { const float r = be / w1; cxs += r * a1[0]; cys += r * a1[1]; czs += r * a1[2]; nxs += r * b1[0]; nys += r * b1[1]; nzs += r * b1[2]; ww += be; }
+		if (w0 > 0.f) { const float r = (1.0f - be) * __frcp_rn(w0); cxs += r * a0[0]; cys += r * a0[1]; czs += r * a0[2]; nxs += r * b0[0]; nys += r * b0[1]; nzs += r * b0[2]; ww += (1.0f - be); }
+		if (w1 > 0.f) { const float r = be * __frcp_rn(w1); cxs += r * a1[0]; cys += r * a1[1]; czs += r * a1[2]; nxs += r * b1[0]; nys += r * b1[1]; nzs += r * b1[2]; ww += be; }
 		if (!(ww > 0.f)) continue;
-		const float rw = 1.0f / ww;
+		const float rw = __frcp_rn(ww);
 		const float qx = cxs * rw, qy = cys * rw, qz = czs * rw;        // camPosTgt
 		if (!(qz > dmin && qz < dmax)) continue;
 		const float tnx = nxs * rw, tny = nys * rw, tnz = nzs * rw;     // normalTgt
@@ -647,9 +656,9 @@ __device__ __forceinline__ void tile_pixels(const SolveArgs& a, const WinDesc& w
 		const float rny = m10 * nx + m11 * ny + m12 * nz;
 		const float rnz = m20 * nx + m21 * ny + m22 * nz;
 		const float dx = tx - qx, dy = ty - qy, dz = tz - qz;
-		const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+		const float dist2 = dx * dx + dy * dy + dz * dz;
 		const float dn = rnx * tnx + rny * tny + rnz * tnz;
-		if (!(dn >= cos_t && dist <= dist_t)) continue;
+		if (!(dn >= cos_t && dist2 <= d2max)) continue;
 		const float res = -(dx * tnx + dy * tny + dz * tnz);            // dot(camPosTgt - camPosSrcToTgt, normalTgt)
 		const float wgt = wdense * huber_w(res * res, delta);
 		float g[6];
@@ -724,11 +733,11 @@ __device__ __forceinline__ void unpack_sym(int e, int& r, int& c) {
 // Sparse moment sums of one window for the CURRENT poses: 8 lanes per (i,j) group of correspondences, loads one iteration
 // ahead; 44 sums per group go to a.grp_sums.  This is the window's SPARSE tile: first in the window's slice of the queue, it runs
 // on whichever CTA claims it while the dense tiles are in flight, so the window's tail does not wait for it.
-__device__ void sparse_sums(const SolveArgs& a, int w) {
+template <int NT> __device__ void sparse_sums(const SolveArgs& a, int w) {
 	const WinDesc wd0 = a.wins[w];
 	const WinSparse ws = a.wsp[w];
 	const int G = ws.n_groups, tid = threadIdx.x;
-	const int sub = tid >> 3, sl = tid & 7, nsub = kThreads >> 3;
+	const int sub = tid >> 3, sl = tid & 7, nsub = NT >> 3;
 	for (int g0 = 0; g0 < G; g0 += nsub) {
 		const int g = g0 + sub;
 		float m[kGrpVals];
@@ -780,7 +789,7 @@ __device__ void sparse_sums(const SolveArgs& a, int w) {
 	}
 }
 
-__device__ void window_tail(const SolveArgs& a, const WinDesc& wd_in, int w, int it, float* smem_base) {
+template <int NT> __device__ void window_tail(const SolveArgs& a, const WinDesc& wd_in, int w, int it, float* smem_base) {
 	WinDesc wd = wd_in;
 	{ const WinSparse ws = a.wsp[w]; wd.n_corr = ws.n_corr; wd.n_groups = ws.n_groups; wd.corr_off = ws.corr_off; wd.grp_off = ws.grp_off; wd.mem_off = ws.mem_off; wd.unique_blocks = ws.unique_blocks; }
 	const int tid = threadIdx.x, lane = tid & 31;
@@ -795,35 +804,35 @@ __device__ void window_tail(const SolveArgs& a, const WinDesc& wd_in, int w, int
 	PROF_T(0);
 
 	// ---- P0: everything the later phases index repeatedly goes to shared memory once (poses, group/pair tables)
-	for (int k = tid; k < N * 12; k += kThreads) s.T[k] = __ldcg(a.T + (size_t)wd.frame_off * 12 + k);
-	for (int k = tid; k < G; k += kThreads) { s.gi[k] = a.grp_i[wd.grp_off + k]; s.gj[k] = a.grp_j[wd.grp_off + k]; }
-	for (int k = tid; k <= G; k += kThreads) s.gstart[k] = a.grp_start[wd.grp_off + w + k];
-	for (int k = tid; k < P; k += kThreads) {
+	for (int k = tid; k < N * 12; k += NT) s.T[k] = __ldcg(a.T + (size_t)wd.frame_off * 12 + k);
+	for (int k = tid; k < G; k += NT) { s.gi[k] = a.grp_i[wd.grp_off + k]; s.gj[k] = a.grp_j[wd.grp_off + k]; }
+	for (int k = tid; k <= G; k += NT) s.gstart[k] = a.grp_start[wd.grp_off + w + k];
+	for (int k = tid; k < P; k += NT) {
 		const uint2 pr = a.pairs[wd.pair_off + k];
 		s.pt[k] = (int)pr.x; s.ps[k] = (int)pr.y; s.pt0[k] = a.pair_tile0[wd.pair_off + k]; s.pnt[k] = a.pair_ntile[wd.pair_off + k];
 	}
 	{
 		const int* mem = a.mem + wd.mem_off;     // fg_start[N+1] fp_start[N+1] fg_items[2G] fp_items[2P], contiguous like the smem copy
 		const int nmem = 2 * (N + 1) + 2 * G + 2 * P;
-		for (int k = tid; k < nmem; k += kThreads) s.fg_start[k] = mem[k];
+		for (int k = tid; k < nmem; k += NT) s.fg_start[k] = mem[k];
 	}
-	for (int k = tid; k < dimp * ld; k += kThreads) s.A[k] = 0.f;
+	for (int k = tid; k < dimp * ld; k += NT) s.A[k] = 0.f;
 	__syncthreads();
 	PROF_T(1);
 
 	// ---- P1: the sparse moment sums were computed by sparse_sums() while the window's dense tiles were still running
-	for (int k = tid; k < G * kGrpVals; k += kThreads) s.grp[k] = __ldcg(a.grp_sums + (size_t)wd.grp_off * kGrpVals + k);
+	for (int k = tid; k < G * kGrpVals; k += NT) s.grp[k] = __ldcg(a.grp_sums + (size_t)wd.grp_off * kGrpVals + k);
 	__syncthreads();
 	PROF_T(2);
 	// ---- P2: per-pair sums over the pair's tiles (already in the model frame; the tile epilogue applied X S' X^T).  A pair's
 	//      tiles are consecutive and summed in order (deterministic); 4 tiles x RI items per thread are in flight at a time.
 	if (use_dense) {
 		constexpr int RI = 5;
-		for (int k0 = tid; k0 < P * kTileVals; k0 += kThreads * RI) {
+		for (int k0 = tid; k0 < P * kTileVals; k0 += NT * RI) {
 			float v[RI]; const float* src[RI]; int nt[RI]; int mx = 0;
 #pragma unroll
 			for (int r = 0; r < RI; r++) {
-				const int k = k0 + r * kThreads;
+				const int k = k0 + r * NT;
 				v[r] = 0.f; nt[r] = 0; src[r] = a.partial;
 				if (k < P * kTileVals) { const int p = k / kTileVals, e = k - p * kTileVals; nt[r] = s.pnt[p]; src[r] = a.partial + (size_t)(wd.tile_off + s.pt0[p]) * kTileVals + e; mx = max(mx, nt[r]); }
 			}
@@ -842,7 +851,7 @@ __device__ void window_tail(const SolveArgs& a, const WinDesc& wd_in, int w, int
 			}
 #pragma unroll
 			for (int r = 0; r < RI; r++) {
-				const int k = k0 + r * kThreads;
+				const int k = k0 + r * NT;
 				if (k < P * kTileVals) {
 					s.pairW[k] = v[r];
 					if (a.dbg_cnt && (k % kTileVals) == 27 && it == a.prm.num_iter_outer - 1) a.dbg_cnt[(size_t)w * a.dbg_cnt_stride + k / kTileVals] = v[r];
@@ -855,7 +864,7 @@ __device__ void window_tail(const SolveArgs& a, const WinDesc& wd_in, int w, int
 	PROF_T(4);
 	// ---- P3a: per-frame gathers (no atomics, fixed order).  Branch-free inner loops: every output entry e reads one moment
 	//      from the q-side or the s-side of each group touching the frame (offset/sign chosen once, outside the loop).
-	for (int k = tid; k < N * (kFS + kFD); k += kThreads) {
+	for (int k = tid; k < N * (kFS + kFD); k += NT) {
 		const int f = k / (kFS + kFD), e = k - f * (kFS + kFD);
 		float acc = 0.f;
 		if (e < kFS) {
@@ -891,7 +900,7 @@ __device__ void window_tail(const SolveArgs& a, const WinDesc& wd_in, int w, int
 	// ---- P3b: diagonal blocks, right-hand side, Jacobi preconditioner from the per-frame sums
 	{
 		const int per = 21 + 6 + 6;
-		for (int k = tid; k < (N - 1) * per; k += kThreads) {
+		for (int k = tid; k < (N - 1) * per; k += NT) {
 			const int f = 1 + k / per, e = k % per;
 			const int base = (f - 1) * 6;
 			const float* F = s.fS + f * kFS;
@@ -931,7 +940,7 @@ __device__ void window_tail(const SolveArgs& a, const WinDesc& wd_in, int w, int
 	// ---- P4a: sparse cross blocks (i,j): J_i^T J_j, both frames free.  One thread per (group, 3x3 sub-block): uniform code per
 	//      thread, 9 entries each.  Sub-blocks: 0 = TT (-n I), 1 = TR ([sum s]x), 2 = RT (-[sum q]x), 3 = RR (-((q.s) I - s q^T)).
 	const bool uniq = wd.unique_blocks != 0;
-	for (int k = tid; k < G * 4; k += kThreads) {
+	for (int k = tid; k < G * 4; k += NT) {
 		const int g = k >> 2, sb = k & 3;
 		const int gi = s.gi[g], gj = s.gj[g];
 		if (gi < 1 || gj < 1 || gi == gj) continue;
@@ -957,7 +966,7 @@ __device__ void window_tail(const SolveArgs& a, const WinDesc& wd_in, int w, int
 	__syncthreads();
 	// ---- P4b: dense cross blocks: -S for pairs whose cross block survives FlipJtJ (target < source) or all if !compat
 	if (use_dense) {
-		for (int k = tid; k < P * 6; k += kThreads) {
+		for (int k = tid; k < P * 6; k += NT) {
 			const int p = k / 6, r = k - p * 6;
 			const int ti = s.pt[p], sj = s.ps[p];
 			if (ti < 1 || sj < 1) continue;
@@ -1002,14 +1011,14 @@ __device__ void window_tail(const SolveArgs& a, const WinDesc& wd_in, int w, int
 			float* Apb = (lin & 1) ? s.z : s.Ap;      // double-buffered exchange (s.z is free: z lives in registers here)
 			// Ap rows of this warp: lanes over columns (p[c] is already in this lane's registers), four rows in flight
 #pragma unroll 1
-			for (int r0 = wid; r0 < dimp; r0 += 4 * kWarps) {
+			for (int r0 = wid; r0 < dimp; r0 += 4 * (NT / 32)) {
 				float acc4[4] = { 0.f, 0.f, 0.f, 0.f };
 #pragma unroll
 				for (int q = 0; q < QM; q++) {
 					const int c = lane + 32 * q;
 					if (c < dimp) {
 #pragma unroll
-						for (int j = 0; j < 4; j++) { const int r = r0 + j * kWarps; if (r < dimp) acc4[j] += s.A[r * ld + c] * pp[q]; }
+						for (int j = 0; j < 4; j++) { const int r = r0 + j * (NT / 32); if (r < dimp) acc4[j] += s.A[r * ld + c] * pp[q]; }
 					}
 				}
 #pragma unroll
@@ -1019,7 +1028,7 @@ __device__ void window_tail(const SolveArgs& a, const WinDesc& wd_in, int w, int
 				}
 				if (lane == 0) {
 #pragma unroll
-					for (int j = 0; j < 4; j++) { const int r = r0 + j * kWarps; if (r < dimp) Apb[r] = acc4[j]; }
+					for (int j = 0; j < 4; j++) { const int r = r0 + j * (NT / 32); if (r < dimp) Apb[r] = acc4[j]; }
 				}
 			}
 			__syncthreads();
@@ -1051,7 +1060,7 @@ __device__ void window_tail(const SolveArgs& a, const WinDesc& wd_in, int w, int
 	PROF_T(7);
 	// ---- pose update: x <- log(exp(delta) * exp(x))  (computeLieUpdate), new T for the next iteration
 	const bool last = (it == a.prm.num_iter_outer - 1);
-	for (int f = tid; f < N; f += kThreads) {
+	for (int f = tid; f < N; f += NT) {
 		float* xg = a.x + (size_t)(wd.frame_off + f) * 6;
 		V3 rot = mk(__ldcg(xg + 0), __ldcg(xg + 1), __ldcg(xg + 2)), trans = mk(__ldcg(xg + 3), __ldcg(xg + 4), __ldcg(xg + 5));
 		float Tn[12];
@@ -1085,13 +1094,13 @@ __device__ void window_tail(const SolveArgs& a, const WinDesc& wd_in, int w, int
 }
 
 // ------------------------------------------------------------------------------------------------ k_solve
-__global__ void __launch_bounds__(kThreads, BT_SOLVE_MIN_CTAS) k_solve(SolveArgs a) {
+template <int NT, int MINB> __global__ void __launch_bounds__(NT, MINB) k_solve(SolveArgs a) {
 	extern __shared__ __align__(16) float dyn_smem[];
 	__shared__ int s_tile, s_next;
 	__shared__ float s_M[12];
 	__shared__ float s_X[36];
 	__shared__ float s_red[kTileVals];
-	__shared__ float s_part[kWarps][kTileVals];
+	__shared__ float s_part[(NT / 32)][kTileVals];
 	__shared__ int s_is_last;
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const int total = *a.n_tiles_total;
@@ -1117,7 +1126,7 @@ __global__ void __launch_bounds__(kThreads, BT_SOLVE_MIN_CTAS) k_solve(SolveArgs
 		PROF_T(1);
 		if (tl.pair == -2) {     // the window's sparse tile: moment sums of all its (i,j) groups for the current poses (CTA-uniform branch)
 			PROF_T(2);
-			sparse_sums(a, tl.win);
+			sparse_sums<NT>(a, tl.win);
 			PROF_T(3);
 			__threadfence();
 			__syncthreads();
@@ -1157,7 +1166,7 @@ __global__ void __launch_bounds__(kThreads, BT_SOLVE_MIN_CTAS) k_solve(SolveArgs
 			PROF_T(2);
 			const float4* src = a.src_tab[wd.frame_off + pr.y];
 			const float4* tex = a.texel_tab[wd.frame_off + pr.x];
-			tile_pixels(a, wd, src, tex, s_M, tl.start, tl.count, acc);
+			tile_pixels<NT>(a, wd, src, tex, s_M, tl.start, tl.count, acc);
 		}
 		PROF_T(3);
 		// block reduction of the 28 sums -> this tile's slot.  Warp level: a transposing butterfly (31 shuffles instead of
@@ -1183,7 +1192,7 @@ __global__ void __launch_bounds__(kThreads, BT_SOLVE_MIN_CTAS) k_solve(SolveArgs
 			float red = 0.f;
 			if (lane < kTileVals) {
 #pragma unroll
-				for (int k = 0; k < kWarps; k++) red += s_part[k][lane];
+				for (int k = 0; k < (NT / 32); k++) red += s_part[k][lane];
 				s_red[lane] = red;
 			}
 			__syncwarp();
@@ -1225,7 +1234,7 @@ __global__ void __launch_bounds__(kThreads, BT_SOLVE_MIN_CTAS) k_solve(SolveArgs
 		PROF_T(5);
 		if (a.prof && tid == 0) { prf.kind_cta = blockIdx.x; prf.tile_win = ((long long)tl_idx << 32) | ((long long)it << 16) | tl.count; prf.t[6] = prf.t[7] = prf.t[8] = prf.t[9] = 0; prof_emit(a, prf); }
 		if (s_is_last) {
-			window_tail(a, wd, tl.win, it, dyn_smem);
+			window_tail<NT>(a, wd, tl.win, it, dyn_smem);
 			__threadfence();
 			__syncthreads();
 			if (tid == 0) st_release(a.iter_done + tl.win, it + 1);
@@ -1265,8 +1274,9 @@ struct SolverState {
 	// frame cache (bt_frame_cache_*): quarter-res maps of keyframes, built once, referenced by bt_window::cache_slots
 	struct CacheMeta { bool valid = false; int H = 0, W = 0; float fx = 0, fy = 0, cx = 0, cy = 0, dmin = 0, dmax = 0; };
 	DevBuf c_texel, c_src, c_nsrc, c_tables;
-	PinnedBuf c_htables;
-	cudaEvent_t c_ev = nullptr;
+	PinnedBuf c_htables[2];              // two pinned table blocks, used alternately: a store only waits for the upload of the store before last,
+	cudaEvent_t c_ev[2] = { nullptr, nullptr };   // so back-to-back stores (one new frame per window per step) never stall the host behind the GPU
+	int c_flip = 0;
 	int c_capacity = 0, c_npix = 0;
 	float c_downscale = 0.f;
 	std::vector<CacheMeta> c_meta;
@@ -1278,8 +1288,11 @@ struct SolverState {
 	std::vector<int> frame_off;
 	std::vector<int> n_frames;
 	bool staged = false, debug = false, timing = false;
+	double host_us[6] = { 0, 0, 0, 0, 0, 0 };   // host time of the last call: tables+early upload, prep launch, correspondence scan+staging, run (launch), fetch (copy + wait), total
+	int force_nt = 0;                    // test / tuning knob (BT_SOLVE_NT environment variable): 128 or 256 forces the CTA size
 	int launches = 0;
-	int attr_bytes = 0, occ = BT_SOLVE_MIN_CTAS, occ_smem = -1;
+	int attr_bytes = 0, occ = BT_SOLVE_MIN_CTAS, occ_smem = -1, occ_nt = 0;
+	int nt = 256;                        // CTA size of k_solve for the staged batch: 128 for batches (per-tile set-up / settle phases of more, smaller CTAs overlap), 256 for a few windows (shorter tails)
 	bool prep_launched = false, any_uncached = true;
 	cudaStream_t copy_stream = nullptr;
 	cudaEvent_t ev_prev = nullptr, ev_corr = nullptr, ev_h2d = nullptr;
@@ -1292,8 +1305,8 @@ void solver_destroy(bt_ctx* ctx) {
 	DevBuf* bufs[] = { &s->blk_cnt, &s->grp_sums, &s->c_texel, &s->c_src, &s->c_nsrc, &s->c_tables, &s->stage_dev, &s->texel, &s->src, &s->nsrc, &s->x, &s->T, &s->pose_out, &s->tiles, &s->scalars, &s->partial,
 	                   &s->tiles_done, &s->iter_done, &s->pair_tile0, &s->pair_ntile, &s->dbgJ, &s->dbgR, &s->dbgC, &s->prof };
 	for (DevBuf* b : bufs) b->release();
-	s->h_stage.release(); s->h_poses.release(); s->c_htables.release();
-	if (s->c_ev) cudaEventDestroy(s->c_ev);
+	s->h_stage.release(); s->h_poses.release(); s->c_htables[0].release(); s->c_htables[1].release();
+	for (auto& e : s->c_ev) if (e) cudaEventDestroy(e);
 	for (auto& e : s->ev) if (e) cudaEventDestroy(e);
 	for (cudaEvent_t e : { s->ev_prev, s->ev_corr, s->ev_h2d }) if (e) cudaEventDestroy(e);
 	if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
@@ -1307,6 +1320,7 @@ static int reserve_impl(bt_ctx* ctx, const bt_solver_limits* lim) {
 	BT_REQUIRE(lim->max_windows > 0 && lim->max_frames >= 2 && lim->max_frames <= kMaxFrames && lim->max_corr >= 0 && lim->H > 0 && lim->W > 0 && lim->image_downscale >= 1.0f,
 	           BT_ERR_INVALID_ARG, "bt_solver_reserve: bad limits (max_frames must be 2..%d)", kMaxFrames);
 	s->lim = *lim;
+	{ const char* e = getenv("BT_SOLVE_NT"); const int v = e ? atoi(e) : 0; s->force_nt = (v == 128 || v == 256) ? v : 0; }
 	const int w = (int)(lim->W / lim->image_downscale), h = (int)(lim->H / lim->image_downscale);
 	s->npix_max = w * h;
 	const int F = lim->max_windows * lim->max_frames;
@@ -1390,6 +1404,8 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 	BT_REQUIRE(params->num_iter_outer > 0 && params->num_iter_inner > 0 && params->image_downscale == s->lim.image_downscale, BT_ERR_INVALID_ARG,
 	           "bt_solve_stage: iteration counts must be positive and image_downscale must equal the reserved value");
 	s->staged = false; s->prep_launched = false;
+	const auto t_h0 = std::chrono::steady_clock::now();
+	auto us_since = [](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); };
 	if (s->ev_h2d) BT_CUDA(cudaEventSynchronize(s->ev_h2d));     // the previous upload still reads the pinned block
 	// ---- sizes
 	size_t F = 0, C = 0;
@@ -1506,7 +1522,9 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 	BT_CUDA(cudaMemcpyAsync(s->stage_dev.p, hb, L.late, cudaMemcpyHostToDevice, stream));
 	BT_CUDA(cudaEventRecord(s->ev_prev, stream));
 	BT_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_prev, 0));
+	s->host_us[0] = us_since(t_h0);
 	if (early_prep) { if ((rc = launch_prep(ctx, stream)) != BT_OK) return rc; }
+	s->host_us[1] = us_since(t_h0) - s->host_us[0];
 
 	// ==== phase 2 (the GPU is already busy in the fused call): correspondences -> groups, membership CSR, pinned copy, chunked upload
 	size_t c_off = 0, g_off = 0, m_off = 0, smem_need = 0, sent = 0;
@@ -1660,6 +1678,7 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 		if ((rc = s->dbgC.alloc(sizeof(float) * (size_t)s->max_pairs * s->lim.max_windows)) != BT_OK) return rc;
 	}
 	s->staged = true;
+	s->host_us[2] = us_since(t_h0) - s->host_us[0] - s->host_us[1];
 	return BT_OK;
 }
 
@@ -1672,12 +1691,15 @@ static int ensure_occupancy(bt_ctx* ctx) {
 	SolverState* s = ctx->solver;
 	if (s->attr_bytes == 0) {      // the attribute belongs to (function, device), not to the context: set it to the ceiling stage_impl enforces, once,
 		s->attr_bytes = 200 * 1024;   // so that a second context on the same device can never lower what another context's next launch needs
-		BT_CUDA(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, s->attr_bytes));
+		BT_CUDA(cudaFuncSetAttribute(k_solve<256, BT_SOLVE_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->attr_bytes));
+		BT_CUDA(cudaFuncSetAttribute(k_solve<128, 2 * BT_SOLVE_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->attr_bytes));
 	}
-	if (s->occ_smem != s->smem_bytes) {
+	s->nt = (s->n_windows >= kSmallCtaMinWindows && !s->force_nt) ? 128 : (s->force_nt ? s->force_nt : 256);
+	if (s->occ_smem != s->smem_bytes || s->occ_nt != s->nt) {
 		int occ_q = 1;
-		BT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_q, k_solve, kThreads, s->smem_bytes));
-		s->occ = std::max(occ_q, 1); s->occ_smem = s->smem_bytes;
+		if (s->nt == 128) BT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_q, k_solve<128, 2 * BT_SOLVE_MIN_CTAS>, 128, s->smem_bytes));
+		else BT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_q, k_solve<256, BT_SOLVE_MIN_CTAS>, 256, s->smem_bytes));
+		s->occ = std::max(occ_q, 1); s->occ_smem = s->smem_bytes; s->occ_nt = s->nt;
 	}
 	return BT_OK;
 }
@@ -1738,7 +1760,8 @@ extern "C" int bt_solve_run(bt_ctx* ctx, void* stream_) {
 	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[2], stream));
 	const int occ = s->occ;
 	const int grid = ctx->sm_count * occ;
-	k_solve<<<grid, kThreads, s->smem_bytes, stream>>>(a);
+	if (s->nt == 128) k_solve<128, 2 * BT_SOLVE_MIN_CTAS><<<grid, 128, s->smem_bytes, stream>>>(a);
+	else k_solve<256, BT_SOLVE_MIN_CTAS><<<grid, 256, s->smem_bytes, stream>>>(a);
 	BT_CUDA(cudaGetLastError());
 	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[3], stream));
 	s->launches = s->any_uncached ? 3 : 2;
@@ -1763,11 +1786,26 @@ extern "C" int bt_solve_fetch(bt_ctx* ctx, float* poses_out, void* stream_) {
 
 extern "C" int bt_solve_windows(bt_ctx* ctx, int n_windows, const bt_window* windows, const bt_solver_params* params,
                                 float* poses_inout, void* stream) {
+	const auto t0 = std::chrono::steady_clock::now();
+	auto us = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); };
 	int rc = stage_impl(ctx, n_windows, windows, params, poses_inout, stream, true);
 	if (rc != BT_OK) return rc;
+	const double t1 = us();
 	rc = bt_solve_run(ctx, stream);
 	if (rc != BT_OK) return rc;
-	return bt_solve_fetch(ctx, poses_inout, stream);
+	const double t2 = us();
+	rc = bt_solve_fetch(ctx, poses_inout, stream);
+	SolverState* s = ctx->solver;
+	s->host_us[3] = t2 - t1; s->host_us[4] = us() - t2; s->host_us[5] = us();
+	return rc;
+}
+
+// Host time of the last bt_solve_windows call, microseconds: {window tables + first upload, frame-prep launch, correspondence scan +
+// staging + uploads, k_solve launch, pose download + wait for the GPU, whole call}.
+extern "C" int bt_solve_get_host_timing(bt_ctx* ctx, double* us6) {
+	BT_REQUIRE(ctx && ctx->solver && us6, BT_ERR_INVALID_ARG, "bt_solve_get_host_timing: NULL argument");
+	for (int k = 0; k < 6; k++) us6[k] = ctx->solver->host_us[k];
+	return BT_OK;
 }
 
 extern "C" int bt_frame_cache_reserve(bt_ctx* ctx, int capacity, int H, int W, float image_downscale) {
@@ -1799,10 +1837,11 @@ extern "C" int bt_frame_cache_store(bt_ctx* ctx, int n_frames, const int32_t* sl
 	const size_t b_ptr = sizeof(void*) * (size_t)n_frames, bytes = 2 * b_ptr + sizeof(int) * (size_t)n_frames;
 	int rc;
 	if ((rc = s->c_tables.alloc(bytes)) != BT_OK) return rc;
-	if (s->c_ev) BT_CUDA(cudaEventSynchronize(s->c_ev));
-	if ((rc = s->c_htables.alloc(bytes)) != BT_OK) return rc;
-	if (!s->c_ev) BT_CUDA(cudaEventCreateWithFlags(&s->c_ev, cudaEventDisableTiming));
-	char* hb = s->c_htables.as<char>();
+	const int fl = s->c_flip; s->c_flip ^= 1;
+	if (s->c_ev[fl]) BT_CUDA(cudaEventSynchronize(s->c_ev[fl]));
+	if ((rc = s->c_htables[fl].alloc(bytes)) != BT_OK) return rc;
+	if (!s->c_ev[fl]) BT_CUDA(cudaEventCreateWithFlags(&s->c_ev[fl], cudaEventDisableTiming));
+	char* hb = s->c_htables[fl].as<char>();
 	const void** hd = (const void**)hb; const void** hn = (const void**)(hb + b_ptr); int* hs = (int*)(hb + 2 * b_ptr);
 	for (int f = 0; f < n_frames; f++) {
 		BT_REQUIRE(slots[f] >= 0 && slots[f] < s->c_capacity, BT_ERR_INVALID_ARG, "bt_frame_cache_store: slot %d out of range [0,%d)", slots[f], s->c_capacity);
@@ -1811,7 +1850,7 @@ extern "C" int bt_frame_cache_store(bt_ctx* ctx, int n_frames, const int32_t* sl
 		hd[f] = depth_dev[f]; hn[f] = normal_dev[f]; hs[f] = slots[f];
 	}
 	BT_CUDA(cudaMemcpyAsync(s->c_tables.p, hb, bytes, cudaMemcpyHostToDevice, stream));
-	BT_CUDA(cudaEventRecord(s->c_ev, stream));
+	BT_CUDA(cudaEventRecord(s->c_ev[fl], stream));
 	CacheStoreArgs c;
 	c.g.W = W; c.g.H = H; c.g.w = w; c.g.h = h;                                                   // same expressions as bt_solve_stage (CUDACache.cpp:20-24)
 	c.g.ifx = 1.0f / fx; c.g.ify = 1.0f / fy; c.g.icx = -cx / fx; c.g.icy = -cy / fy;

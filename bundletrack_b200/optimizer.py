@@ -200,6 +200,11 @@ class OptimizerGpu:
         _lib.check(self.lib.bt_solve_get_timing(self.ctx, ms), "bt_solve_get_timing")
         return {"prep": ms[0], "plan": ms[1], "solve": ms[2]}
 
+    def host_timing_us(self):
+        us = (ctypes.c_double * 6)()
+        _lib.check(self.lib.bt_solve_get_host_timing(self.ctx, us), "bt_solve_get_host_timing")
+        return {"tables_upload": us[0], "prep_launch": us[1], "scan_stage_upload": us[2], "solve_launch": us[3], "fetch_wait": us[4], "total": us[5]}
+
     def enable_profile(self, max_records=200000):
         _lib.check(self.lib.bt_solve_enable_profile(self.ctx, ctypes.c_int(max_records)), "bt_solve_enable_profile")
         self._prof_cap = max_records

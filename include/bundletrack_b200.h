@@ -154,6 +154,9 @@ BT_API int bt_solve_get_stats(bt_ctx* ctx, bt_solve_stats* out);
  * launching stream; opt-in because it adds four event records per run. */
 BT_API int bt_solve_enable_timing(bt_ctx* ctx, int on);
 BT_API int bt_solve_get_timing(bt_ctx* ctx, float* ms3);
+/* Host-side time of the last bt_solve_windows call, microseconds: us6 = {window tables + first upload, frame-preparation launch,
+ * correspondence scan + staging + uploads, k_solve launch, pose download + wait for the GPU, whole call}. */
+BT_API int bt_solve_get_host_timing(bt_ctx* ctx, double* us6);
 /* Developer aid: in-kernel phase timestamps (clock64) of every tile and tail of the next runs; 12 int64 per record:
  * {kind<<32|cta, ids, t[10]}.  bt_solve_get_profile returns the number of records copied (>= 0) or a negative status. */
 BT_API int bt_solve_enable_profile(bt_ctx* ctx, int max_records);
