@@ -129,7 +129,8 @@ def make_batch(args, rank, dev):
             poses[f] = sc.poses_gt[f] @ synth.se3(synth.so3_exp(rng.normal(0, np.deg2rad(1.0), 3)), rng.normal(0, 0.003, 3))
         depth = [torch.from_numpy(sc.depth[f]).to(dev) for f in range(sc.n_frames)]
         normal = [torch.from_numpy(sc.normal[f]).to(dev) for f in range(sc.n_frames)]
-        wins.append(SolveWindow(corr_k, sc.H, sc.W, depth, normal, poses.astype(np.float32), sc.K))
+        # the per-pair counts travel with the correspondences like Bundler::optimizeGPU's n_match_per_pair (Bundler.cpp:298-351)
+        wins.append(SolveWindow(corr_k, sc.H, sc.W, depth, normal, poses.astype(np.float32), sc.K, corr_block_n=SolveWindow.block_counts(sc.corr)))
         host.append((sc, poses.astype(np.float32)))
     return wins, host
 
@@ -505,7 +506,7 @@ def main():
     opt.reserve_frame_cache(nF, wins[0].H, wins[0].W)
     slots = list(range(nF))
     opt.store_frames(slots, [d for w in wins for d in w.depths], [n_ for w in wins for n_ in w.normals], wins[0].H, wins[0].W, wins[0].K)
-    cwins = [SolveWindow(w.corr, w.H, w.W, None, None, w.poses, w.K, cache_slots=slots[i * N:(i + 1) * N]) for i, w in enumerate(wins)]
+    cwins = [SolveWindow(w.corr, w.H, w.W, None, None, w.poses, w.K, cache_slots=slots[i * N:(i + 1) * N], corr_block_n=w.corr_block_n) for i, w in enumerate(wins)]
     new_slots = [i * N + (N - 1) for i in range(len(wins))]
     new_d = [w.depths[N - 1] for w in wins]; new_n = [w.normals[N - 1] for w in wins]
     def store_new():

@@ -269,29 +269,22 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], uint32_t nrm_
 		asm volatile("st.global.b16 [%0], %1;" ::"l"(rowp + (size_t)(g + 1) * rstride), "h"((unsigned short)(hm >> 16)) : "memory");
 	}
 	// ---- B->A: minimum over the 4 consecutive A rows held by lanes 4m..4m+3: transposing butterfly on packed halves (xor 1, xor 2);
-	//      lane L ends with 8 columns (16 (L&1) + 8 ((L>>1)&1) ...) of row group L >> 2.  The "which half do I keep / send" choice is
-	//      integer arithmetic on the multiply pipe (keep = lo + bit (hi - lo)) instead of two selects on the ALU pipe, which the
-	//      min / pack / shuffle work of this epilogue already saturates.
+	//      lane L ends with 8 columns (16 (L&1) + 8 ((L>>1)&1) ...) of row group L >> 2.  (Choosing keep / send with integer multiply-adds
+	//      on the FMA pipe instead of selects was measured: 0.110 vs 0.101 ms for the 45-pair batch - the selects stay.)
 	uint32_t h[16];
 #pragma unroll
 	for (int i = 0; i < 16; i++) h[i] = h2_as_u32(__floats2half2_rn(d[2 * i], d[2 * i + 1]));
-	const uint32_t b0 = (uint32_t)(lane & 1), b1 = (uint32_t)((lane >> 1) & 1), nb0 = 0u - b0, nb1 = 0u - b1;
+	const bool b0 = (lane & 1) != 0, b1 = (lane & 2) != 0;
 	uint32_t r[8];
 #pragma unroll
 	for (int i = 0; i < 8; i++) {
-		const uint32_t diff = h[i + 8] - h[i];
-		uint32_t keep, send;
-		asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(keep) : "r"(diff), "r"(b0), "r"(h[i]));           // b0 ? h[i+8] : h[i]
-		asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(send) : "r"(diff), "r"(nb0), "r"(h[i + 8]));      // b0 ? h[i] : h[i+8]
+		const uint32_t send = b0 ? h[i] : h[i + 8], keep = b0 ? h[i + 8] : h[i];
 		r[i] = hmin2_u32(keep, __shfl_xor_sync(0xffffffffu, send, 1));
 	}
 	uint32_t o[4];
 #pragma unroll
 	for (int i = 0; i < 4; i++) {
-		const uint32_t diff = r[i + 4] - r[i];
-		uint32_t keep, send;
-		asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(keep) : "r"(diff), "r"(b1), "r"(r[i]));
-		asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(send) : "r"(diff), "r"(nb1), "r"(r[i + 4]));
+		const uint32_t send = b1 ? r[i] : r[i + 4], keep = b1 ? r[i + 4] : r[i];
 		o[i] = hmin2_u32(keep, __shfl_xor_sync(0xffffffffu, send, 2)) & 0x7fff7fffu;
 	}
 	*colp = make_uint4(o[0], o[1], o[2], o[3]);

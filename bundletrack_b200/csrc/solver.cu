@@ -50,7 +50,7 @@ namespace bt {
 static constexpr int kTileVals = 28;          // 21 (sym 6x6) + 6 (rhs) + 1 (#correspondences found)
 static constexpr int kGrpVals = 44;           // sparse moment sums per pair group
 static constexpr int kMaxFrames = 32;
-static constexpr int kSmallCtaMinWindows = 8;  // batches of at least this many windows run k_solve with 128-thread CTAs
+static constexpr int kSmallCtaMinWindows = 1 << 30;  // (measured on B200: 128-thread CTAs are SLOWER, 0.55 vs 0.46 ms for 32 windows - the variant stays behind BT_SOLVE_NT=128 only)
 static constexpr float kEps = 0.000001f;      // FLOAT_EPSILON, /root/reference/src/cuda/SolverUtil.h:10
 
 struct WinDesc {
@@ -213,6 +213,14 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 	int v;
 	asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
 	return v;
+}
+// ticket with release (orders this thread's - and, through the preceding __syncwarp / barrier, its warp's / CTA's - earlier writes
+// before it) and acquire (the CTA that draws the last ticket sees every other tile's writes) semantics in ONE instruction; a full
+// __threadfence() by every writer lane in front of a relaxed atomic cost ~1 k cycles per tile
+__device__ __forceinline__ int ticket_acq_rel(int* p) {
+	int old;
+	asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(old) : "l"(p) : "memory");
+	return old;
 }
 __device__ __forceinline__ void st_release(int* p, int v) {
 	asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -1128,12 +1136,10 @@ template <int NT, int MINB> __global__ void __launch_bounds__(NT, MINB) k_solve(
 			PROF_T(2);
 			sparse_sums<NT>(a, tl.win);
 			PROF_T(3);
-			__threadfence();
-			__syncthreads();
+			__syncthreads();      // (every thread's sums are written; the barrier orders them before thread 0's release below)
 			if (tid == 0) {
-				const int done = atomicAdd(a.tiles_done + tl.win, 1) + 1;
+				const int done = ticket_acq_rel(a.tiles_done + tl.win) + 1;
 				s_is_last = (done == (it + 1) * wd.n_tiles);
-				if (s_is_last) __threadfence();
 			}
 			PROF_T(4);
 			__syncthreads();
@@ -1219,13 +1225,11 @@ template <int NT, int MINB> __global__ void __launch_bounds__(NT, MINB) k_solve(
 					}
 				}
 				__stcg(a.partial + (size_t)tl_idx * kTileVals + lane, out);
-				__threadfence();      // the writers order their store before the ticket below
 			}
-			__syncwarp();
+			__syncwarp();             // orders the 28 lanes' stores before lane 0's release
 			if (lane == 0) {
-				const int done = atomicAdd(a.tiles_done + tl.win, 1) + 1;
+				const int done = ticket_acq_rel(a.tiles_done + tl.win) + 1;
 				s_is_last = (done == (it + 1) * wd.n_tiles);
-				if (s_is_last) __threadfence();
 			}
 		}
 		PROF_T(4);
@@ -1557,8 +1561,23 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 				sent = c_off + n_valid;
 			}
 		} else {
-			// one 8-byte compare per entry (imgIdx_i | imgIdx_j << 32, little endian); range and order are only checked where a run ends
 			static_assert(offsetof(bt_entryj, imgIdx_i) == 0 && offsetof(bt_entryj, imgIdx_j) == 4, "EntryJ header layout");
+			if (bw.block_n && bw.n_blocks > 0) {
+				// the caller names the blocks (Bundler::optimizeGPU emits the entries pair by pair and hands n_match_per_pair along,
+				// /root/reference/src/Bundler.cpp:298-351): only the first entry of every block is read - no pass over the 64 KB of a window
+				long long off = 0;
+				for (int b = 0; b < bw.n_blocks; b++) {
+					const int nb = bw.block_n[b];
+					BT_REQUIRE(nb >= 0 && off + nb <= bw.n_corr, BT_ERR_INVALID_ARG, "window %d: correspondence block %d overruns n_corr", w, b);
+					if (nb == 0) continue;
+					const uint32_t ei = bw.block_i ? bw.block_i[b] : bw.corr[off].imgIdx_i, ej = bw.block_j ? bw.block_j[b] : bw.corr[off].imgIdx_j;
+					BT_REQUIRE(ei < (uint32_t)N && ej < (uint32_t)N, BT_ERR_INVALID_ARG, "window %d: correspondence block %d references a frame outside [0,%d)", w, b, N);
+					hgi[g_off + ng] = (int)ei; hgj[g_off + ng] = (int)ej; hgs[g_off + w + ng] = (int)off; ng++;
+					off += nb;
+				}
+				BT_REQUIRE(off == bw.n_corr, BT_ERR_INVALID_ARG, "window %d: the correspondence blocks cover %lld of %d entries", w, off, bw.n_corr);
+			} else {
+			// one 8-byte compare per entry (imgIdx_i | imgIdx_j << 32, little endian); range and order are only checked where a run ends
 			unsigned long long prev_raw = 0ull;
 			bool have_prev = false;
 			long long prev_key = -1;
@@ -1572,6 +1591,7 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 				if (key < prev_key) { grouped = false; break; }
 				hgi[g_off + ng] = (int)ei; hgj[g_off + ng] = (int)ej; hgs[g_off + w + ng] = c; ng++;
 				prev_raw = raw; prev_key = key; have_prev = true;
+			}
 			}
 		}
 		if (bw.corr_dev) {

@@ -53,10 +53,10 @@ public:
 	OptimizerGpu(const OptimizerGpu&) = delete;
 	OptimizerGpu& operator=(const OptimizerGpu&) = delete;
 
-	// Same argument list as the reference.  n_match_per_pair and colors_gpu are unused there too (LossGPU.cu:53, SBA.cpp:28-32).
+	// Same argument list as the reference.  colors_gpu is unused there too (LossGPU.cu:53, SBA.cpp:28-32); n_match_per_pair is unused there and optional here.
 	// `poses` is in-out: every frame of the window is overwritten with its optimised cam->model pose.
 	template <class EntryJT, class Uchar4T, class Float4T, class Mat4, class Alloc, class Mat3>
-	void optimizeFrames(const std::vector<EntryJT>& global_corres, const std::vector<int>& /*n_match_per_pair*/, int n_frames, int H, int W,
+	void optimizeFrames(const std::vector<EntryJT>& global_corres, const std::vector<int>& n_match_per_pair, int n_frames, int H, int W,
 	                    const std::vector<float*>& depths_gpu, const std::vector<Uchar4T*>& /*colors_gpu*/, const std::vector<Float4T*>& normals_gpu,
 	                    std::vector<Mat4, Alloc>& poses, const Mat3& K, void* stream = nullptr) {
 		static_assert(sizeof(EntryJT) == sizeof(bt_entryj), "EntryJ must be the 32-byte reference struct");
@@ -74,6 +74,11 @@ public:
 		win.depth_dev = dptr.data(); win.normal_dev = nptr.data();
 		win.fx = K(0, 0); win.fy = K(1, 1); win.cx = K(0, 2); win.cy = K(1, 2);
 		win.dense_pairs = nullptr; win.n_dense_pairs = 0; win.compat_flip = 1;
+		// Bundler::optimizeGPU pushes one count per frame pair next to the entries it emits pair by pair (Bundler.cpp:298-324): when the
+		// counts cover the list they save the library its own grouping pass over the entries
+		long long covered = 0;
+		for (int v : n_match_per_pair) covered += v;
+		if (!n_match_per_pair.empty() && covered == (long long)global_corres.size()) { win.n_blocks = (int)n_match_per_pair.size(); win.block_n = n_match_per_pair.data(); }
 		const bt_solver_params prm = cfg_.to_params();
 		check(bt_solve_windows(ctx_, 1, &win, &prm, flat.data(), stream), "bt_solve_windows");
 		for (int f = 0; f < n_frames; f++)

@@ -30,11 +30,13 @@ class SolveWindow:
 
     def __init__(self, corr: np.ndarray, H: int, W: int, depths_gpu: Sequence, normals_gpu: Sequence, poses: np.ndarray, K,
                  dense_pairs: Optional[np.ndarray] = None, compat_flip: bool = True, cache_slots: Optional[Sequence[int]] = None,
-                 corr_dev=None, blocks=None):
+                 corr_dev=None, blocks=None, corr_block_n=None):
         self.corr = np.ascontiguousarray(corr if corr is not None else np.zeros(0, ENTRYJ_DTYPE), dtype=ENTRYJ_DTYPE)
         # device-resident correspondences (bt_match_pairs output): corr_dev = device EntryJ buffer, blocks = (off, n, i, j) host arrays
         self.corr_dev = corr_dev
         self.blocks = None if blocks is None else tuple(np.ascontiguousarray(b, t) for b, t in zip(blocks, (np.int32, np.int32, np.uint32, np.uint32)))
+        # host correspondences: optional per-pair counts (Bundler::optimizeGPU's n_match_per_pair): the library then skips its grouping pass
+        self.corr_block_n = None if corr_block_n is None else np.ascontiguousarray(corr_block_n, np.int32)
         self.H, self.W = int(H), int(W)
         self.depths = [_ptr(d) for d in (depths_gpu or [])]
         self.normals = [_ptr(n) for n in (normals_gpu or [])]
@@ -46,7 +48,16 @@ class SolveWindow:
         self.cache_slots = None if cache_slots is None else np.ascontiguousarray(cache_slots, np.int32)
         self._keep = (depths_gpu, normals_gpu)
 
-    _MARSHALLED = frozenset(("corr", "H", "W", "depths", "normals", "poses", "K", "dense_pairs", "compat_flip", "cache_slots", "corr_dev", "blocks"))
+    @staticmethod
+    def block_counts(corr: np.ndarray) -> np.ndarray:
+        """Run lengths of (imgIdx_i, imgIdx_j) in an EntryJ array that is already grouped pair by pair (what n_match_per_pair holds)."""
+        if len(corr) == 0:
+            return np.zeros(0, np.int32)
+        key = corr["imgIdx_i"].astype(np.int64) << 32 | corr["imgIdx_j"].astype(np.int64)
+        cut = np.flatnonzero(np.diff(key) != 0) + 1
+        return np.diff(np.concatenate([[0], cut, [len(corr)]])).astype(np.int32)
+
+    _MARSHALLED = frozenset(("corr_block_n", "corr", "H", "W", "depths", "normals", "poses", "K", "dense_pairs", "compat_flip", "cache_slots", "corr_dev", "blocks"))
 
     def __setattr__(self, name, value):
         if name in SolveWindow._MARSHALLED:
@@ -75,6 +86,9 @@ class SolveWindow:
                 cw.corr_dev = _ptr(self.corr_dev)
                 cw.n_blocks = len(off)
                 cw.block_off, cw.block_n, cw.block_i, cw.block_j = off.ctypes.data, nb.ctypes.data, bi.ctypes.data, bj.ctypes.data
+            elif self.corr_block_n is not None and len(self.corr_block_n):
+                cw.n_blocks = len(self.corr_block_n)
+                cw.block_n = self.corr_block_n.ctypes.data
             cw.fx, cw.fy, cw.cx, cw.cy = self.K
             zero = None
             if self.dense_pairs is not None:
@@ -85,7 +99,7 @@ class SolveWindow:
                 cw.dense_pairs, cw.n_dense_pairs = None, 0
             cw.compat_flip = 1 if self.compat_flip else 0
             self.__dict__["_cwin"] = cw
-            self.__dict__["_cwin_keep"] = (dp, nq, zero, self.corr, self.dense_pairs, self.cache_slots, self.corr_dev, self.blocks)
+            self.__dict__["_cwin_keep"] = (dp, nq, zero, self.corr, self.dense_pairs, self.cache_slots, self.corr_dev, self.blocks, self.corr_block_n)
         return cw
 
     @property

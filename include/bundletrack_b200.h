@@ -99,6 +99,10 @@ typedef struct {
 	 * block_off[b+1] == block_off[b] + block_n[b].  block_* are HOST arrays - bt_match_pairs' n_entry_out / entry_off_out read
 	 * back (a few dozen ints) and the pair list the caller gave it.  When corr_dev is non-NULL, corr / n_corr are ignored. */
 	const bt_entryj* corr_dev;
+	/* With HOST correspondences (corr_dev == NULL) block_n / n_blocks are optional too: the caller states that `corr` is n_blocks blocks
+	 * back to back, block b holding block_n[b] entries of ONE (imgIdx_i, imgIdx_j) pair (read from the block's first entry, or from
+	 * block_i / block_j when given) - what Bundler::optimizeGPU's n_match_per_pair describes (Bundler.cpp:298-351).  The library then
+	 * skips its own grouping pass over the entries.  block_off is not read for host correspondences. */
 	int n_blocks;
 	const int32_t* block_off;
 	const int32_t* block_n;

@@ -292,3 +292,20 @@ def test_pinned_correspondences_are_read_in_place(opt, cuda_device):
     s1 = opt.optimizeWindows([SolveWindow(views[0], ws[0].H, ws[0].W, maps[0][0], maps[0][1], ws[0].poses_init, ws[0].K)])[0]
     s0 = opt.optimizeWindows([SolveWindow(ws[0].corr[perm], ws[0].H, ws[0].W, maps[0][0], maps[0][1], ws[0].poses_init, ws[0].K)])[0]
     assert np.array_equal(s1, s0)
+
+
+def test_caller_provided_blocks_equal_the_grouping_pass(opt, cuda_device):
+    """bt_window::block_n with host correspondences (Bundler::optimizeGPU's n_match_per_pair): same poses, bit for bit, as the
+    library's own grouping pass; inconsistent counts are rejected."""
+    from bundletrack_b200.optimizer import SolveWindow
+    from bundletrack_b200 import _lib
+    w = synth.make_window(81, n_frames=6, n_corr=900)
+    depth, normal = _upload(w, cuda_device)
+    plain = opt.optimizeWindows([SolveWindow(w.corr, w.H, w.W, depth, normal, w.poses_init, w.K)])[0]
+    cnt = SolveWindow.block_counts(w.corr)
+    assert cnt.sum() == len(w.corr) and len(cnt) > 5
+    blocks = opt.optimizeWindows([SolveWindow(w.corr, w.H, w.W, depth, normal, w.poses_init, w.K, corr_block_n=cnt)])[0]
+    assert np.array_equal(plain, blocks)
+    bad = cnt.copy(); bad[0] += 1
+    with pytest.raises(_lib.BtError):
+        opt.optimizeWindows([SolveWindow(w.corr, w.H, w.W, depth, normal, w.poses_init, w.K, corr_block_n=bad)])
