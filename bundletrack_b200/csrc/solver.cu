@@ -214,6 +214,14 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 	asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
 	return v;
 }
+// Polling load for the iteration flags: relaxed, i.e. WITHOUT the L1 invalidation (CCTL.IVALL) every ld.acquire.gpu carries - a CTA
+// spinning on an acquire load flushed its SM's L1 five million times per launch (ncu), under the feet of the co-resident CTA's
+// texel taps.  The waiter confirms with ONE acquire load once the relaxed load has seen the value.
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+	int v;
+	asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
 // ticket with release (orders this thread's - and, through the preceding __syncwarp / barrier, its warp's / CTA's - earlier writes
 // before it) and acquire (the CTA that draws the last ticket sees every other tile's writes) semantics in ONE instruction; a full
 // __threadfence() by every writer lane in front of a relaxed atomic cost ~1 k cycles per tile
@@ -1128,7 +1136,7 @@ template <int NT, int MINB> __global__ void __launch_bounds__(NT, MINB) k_solve(
 		const Tile tl = a.tiles[tl_idx];
 		const WinDesc wd = a.wins[tl.win];
 		if (it > 0) {   // this window's previous GN iteration must have published its poses
-			if (tid == 0) { while (ld_acquire(a.iter_done + tl.win) < it) __nanosleep(64); }
+			if (tid == 0) { while (ld_relaxed(a.iter_done + tl.win) < it) __nanosleep(128); (void)ld_acquire(a.iter_done + tl.win); }
 			__syncthreads();
 		}
 		PROF_T(1);
