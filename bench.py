@@ -525,16 +525,31 @@ def main():
     poses = opt.fetch()
     ms_step = float(np.median(blk_ms)) / args.steps
     t_val = torch.tensor([ms_step], device=dev)
-    # ---- e2e: per step the new frames are stored and host correspondences/poses/tables go in, host poses come out
+    # ---- e2e: per step the new frames are stored and host correspondences/poses/tables go in, host poses come out.  Streaming form
+    #      (bt_solve_windows_begin / _end, two batches in flight): step k's host work overlaps step k-1's GPU work; every step still
+    #      uploads its own inputs and downloads a batch of poses.
     def step_e2e():
         store_new()
-        step_e2e.out = opt.optimizeWindows(cwins)
-    for _ in range(args.warmup):
+        opt.begin(cwins)
+        if step_e2e.inflight:
+            step_e2e.out = opt.end()
+        step_e2e.inflight = True
+    step_e2e.inflight = False
+    for _ in range(max(args.warmup, 2)):
         step_e2e()
     _, wall_ms = timed_blocks(step_e2e, args.steps, args.min_seconds, sync_all, 0.6)
-    host_us = opt.host_timing_us()
+    step_e2e.out = opt.end(); step_e2e.inflight = False
     out_poses = step_e2e.out
     t_e2e = torch.tensor([float(np.median(wall_ms)) / args.steps], device=dev)
+    # the blocking form of the same call, one batch at a time (what a caller without the streaming loop gets)
+    def step_sync():
+        store_new()
+        step_sync.out = opt.optimizeWindows(cwins)
+    for _ in range(args.warmup):
+        step_sync()
+    _, sync_wall = timed_blocks(step_sync, args.steps, min(args.min_seconds, 0.3), sync_all, 0.7)
+    host_us = opt.host_timing_us()
+    t_sync = torch.tensor([float(np.median(sync_wall)) / args.steps], device=dev)
     # ---- the reference's own calling pattern, for comparison: every map rebuilt inside every call
     opt.stage(wins)
     for _ in range(args.warmup):
@@ -547,7 +562,7 @@ def main():
     t_rb = torch.tensor([float(np.median(rb_ms)) / args.steps, float(np.median(rb_wall)) / args.steps], device=dev)
     clocks = sampler.stop()      # sampled across all timed regions
     if world > 1:
-        for t in (t_val, t_e2e, t_rb):
+        for t in (t_val, t_e2e, t_rb, t_sync):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         from bundletrack_b200.sharding import gather_poses   # NCCL only gathers the results (windows are sharded per rank)
         gather_poses(poses, args.windows * world, [N] * (args.windows * world), rank, world, device=dev)
@@ -579,7 +594,6 @@ def main():
                 "issue": {"warp_inst_per_launch": prof.get("warp_inst_per_launch"),
                           "frac_of_issue_peak": (prof["warp_inst_per_launch"] / (tm["solve"] * 1e-3 * sm_clock * 148 * 4)) if prof.get("warp_inst_per_launch") else None,
                           "note": "warp instructions of the committed ncu capture / (live kernel time x 4 schedulers x 148 SMs x SM clock)"}}
-        matcher = matcher_microbench(dev, stream)
         one = [wins[0]]
         for _ in range(5):
             opt.optimizeWindows(one)
@@ -592,13 +606,17 @@ def main():
         tm1 = opt.timing_ms()
         single = {"e2e_ms": single_ms, "kernel_ms": {"prep": tm1["prep"], "solve": tm1["solve"]},
                   "note": "bt_solve_windows on ONE 10-keyframe x 2000-correspondence window, host buffers in/out, all maps rebuilt in the call (the reference's call)"}
+        # (before the matcher / cfg3 blocks allocate gigabytes: the reference's per-call cudaMalloc/cudaFree pattern slows down with the memory the process holds)
+        cb = cpu_baseline(host, args.cpu_windows, check_against=out_poses[0], single_window=(wins[0], single_ms))
+        matcher = matcher_microbench(dev, stream)
         extras = frontend_microbench(opt, dev, stream)
         cfg3 = cfg3_microbench(dev, stream) if not args.skip_cfg3 else None
-        cb = cpu_baseline(host, args.cpu_windows, check_against=out_poses[0], single_window=(wins[0], single_ms))
         launches_per_step = 1 + int(stats["n_kernel_launches"])
         out = dict(base, value=value, ms_per_step=ms_step, gpu_launches=launches_per_step * args.steps * len(blk_ms),
                    e2e={"value": e2e_val, "unit": "windows/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": float(t_e2e.item()),
-                        "host_us_last_call": host_us},
+                        "api": "bt_frame_cache_store + bt_solve_windows_begin / bt_solve_windows_end (two batches in flight)",
+                        "blocking_call": {"value": world * args.windows / (float(t_sync.item()) * 1e-3), "ms_per_step": float(t_sync.item()), "api": "bt_frame_cache_store + bt_solve_windows",
+                                          "host_us_last_call": host_us}},
                    roofline=roof, cpu_baseline=cb, clocks=clocks,
                    timing={"blocks": len(blk_ms), "steps_per_block": args.steps, "block_ms_min_med_max": [float(np.min(blk_ms)), float(np.median(blk_ms)), float(np.max(blk_ms))],
                            "launches_per_step": launches_per_step, "numa_node": numa},

@@ -459,6 +459,80 @@ __global__ void __launch_bounds__(1024, 2) k_frame_cache_store(CacheStoreArgs c)
 	if (threadIdx.x == 0) c.nsrc[slot] = n;
 }
 
+// The same store spread over one CTA per 1024 quarter-res pixels (count + build, like k_prep_count / k_prep_frames): a handful of new
+// frames per step - one per tracked window - otherwise runs on a handful of CTAs walking 19 rounds each (50 us for 32 frames).
+__device__ __forceinline__ bool geom_sample(const FrameGeom& g, int idx, unsigned& xi, unsigned& yi) {
+	const int x = idx % g.w, y = idx / g.w;
+	xi = (unsigned)((float)x * g.scaleW + 0.5f); yi = (unsigned)((float)y * g.scaleH + 0.5f);
+	return xi < (unsigned)g.W && yi < (unsigned)g.H;
+}
+__global__ void __launch_bounds__(1024, 2) k_cache_count(CacheStoreArgs c, int* __restrict__ blk_cnt) {
+	const int f = blockIdx.y, b = blockIdx.x;
+	const int npix = c.g.w * c.g.h, idx = b * 1024 + threadIdx.x;
+	__shared__ int s_w[32];
+	bool valid = false;
+	if (idx < npix) {       // must agree bit for bit with k_cache_build: z = 0 for a missing / too-near sample
+		unsigned xi, yi;
+		float z = 0.f;
+		if (geom_sample(c.g, idx, xi, yi)) { const float d = __ldg(c.depth[f] + (size_t)yi * c.g.W + xi); if (d >= 0.1f) z = d; }
+		valid = (z > c.dmin && z < c.dmax);
+	}
+	const unsigned bal = __ballot_sync(0xffffffffu, valid);
+	if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = __popc(bal);
+	__syncthreads();
+	if (threadIdx.x < 32) {
+		int t = s_w[threadIdx.x];
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+		if (threadIdx.x == 0) blk_cnt[f * gridDim.x + b] = t;
+	}
+}
+__global__ void __launch_bounds__(1024, 2) k_cache_build(CacheStoreArgs c, const int* __restrict__ blk_cnt) {
+	const int f = blockIdx.y, b = blockIdx.x;
+	__shared__ int s_w[32];
+	__shared__ int s_base;
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const int npix = c.g.w * c.g.h;
+	if (b * 1024 >= npix) return;
+	const int slot = c.slots[f];
+	if (wid == 0) {      // offset of this block = valid pixels of the blocks before it
+		int t = 0;
+		for (int q = lane; q < b; q += 32) t += blk_cnt[f * gridDim.x + q];
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+		if (lane == 0) s_base = t;
+	}
+	float4* texel = c.texel + (size_t)slot * c.slot_stride;
+	float4* src = c.src + (size_t)slot * c.slot_stride;
+	const int idx = b * 1024 + tid;
+	float4 cp = make_float4(0.f, 0.f, 0.f, 0.f), nr = make_float4(0.f, 0.f, 0.f, 0.f);
+	bool valid = false;
+	if (idx < npix) {
+		unsigned xi, yi;
+		if (geom_sample(c.g, idx, xi, yi)) {
+			const size_t sidx = (size_t)yi * c.g.W + xi;
+			const float d = __ldg(c.depth[f] + sidx);
+			nr = __ldg(c.normal[f] + sidx);
+			if (d >= 0.1f) cp = make_float4(c.g.ifx * ((float)xi * d) + c.g.icx * d, c.g.ify * ((float)yi * d) + c.g.icy * d, d, 1.0f);
+		}
+		texel[2 * idx] = make_float4(cp.x, cp.y, cp.z, nr.x);
+		texel[2 * idx + 1] = make_float4(nr.y, nr.z, 0.f, 0.f);
+		valid = (cp.z > c.dmin && cp.z < c.dmax);
+	}
+	const unsigned bal = __ballot_sync(0xffffffffu, valid);
+	if (lane == 0) s_w[wid] = __popc(bal);
+	__syncthreads();
+	int off = (lane < wid) ? s_w[lane] : 0;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) off += __shfl_xor_sync(0xffffffffu, off, o);
+	if (valid) {
+		const int o = s_base + off + __popc(bal & ((1u << lane) - 1u));
+		src[2 * o] = make_float4(cp.x, cp.y, cp.z, nr.x);
+		src[2 * o + 1] = make_float4(nr.y, nr.z, nr.w, 0.f);
+	}
+	if ((b + 1) * 1024 >= npix && tid == 1023) c.nsrc[slot] = s_base + off + __popc(bal);
+}
+
 // ------------------------------------------------------------------------------------------------ tile plan
 __device__ __forceinline__ int chunks_for(int n, int chunk, int& per) {
 	if (n <= 0) { per = 0; return 0; }
@@ -1285,7 +1359,7 @@ struct SolverState {
 	StageLayout layout{};
 	// frame cache (bt_frame_cache_*): quarter-res maps of keyframes, built once, referenced by bt_window::cache_slots
 	struct CacheMeta { bool valid = false; int H = 0, W = 0; float fx = 0, fy = 0, cx = 0, cy = 0, dmin = 0, dmax = 0; };
-	DevBuf c_texel, c_src, c_nsrc, c_tables;
+	DevBuf c_texel, c_src, c_nsrc, c_tables, c_blk;
 	PinnedBuf c_htables[2];              // two pinned table blocks, used alternately: a store only waits for the upload of the store before last,
 	cudaEvent_t c_ev[2] = { nullptr, nullptr };   // so back-to-back stores (one new frame per window per step) never stall the host behind the GPU
 	int c_flip = 0;
@@ -1294,6 +1368,12 @@ struct SolverState {
 	std::vector<CacheMeta> c_meta;
 	int prof_cap = 0;
 	PinnedBuf h_stage, h_poses;
+	// streaming form (bt_solve_windows_begin / _end): two batches may be in flight; each has its own pinned pose block and completion event
+	PinnedBuf h_pipe[2];
+	cudaEvent_t ev_pipe[2] = { nullptr, nullptr };
+	bool pipe_pending[2] = { false, false };
+	int pipe_frames[2] = { 0, 0 };
+	int pipe_head = 0, pipe_tail = 0;
 	// last staged batch
 	int n_windows = 0, frames_total = 0, smem_bytes = 0, chunk = 1024;
 	bt_solver_params prm{};
@@ -1314,10 +1394,11 @@ struct SolverState {
 void solver_destroy(bt_ctx* ctx) {
 	SolverState* s = ctx->solver;
 	if (!s) return;
-	DevBuf* bufs[] = { &s->blk_cnt, &s->grp_sums, &s->c_texel, &s->c_src, &s->c_nsrc, &s->c_tables, &s->stage_dev, &s->texel, &s->src, &s->nsrc, &s->x, &s->T, &s->pose_out, &s->tiles, &s->scalars, &s->partial,
+	DevBuf* bufs[] = { &s->blk_cnt, &s->grp_sums, &s->c_texel, &s->c_src, &s->c_nsrc, &s->c_tables, &s->c_blk, &s->stage_dev, &s->texel, &s->src, &s->nsrc, &s->x, &s->T, &s->pose_out, &s->tiles, &s->scalars, &s->partial,
 	                   &s->tiles_done, &s->iter_done, &s->pair_tile0, &s->pair_ntile, &s->dbgJ, &s->dbgR, &s->dbgC, &s->prof };
 	for (DevBuf* b : bufs) b->release();
-	s->h_stage.release(); s->h_poses.release(); s->c_htables[0].release(); s->c_htables[1].release();
+	s->h_stage.release(); s->h_poses.release(); s->h_pipe[0].release(); s->h_pipe[1].release();
+	for (auto& e : s->ev_pipe) if (e) cudaEventDestroy(e); s->c_htables[0].release(); s->c_htables[1].release();
 	for (auto& e : s->c_ev) if (e) cudaEventDestroy(e);
 	for (auto& e : s->ev) if (e) cudaEventDestroy(e);
 	for (cudaEvent_t e : { s->ev_prev, s->ev_corr, s->ev_h2d }) if (e) cudaEventDestroy(e);
@@ -1828,6 +1909,42 @@ extern "C" int bt_solve_windows(bt_ctx* ctx, int n_windows, const bt_window* win
 	return rc;
 }
 
+// Streaming form of bt_solve_windows: `begin` stages and launches a batch and queues the download of its poses, `end` waits for the
+// OLDEST batch begun and hands its poses out.  Up to two batches may be in flight, so the host side of batch k+1 (tables, grouping,
+// uploads, launches) overlaps the GPU side of batch k; everything is ordered on `stream`.
+extern "C" int bt_solve_windows_begin(bt_ctx* ctx, int n_windows, const bt_window* windows, const bt_solver_params* params, const float* poses_in, void* stream_) {
+	BT_REQUIRE(ctx && ctx->solver, BT_ERR_INVALID_ARG, "bt_solve_windows_begin: call bt_solver_reserve first");
+	SolverState* s = ctx->solver;
+	const int slot = s->pipe_head;
+	BT_REQUIRE(!s->pipe_pending[slot], BT_ERR_INVALID_ARG, "bt_solve_windows_begin: two batches are already in flight - call bt_solve_windows_end first");
+	int rc = stage_impl(ctx, n_windows, windows, params, poses_in, stream_, true);
+	if (rc != BT_OK) return rc;
+	rc = bt_solve_run(ctx, stream_);
+	if (rc != BT_OK) return rc;
+	cudaStream_t stream = (cudaStream_t)stream_;
+	const size_t bytes = sizeof(float) * 16 * (size_t)s->frames_total;
+	if ((rc = s->h_pipe[slot].alloc(bytes + 64)) != BT_OK) return rc;
+	if (!s->ev_pipe[slot]) BT_CUDA(cudaEventCreateWithFlags(&s->ev_pipe[slot], cudaEventDisableTiming));
+	BT_CUDA(cudaMemcpyAsync(s->h_pipe[slot].p, s->pose_out.p, bytes, cudaMemcpyDeviceToHost, stream));
+	BT_CUDA(cudaMemcpyAsync(s->h_pipe[slot].as<char>() + bytes, s->scalars.p, 32, cudaMemcpyDeviceToHost, stream));
+	BT_CUDA(cudaEventRecord(s->ev_pipe[slot], stream));
+	s->pipe_pending[slot] = true; s->pipe_frames[slot] = s->frames_total; s->pipe_head ^= 1;
+	return BT_OK;
+}
+extern "C" int bt_solve_windows_end(bt_ctx* ctx, float* poses_out) {
+	BT_REQUIRE(ctx && ctx->solver && poses_out, BT_ERR_INVALID_ARG, "bt_solve_windows_end: NULL argument");
+	SolverState* s = ctx->solver;
+	const int slot = s->pipe_tail;
+	BT_REQUIRE(s->pipe_pending[slot], BT_ERR_INVALID_ARG, "bt_solve_windows_end: no batch in flight");
+	BT_CUDA(cudaEventSynchronize(s->ev_pipe[slot]));
+	s->pipe_pending[slot] = false; s->pipe_tail ^= 1;
+	const size_t bytes = sizeof(float) * 16 * (size_t)s->pipe_frames[slot];
+	const int total = *(int*)(s->h_pipe[slot].as<char>() + bytes);
+	BT_REQUIRE(total >= 0, BT_ERR_CAPACITY, "bt_solve_windows_end: tile list overflow (more dense tiles than reserved)");
+	memcpy(poses_out, s->h_pipe[slot].p, bytes);
+	return BT_OK;
+}
+
 // Host time of the last bt_solve_windows call, microseconds: {window tables + first upload, frame-prep launch, correspondence scan +
 // staging + uploads, k_solve launch, pose download + wait for the GPU, whole call}.
 extern "C" int bt_solve_get_host_timing(bt_ctx* ctx, double* us6) {
@@ -1847,6 +1964,7 @@ extern "C" int bt_frame_cache_reserve(bt_ctx* ctx, int capacity, int H, int W, f
 	if ((rc = s->c_texel.alloc(sizeof(float4) * 2 * (size_t)w * h * capacity)) != BT_OK) return rc;
 	if ((rc = s->c_src.alloc(sizeof(float4) * 2 * (size_t)w * h * capacity)) != BT_OK) return rc;
 	if ((rc = s->c_nsrc.alloc(sizeof(int) * (size_t)capacity)) != BT_OK) return rc;
+	if ((rc = s->c_blk.alloc(sizeof(int) * (size_t)capacity * ((w * h + 1023) / 1024))) != BT_OK) return rc;
 	s->c_capacity = capacity; s->c_npix = w * h; s->c_downscale = image_downscale;
 	s->c_meta.assign(capacity, SolverState::CacheMeta());
 	return BT_OK;
@@ -1887,7 +2005,12 @@ extern "C" int bt_frame_cache_store(bt_ctx* ctx, int n_frames, const int32_t* sl
 	c.depth = (const float* const*)db; c.normal = (const float4* const*)(db + b_ptr); c.slots = (const int*)(db + 2 * b_ptr);
 	c.texel = s->c_texel.as<float4>(); c.src = s->c_src.as<float4>(); c.nsrc = s->c_nsrc.as<int>(); c.slot_stride = 2 * (size_t)s->c_npix;
 	c.dmin = depth_min; c.dmax = depth_max;
-	k_frame_cache_store<<<n_frames, 1024, 0, stream>>>(c);
+	if (n_frames >= 2 * ctx->sm_count) k_frame_cache_store<<<n_frames, 1024, 0, stream>>>(c);      // many frames: one CTA per frame fills the machine
+	else {
+		const dim3 grid((unsigned)((w * h + 1023) / 1024), (unsigned)n_frames);
+		k_cache_count<<<grid, 1024, 0, stream>>>(c, s->c_blk.as<int>());
+		k_cache_build<<<grid, 1024, 0, stream>>>(c, s->c_blk.as<int>());
+	}
 	BT_CUDA(cudaGetLastError());
 	for (int f = 0; f < n_frames; f++) {
 		SolverState::CacheMeta& m = s->c_meta[slots[f]];

@@ -175,6 +175,21 @@ class OptimizerGpu:
         del keep
         return self._split(windows, poses)
 
+    # ---- streaming form: up to two batches in flight, the host side of batch k+1 overlaps the GPU side of batch k ----------------
+    def begin(self, windows: List[SolveWindow]):
+        arr, poses, keep = self._marshal(windows)
+        _lib.check(self.lib.bt_solve_windows_begin(self.ctx, ctypes.c_int(len(windows)), arr, ctypes.byref(self.params),
+                                                   poses.ctypes.data_as(ctypes.c_void_p), self.stream), "bt_solve_windows_begin")
+        if not hasattr(self, "_inflight"):
+            self._inflight = []
+        self._inflight.append((windows, poses, keep, arr))
+
+    def end(self) -> List[np.ndarray]:
+        windows, poses, _, _ = self._inflight.pop(0)
+        out = np.empty_like(poses)
+        _lib.check(self.lib.bt_solve_windows_end(self.ctx, out.ctypes.data_as(ctypes.c_void_p)), "bt_solve_windows_end")
+        return self._split(windows, out)
+
     @staticmethod
     def _split(windows, poses):
         out, o = [], 0

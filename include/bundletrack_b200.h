@@ -135,6 +135,14 @@ BT_API int bt_solver_reserve(bt_ctx* ctx, const bt_solver_limits* lim);
 BT_API int bt_solve_windows(bt_ctx* ctx, int n_windows, const bt_window* windows, const bt_solver_params* params,
                      float* poses_inout, void* stream);
 
+/* Streaming form: `begin` stages + launches a batch and queues the download of its poses, `end` waits for the OLDEST batch begun and
+ * copies its poses (same layout as bt_solve_windows) to poses_out.  At most two batches may be in flight: the host side of batch k+1
+ * then overlaps the GPU side of batch k.  The windows' host arrays (corr, pointer tables, block arrays) may be reused as soon as
+ * `begin` returns unless they are page-locked and read in place (then: until the matching `end`). */
+BT_API int bt_solve_windows_begin(bt_ctx* ctx, int n_windows, const bt_window* windows, const bt_solver_params* params,
+                           const float* poses_in, void* stream);
+BT_API int bt_solve_windows_end(bt_ctx* ctx, float* poses_out);
+
 /* The same call split at the host<->device boundary, so a caller (and bench.py) can keep inputs resident:
  *   stage : host -> device copies of correspondences, poses, window tables (async on `stream`)
  *   run   : the kernels only (frame cache, plan, persistent GN/PCG solve); asynchronous

@@ -309,3 +309,27 @@ def test_caller_provided_blocks_equal_the_grouping_pass(opt, cuda_device):
     bad = cnt.copy(); bad[0] += 1
     with pytest.raises(_lib.BtError):
         opt.optimizeWindows([SolveWindow(w.corr, w.H, w.W, depth, normal, w.poses_init, w.K, corr_block_n=bad)])
+
+
+def test_streaming_begin_end_equals_blocking_call(cuda_device):
+    """bt_solve_windows_begin / _end with two batches in flight return, in order, exactly the poses of the blocking call; a third
+    begin without an end is refused."""
+    from bundletrack_b200.optimizer import OptimizerGpu, SolveWindow
+    from bundletrack_b200 import _lib
+    o = OptimizerGpu(None, max_windows=3, max_frames=6, max_corr=2000)
+    ws = [synth.make_window(90 + k, n_frames=4 + (k % 3), n_corr=400 + 100 * k) for k in range(4)]
+    ups = [_upload(w, cuda_device) for w in ws]
+    batches = [[SolveWindow(ws[k].corr, ws[k].H, ws[k].W, ups[k][0], ups[k][1], ws[k].poses_init, ws[k].K) for k in sel] for sel in ((0, 1), (2,), (3, 0, 1))]
+    want = [o.optimizeWindows(b) for b in batches]
+    o.begin(batches[0]); o.begin(batches[1])
+    with pytest.raises(_lib.BtError):
+        o.begin(batches[2])
+    got0 = o.end()
+    o.begin(batches[2])
+    got1 = o.end(); got2 = o.end()
+    for w_, g_ in zip(want, (got0, got1, got2)):
+        for a, b in zip(w_, g_):
+            assert np.array_equal(a, b)
+    with pytest.raises(_lib.BtError):
+        o.end()
+    o.close()
