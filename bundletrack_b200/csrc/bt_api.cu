@@ -48,6 +48,7 @@ extern "C" void bt_ctx_destroy(bt_ctx* ctx) {
 	bt::matcher_destroy(ctx);
 	bt::ransac_destroy(ctx);
 	bt::prune_destroy(ctx);
+	bt::mcache_destroy(ctx);
 	bt::front_destroy(ctx);
 	delete ctx;
 }

@@ -61,6 +61,7 @@ struct MatcherState;  // knn.cu
 struct RansacState;   // ransac.cu
 struct FrontState;    // frontend.cu
 struct PruneState;    // prune.cu
+struct MatchCache;    // prune.cu
 
 }  // namespace bt
 
@@ -73,6 +74,7 @@ struct bt_ctx {
 	bt::RansacState* ransac = nullptr;
 	bt::FrontState* front = nullptr;
 	bt::PruneState* prune = nullptr;
+	bt::MatchCache* mcache = nullptr;
 };
 
 namespace bt {
@@ -80,5 +82,6 @@ void solver_destroy(bt_ctx* ctx);
 void matcher_destroy(bt_ctx* ctx);
 void ransac_destroy(bt_ctx* ctx);
 void prune_destroy(bt_ctx* ctx);
+void mcache_destroy(bt_ctx* ctx);
 void front_destroy(bt_ctx* ctx);
 }

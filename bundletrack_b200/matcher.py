@@ -197,8 +197,9 @@ class MatchPipeline:
         dB = (_lib.DescView * n)()
         for i, (fa, fb) in enumerate(pairs):
             A[i], B[i] = self._frame(fa), self._frame(fb)
-            for view, t in ((dA[i], fa["desc"]), (dB[i], fb["desc"])):
-                view.dev, view.n, view.dim, view.pitch_bytes = t.data_ptr(), t.shape[0], t.shape[1], (t.stride(0) * 4 if t.shape[0] > 1 else t.shape[1] * 4)
+            for view, t in ((dA[i], fa.get("desc")), (dB[i], fb.get("desc"))):
+                if t is not None:      # (frames whose descriptors live in the pool need no view)
+                    view.dev, view.n, view.dim, view.pitch_bytes = t.data_ptr(), t.shape[0], t.shape[1], (t.stride(0) * 4 if t.shape[0] > 1 else t.shape[1] * 4)
         return A, B, dA, dB
 
     def prune_mutual(self, pairs, idxAB, idxBA, H, W, K, k=5):
@@ -271,3 +272,93 @@ class MatchPipeline:
         bi = np.array([fb["window_index"] for _, fb in pairs], np.uint32)
         bj = np.array([fa["window_index"] for fa, _ in pairs], np.uint32)
         return np.asarray(entry_off, np.int32), np.asarray(n_entry, np.int32), bi, bj
+
+
+class FindCorres:
+    """`SiftManager::findCorres` (/root/reference/src/FeatureManager.cpp:173-242) on the device-resident chain: per pair (A newer)
+    kNN both ways -> prune -> mutual union -> [non-neighbour: map-point propagation] -> RANSAC -> EntryJ, with the `_matches` cache
+    (a pair is matched once), the map-point bookkeeping (bt_tracks_*) and the Frame::FAIL outcome.  Descriptors live in the pool."""
+
+    def __init__(self, pipeline: "MatchPipeline", max_pairs_cached: int = 512, max_entries_per_pair: int = 0):
+        from .policy import Tracks
+        self.mp = pipeline
+        self.lib = pipeline.lib
+        self.ctx = pipeline.ctx
+        self.tracks = Tracks()
+        self.slot_entries = max_entries_per_pair or 3 * pipeline.max_feats
+        _lib.check(self.lib.bt_match_cache_reserve(self.ctx, ctypes.c_int(max_pairs_cached), ctypes.c_int(self.slot_entries)), "bt_match_cache_reserve")
+        self.failed = set()          # ids of frames the reference would mark Frame::FAIL
+
+    def has(self, id_a: int, id_b: int) -> bool:
+        return bool(self.lib.bt_match_cache_has(self.ctx, ctypes.c_int(id_a), ctypes.c_int(id_b)))
+
+    def find_corres(self, pairs, slots, H, W, K, seed: int = 0):
+        """pairs: list of (frameA newer, frameB older) dicts as for MatchPipeline.match_pairs; slots: their descriptor-pool slots.
+        Pairs already in the cache are skipped (FeatureManager.cpp:176).  The pairs of ONE call must not depend on each other's map
+        points (the reference matches them one after the other): hand a new frame's neighbour pair first, then its other pairs.
+        Returns {(idA, idB): (n_entries, status)} of the pairs processed in this call."""
+        import numpy as np
+        import torch
+        todo = [(k, p) for k, p in enumerate(pairs) if not self.has(p[0]["id"], p[1]["id"])]
+        if not todo:
+            return {}
+        prs = [p for _, p in todo]
+        sl = [slots[k] for k, _ in todo]
+        n = len(prs)
+        A, B, _, _ = self.mp._views(prs)      # (descriptor views unused: the pool is named by slot)
+        extra = (_lib.MatchExtra * n)()
+        keep = []
+        for i, (a, b) in enumerate(prs):
+            if abs(a["id"] - b["id"]) != 1:
+                uv = np.ascontiguousarray(self.tracks.propagate(a["id"], b["id"], np.zeros((0, 4), np.float32)), np.float32)
+                keep.append(uv)
+                extra[i].uv, extra[i].n = (uv.ctypes.data if len(uv) else None), len(uv)
+        cap = sum(a["kpts"].shape[0] + b["kpts"].shape[0] + extra[i].n for i, (a, b) in enumerate(prs))
+        dev = prs[0][0]["kpts"].device
+        ent = torch.empty((max(cap, 1), 8), dtype=torch.int32, device=dev)
+        uvo = torch.empty((max(cap, 1), 4), dtype=torch.float32, device=dev)
+        meta = torch.zeros((3, n), dtype=torch.int32, device=dev)              # n_entry, entry_off, status
+        tot = torch.zeros(4, dtype=torch.int32, device=dev)
+        sa = (ctypes.c_int32 * n)(*[int(a) for a, _ in sl]); sb = (ctypes.c_int32 * n)(*[int(b) for _, b in sl])
+        mp = self.mp
+        _lib.check(self.lib.bt_match_pairs_ex(self.ctx, ctypes.c_int(n), A, B, None, None, sa, sb, ctypes.c_int(H), ctypes.c_int(W),
+                                              ctypes.c_float(K[0]), ctypes.c_float(K[1]), ctypes.c_float(K[2]), ctypes.c_float(K[3]), ctypes.byref(mp.prune),
+                                              ctypes.c_int(mp.ransac_trials), ctypes.c_float(mp.ransac_inlier_dist), ctypes.c_uint64(seed), extra,
+                                              ctypes.c_void_p(ent.data_ptr()), ctypes.c_int(cap), ctypes.c_void_p(meta[0].data_ptr()), ctypes.c_void_p(meta[1].data_ptr()),
+                                              ctypes.c_void_p(tot.data_ptr()), ctypes.c_void_p(meta[2].data_ptr()), ctypes.c_void_p(uvo.data_ptr()), mp.stream), "bt_match_pairs_ex")
+        m = meta.cpu().numpy()                                                  # 3 x n ints: the only per-call read-back besides the inliers' pixel coordinates
+        uv_h = uvo[: int((m[0] + m[1]).max())].cpu().numpy() if m[0].sum() else np.zeros((0, 4), np.float32)
+        ida = (ctypes.c_int32 * n)(*[int(a["id"]) for a, _ in prs]); idb = (ctypes.c_int32 * n)(*[int(b["id"]) for _, b in prs])
+        n_h = np.ascontiguousarray(m[0]); off_h = np.ascontiguousarray(m[1]); st_h = np.ascontiguousarray(m[2])
+        _lib.check(self.lib.bt_match_cache_put(self.ctx, ctypes.c_int(n), ida, idb, ctypes.c_void_p(ent.data_ptr()), n_h.ctypes.data_as(ctypes.c_void_p),
+                                               off_h.ctypes.data_as(ctypes.c_void_p), st_h.ctypes.data_as(ctypes.c_void_p), mp.stream), "bt_match_cache_put")
+        out = {}
+        for i, (a, b) in enumerate(prs):
+            if n_h[i] > 0:        # updateFramePairMapPoints on the surviving matches (all inliers)
+                self.tracks.update_pair(a["id"], b["id"], uv_h[off_h[i]:off_h[i] + n_h[i]])
+            if st_h[i] == 2:
+                self.failed.add(a["id"])
+            out[(a["id"], b["id"])] = (int(n_h[i]), int(st_h[i]))
+        self._keep = (ent, uvo, keep)
+        return out
+
+    def window_entries(self, frames, device):
+        """The EntryJ list Bundler::optimizeGPU builds for the window `frames` (oldest first; window index = position), straight from
+        the cache: returns (device EntryJ tensor, blocks) for SolveWindow(corr_dev=..., blocks=...)."""
+        import numpy as np
+        import torch
+        prs = [(frames[j]["id"], frames[i]["id"], i, j) for i in range(len(frames)) for j in range(i + 1, len(frames))]
+        n = len(prs)
+        ida = (ctypes.c_int32 * n)(*[p[0] for p in prs]); idb = (ctypes.c_int32 * n)(*[p[1] for p in prs])
+        wi = np.array([p[2] for p in prs], np.uint32); wj = np.array([p[3] for p in prs], np.uint32)
+        cap = n * self.slot_entries
+        dst = torch.empty((max(min(cap, 1 << 22), 1), 8), dtype=torch.int32, device=device)
+        off = np.zeros(n, np.int32); cnt = np.zeros(n, np.int32)
+        _lib.check(self.lib.bt_match_cache_gather(self.ctx, ctypes.c_int(n), ida, idb, wi.ctypes.data_as(ctypes.c_void_p), wj.ctypes.data_as(ctypes.c_void_p),
+                                                  ctypes.c_void_p(dst.data_ptr()), ctypes.c_int(dst.shape[0]), off.ctypes.data_as(ctypes.c_void_p), cnt.ctypes.data_as(ctypes.c_void_p),
+                                                  self.mp.stream), "bt_match_cache_gather")
+        return dst, (off, cnt, wi, wj)
+
+    def forget_frame(self, frame_id: int):
+        _lib.check(self.lib.bt_match_cache_forget_frame(self.ctx, ctypes.c_int(frame_id)), "bt_match_cache_forget_frame")
+        self.tracks.forget_frame(frame_id)

@@ -275,6 +275,40 @@ BT_API int bt_match_pairs_pool(bt_ctx* ctx, int n_pairs, const bt_match_frame* A
                         bt_entryj* entry_out, int entry_capacity, int32_t* n_entry_out, int32_t* entry_off_out,
                         int32_t* total_out, void* stream);
 
+/* The rest of SiftManager::findCorres (/root/reference/src/FeatureManager.cpp:173-242) around the same chain:
+ *  - extra[p]: the matches findCorresByMapPoints (:489-520) would APPEND for a NON-neighbour pair - bt_tracks_propagate's output for
+ *    (A[p].frame_id, B[p].frame_id) called with n_existing = 0; the device drops the ones whose (uA,vA) or (uB,vB) already occurs among
+ *    the pair's mutual matches, looks the 3-D points up at round(u), round(v) and appends the rest before RANSAC.  Ignored for
+ *    neighbour pairs (|idA - idB| == 1), as in the reference.
+ *  - status_out[p] (DEVICE, optional): BT_PAIR_OK (>= 5 inliers emitted), BT_PAIR_EMPTY (matches cleared, frame status unchanged) or
+ *    BT_PAIR_FAIL (a neighbour pair ended with fewer than 5 matches: the reference marks frame A Frame::FAIL, :233-241,282-286).
+ *  - uv_out (DEVICE float4 per emitted entry, optional): (uA, vA, uB, vB) of the entry - what updateFramePairMapPoints (:448-485) is fed
+ *    through bt_tracks_update_pair. */
+typedef struct { const float* uv; int n; } bt_match_extra;   /* HOST: n x (uA, vA, uB, vB) */
+enum { BT_PAIR_OK = 0, BT_PAIR_EMPTY = 1, BT_PAIR_FAIL = 2 };
+BT_API int bt_match_pairs_ex(bt_ctx* ctx, int n_pairs, const bt_match_frame* A, const bt_match_frame* B,
+                      const bt_desc_view* dA, const bt_desc_view* dB, const int32_t* slotA, const int32_t* slotB,
+                      int H, int W, float fx, float fy, float cx, float cy, const bt_prune_params* prune,
+                      int ransac_trials, float ransac_inlier_dist, uint64_t ransac_seed, const bt_match_extra* extra,
+                      bt_entryj* entry_out, int entry_capacity, int32_t* n_entry_out, int32_t* entry_off_out, int32_t* total_out,
+                      int32_t* status_out, float* uv_out, void* stream);
+
+/* Per-pair result cache: SiftManager::_matches (findCorres returns at once for a pair it has seen, FeatureManager.cpp:176;
+ * forgetFrame drops a frame's pairs, :131-148).  Entries stay on the device; frames are named by Frame::_id.
+ *   put     stores the blocks a bt_match_pairs* call produced (host copies of its n_entry / entry_off / status arrays).
+ *   has     1 / 0.
+ *   gather  writes the cached blocks of the listed pairs back to back into dst_dev with imgIdx_i / imgIdx_j rewritten to the given
+ *           window indices (a frame's index changes from window to window) and fills block_off / block_n for bt_window::corr_dev;
+ *           pairs with no cached matches contribute empty blocks. */
+BT_API int bt_match_cache_reserve(bt_ctx* ctx, int max_pairs_cached, int max_entries_per_pair);
+BT_API int bt_match_cache_put(bt_ctx* ctx, int n_pairs, const int32_t* idA, const int32_t* idB, const bt_entryj* entry_dev,
+                       const int32_t* n_entry_host, const int32_t* entry_off_host, const int32_t* status_host, void* stream);
+BT_API int bt_match_cache_has(bt_ctx* ctx, int idA, int idB);
+BT_API int bt_match_cache_status(bt_ctx* ctx, int idA, int idB, int* n_entry, int* status);
+BT_API int bt_match_cache_gather(bt_ctx* ctx, int n_pairs, const int32_t* idA, const int32_t* idB, const uint32_t* win_i, const uint32_t* win_j,
+                          bt_entryj* dst_dev, int capacity, int32_t* block_off_host, int32_t* block_n_host, void* stream);
+BT_API int bt_match_cache_forget_frame(bt_ctx* ctx, int frame_id);
+
 /* ---- frame front end: Frame::processDepth + Frame::depthToCloudAndNormals -------------------------
  * /root/reference/src/Frame.cpp:152-233 -> CUDAImageUtil::erodeDepthMap, gaussFilterDepthMap x2,
  * convertDepthFloatToCameraSpaceFloat4, computeNormals (src/cuda/CUDAImageUtil.cu:676-806,310-336,342-423), fused into

@@ -154,14 +154,29 @@ def collect_mutual(A, B, mAB, mBA):
     return np.asarray(rows, np.float32).reshape(-1, 10)
 
 
-def find_corres(A, B, K, prune, u3, ransac_inlier_dist, k=5):
-    """findCorresbyNN + runRansacBetween for one pair (A newer).  prune = (max_dist_nn, cos_nn, max_dist_n, cos_n).
-    Returns (mutual rows, inlier row ids or None if the pair was dropped)."""
+def find_corres(A, B, K, prune, u3, ransac_inlier_dist, k=5, propagated=None):
+    """findCorresbyNN [+ findCorresByMapPoints for a non-neighbour pair] + runRansacBetween for one pair (A newer).
+    prune = (max_dist_nn, cos_nn, max_dist_n, cos_n).  propagated: [m,4] (uA,vA,uB,vB) of the map points both frames observe, in
+    the order SiftManager::findCorresByMapPoints walks them (/root/reference/src/FeatureManager.cpp:489-520): appended unless an
+    existing match has the same (uA,vA) or (uB,vB), with the organised-cloud points at round(u), round(v).
+    Returns (mutual rows incl. the appended ones, inlier row ids or None if the pair was dropped)."""
     iAB, _ = knn(A["desc"], B["desc"], k)
     iBA, _ = knn(B["desc"], A["desc"], k)
     neighbor = abs(A["id"] - B["id"]) == 1
     max_dist, cos_max = (prune[2], prune[3]) if neighbor else (prune[0], prune[1])
     rows = collect_mutual(A, B, prune_matches(A, B, iAB, K, max_dist, cos_max), prune_matches(B, A, iBA, K, max_dist, cos_max))
+    if propagated is not None and not neighbor and len(propagated):
+        H, W = A["depth"].shape
+        extra = []
+        for uA, vA, uB, vB in np.asarray(propagated, np.float32):
+            if len(rows) and (((rows[:, 0] == uA) & (rows[:, 1] == vA)) | ((rows[:, 2] == uB) & (rows[:, 3] == vB))).any():
+                continue
+            ua, va, ub, vb = _round_half_away(uA), _round_half_away(vA), _round_half_away(uB), _round_half_away(vB)
+            pa = _cloud_point(A["depth"], K, ua, va) if (0 <= ua < W and 0 <= va < H) else np.zeros(3, np.float32)
+            pb = _cloud_point(B["depth"], K, ub, vb) if (0 <= ub < W and 0 <= vb < H) else np.zeros(3, np.float32)
+            extra.append(np.concatenate([[uA, vA, uB, vB], pa, pb]).astype(np.float32))
+        if extra:
+            rows = np.concatenate([rows.reshape(-1, 10), np.asarray(extra, np.float32)], 0)
     if len(rows) <= 5:
         return rows, None
     PA = rows[:, 4:7] @ A["pose"][:3, :3].T.astype(np.float32) + A["pose"][:3, 3].astype(np.float32)

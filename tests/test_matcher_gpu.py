@@ -386,3 +386,78 @@ def test_device_resident_handoff_equals_host_path(cuda_device):
 def torch_from(x, dev):
     import torch
     return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+
+def test_find_corres_sequence_with_propagation_cache_and_fail(cuda_device):
+    """SiftManager::findCorres over a 5-frame sequence on the device chain (FindCorres): every new frame is matched against its
+    neighbour first, then against the older frames WITH the map-point matches propagated through the frames in between
+    (findCorresByMapPoints), pair by pair like the reference; compared with the oracle's find_corres + Tracks restatement.  Then the
+    cache: a second request matches nothing, the window's EntryJ list comes straight from the cache and drives the solver to the
+    poses of the host path; a frame with too few neighbour matches is reported Frame::FAIL."""
+    import torch
+    from bundletrack_b200.matcher import MatchPipeline, FindCorres
+    from bundletrack_b200.optimizer import OptimizerGpu, SolveWindow
+    from oracle import policy_oracle as po
+    yml = {"bundle": {"num_iter_outter": 7, "num_iter_inner": 5, "robust_delta": 0.005, "image_downscale": 4}, "p2p": {"max_dist": 0.02, "max_normal_angle": 45},
+           "feature_corres": {"max_dist_no_neighbor": 0.02, "max_normal_no_neighbor": 45, "max_dist_neighbor": 10000, "max_normal_neighbor": 180},
+           "ransac": {"max_iter": 2000, "inlier_dist": 0.01}}
+    N = 5
+    w, host, devf = _feature_window(21, N, 500, cuda_device)
+    mp = MatchPipeline(yml, max_pairs=8, max_feats=512)
+    mp.pool_reserve(N)
+    for f in range(N):
+        mp.pool_store(f, devf[f]["desc"])
+    fc = FindCorres(mp)
+    u3 = np.load(os.path.join(GOLD, "curand_xorwow_seed0.npy"))[:2000]
+    prm = (mp.prune.max_dist_no_neighbor, mp.prune.cos_max_normal_no_neighbor, mp.prune.max_dist_neighbor, mp.prune.cos_max_normal_neighbor)
+    otracks = po.Tracks()
+    n_prop_used = 0
+    host_entries = {}
+    for f in range(1, N):
+        for a, b in [(f, f - 1)] + [(f, j) for j in range(f - 2, -1, -1)]:
+            res = fc.find_corres([(devf[a], devf[b])], [(a, b)], w.H, w.W, w.K)
+            n_dev, st_dev = res[(a, b)]
+            neighbor = a - b == 1
+            prop = None if neighbor else otracks.propagate(a, b, np.zeros((0, 4), np.float32))
+            rows, ids = mo.find_corres(host[a], host[b], w.K, prm, u3, 0.01, propagated=prop)
+            n_want = 0 if ids is None else len(ids)
+            assert abs(n_dev - n_want) <= max(2, n_want // 50), (a, b, n_dev, n_want)
+            if n_want >= 8 or n_want == 0 and n_dev == 0:
+                assert st_dev == (0 if n_want else (2 if neighbor else 1)), (a, b, st_dev)
+            # the device's entries are rows of the oracle's candidate list (mutual matches + appended propagated ones), bit for bit
+            ent, blocks = fc.window_entries([{"id": b}, {"id": a}], cuda_device)
+            e = ent[: int(blocks[1][0])].cpu().numpy().view(np.uint8).reshape(-1).view(synth.ENTRYJ_DTYPE)
+            assert len(e) == n_dev and (e["imgIdx_i"] == 0).all() and (e["imgIdx_j"] == 1).all()
+            host_entries[(a, b)] = e
+            if n_dev:
+                allrows = np.concatenate([rows[:, 7:10], rows[:, 4:7]], 1)
+                n_nn = len(mo.find_corres(host[a], host[b], w.K, prm, u3, 0.01)[0])
+                for x in e:
+                    d = np.abs(allrows - np.concatenate([x["pos_i"], x["pos_j"]])).max(axis=1)
+                    assert d.min() <= 2e-6
+                    n_prop_used += int(d.argmin() >= n_nn)
+            if ids is not None:      # updateFramePairMapPoints of the restatement
+                otracks.update_pair(a, b, rows[ids][:, :4])
+    assert n_prop_used >= 3, n_prop_used                      # propagated map-point matches made it through RANSAC into the EntryJ list
+    assert fc.tracks.stats()[0] > 20
+    # ---- the cache: nothing is matched twice; a window's list is assembled from it
+    assert fc.find_corres([(devf[4], devf[2]), (devf[3], devf[0])], [(4, 2), (3, 0)], w.H, w.W, w.K) == {}
+    frames = [{"id": k} for k in range(N)]
+    ent, blocks = fc.window_entries(frames, cuda_device)
+    total = int(blocks[1].sum())
+    assert total == sum(len(v) for v in host_entries.values()) and total >= 40
+    corr_h = ent[:total].cpu().numpy().view(np.uint8).reshape(-1).view(synth.ENTRYJ_DTYPE)
+    opt = OptimizerGpu(yml, max_windows=1, max_frames=8, max_corr=8192)
+    depth = [f["depth"] for f in devf]; normal = [f["normal"] for f in devf]
+    via_dev = opt.optimizeWindows([SolveWindow(None, w.H, w.W, depth, normal, w.poses_init, w.K, corr_dev=ent, blocks=blocks)])[0]
+    via_host = opt.optimizeWindows([SolveWindow(corr_h, w.H, w.W, depth, normal, w.poses_init, w.K)])[0]
+    assert np.array_equal(via_dev, via_host)
+    opt.close()
+    # ---- forgetFrame drops the frame's pairs; a neighbour pair with (almost) no features is a Frame::FAIL
+    fc.forget_frame(4)
+    assert not fc.has(4, 3) and fc.has(3, 2)
+    few = dict(devf[4], kpts=devf[4]["kpts"][:0].contiguous(), id=4)       # feature detection found nothing
+    mp.pool_store(4, devf[4]["desc"][:0].contiguous())
+    res = fc.find_corres([(few, devf[3])], [(4, 3)], w.H, w.W, w.K)
+    assert res[(4, 3)] == (0, 2) and 4 in fc.failed
+    mp.close()
