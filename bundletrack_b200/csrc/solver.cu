@@ -50,6 +50,7 @@ namespace bt {
 static constexpr int kTileVals = 28;          // 21 (sym 6x6) + 6 (rhs) + 1 (#correspondences found)
 static constexpr int kGrpVals = 44;           // sparse moment sums per pair group
 static constexpr int kMaxFrames = 32;
+static constexpr size_t kTailSmemMax = 224 * 1024;   // dynamic shared memory a tail may use (227 KB per CTA minus k_solve's static arrays)
 static constexpr int kSmallCtaMinWindows = 1 << 30;  // (measured on B200: 128-thread CTAs are SLOWER, 0.55 vs 0.46 ms for 32 windows - the variant stays behind BT_SOLVE_NT=128 only)
 static constexpr float kEps = 0.000001f;      // FLOAT_EPSILON, /root/reference/src/cuda/SolverUtil.h:10
 
@@ -111,6 +112,7 @@ struct SolveArgs {
 	int* queue;           // [1]
 	long long* n_src_px;  // [1] stats
 	int chunk;
+	int grp_in_smem;      // 0: the tail reads the groups' moment sums from global memory (windows too big for shared memory)
 	int grid_ctas;        // CTAs k_solve will be launched with (tile planning targets one wave for small batches)
 	bt_solver_params prm;
 	float* dbg_JtJ; float* dbg_Jtr; int dbg_stride;   // optional dense-system dump (last GN iteration)
@@ -786,12 +788,14 @@ struct TailSmem {
 	int dimp, ld;
 };
 static constexpr int kFS = 20, kFD = 28;
-__host__ __device__ inline size_t tail_smem_floats(int N, int P, int G) {
+// (grp_in_smem = false: big windows - 30 frames, 435 groups - leave the 44 moment sums per group in global memory and read them
+// through L2; with them the tail of such a window would need 279 KB of shared memory)
+__host__ __device__ inline size_t tail_smem_floats(int N, int P, int G, bool grp_in_smem = true) {
 	const int dimp = 6 * (N - 1), ld = dimp | 1;
-	return (size_t)N * 12 + (size_t)dimp * ld + 7 * (size_t)dimp + (size_t)P * kTileVals + (size_t)G * kGrpVals +
+	return (size_t)N * 12 + (size_t)dimp * ld + 7 * (size_t)dimp + (size_t)P * kTileVals + (grp_in_smem ? (size_t)G * kGrpVals : 0) +
 	       (size_t)N * (kFS + kFD) + (size_t)(3 * G + 1 + 4 * P) + (size_t)(2 * (N + 1) + 2 * G + 2 * P) + 16;
 }
-__device__ inline void tail_carve(float* base, int N, int P, int G, TailSmem& s) {
+__device__ inline void tail_carve(float* base, int N, int P, int G, TailSmem& s, bool grp_in_smem) {
 	s.dimp = 6 * (N - 1); s.ld = s.dimp | 1;
 	float* q = base;
 	s.T = q; q += N * 12;
@@ -799,7 +803,7 @@ __device__ inline void tail_carve(float* base, int N, int P, int G, TailSmem& s)
 	s.rhs = q; q += s.dimp; s.Minv = q; q += s.dimp; s.r = q; q += s.dimp; s.z = q; q += s.dimp;
 	s.p = q; q += s.dimp; s.Ap = q; q += s.dimp; s.delta = q; q += s.dimp;
 	s.pairW = q; q += P * kTileVals;
-	s.grp = q; q += G * kGrpVals;
+	s.grp = q; if (grp_in_smem) q += G * kGrpVals;
 	s.fS = q; q += N * kFS; s.fD = q; q += N * kFD;
 	int* iq = reinterpret_cast<int*>(q);
 	s.gi = iq; iq += G; s.gj = iq; iq += G; s.gstart = iq; iq += G + 1;
@@ -885,7 +889,9 @@ template <int NT> __device__ void window_tail(const SolveArgs& a, const WinDesc&
 	const int tid = threadIdx.x, lane = tid & 31;
 	const int N = wd.n_frames, P = wd.n_pairs, G = wd.n_groups;
 	TailSmem s;
-	tail_carve(smem_base, N, P, G, s);
+	const bool gsm = a.grp_in_smem != 0;
+	tail_carve(smem_base, N, P, G, s, gsm);
+	const float* grp_g = a.grp_sums + (size_t)wd.grp_off * kGrpVals;      // the same sums in global memory (written with st.cg by the sparse tile)
 	const int dimp = s.dimp, ld = s.ld;
 	const float wS = a.prm.w_sparse;
 	const bool use_dense = a.prm.w_dense > 0.f && P > 0;
@@ -911,7 +917,7 @@ template <int NT> __device__ void window_tail(const SolveArgs& a, const WinDesc&
 	PROF_T(1);
 
 	// ---- P1: the sparse moment sums were computed by sparse_sums() while the window's dense tiles were still running
-	for (int k = tid; k < G * kGrpVals; k += NT) s.grp[k] = __ldcg(a.grp_sums + (size_t)wd.grp_off * kGrpVals + k);
+	if (gsm) for (int k = tid; k < G * kGrpVals; k += NT) s.grp[k] = __ldcg(grp_g + k);
 	__syncthreads();
 	PROF_T(2);
 	// ---- P2: per-pair sums over the pair's tiles (already in the model frame; the tile epilogue applied X S' X^T).  A pair's
@@ -969,8 +975,9 @@ template <int NT> __device__ void window_tail(const SolveArgs& a, const WinDesc&
 			else { oq = 43; os = 43; }
 			for (int q = s.fg_start[f]; q < s.fg_start[f + 1]; q++) {
 				const int item = s.fg_items[q];
-				const float* m = s.grp + (item & 0xffff) * kGrpVals;
-				acc += (item >> 16) ? sg * m[os] : m[oq];      // role 0: this frame is the group's i (q side); 1: j (s side)
+				const int mo = (item & 0xffff) * kGrpVals + ((item >> 16) ? os : oq);      // role 0: this frame is the group's i (q side); 1: j (s side)
+				const float mv = gsm ? s.grp[mo] : __ldcg(grp_g + mo);
+				acc += (item >> 16) ? sg * mv : mv;
 			}
 			s.fS[f * kFS + e] = acc;
 		} else {
@@ -1034,7 +1041,10 @@ template <int NT> __device__ void window_tail(const SolveArgs& a, const WinDesc&
 		const int g = k >> 2, sb = k & 3;
 		const int gi = s.gi[g], gj = s.gj[g];
 		if (gi < 1 || gj < 1 || gi == gj) continue;
-		const float* m = s.grp + g * kGrpVals;
+		float ml[28];
+#pragma unroll
+		for (int q = 0; q < 28; q++) ml[q] = gsm ? s.grp[g * kGrpVals + q] : __ldcg(grp_g + (size_t)g * kGrpVals + q);
+		const float* m = ml;
 		const int r0 = (sb >> 1) * 3, c0 = (sb & 1) * 3;
 		const float tr = m[19] + m[23] + m[27];
 #pragma unroll
@@ -1381,6 +1391,7 @@ struct SolverState {
 	std::vector<int> n_frames;
 	bool staged = false, debug = false, timing = false;
 	double host_us[6] = { 0, 0, 0, 0, 0, 0 };   // host time of the last call: tables+early upload, prep launch, correspondence scan+staging, run (launch), fetch (copy + wait), total
+	bool grp_in_smem = true;
 	int force_nt = 0;                    // test / tuning knob (BT_SOLVE_NT environment variable): 128 or 256 forces the CTA size
 	int launches = 0;
 	int attr_bytes = 0, occ = BT_SOLVE_MIN_CTAS, occ_smem = -1, occ_nt = 0;
@@ -1620,7 +1631,7 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 	s->host_us[1] = us_since(t_h0) - s->host_us[0];
 
 	// ==== phase 2 (the GPU is already busy in the fused call): correspondences -> groups, membership CSR, pinned copy, chunked upload
-	size_t c_off = 0, g_off = 0, m_off = 0, smem_need = 0, sent = 0;
+	size_t c_off = 0, g_off = 0, m_off = 0, smem_need = 0, smem_lean = 0, sent = 0;
 	const bt_entryj* run_src = nullptr; size_t run_dst = 0, run_n = 0;      // pending in-place transfer from page-locked caller memory
 	std::vector<int> bin;
 	std::vector<char> seen;
@@ -1766,6 +1777,7 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 			m_off += (size_t)(2 * (N + 1) + 2 * ng + 2 * np);
 		}
 		smem_need = std::max(smem_need, tail_smem_floats(N, np, ng) * sizeof(float));
+		smem_lean = std::max(smem_lean, tail_smem_floats(N, np, ng, false) * sizeof(float));
 		c_off += n_valid; g_off += ng; p_off += np;
 		// upload what has accumulated once it is worth a copy (>= 256 KB), and whatever is left after the last window
 		if ((c_off - sent) * sizeof(bt_entryj) >= 256 * 1024 || (w + 1 == n_windows && c_off > sent)) {
@@ -1774,7 +1786,9 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 		}
 	}
 	if (run_n) BT_CUDA(cudaMemcpyAsync(s->stage_dev.as<char>() + L.corr + run_dst * sizeof(bt_entryj), run_src, run_n * sizeof(bt_entryj), cudaMemcpyHostToDevice, s->copy_stream));
-	BT_REQUIRE(smem_need <= 200 * 1024, BT_ERR_CAPACITY, "bt_solve_stage: window needs %zu bytes of shared memory (> 200 KB)", smem_need);
+	s->grp_in_smem = smem_need <= kTailSmemMax;
+	if (!s->grp_in_smem) smem_need = smem_lean;
+	BT_REQUIRE(smem_need <= kTailSmemMax, BT_ERR_CAPACITY, "bt_solve_stage: window needs %zu bytes of shared memory (> %d KB)", smem_need, (int)(kTailSmemMax / 1024));
 	s->smem_bytes = (int)smem_need;
 	BT_CUDA(cudaMemcpyAsync(s->stage_dev.as<char>() + L.late, hb + L.late, L.corr - L.late, cudaMemcpyHostToDevice, s->copy_stream));      // group tables, CSR, WinSparse
 	BT_CUDA(cudaEventRecord(s->ev_corr, s->copy_stream));
@@ -1799,7 +1813,7 @@ extern "C" int bt_solve_stage(bt_ctx* ctx, int n_windows, const bt_window* windo
 static int ensure_occupancy(bt_ctx* ctx) {
 	SolverState* s = ctx->solver;
 	if (s->attr_bytes == 0) {      // the attribute belongs to (function, device), not to the context: set it to the ceiling stage_impl enforces, once,
-		s->attr_bytes = 200 * 1024;   // so that a second context on the same device can never lower what another context's next launch needs
+		s->attr_bytes = (int)kTailSmemMax;   // so that a second context on the same device can never lower what another context's next launch needs
 		BT_CUDA(cudaFuncSetAttribute(k_solve<256, BT_SOLVE_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->attr_bytes));
 		BT_CUDA(cudaFuncSetAttribute(k_solve<128, 2 * BT_SOLVE_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->attr_bytes));
 	}
@@ -1831,7 +1845,7 @@ static SolveArgs make_args(bt_ctx* ctx) {
 	a.pair_tile0 = s->pair_tile0.as<int>(); a.pair_ntile = s->pair_ntile.as<int>();
 	a.n_tiles_total = s->scalars.as<int>(); a.queue = s->scalars.as<int>() + 1; a.n_src_px = (long long*)(s->scalars.as<char>() + 16);
 	a.tiles_done = s->tiles_done.as<int>(); a.iter_done = s->iter_done.as<int>();
-	a.chunk = s->chunk; a.prm = s->prm; a.grid_ctas = ctx->sm_count * s->occ;
+	a.chunk = s->chunk; a.grp_in_smem = s->grp_in_smem ? 1 : 0; a.prm = s->prm; a.grid_ctas = ctx->sm_count * s->occ;
 	if (s->prof_cap > 0) { a.prof = s->prof.as<long long>(); a.prof_cap = s->prof_cap; }
 	if (s->debug) { a.dbg_JtJ = s->dbgJ.as<float>(); a.dbg_Jtr = s->dbgR.as<float>(); a.dbg_stride = 6 * s->lim.max_frames; a.dbg_cnt = s->dbgC.as<float>(); a.dbg_cnt_stride = s->max_pairs; }
 	return a;
