@@ -185,6 +185,8 @@ class OptimizerGpu:
         self._inflight.append((windows, poses, keep, arr))
 
     def end(self) -> List[np.ndarray]:
+        if not getattr(self, "_inflight", None):      # nothing begun: let the library say so
+            _lib.check(self.lib.bt_solve_windows_end(self.ctx, ctypes.c_void_p(0)), "bt_solve_windows_end")
         windows, poses, _, _ = self._inflight.pop(0)
         out = np.empty_like(poses)
         _lib.check(self.lib.bt_solve_windows_end(self.ctx, out.ctypes.data_as(ctypes.c_void_p)), "bt_solve_windows_end")
