@@ -72,7 +72,15 @@ struct WinDesc {
 // correspondences while the GPU already works); window_tail reads them from here, the copies inside WinDesc are unused.
 struct WinSparse { int n_corr, n_groups, corr_off, grp_off, mem_off, unique_blocks, pad0, pad1; };
 
-struct Tile { int win; int pair; int start; int count; };  // pair == -2 => the window's sparse tile (moment sums of its correspondences)
+// One unit of work of k_solve.  Everything the tile's prologue needs travels in the record (frame slots, map pointers, the window's
+// tile count), so that claiming a tile costs ONE dependent load - and that one is issued a whole tile ahead (k_solve keeps the next
+// record in shared memory).  pair == -2 => the window's sparse tile (moment sums of its correspondences).
+struct __align__(16) Tile {
+	int win; int pair; int start; int count;
+	int tgt_slot; int src_slot;          // global frame slots (frame_off + target / source) of the pair
+	int n_tiles_win; int pad;            // tiles of the window per GN iteration (dense + the sparse one)
+	const float4* src; const float4* tex;   // compacted source list of the source frame, texel map of the target frame
+};
 
 struct SolveArgs {
 	const WinDesc* wins;
@@ -114,6 +122,7 @@ struct SolveArgs {
 	int chunk;
 	int grp_in_smem;      // 0: the tail reads the groups' moment sums from global memory (windows too big for shared memory)
 	int grid_ctas;        // CTAs k_solve will be launched with (tile planning targets one wave for small batches)
+	float d2max;          // largest float whose correctly rounded square root is <= prm.dense_dist_thresh (computed once on the host)
 	bt_solver_params prm;
 	float* dbg_JtJ; float* dbg_Jtr; int dbg_stride;   // optional dense-system dump (last GN iteration)
 	float* dbg_cnt; int dbg_cnt_stride;               // optional per-pair #correspondences found (last GN iteration)
@@ -206,6 +215,27 @@ __device__ __noinline__ void se3_log(const float T[12], V3& rot, V3& trans) {
 __device__ __forceinline__ float huber_w(float e, float delta) {  // rho.y of huberLoss, SolverBundlingUtil.h:24-39
 	return (e <= delta * delta) ? 1.0f : delta / sqrtf(e);
 }
+// The dense pixel loop's quotients.  The reference is compiled with -use_fast_math (/root/reference/CMakeLists.txt): its `a / b` is
+// rcp.approx x a and its sqrt is approximate as well, so one MUFU reciprocal (1 ulp) is as faithful to it as a correctly rounded
+// one - and a correctly rounded __frcp_rn / IEEE division costs 10-20 instructions each, four times per pixel.
+#ifdef BT_DENSE_EXACT_RCP      // (variant build for A/B parity measurements: correctly rounded reciprocals / IEEE Huber weight)
+__device__ __forceinline__ float rcp_fast(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ float huber_w_fast(float e, float delta) { return huber_w(e, delta); }
+#else
+__device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float huber_w_fast(float e, float delta) {
+	float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e));
+	return (e <= delta * delta) ? 1.0f : delta * r;
+}
+#endif
+// 256-bit global load through the read-only path (sm_100: LDG.E.ENL2.256.CONSTANT): one instruction per 32-byte texel / source record
+struct __align__(32) F8 { float4 lo, hi; };
+__device__ __forceinline__ F8 ldg256(const float4* p) {
+	F8 r;
+	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w) : "l"(p));
+	return r;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -232,6 +262,13 @@ __device__ __forceinline__ int ticket_acq_rel(int* p) {
 	asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(old) : "l"(p) : "memory");
 	return old;
 }
+// asynchronous global -> shared copy of one 48-byte tile record (no registers held while it is in flight)
+__device__ __forceinline__ void tile_fetch_async(void* smem_dst, const void* gsrc) {
+	const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n cp.async.cg.shared.global [%2], [%3], 16;\n cp.async.cg.shared.global [%4], [%5], 16;"
+	             ::"r"(d), "l"(gsrc), "r"(d + 16), "l"((const char*)gsrc + 16), "r"(d + 32), "l"((const char*)gsrc + 32) : "memory");
+}
+__device__ __forceinline__ void tile_fetch_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void st_release(int* p, int v) {
 	asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -643,7 +680,7 @@ __device__ void plan_body(const SolveArgs& a, WinDesc* wins_rw) {
 				if (p < np) a.pair_tile0[poff + p] = 1 + carry + incl - v;      // slot 0 of the window is its sparse tile
 				carry += __shfl_sync(0xffffffffu, incl, 31);
 			}
-			if (lane == 0 && fits) { Tile tl; tl.win = w; tl.pair = -2; tl.start = 0; tl.count = 0; a.tiles[s_cnt[wl]] = tl; }
+			if (lane == 0 && fits) { Tile tl; tl.win = w; tl.pair = -2; tl.start = 0; tl.count = 0; tl.tgt_slot = tl.src_slot = 0; tl.n_tiles_win = wins_rw[w].n_tiles; tl.pad = 0; tl.src = tl.tex = nullptr; a.tiles[s_cnt[wl]] = tl; }
 		}
 		__syncthreads();
 		PROF_T(3);
@@ -656,7 +693,11 @@ __device__ void plan_body(const SolveArgs& a, WinDesc* wins_rw) {
 				int per;
 				const int nch = chunks_for(n, chunk, per);
 				int t = s_cnt[lo - base] + a.pair_tile0[q];
-				for (int c = 0; c < nch; c++) { Tile tl; tl.win = lo; tl.pair = q - pair_off_w; tl.start = c * per; tl.count = min(per, n - c * per); a.tiles[t++] = tl; }
+				Tile tl; tl.win = lo; tl.pair = q - pair_off_w; tl.pad = 0;
+				tl.src_slot = a.pair_src_slot[q]; tl.tgt_slot = a.wins[lo].frame_off + (int)a.pairs[q].x;
+				tl.n_tiles_win = wins_rw[lo].n_tiles;
+				tl.src = a.src_tab[tl.src_slot]; tl.tex = a.texel_tab[tl.tgt_slot];
+				for (int c = 0; c < nch; c++) { tl.start = c * per; tl.count = min(per, n - c * per); a.tiles[t++] = tl; }
 			}
 		}
 		__syncthreads();
@@ -665,7 +706,7 @@ __device__ void plan_body(const SolveArgs& a, WinDesc* wins_rw) {
 		__syncthreads();
 	}
 	if (tid == 0) {
-		*a.n_tiles_total = (s_carry <= a.max_tiles) ? s_carry : -1;   // -1 => capacity error reported by the host
+		*a.n_tiles_total = (s_carry <= a.max_tiles && (long long)s_carry * a.prm.num_iter_outer < 0x7fffff00ll) ? s_carry : -1;   // -1 => capacity error reported by the host
 		*a.n_src_px = (long long)s_px;
 	}
 	PROF_T(5);
@@ -690,28 +731,27 @@ template <int NT> __device__ __forceinline__ void tile_pixels(const SolveArgs& a
 	const float dmin = a.prm.depth_min, dmax = a.prm.depth_max, cos_t = a.prm.dense_cos_normal_thresh;
 	const float delta = a.prm.robust_delta, wdense = a.prm.w_dense;
 	// `sqrtf(d2) <= dist_t` evaluated as `d2 <= d2max`, d2max = the largest float whose correctly rounded square root is <= dist_t
-	// (same truth value for every float, no square root in the loop)
-	float d2max = a.prm.dense_dist_thresh * a.prm.dense_dist_thresh;
-	while (d2max > 0.f && sqrtf(d2max) > a.prm.dense_dist_thresh) d2max = __int_as_float(__float_as_int(d2max) - 1);
-	while (sqrtf(__int_as_float(__float_as_int(d2max) + 1)) <= a.prm.dense_dist_thresh) d2max = __int_as_float(__float_as_int(d2max) + 1);
+	// (same truth value for every float, no square root in the loop; found once on the host, make_args)
+	const float d2max = a.d2max;
 	const float4* sp = src + 2 * (size_t)start;
 	int k = threadIdx.x;
-	float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0, n0 = c0, n1 = c0, f0 = c0, f1 = c0;   // current, next, next-next source records
-	if (k < count) { c0 = __ldg(sp + 2 * k); c1 = __ldg(sp + 2 * k + 1); }
-	if (k + NT < count) { n0 = __ldg(sp + 2 * (k + NT)); n1 = __ldg(sp + 2 * (k + NT) + 1); }
+	F8 cc, nn, ff;      // current, next, next-next source records
+	cc.lo = cc.hi = nn.lo = nn.hi = ff.lo = ff.hi = make_float4(0.f, 0.f, 0.f, 0.f);
+	if (k < count) cc = ldg256(sp + 2 * k);
+	if (k + NT < count) nn = ldg256(sp + 2 * (k + NT));
 	for (; k < count; k += NT) {
 		const int k2 = k + 2 * NT;
-		if (k2 < count) { f0 = __ldg(sp + 2 * k2); f1 = __ldg(sp + 2 * k2 + 1); }
-		const float4 s0 = c0, s1 = c1;
-		c0 = n0; c1 = n1; n0 = f0; n1 = f1;
+		if (k2 < count) ff = ldg256(sp + 2 * k2);
+		const float4 s0 = cc.lo, s1 = cc.hi;
+		cc = nn; nn = ff;
 		const float px = s0.x, py = s0.y, pz = s0.z, nx = s0.w, ny = s1.x, nz = s1.y;
 		// camPosSrcToTgt = transform * camPosSrc ; nrmj = transform(3x3) * n  (w of the normal is 0)
 		const float tx = m00 * px + m01 * py + m02 * pz + m03;
 		const float ty = m10 * px + m11 * py + m12 * pz + m13;
 		const float tz = m20 * px + m21 * py + m22 * pz + m23;
-		// cameraToDepth, CUDACameraUtil.h:9-14.  One correctly rounded reciprocal serves both quotients (the reference itself is built
-		// with -use_fast_math: its divisions are approximate; either way the result differs from the exact quotient by an ulp or two)
-		const float itz = __frcp_rn(tz);
+		// cameraToDepth, CUDACameraUtil.h:9-14.  One reciprocal serves both quotients (the reference itself is built with
+		// -use_fast_math: its divisions are rcp.approx too; either way the result differs from the exact quotient by an ulp or two)
+		const float itz = rcp_fast(tz);
 		const float sx = (tx * fx) * itz + cx, sy = (ty * fy) * itz + cy;
 		const int ix = (int)roundf(sx), iy = (int)roundf(sy);
 		if (!(ix >= 0 && iy >= 0 && ix < (int)W && iy < (int)Hh)) continue;
@@ -724,23 +764,23 @@ template <int NT> __device__ __forceinline__ void tile_pixels(const SolveArgs& a
 		const bool inx0 = (unsigned)x0 < W, inx1 = (unsigned)(x0 + 1) < W, iny0 = (unsigned)y0 < Hh, iny1 = (unsigned)(y0 + 1) < Hh;
 		if (iny0) {
 			const float4* row = tex + 2 * ((size_t)y0 * W);
-			if (inx0) { const float4 cp = __ldg(row + 2 * x0); const float2 nr = __ldg(reinterpret_cast<const float2*>(row + 2 * x0 + 1)); const float wt = 1.0f - al;
+			if (inx0) { const F8 t8 = ldg256(row + 2 * x0); const float4 cp = t8.lo; const float2 nr = make_float2(t8.hi.x, t8.hi.y); const float wt = 1.0f - al;
 				a0[0] += wt * cp.x; a0[1] += wt * cp.y; a0[2] += wt * cp.z; b0[0] += wt * cp.w; b0[1] += wt * nr.x; b0[2] += wt * nr.y; w0 += wt; }
-			if (inx1) { const float4 cp = __ldg(row + 2 * (x0 + 1)); const float2 nr = __ldg(reinterpret_cast<const float2*>(row + 2 * (x0 + 1) + 1)); const float wt = al;
+			if (inx1) { const F8 t8 = ldg256(row + 2 * (x0 + 1)); const float4 cp = t8.lo; const float2 nr = make_float2(t8.hi.x, t8.hi.y); const float wt = al;
 				a0[0] += wt * cp.x; a0[1] += wt * cp.y; a0[2] += wt * cp.z; b0[0] += wt * cp.w; b0[1] += wt * nr.x; b0[2] += wt * nr.y; w0 += wt; }
 		}
 		if (iny1) {
 			const float4* row = tex + 2 * ((size_t)(y0 + 1) * W);
-			if (inx0) { const float4 cp = __ldg(row + 2 * x0); const float2 nr = __ldg(reinterpret_cast<const float2*>(row + 2 * x0 + 1)); const float wt = 1.0f - al;
+			if (inx0) { const F8 t8 = ldg256(row + 2 * x0); const float4 cp = t8.lo; const float2 nr = make_float2(t8.hi.x, t8.hi.y); const float wt = 1.0f - al;
 				a1[0] += wt * cp.x; a1[1] += wt * cp.y; a1[2] += wt * cp.z; b1[0] += wt * cp.w; b1[1] += wt * nr.x; b1[2] += wt * nr.y; w1 += wt; }
-			if (inx1) { const float4 cp = __ldg(row + 2 * (x0 + 1)); const float2 nr = __ldg(reinterpret_cast<const float2*>(row + 2 * (x0 + 1) + 1)); const float wt = al;
+			if (inx1) { const F8 t8 = ldg256(row + 2 * (x0 + 1)); const float4 cp = t8.lo; const float2 nr = make_float2(t8.hi.x, t8.hi.y); const float wt = al;
 				a1[0] += wt * cp.x; a1[1] += wt * cp.y; a1[2] += wt * cp.z; b1[0] += wt * cp.w; b1[1] += wt * nr.x; b1[2] += wt * nr.y; w1 += wt; }
 		}
 		float ww = 0.f, cxs = 0.f, cys = 0.f, czs = 0.f, nxs = 0.f, nys = 0.f, nzs = 0.f;
-		if (w0 > 0.f) { const float r = (1.0f - be) * __frcp_rn(w0); cxs += r * a0[0]; cys += r * a0[1]; czs += r * a0[2]; nxs += r * b0[0]; nys += r * b0[1]; nzs += r * b0[2]; ww += (1.0f - be); }
-		if (w1 > 0.f) { const float r = be * __frcp_rn(w1); cxs += r * a1[0]; cys += r * a1[1]; czs += r * a1[2]; nxs += r * b1[0]; nys += r * b1[1]; nzs += r * b1[2]; ww += be; }
+		if (w0 > 0.f) { const float r = (1.0f - be) * rcp_fast(w0); cxs += r * a0[0]; cys += r * a0[1]; czs += r * a0[2]; nxs += r * b0[0]; nys += r * b0[1]; nzs += r * b0[2]; ww += (1.0f - be); }
+		if (w1 > 0.f) { const float r = be * rcp_fast(w1); cxs += r * a1[0]; cys += r * a1[1]; czs += r * a1[2]; nxs += r * b1[0]; nys += r * b1[1]; nzs += r * b1[2]; ww += be; }
 		if (!(ww > 0.f)) continue;
-		const float rw = __frcp_rn(ww);
+		const float rw = rcp_fast(ww);
 		const float qx = cxs * rw, qy = cys * rw, qz = czs * rw;        // camPosTgt
 		if (!(qz > dmin && qz < dmax)) continue;
 		const float tnx = nxs * rw, tny = nys * rw, tnz = nzs * rw;     // normalTgt
@@ -752,7 +792,7 @@ template <int NT> __device__ __forceinline__ void tile_pixels(const SolveArgs& a
 		const float dn = rnx * tnx + rny * tny + rnz * tnz;
 		if (!(dn >= cos_t && dist2 <= d2max)) continue;
 		const float res = -(dx * tnx + dy * tny + dz * tnz);            // dot(camPosTgt - camPosSrcToTgt, normalTgt)
-		const float wgt = wdense * huber_w(res * res, delta);
+		const float wgt = wdense * huber_w_fast(res * res, delta);
 		float g[6];
 		g[0] = tnx; g[1] = tny; g[2] = tnz;
 		g[3] = ty * tnz - tz * tny; g[4] = tz * tnx - tx * tnz; g[5] = tx * tny - ty * tnx;   // p' x n_tgt
@@ -1196,7 +1236,8 @@ template <int NT> __device__ void window_tail(const SolveArgs& a, const WinDesc&
 // ------------------------------------------------------------------------------------------------ k_solve
 template <int NT, int MINB> __global__ void __launch_bounds__(NT, MINB) k_solve(SolveArgs a) {
 	extern __shared__ __align__(16) float dyn_smem[];
-	__shared__ int s_tile, s_next;
+	__shared__ int s_tile, s_it, s_idx;
+	__shared__ Tile s_tl[2];      // the tile being processed and the one claimed for the next round (thread 0 fetches its record a tile ahead)
 	__shared__ float s_M[12];
 	__shared__ float s_X[36];
 	__shared__ float s_red[kTileVals];
@@ -1205,22 +1246,26 @@ template <int NT, int MINB> __global__ void __launch_bounds__(NT, MINB) k_solve(
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const int total = *a.n_tiles_total;
 	if (total <= 0) return;
-	const long long all = (long long)total * a.prm.num_iter_outer;
-	if (tid == 0) s_tile = atomicAdd(a.queue, 1);
+	const int all = total * a.prm.num_iter_outer;      // (the tile plan reports an overflow when this does not fit 31 bits)
+	if (tid == 0) {
+		const int t0 = atomicAdd(a.queue, 1);
+		s_tile = t0;
+		if (t0 < all) { const int it0 = t0 / total; s_it = it0; s_idx = t0 - it0 * total; s_tl[0] = a.tiles[t0 - it0 * total]; }
+	}
+	int cur = 0;
 	for (;;) {
 		__syncthreads();
-		const long long t = s_tile;
-		if (t >= all) break;
-		__syncthreads();
+		if (s_tile >= all) break;
+		const int it = s_it, tl_idx = s_idx;
+		const Tile& tl = s_tl[cur];      // (read from shared memory where it is used: 12 registers less across the pixel loop)
 		// claim the NEXT tile now: the atomic's round trip hides behind this tile.  Safe for the iteration dependencies:
 		// a CTA only ever waits on tiles with a smaller index than the one it is processing, never on its look-ahead.
-		if (tid == 0) s_next = atomicAdd(a.queue, 1);
+		int nxt = 0;
+		if (tid == 0) nxt = atomicAdd(a.queue, 1);
 		ProfRec prf; PROF_T(0);
-		const int it = (int)(t / total), tl_idx = (int)(t - (long long)it * total);
-		const Tile tl = a.tiles[tl_idx];
-		const WinDesc wd = a.wins[tl.win];
+		const WinDesc& wd = a.wins[tl.win];      // (fields are read where they are used: geometry in the pixel loop, the rest in the tail)
 		if (it > 0) {   // this window's previous GN iteration must have published its poses
-			if (tid == 0) { while (ld_relaxed(a.iter_done + tl.win) < it) __nanosleep(128); (void)ld_acquire(a.iter_done + tl.win); }
+			if (tid == 0) { while (ld_relaxed(a.iter_done + tl.win) < it) __nanosleep(64); (void)ld_acquire(a.iter_done + tl.win); }
 			__syncthreads();
 		}
 		PROF_T(1);
@@ -1228,10 +1273,15 @@ template <int NT, int MINB> __global__ void __launch_bounds__(NT, MINB) k_solve(
 			PROF_T(2);
 			sparse_sums<NT>(a, tl.win);
 			PROF_T(3);
+			int itn = 0, idxn = 0;      // thread 0: the record of the tile claimed above (in flight across the barrier and the ticket)
+			if (tid == 0 && nxt < all) { itn = nxt / total; idxn = nxt - itn * total; tile_fetch_async(&s_tl[cur ^ 1], a.tiles + idxn); }
 			__syncthreads();      // (every thread's sums are written; the barrier orders them before thread 0's release below)
 			if (tid == 0) {
 				const int done = ticket_acq_rel(a.tiles_done + tl.win) + 1;
-				s_is_last = (done == (it + 1) * wd.n_tiles);
+				s_is_last = (done == (it + 1) * tl.n_tiles_win);
+				s_tile = nxt;
+				if (nxt < all) { s_it = itn; s_idx = idxn; }
+				tile_fetch_wait();
 			}
 			PROF_T(4);
 			__syncthreads();
@@ -1240,10 +1290,9 @@ template <int NT, int MINB> __global__ void __launch_bounds__(NT, MINB) k_solve(
 #pragma unroll
 		for (int k = 0; k < kTileVals; k++) acc.v[k] = 0.f;
 		if (tl.pair >= 0) {
-			const uint2 pr = a.pairs[wd.pair_off + tl.pair];   // x = target i, y = source j
 			if (tid < 12) {   // transform = T_i^-1 T_j (rigid inverse), row r, col c
-				const float* Ti = a.T + (size_t)(wd.frame_off + pr.x) * 12;
-				const float* Tj = a.T + (size_t)(wd.frame_off + pr.y) * 12;
+				const float* Ti = a.T + (size_t)tl.tgt_slot * 12;
+				const float* Tj = a.T + (size_t)tl.src_slot * 12;
 				const int r = tid >> 2, c = tid & 3;
 				float v = 0.f;
 				for (int k = 0; k < 3; k++) {
@@ -1252,7 +1301,7 @@ template <int NT, int MINB> __global__ void __launch_bounds__(NT, MINB) k_solve(
 				}
 				s_M[tid] = v;
 			} else if (tid >= 32 && tid < 68) {   // X_i = [[R,0],[[t]x R, R]] of the TARGET frame: maps the tile's sums to the model frame
-				const float* Ti = a.T + (size_t)(wd.frame_off + pr.x) * 12;
+				const float* Ti = a.T + (size_t)tl.tgt_slot * 12;
 				const int e = tid - 32, r = e / 6, c = e - r * 6;
 				float v;
 				if (r < 3) v = (c < 3) ? __ldcg(Ti + r * 4 + c) : 0.f;
@@ -1262,11 +1311,11 @@ template <int NT, int MINB> __global__ void __launch_bounds__(NT, MINB) k_solve(
 			}
 			__syncthreads();
 			PROF_T(2);
-			const float4* src = a.src_tab[wd.frame_off + pr.y];
-			const float4* tex = a.texel_tab[wd.frame_off + pr.x];
-			tile_pixels<NT>(a, wd, src, tex, s_M, tl.start, tl.count, acc);
+			tile_pixels<NT>(a, wd, tl.src, tl.tex, s_M, tl.start, tl.count, acc);
 		}
 		PROF_T(3);
+		int itn = 0, idxn = 0;
+		if (tid == 0 && nxt < all) { itn = nxt / total; idxn = nxt - itn * total; tile_fetch_async(&s_tl[cur ^ 1], a.tiles + idxn); }   // the next tile's record, in flight behind the reduction
 		// block reduction of the 28 sums -> this tile's slot.  Warp level: a transposing butterfly (31 shuffles instead of
 		// 28 x 5): after the five steps lane L holds the warp total of value L.
 		{
@@ -1321,7 +1370,10 @@ template <int NT, int MINB> __global__ void __launch_bounds__(NT, MINB) k_solve(
 			__syncwarp();             // orders the 28 lanes' stores before lane 0's release
 			if (lane == 0) {
 				const int done = ticket_acq_rel(a.tiles_done + tl.win) + 1;
-				s_is_last = (done == (it + 1) * wd.n_tiles);
+				s_is_last = (done == (it + 1) * tl.n_tiles_win);
+				s_tile = nxt;
+				if (nxt < all) { s_it = itn; s_idx = idxn; }
+				tile_fetch_wait();
 			}
 		}
 		PROF_T(4);
@@ -1335,7 +1387,7 @@ template <int NT, int MINB> __global__ void __launch_bounds__(NT, MINB) k_solve(
 			__syncthreads();
 			if (tid == 0) st_release(a.iter_done + tl.win, it + 1);
 		}
-		if (tid == 0) s_tile = s_next;
+		cur ^= 1;
 	}
 }
 
@@ -1393,6 +1445,7 @@ struct SolverState {
 	double host_us[6] = { 0, 0, 0, 0, 0, 0 };   // host time of the last call: tables+early upload, prep launch, correspondence scan+staging, run (launch), fetch (copy + wait), total
 	bool grp_in_smem = true;
 	int force_nt = 0;                    // test / tuning knob (BT_SOLVE_NT environment variable): 128 or 256 forces the CTA size
+	int force_chunk = 0;                 // tuning knob (BT_SOLVE_CHUNK): source pixels per dense tile
 	int launches = 0;
 	int attr_bytes = 0, occ = BT_SOLVE_MIN_CTAS, occ_smem = -1, occ_nt = 0;
 	int nt = 256;                        // CTA size of k_solve for the staged batch: 128 for batches (per-tile set-up / settle phases of more, smaller CTAs overlap), 256 for a few windows (shorter tails)
@@ -1425,6 +1478,7 @@ static int reserve_impl(bt_ctx* ctx, const bt_solver_limits* lim) {
 	           BT_ERR_INVALID_ARG, "bt_solver_reserve: bad limits (max_frames must be 2..%d)", kMaxFrames);
 	s->lim = *lim;
 	{ const char* e = getenv("BT_SOLVE_NT"); const int v = e ? atoi(e) : 0; s->force_nt = (v == 128 || v == 256) ? v : 0; }
+	{ const char* e = getenv("BT_SOLVE_CHUNK"); const int v = e ? atoi(e) : 0; s->force_chunk = (v >= 256 && v <= 16384) ? (v + 255) / 256 * 256 : 0; }
 	const int w = (int)(lim->W / lim->image_downscale), h = (int)(lim->H / lim->image_downscale);
 	s->npix_max = w * h;
 	const int F = lim->max_windows * lim->max_frames;
@@ -1613,7 +1667,7 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 		const long long est_px = (long long)p_off * (s->npix_max / 8);   // ~12 % valid
 		long long c = est_px / ((long long)ctx->sm_count * 2 * 4);
 		c = std::max(256LL, std::min(2048LL, c));
-		s->chunk = (int)((c + 255) / 256 * 256);
+		s->chunk = s->force_chunk ? s->force_chunk : (int)((c + 255) / 256 * 256);
 	}
 	s->layout = L;
 	if (!s->copy_stream) {
@@ -1846,6 +1900,16 @@ static SolveArgs make_args(bt_ctx* ctx) {
 	a.n_tiles_total = s->scalars.as<int>(); a.queue = s->scalars.as<int>() + 1; a.n_src_px = (long long*)(s->scalars.as<char>() + 16);
 	a.tiles_done = s->tiles_done.as<int>(); a.iter_done = s->iter_done.as<int>();
 	a.chunk = s->chunk; a.grp_in_smem = s->grp_in_smem ? 1 : 0; a.prm = s->prm; a.grid_ctas = ctx->sm_count * s->occ;
+	{   // `sqrtf(d2) <= dist_t` <=> `d2 <= d2max` for every float d2 (sqrtf is correctly rounded and monotonic)
+		const float th = s->prm.dense_dist_thresh;
+		float d2max = th * th;
+		auto nextf = [](float v, int d) { int32_t b; memcpy(&b, &v, 4); b += d; float r; memcpy(&r, &b, 4); return r; };
+		if (th > 0.f) {
+			while (d2max > 0.f && sqrtf(d2max) > th) d2max = nextf(d2max, -1);
+			while (sqrtf(nextf(d2max, 1)) <= th) d2max = nextf(d2max, 1);
+		} else d2max = (th == 0.f) ? 0.f : -1.f;
+		a.d2max = d2max;
+	}
 	if (s->prof_cap > 0) { a.prof = s->prof.as<long long>(); a.prof_cap = s->prof_cap; }
 	if (s->debug) { a.dbg_JtJ = s->dbgJ.as<float>(); a.dbg_Jtr = s->dbgR.as<float>(); a.dbg_stride = 6 * s->lim.max_frames; a.dbg_cnt = s->dbgC.as<float>(); a.dbg_cnt_stride = s->max_pairs; }
 	return a;
