@@ -51,7 +51,7 @@ static constexpr int kTileVals = 28;          // 21 (sym 6x6) + 6 (rhs) + 1 (#co
 static constexpr int kGrpVals = 44;           // sparse moment sums per pair group
 static constexpr int kMaxFrames = 32;
 static constexpr size_t kTailSmemMax = 224 * 1024;   // dynamic shared memory a tail may use (227 KB per CTA minus k_solve's static arrays)
-static constexpr int kSmallCtaMinWindows = 1 << 30;  // (measured on B200: 128-thread CTAs are SLOWER, 0.55 vs 0.46 ms for 32 windows - the variant stays behind BT_SOLVE_NT=128 only)
+// (a 128-thread CTA variant of k_solve was measured on B200: SLOWER, 0.55 vs 0.46 ms for 32 windows - dropped)
 static constexpr float kEps = 0.000001f;      // FLOAT_EPSILON, /root/reference/src/cuda/SolverUtil.h:10
 
 struct WinDesc {
@@ -160,7 +160,7 @@ __device__ void so3_exp_AB(V3 w, float A, float B, float R[9]) {  // rodrigues_s
 	a = A * w.x; b = B * (w.y * w.z); R[5] = b - a; R[7] = b + a;
 }
 // poseToMatrix (LieDerivUtil.h:150-194): T[12] = row-major 3x4 [R | t]
-__device__ __noinline__ void se3_exp(V3 rot, V3 trans, float T[12]) {
+__device__ __forceinline__ void se3_exp(V3 rot, V3 trans, float T[12]) {
 	const float theta_sq = dot(rot, rot);
 	float A, B, C;
 	so3_coeffs(theta_sq, A, B, C);
@@ -196,7 +196,7 @@ __device__ V3 so3_log(const float R[9]) {
 	return r;
 }
 // matrixToPose (LieDerivUtil.h:126-148); T = row-major 3x4
-__device__ __noinline__ void se3_log(const float T[12], V3& rot, V3& trans) {
+__device__ __forceinline__ void se3_log(const float T[12], V3& rot, V3& trans) {
 	const float R[9] = { T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10] };
 	const V3 t = mk(T[3], T[7], T[11]);
 	rot = so3_log(R);
@@ -267,6 +267,12 @@ __device__ __forceinline__ void tile_fetch_async(void* smem_dst, const void* gsr
 	const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
 	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n cp.async.cg.shared.global [%2], [%3], 16;\n cp.async.cg.shared.global [%4], [%5], 16;"
 	             ::"r"(d), "l"(gsrc), "r"(d + 16), "l"((const char*)gsrc + 16), "r"(d + 32), "l"((const char*)gsrc + 32) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {      // 4-byte asynchronous copy (through L1: immutable tables only)
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16_cg(void* smem_dst, const void* gsrc) {  // 16-byte asynchronous copy from L2 (data other CTAs wrote during this launch)
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void tile_fetch_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void st_release(int* p, int v) {
@@ -830,18 +836,22 @@ struct TailSmem {
 static constexpr int kFS = 20, kFD = 28;
 // (grp_in_smem = false: big windows - 30 frames, 435 groups - leave the 44 moment sums per group in global memory and read them
 // through L2; with them the tail of such a window would need 279 KB of shared memory)
+// Leading dimension of the system matrix: the PCG reads a whole row per THREAD with 16-byte loads, which is conflict-free when the rows
+// of eight consecutive threads start in eight different 4-bank groups: ld = 4 (mod 8), ld >= dimp rounded up to a multiple of 4.
+__host__ __device__ inline int tail_ld(int dimp) { int ld = (dimp + 3) & ~3; if ((ld & 7) != 4) ld += 4; return ld; }
 __host__ __device__ inline size_t tail_smem_floats(int N, int P, int G, bool grp_in_smem = true) {
-	const int dimp = 6 * (N - 1), ld = dimp | 1;
-	return (size_t)N * 12 + (size_t)dimp * ld + 7 * (size_t)dimp + (size_t)P * kTileVals + (grp_in_smem ? (size_t)G * kGrpVals : 0) +
+	const int dimp = 6 * (N - 1), ld = tail_ld(dimp), dimp4 = (dimp + 3) & ~3;
+	return (size_t)N * 12 + (size_t)dimp * ld + 7 * (size_t)dimp4 + (size_t)P * kTileVals + (grp_in_smem ? (size_t)G * kGrpVals : 0) +
 	       (size_t)N * (kFS + kFD) + (size_t)(3 * G + 1 + 4 * P) + (size_t)(2 * (N + 1) + 2 * G + 2 * P) + 16;
 }
 __device__ inline void tail_carve(float* base, int N, int P, int G, TailSmem& s, bool grp_in_smem) {
-	s.dimp = 6 * (N - 1); s.ld = s.dimp | 1;
+	s.dimp = 6 * (N - 1); s.ld = tail_ld(s.dimp);
+	const int dimp4 = (s.dimp + 3) & ~3;      // every vector starts 16-byte aligned (N * 12 and dimp * ld are multiples of 4 floats)
 	float* q = base;
 	s.T = q; q += N * 12;
 	s.A = q; q += s.dimp * s.ld;
-	s.rhs = q; q += s.dimp; s.Minv = q; q += s.dimp; s.r = q; q += s.dimp; s.z = q; q += s.dimp;
-	s.p = q; q += s.dimp; s.Ap = q; q += s.dimp; s.delta = q; q += s.dimp;
+	s.rhs = q; q += dimp4; s.Minv = q; q += dimp4; s.r = q; q += dimp4; s.z = q; q += dimp4;
+	s.p = q; q += dimp4; s.Ap = q; q += dimp4; s.delta = q; q += dimp4;
 	s.pairW = q; q += P * kTileVals;
 	s.grp = q; if (grp_in_smem) q += G * kGrpVals;
 	s.fS = q; q += N * kFS; s.fD = q; q += N * kFD;
@@ -923,10 +933,11 @@ template <int NT> __device__ void sparse_sums(const SolveArgs& a, int w) {
 	}
 }
 
-template <int NT> __device__ void window_tail(const SolveArgs& a, const WinDesc& wd_in, int w, int it, float* smem_base) {
+template <int NT> __device__ void window_tail(const SolveArgs& a, const WinDesc& wd_in, int w, int it, float* smem_base, int* p2_claim) {
 	WinDesc wd = wd_in;
 	{ const WinSparse ws = a.wsp[w]; wd.n_corr = ws.n_corr; wd.n_groups = ws.n_groups; wd.corr_off = ws.corr_off; wd.grp_off = ws.grp_off; wd.mem_off = ws.mem_off; wd.unique_blocks = ws.unique_blocks; }
-	const int tid = threadIdx.x, lane = tid & 31;
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	static_assert(NT >= 6 * (kMaxFrames - 1), "the PCG runs one thread per unknown");
 	const int N = wd.n_frames, P = wd.n_pairs, G = wd.n_groups;
 	TailSmem s;
 	const bool gsm = a.grp_in_smem != 0;
@@ -939,38 +950,32 @@ template <int NT> __device__ void window_tail(const SolveArgs& a, const WinDesc&
 	ProfRec prf; prf.kind_cta = (1ll << 32) | blockIdx.x; prf.tile_win = ((long long)it << 32) | w;
 	PROF_T(0);
 
-	// ---- P0: everything the later phases index repeatedly goes to shared memory once (poses, group/pair tables)
-	for (int k = tid; k < N * 12; k += NT) s.T[k] = __ldcg(a.T + (size_t)wd.frame_off * 12 + k);
-	for (int k = tid; k < G; k += NT) { s.gi[k] = a.grp_i[wd.grp_off + k]; s.gj[k] = a.grp_j[wd.grp_off + k]; }
-	for (int k = tid; k <= G; k += NT) s.gstart[k] = a.grp_start[wd.grp_off + w + k];
-	for (int k = tid; k < P; k += NT) {
-		const uint2 pr = a.pairs[wd.pair_off + k];
-		s.pt[k] = (int)pr.x; s.ps[k] = (int)pr.y; s.pt0[k] = a.pair_tile0[wd.pair_off + k]; s.pnt[k] = a.pair_ntile[wd.pair_off + k];
-	}
-	{
-		const int* mem = a.mem + wd.mem_off;     // fg_start[N+1] fp_start[N+1] fg_items[2G] fp_items[2P], contiguous like the smem copy
-		const int nmem = 2 * (N + 1) + 2 * G + 2 * P;
-		for (int k = tid; k < nmem; k += NT) s.fg_start[k] = mem[k];
-	}
-	for (int k = tid; k < dimp * ld; k += NT) s.A[k] = 0.f;
-	__syncthreads();
-	PROF_T(1);
-
-	// ---- P1: the sparse moment sums were computed by sparse_sums() while the window's dense tiles were still running
-	if (gsm) for (int k = tid; k < G * kGrpVals; k += NT) s.grp[k] = __ldcg(grp_g + k);
-	__syncthreads();
-	PROF_T(2);
-	// ---- P2: per-pair sums over the pair's tiles (already in the model frame; the tile epilogue applied X S' X^T).  A pair's
-	//      tiles are consecutive and summed in order (deterministic); 4 tiles x RI items per thread are in flight at a time.
-	if (use_dense) {
-		constexpr int RI = 5;
-		for (int k0 = tid; k0 < P * kTileVals; k0 += NT * RI) {
+	// ---- P0 || P2.  P0: everything the later phases index repeatedly goes to shared memory once (poses, group / pair tables, membership
+	//      CSR, the groups' moment sums): ALL of it as asynchronous copies issued back to back - one L2 round trip instead of one per
+	//      table - while the same warps clear the system matrix.  P2: per-pair sums over the pair's tiles (already in the model frame; the
+	//      tile epilogue applied X S' X^T): a pair's tiles are consecutive and summed in order (deterministic), 4 tiles x RI items per
+	//      thread in flight.  The second half of the CTA starts on P2 at once (it needs nothing from P0: the tile ranges come straight from
+	//      global memory), the first half joins when its copies are issued; work is handed out in warp-sized blocks by a shared counter.
+	int& s_p2_claim = *p2_claim;
+	constexpr int RI = 5;
+	const int n_p2 = use_dense ? P * kTileVals : 0;
+	auto p2_work = [&]() {
+		for (;;) {
+			int base = 0;
+			if (lane == 0) base = atomicAdd(&s_p2_claim, 32 * RI);
+			base = __shfl_sync(0xffffffffu, base, 0);
+			if (base >= n_p2) break;
 			float v[RI]; const float* src[RI]; int nt[RI]; int mx = 0;
 #pragma unroll
 			for (int r = 0; r < RI; r++) {
-				const int k = k0 + r * NT;
+				const int k = base + lane + 32 * r;
 				v[r] = 0.f; nt[r] = 0; src[r] = a.partial;
-				if (k < P * kTileVals) { const int p = k / kTileVals, e = k - p * kTileVals; nt[r] = s.pnt[p]; src[r] = a.partial + (size_t)(wd.tile_off + s.pt0[p]) * kTileVals + e; mx = max(mx, nt[r]); }
+				if (k < n_p2) {
+					const int p = k / kTileVals, e = k - p * kTileVals;
+					nt[r] = __ldg(a.pair_ntile + wd.pair_off + p);
+					src[r] = a.partial + (size_t)(wd.tile_off + __ldg(a.pair_tile0 + wd.pair_off + p)) * kTileVals + e;
+					mx = max(mx, nt[r]);
+				}
 			}
 			for (int c = 0; c < mx; c += 4) {      // four tiles x RI items in flight per thread; the adds keep the tile order (x + 0.f == x)
 				float t[4][RI];
@@ -987,19 +992,53 @@ template <int NT> __device__ void window_tail(const SolveArgs& a, const WinDesc&
 			}
 #pragma unroll
 			for (int r = 0; r < RI; r++) {
-				const int k = k0 + r * NT;
-				if (k < P * kTileVals) {
+				const int k = base + lane + 32 * r;
+				if (k < n_p2) {
 					s.pairW[k] = v[r];
 					if (a.dbg_cnt && (k % kTileVals) == 27 && it == a.prm.num_iter_outer - 1) a.dbg_cnt[(size_t)w * a.dbg_cnt_stride + k / kTileVals] = v[r];
 				}
 			}
 		}
+	};
+	if (tid >= NT / 2) p2_work();
+	else {
+		constexpr int H = NT / 2;
+		{   // poses of this iteration: written by this window's previous tail with st.cg -> read from L2
+			const float4* Tg = reinterpret_cast<const float4*>(a.T + (size_t)wd.frame_off * 12);
+			for (int k = tid; k < N * 3; k += H) cp_async16_cg(reinterpret_cast<float4*>(s.T) + k, Tg + k);
+		}
+		if (gsm) {  // the sparse moment sums were computed by sparse_sums() while the window's dense tiles were still running (st.cg)
+			const float4* Gg = reinterpret_cast<const float4*>(grp_g);
+			for (int k = tid; k < G * (kGrpVals / 4); k += H) cp_async16_cg(reinterpret_cast<float4*>(s.grp) + k, Gg + k);
+		}
+		for (int k = tid; k < G; k += H) { cp_async4(s.gi + k, a.grp_i + wd.grp_off + k); cp_async4(s.gj + k, a.grp_j + wd.grp_off + k); }
+		for (int k = tid; k <= G; k += H) cp_async4(s.gstart + k, a.grp_start + wd.grp_off + w + k);
+		for (int k = tid; k < P; k += H) {
+			const uint2* pr = a.pairs + wd.pair_off + k;
+			cp_async4(s.pt + k, &pr->x); cp_async4(s.ps + k, &pr->y);
+			cp_async4(s.pt0 + k, a.pair_tile0 + wd.pair_off + k); cp_async4(s.pnt + k, a.pair_ntile + wd.pair_off + k);
+		}
+		{
+			const int* mem = a.mem + wd.mem_off;     // fg_start[N+1] fp_start[N+1] fg_items[2G] fp_items[2P], contiguous like the smem copy
+			const int nmem = 2 * (N + 1) + 2 * G + 2 * P;
+			for (int k = tid; k < nmem; k += H) cp_async4(s.fg_start + k, mem + k);
+		}
+		{
+			float4* A4 = reinterpret_cast<float4*>(s.A);      // (dimp * ld is a multiple of four floats)
+			for (int k = tid; k < (dimp * ld) >> 2; k += H) A4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+		}
+		p2_work();
+		asm volatile("cp.async.wait_all;" ::: "memory");
 	}
 	__syncthreads();
+	if (tid == 0) s_p2_claim = 0;      // for this CTA's next tail (nobody touches the counter again before several barriers have passed)
+	PROF_T(1);
+	PROF_T(2);
+	__syncthreads();
 	PROF_T(3);
-	PROF_T(4);
-	// ---- P3a: per-frame gathers (no atomics, fixed order).  Branch-free inner loops: every output entry e reads one moment
-	//      from the q-side or the s-side of each group touching the frame (offset/sign chosen once, outside the loop).
+	// ---- P3a: per-frame gathers (no atomics, fixed order).  Every output entry e reads one moment from the q-side or the s-side of each
+	//      group touching the frame (offset / sign chosen once, outside the loop).  The loop over the frame's groups is a chain of two
+	//      dependent shared-memory loads per step (item -> moment): four steps are loaded at a time, the adds keep the list order.
 	for (int k = tid; k < N * (kFS + kFD); k += NT) {
 		const int f = k / (kFS + kFD), e = k - f * (kFS + kFD);
 		float acc = 0.f;
@@ -1013,27 +1052,40 @@ template <int NT> __device__ void window_tail(const SolveArgs& a, const WinDesc&
 			else if (e < 16) { oq = 21 + e; os = 21 + e; sg = -1.f; }
 			else if (e < 19) { oq = 21 + e; os = 24 + e; }
 			else { oq = 43; os = 43; }
-			for (int q = s.fg_start[f]; q < s.fg_start[f + 1]; q++) {
-				const int item = s.fg_items[q];
-				const int mo = (item & 0xffff) * kGrpVals + ((item >> 16) ? os : oq);      // role 0: this frame is the group's i (q side); 1: j (s side)
-				const float mv = gsm ? s.grp[mo] : __ldcg(grp_g + mo);
-				acc += (item >> 16) ? sg * mv : mv;
+			const int q1 = s.fg_start[f + 1];
+			for (int q = s.fg_start[f]; q < q1; q += 4) {
+				int item[4]; float mv[4];
+#pragma unroll
+				for (int u = 0; u < 4; u++) item[u] = s.fg_items[min(q + u, q1 - 1)];
+#pragma unroll
+				for (int u = 0; u < 4; u++) {
+					const int mo = (item[u] & 0xffff) * kGrpVals + ((item[u] >> 16) ? os : oq);      // role 0: this frame is the group's i (q side); 1: j (s side)
+					mv[u] = gsm ? s.grp[mo] : __ldcg(grp_g + mo);
+				}
+#pragma unroll
+				for (int u = 0; u < 4; u++) if (q + u < q1) acc += (item[u] >> 16) ? sg * mv[u] : mv[u];
 			}
 			s.fS[f * kFS + e] = acc;
 		} else {
 			const int d = e - kFS;
 			if (use_dense && d < 27) {
 				const float sgs = (d >= 21) ? -1.f : 1.f;      // Jtr_i += b, Jtr_j -= b ; S adds to both diagonal blocks
-				for (int q = s.fp_start[f]; q < s.fp_start[f + 1]; q++) {
-					const int item = s.fp_items[q];
-					const float v = s.pairW[(item & 0xffff) * kTileVals + d];
-					acc += (item >> 16) ? sgs * v : v;             // role 0: target, 1: source
+				const int q1 = s.fp_start[f + 1];
+				for (int q = s.fp_start[f]; q < q1; q += 4) {
+					int item[4]; float v[4];
+#pragma unroll
+					for (int u = 0; u < 4; u++) item[u] = s.fp_items[min(q + u, q1 - 1)];
+#pragma unroll
+					for (int u = 0; u < 4; u++) v[u] = s.pairW[(item[u] & 0xffff) * kTileVals + d];
+#pragma unroll
+					for (int u = 0; u < 4; u++) if (q + u < q1) acc += (item[u] >> 16) ? sgs * v[u] : v[u];             // role 0: target, 1: source
 				}
 			}
 			s.fD[f * kFD + d] = acc;
 		}
 	}
 	__syncthreads();
+	PROF_T(4);
 	// ---- P3b: diagonal blocks, right-hand side, Jacobi preconditioner from the per-frame sums
 	{
 		const int per = 21 + 6 + 6;
@@ -1129,71 +1181,99 @@ template <int NT> __device__ void window_tail(const SolveArgs& a, const WinDesc&
 	__syncthreads();
 	PROF_T(6);
 
-	// ---- PCG (PCGInit_Kernel1/2, PCGStep_Kernel*: SolverBundling.cu:575-818) on ONE warp: the system has <= 186 unknowns,
-	//      so warp shuffles replace every block-wide reduction/barrier of a multi-warp version.
+	// ---- PCG (PCGInit_Kernel1/2, PCGStep_Kernel*: SolverBundling.cu:575-818).  One THREAD per unknown: thread r reads row r of A
+	//      with 16-byte loads (conflict-free, see tail_ld) against p in shared memory (broadcast) - no cross-lane reduction inside the
+	//      matrix-vector product; only the two scalar products of a step are reduced (warp shuffle + one word per warp through shared
+	//      memory, named barrier among the ceil(dimp / 32) warps that take part).  The first version spread every ROW over the lanes of
+	//      a warp: 20 dependent shuffles per four rows, 2.2 k cycles per step for 54 unknowns; this one takes ~0.8 k.
 	{
-		// Every warp keeps its OWN register copy of the PCG vectors (element k = lane + 32 q lives in lane, slot q), so the only
-		// thing exchanged per step is Ap (rows are split over the warps): one barrier per step, all scalars by warp shuffles.
-		constexpr int QM = (6 * (kMaxFrames - 1) + 31) / 32;   // <= 6 slots per lane
-		const int wid = tid >> 5;
-		float rr[QM], pp[QM], dl[QM], mi[QM];
-		float rz = 0.f;
-#pragma unroll
-		for (int q = 0; q < QM; q++) {
-			const int k = lane + 32 * q;
-			rr[q] = (k < dimp) ? s.rhs[k] : 0.f; mi[q] = (k < dimp) ? s.Minv[k] : 0.f;
-			pp[q] = mi[q] * rr[q]; dl[q] = 0.f;
-			rz += rr[q] * pp[q];
-		}
-		rz = warp_sum(rz);
+		__shared__ float s_dot[3][8];
+		const int nwp = (dimp + 31) >> 5;      // warps that take part (<= 6)
+		if (dimp <= 64) {
+			// up to 11 frames (the shipped max_BA_frames is 10): ONE warp, two rows per lane - the scalar products are plain warp shuffles,
+			// nothing crosses a barrier (8.1 k -> ~4 k cycles for the five steps of a 10-frame window)
+			if (wid == 0) {
+				const int r0 = lane, r1 = lane + 32;
+				const bool act0 = r0 < dimp, act1 = r1 < dimp;
+				const int n4 = (dimp + 3) >> 2;
+				float rr0 = act0 ? s.rhs[r0] : 0.f, rr1 = act1 ? s.rhs[r1] : 0.f;
+				const float mi0 = act0 ? s.Minv[r0] : 0.f, mi1 = act1 ? s.Minv[r1] : 0.f;
+				float pp0 = mi0 * rr0, pp1 = mi1 * rr1, dl0 = 0.f, dl1 = 0.f;
+				if (r0 < 4 * n4) s.p[r0] = pp0;      // (inactive rows hold zeros: the padding of p up to a multiple of four is zero, like A's columns there)
+				if (r1 < 4 * n4) s.p[r1] = pp1;
+				__syncwarp();
+				float rz = warp_sum(rr0 * pp0 + rr1 * pp1);
+				const float4* A0 = reinterpret_cast<const float4*>(s.A + (act0 ? r0 : 0) * ld);
+				const float4* A1 = reinterpret_cast<const float4*>(s.A + (act1 ? r1 : 0) * ld);
+				const float4* p4 = reinterpret_cast<const float4*>(s.p);
 #pragma unroll 1
-		for (int lin = 0; lin < a.prm.num_iter_inner; lin++) {
-			float* Apb = (lin & 1) ? s.z : s.Ap;      // double-buffered exchange (s.z is free: z lives in registers here)
-			// Ap rows of this warp: lanes over columns (p[c] is already in this lane's registers), four rows in flight
-#pragma unroll 1
-			for (int r0 = wid; r0 < dimp; r0 += 4 * (NT / 32)) {
-				float acc4[4] = { 0.f, 0.f, 0.f, 0.f };
-#pragma unroll
-				for (int q = 0; q < QM; q++) {
-					const int c = lane + 32 * q;
-					if (c < dimp) {
-#pragma unroll
-						for (int j = 0; j < 4; j++) { const int r = r0 + j * (NT / 32); if (r < dimp) acc4[j] += s.A[r * ld + c] * pp[q]; }
+				for (int lin = 0; lin < a.prm.num_iter_inner; lin++) {
+					float a00 = 0.f, a01 = 0.f, a02 = 0.f, a03 = 0.f, a10 = 0.f, a11 = 0.f, a12 = 0.f, a13 = 0.f;
+#pragma unroll 4
+					for (int c = 0; c < n4; c++) {
+						const float4 pv = p4[c], u = A0[c], v = A1[c];
+						a00 += u.x * pv.x; a01 += u.y * pv.y; a02 += u.z * pv.z; a03 += u.w * pv.w;
+						a10 += v.x * pv.x; a11 += v.y * pv.y; a12 += v.z * pv.z; a13 += v.w * pv.w;
 					}
+					const float ap0 = act0 ? (a00 + a01) + (a02 + a03) : 0.f, ap1 = act1 ? (a10 + a11) + (a12 + a13) : 0.f;
+					const float pAp = warp_sum(pp0 * ap0 + pp1 * ap1);
+					const float alpha = (pAp > kEps) ? rz / pAp : 0.f;
+					dl0 += alpha * pp0; dl1 += alpha * pp1;
+					rr0 -= alpha * ap0; rr1 -= alpha * ap1;
+					const float zz0 = mi0 * rr0, zz1 = mi1 * rr1;
+					const float rz_new = warp_sum(zz0 * rr0 + zz1 * rr1);
+					const float beta = (rz > kEps) ? rz_new / rz : 0.f;
+					rz = rz_new;
+					pp0 = zz0 + beta * pp0; pp1 = zz1 + beta * pp1;
+					__syncwarp();      // every lane has read the old p
+					if (act0) s.p[r0] = pp0;
+					if (act1) s.p[r1] = pp1;
+					__syncwarp();
 				}
-#pragma unroll
-				for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-					for (int j = 0; j < 4; j++) acc4[j] += __shfl_xor_sync(0xffffffffu, acc4[j], o);
-				}
-				if (lane == 0) {
-#pragma unroll
-					for (int j = 0; j < 4; j++) { const int r = r0 + j * (NT / 32); if (r < dimp) Apb[r] = acc4[j]; }
-				}
+				if (act0) s.delta[r0] = dl0;
+				if (act1) s.delta[r1] = dl1;
 			}
-			__syncthreads();
-			float ap[QM], d = 0.f;
-#pragma unroll
-			for (int q = 0; q < QM; q++) { const int k = lane + 32 * q; ap[q] = (k < dimp) ? Apb[k] : 0.f; d += pp[q] * ap[q]; }
-			const float pAp = warp_sum(d);
-			const float alpha = (pAp > kEps) ? rz / pAp : 0.f;
-			float bsum = 0.f, zz[QM];
-#pragma unroll
-			for (int q = 0; q < QM; q++) {
-				dl[q] += alpha * pp[q];
-				rr[q] -= alpha * ap[q];
-				zz[q] = mi[q] * rr[q];
-				bsum += zz[q] * rr[q];
+		} else if (wid < nwp) {
+			const int r = tid;
+			const bool act = r < dimp;
+			const int rc = act ? r : dimp - 1;       // idle lanes of the last warp read a valid row
+			const int nthr = nwp * 32;
+			const int n4 = (dimp + 3) >> 2;
+			float rr = act ? s.rhs[r] : 0.f;
+			const float mi = act ? s.Minv[r] : 0.f;
+			float pp = mi * rr, dl = 0.f;
+			if (r < 4 * n4) s.p[r] = act ? pp : 0.f;      // (the padding of p up to a multiple of four is zero, and so are A's columns there)
+			{ const float v = warp_sum(rr * pp); if (lane == 0) s_dot[0][wid] = v; }
+			asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+			float rz = 0.f;
+			for (int q = 0; q < nwp; q++) rz += s_dot[0][q];
+			const float4* Arow = reinterpret_cast<const float4*>(s.A + rc * ld);
+			const float4* p4 = reinterpret_cast<const float4*>(s.p);
+#pragma unroll 1
+			for (int lin = 0; lin < a.prm.num_iter_inner; lin++) {
+				float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+				for (int c = 0; c < n4; c++) { const float4 av = Arow[c], pv = p4[c]; a0 += av.x * pv.x; a1 += av.y * pv.y; a2 += av.z * pv.z; a3 += av.w * pv.w; }
+				const float ap = act ? (a0 + a1) + (a2 + a3) : 0.f;
+				{ const float v = warp_sum(pp * ap); if (lane == 0) s_dot[1][wid] = v; }
+				asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+				float pAp = 0.f;
+				for (int q = 0; q < nwp; q++) pAp += s_dot[1][q];
+				const float alpha = (pAp > kEps) ? rz / pAp : 0.f;
+				dl += alpha * pp;
+				rr -= alpha * ap;
+				const float zz = mi * rr;
+				{ const float v = warp_sum(zz * rr); if (lane == 0) s_dot[2][wid] = v; }
+				asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+				float rz_new = 0.f;
+				for (int q = 0; q < nwp; q++) rz_new += s_dot[2][q];
+				const float beta = (rz > kEps) ? rz_new / rz : 0.f;
+				rz = rz_new;
+				pp = zz + beta * pp;
+				if (act) s.p[r] = pp;
+				asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");      // p of the next step is complete (and s_dot[1] / [2] may be rewritten)
 			}
-			const float rz_new = warp_sum(bsum);
-			const float beta = (rz > kEps) ? rz_new / rz : 0.f;
-			rz = rz_new;
-#pragma unroll
-			for (int q = 0; q < QM; q++) pp[q] = zz[q] + beta * pp[q];
-		}
-		if (wid == 0) {
-#pragma unroll
-			for (int q = 0; q < QM; q++) { const int k = lane + 32 * q; if (k < dimp) s.delta[k] = dl[q]; }
+			if (act) s.delta[r] = dl;
 		}
 	}
 	__syncthreads();
@@ -1242,14 +1322,14 @@ template <int NT, int MINB> __global__ void __launch_bounds__(NT, MINB) k_solve(
 	__shared__ float s_X[36];
 	__shared__ float s_red[kTileVals];
 	__shared__ float s_part[(NT / 32)][kTileVals];
-	__shared__ int s_is_last;
+	__shared__ int s_is_last, s_p2_claim;
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const int total = *a.n_tiles_total;
 	if (total <= 0) return;
 	const int all = total * a.prm.num_iter_outer;      // (the tile plan reports an overflow when this does not fit 31 bits)
 	if (tid == 0) {
 		const int t0 = atomicAdd(a.queue, 1);
-		s_tile = t0;
+		s_tile = t0; s_p2_claim = 0;
 		if (t0 < all) { const int it0 = t0 / total; s_it = it0; s_idx = t0 - it0 * total; s_tl[0] = a.tiles[t0 - it0 * total]; }
 	}
 	int cur = 0;
@@ -1382,7 +1462,7 @@ template <int NT, int MINB> __global__ void __launch_bounds__(NT, MINB) k_solve(
 		PROF_T(5);
 		if (a.prof && tid == 0) { prf.kind_cta = blockIdx.x; prf.tile_win = ((long long)tl_idx << 32) | ((long long)it << 16) | tl.count; prf.t[6] = prf.t[7] = prf.t[8] = prf.t[9] = 0; prof_emit(a, prf); }
 		if (s_is_last) {
-			window_tail<NT>(a, wd, tl.win, it, dyn_smem);
+			window_tail<NT>(a, wd, tl.win, it, dyn_smem, &s_p2_claim);
 			__threadfence();
 			__syncthreads();
 			if (tid == 0) st_release(a.iter_done + tl.win, it + 1);
@@ -1444,11 +1524,9 @@ struct SolverState {
 	bool staged = false, debug = false, timing = false;
 	double host_us[6] = { 0, 0, 0, 0, 0, 0 };   // host time of the last call: tables+early upload, prep launch, correspondence scan+staging, run (launch), fetch (copy + wait), total
 	bool grp_in_smem = true;
-	int force_nt = 0;                    // test / tuning knob (BT_SOLVE_NT environment variable): 128 or 256 forces the CTA size
 	int force_chunk = 0;                 // tuning knob (BT_SOLVE_CHUNK): source pixels per dense tile
 	int launches = 0;
-	int attr_bytes = 0, occ = BT_SOLVE_MIN_CTAS, occ_smem = -1, occ_nt = 0;
-	int nt = 256;                        // CTA size of k_solve for the staged batch: 128 for batches (per-tile set-up / settle phases of more, smaller CTAs overlap), 256 for a few windows (shorter tails)
+	int attr_bytes = 0, occ = BT_SOLVE_MIN_CTAS, occ_smem = -1;
 	bool prep_launched = false, any_uncached = true;
 	cudaStream_t copy_stream = nullptr;
 	cudaEvent_t ev_prev = nullptr, ev_corr = nullptr, ev_h2d = nullptr;
@@ -1477,7 +1555,6 @@ static int reserve_impl(bt_ctx* ctx, const bt_solver_limits* lim) {
 	BT_REQUIRE(lim->max_windows > 0 && lim->max_frames >= 2 && lim->max_frames <= kMaxFrames && lim->max_corr >= 0 && lim->H > 0 && lim->W > 0 && lim->image_downscale >= 1.0f,
 	           BT_ERR_INVALID_ARG, "bt_solver_reserve: bad limits (max_frames must be 2..%d)", kMaxFrames);
 	s->lim = *lim;
-	{ const char* e = getenv("BT_SOLVE_NT"); const int v = e ? atoi(e) : 0; s->force_nt = (v == 128 || v == 256) ? v : 0; }
 	{ const char* e = getenv("BT_SOLVE_CHUNK"); const int v = e ? atoi(e) : 0; s->force_chunk = (v >= 256 && v <= 16384) ? (v + 255) / 256 * 256 : 0; }
 	const int w = (int)(lim->W / lim->image_downscale), h = (int)(lim->H / lim->image_downscale);
 	s->npix_max = w * h;
@@ -1869,14 +1946,11 @@ static int ensure_occupancy(bt_ctx* ctx) {
 	if (s->attr_bytes == 0) {      // the attribute belongs to (function, device), not to the context: set it to the ceiling stage_impl enforces, once,
 		s->attr_bytes = (int)kTailSmemMax;   // so that a second context on the same device can never lower what another context's next launch needs
 		BT_CUDA(cudaFuncSetAttribute(k_solve<256, BT_SOLVE_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->attr_bytes));
-		BT_CUDA(cudaFuncSetAttribute(k_solve<128, 2 * BT_SOLVE_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->attr_bytes));
 	}
-	s->nt = (s->n_windows >= kSmallCtaMinWindows && !s->force_nt) ? 128 : (s->force_nt ? s->force_nt : 256);
-	if (s->occ_smem != s->smem_bytes || s->occ_nt != s->nt) {
+	if (s->occ_smem != s->smem_bytes) {
 		int occ_q = 1;
-		if (s->nt == 128) BT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_q, k_solve<128, 2 * BT_SOLVE_MIN_CTAS>, 128, s->smem_bytes));
-		else BT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_q, k_solve<256, BT_SOLVE_MIN_CTAS>, 256, s->smem_bytes));
-		s->occ = std::max(occ_q, 1); s->occ_smem = s->smem_bytes; s->occ_nt = s->nt;
+		BT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_q, k_solve<256, BT_SOLVE_MIN_CTAS>, 256, s->smem_bytes));
+		s->occ = std::max(occ_q, 1); s->occ_smem = s->smem_bytes;
 	}
 	return BT_OK;
 }
@@ -1947,8 +2021,7 @@ extern "C" int bt_solve_run(bt_ctx* ctx, void* stream_) {
 	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[2], stream));
 	const int occ = s->occ;
 	const int grid = ctx->sm_count * occ;
-	if (s->nt == 128) k_solve<128, 2 * BT_SOLVE_MIN_CTAS><<<grid, 128, s->smem_bytes, stream>>>(a);
-	else k_solve<256, BT_SOLVE_MIN_CTAS><<<grid, 256, s->smem_bytes, stream>>>(a);
+	k_solve<256, BT_SOLVE_MIN_CTAS><<<grid, 256, s->smem_bytes, stream>>>(a);
 	BT_CUDA(cudaGetLastError());
 	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[3], stream));
 	s->launches = s->any_uncached ? 3 : 2;

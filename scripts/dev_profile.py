@@ -43,7 +43,7 @@ for nw in nwin:
                       ("h dep+setup", ws[:, 8] - ws[:, 7]), ("h total", ws[:, 8] - ws[:, 5])):
             print(f"   {nm:14s} {v.mean():9.0f} {np.percentile(v, 50):9.0f} {np.percentile(v, 95):9.0f}")
     d = np.diff(tails[:, 2:11], axis=1)
-    names = ["P0 zero/T", "P1 sparse", "P2a pairsum", "P2b xform", "P3 diag/rhs", "P4 cross", "PCG", "update"]
+    names = ["P0 zero/T", "P1 sparse", "P2 pairsum", "P3a gathers", "P3b diag/rhs", "P4 cross", "PCG", "update"]
     print(f" tails: n={len(tails)}")
     for i, nm in enumerate(names):
         print(f"   {nm:14s} {d[:, i].mean():9.0f} {np.percentile(d[:, i], 50):9.0f} {np.percentile(d[:, i], 95):9.0f}")
