@@ -233,61 +233,52 @@ __device__ __forceinline__ uint32_t hmin2_u32(uint32_t a, uint32_t b) {
 	return h2_as_u32(r);
 }
 
-// d2 (scaled) of two adjacent columns: one packed FFMA2 + one packed FADD2 (sm_100 f32x2 arithmetic) instead of two of each
-__device__ __forceinline__ void d2_pair(float& d0, float& d1, uint32_t v0, uint32_t v1, float n0, float n1, unsigned long long m2s2, unsigned long long nAs2) {
-	unsigned long long vv, nn, rr;
-	asm("mov.b64 %0, {%1, %2};" : "=l"(vv) : "r"(v0), "r"(v1));
-	asm("mov.b64 %0, {%1, %2};" : "=l"(nn) : "f"(n0), "f"(n1));
-	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rr) : "l"(m2s2), "l"(vv), "l"(nn));
-	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rr) : "l"(rr), "l"(nAs2));
-	asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(rr));
-}
+// ---- the epilogue's view of the accumulator -----------------------------------------------------------------------------------
+// tcgen05.ld.16x256b hands a thread the m16n8 accumulator fragment (probed on a B200, scripts/probe/tmem_layout.cu): register 4j + e of
+// thread T = TMEM lane base + T/4 + 8 (e >> 1), column 8j + 2 (T % 4) + (e & 1).  Two such loads (lanes +0..15, +16..31) give a thread
+// FOUR rows (T/4 + 8k, k = 0..3) x the column pairs (8j + 2m, 8j + 2m + 1), m = T % 4.  Both group minima the matcher needs then stay
+// inside the thread when a "group" is four indices 8 apart in a block of 32 - rows {r, r+8, r+16, r+24}, columns {c, c+8, c+16, c+24}:
+//   B->A  min over the thread's four rows, per column                      (3 packed-fp16 min per column pair)
+//   A->B  min over four column pairs 8 apart, per row                      (3 packed-fp16 min per two groups)
+// no shuffle, no select, no cross-half step (the first version grouped 4 CONSECUTIVE rows / columns of the 32x32b layout: 24 selects +
+// 12 shuffles + 24 fp32 min per 32 columns, and the ALU pipe, not the tensor pipe, paced the kernel).
+// In POSITION space pos(i) = (i & ~31) + 4 (i % 8) + (i % 32) / 8 such a group is four CONSECUTIVE positions; both group-minimum matrices
+// are stored by position, and a thread's results land on 8 / 16 contiguous bytes.  k_knn_select works in position space and converts
+// back with unpos() where it touches real rows.
+__host__ __device__ __forceinline__ int knn_unpos(int p) { return (p & ~31) + 8 * (p & 3) + ((p & 31) >> 2); }
 
-// One 32-column chunk of the accumulator, thread = A row: d2 (scaled) -> both group reductions -> global.
-// nrm_s: shared-memory address (32-bit) of this chunk's 32 scaled |b~|^2.
-__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], uint32_t nrm_s, float nAs, float m2s,
-                                          __half* __restrict__ rowp, size_t rstride, uint4* __restrict__ colp, int lane) {
-	float d[32];
-	unsigned long long m2s2, nAs2;
-	asm("mov.b64 %0, {%1, %1};" : "=l"(m2s2) : "f"(m2s));
-	asm("mov.b64 %0, {%1, %1};" : "=l"(nAs2) : "f"(nAs));
+#define TMEM_LD_16x256b_x8(taddr, v)                                                                                          \
+	asm volatile("tcgen05.ld.sync.aligned.16x256b.x8.b32 "                                                                    \
+	             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                      \
+	             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                      \
+	             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),     \
+	               "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),          \
+	               "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),         \
+	               "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                       \
+	             : "r"(taddr))
+
+// one 16-lane load (two of the thread's rows x 8 column pairs): d2 (scaled) = |a~|^2 + |b~|^2 - 2 a~.b~ with packed f32x2 arithmetic,
+// clamped at zero and rounded to fp16 pairs (cvt.rn.relu: a rounding-level negative d2 becomes +0, so the halves order like unsigned integers)
+__device__ __forceinline__ void epi_rows(const uint32_t (&v)[32], const unsigned long long (&nb)[8], float nAs0, float nAs1, unsigned long long m2s2,
+                                         uint32_t (&h0)[8], uint32_t (&h1)[8]) {
+	unsigned long long na0, na1;
+	asm("mov.b64 %0, {%1, %1};" : "=l"(na0) : "f"(nAs0));
+	asm("mov.b64 %0, {%1, %1};" : "=l"(na1) : "f"(nAs1));
 #pragma unroll
-	for (int j = 0; j < 32; j += 4) {
-		float n0, n1, n2, n3;
-		asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(n0), "=f"(n1), "=f"(n2), "=f"(n3) : "r"(nrm_s + 4u * j));
-		d2_pair(d[j], d[j + 1], v[j], v[j + 1], n0, n1, m2s2, nAs2);
-		d2_pair(d[j + 2], d[j + 3], v[j + 2], v[j + 3], n2, n3, m2s2, nAs2);
+	for (int j = 0; j < 8; j++) {
+		unsigned long long x0, x1;
+		float lo, hi;
+		asm("mov.b64 %0, {%1, %2};" : "=l"(x0) : "r"(v[4 * j]), "r"(v[4 * j + 1]));
+		asm("mov.b64 %0, {%1, %2};" : "=l"(x1) : "r"(v[4 * j + 2]), "r"(v[4 * j + 3]));
+		asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(x0) : "l"(m2s2), "l"(x0), "l"(nb[j]));
+		asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(x1) : "l"(m2s2), "l"(x1), "l"(nb[j]));
+		asm("add.rn.f32x2 %0, %1, %2;" : "=l"(x0) : "l"(x0), "l"(na0));
+		asm("add.rn.f32x2 %0, %1, %2;" : "=l"(x1) : "l"(x1), "l"(na1));
+		asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x0));
+		asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(h0[j]) : "f"(hi), "f"(lo));
+		asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x1));
+		asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(h1[j]) : "f"(hi), "f"(lo));
 	}
-	// ---- A->B: minimum of every group of 4 consecutive B columns (registers only); |x| clears a rounding-level negative sign so the
-	//      stored halves order like unsigned integers
-#pragma unroll
-	for (int g = 0; g < 8; g += 2) {
-		const float m0 = fminf(fminf(d[4 * g], d[4 * g + 1]), fminf(d[4 * g + 2], d[4 * g + 3]));
-		const float m1 = fminf(fminf(d[4 * g + 4], d[4 * g + 5]), fminf(d[4 * g + 6], d[4 * g + 7]));
-		const uint32_t hm = h2_as_u32(__floats2half2_rn(m0, m1)) & 0x7fff7fffu;
-		asm volatile("st.global.b16 [%0], %1;" ::"l"(rowp + (size_t)g * rstride), "h"((unsigned short)hm) : "memory");
-		asm volatile("st.global.b16 [%0], %1;" ::"l"(rowp + (size_t)(g + 1) * rstride), "h"((unsigned short)(hm >> 16)) : "memory");
-	}
-	// ---- B->A: minimum over the 4 consecutive A rows held by lanes 4m..4m+3: transposing butterfly on packed halves (xor 1, xor 2);
-	//      lane L ends with 8 columns (16 (L&1) + 8 ((L>>1)&1) ...) of row group L >> 2.  (Choosing keep / send with integer multiply-adds
-	//      on the FMA pipe instead of selects was measured: 0.110 vs 0.101 ms for the 45-pair batch - the selects stay.)
-	uint32_t h[16];
-#pragma unroll
-	for (int i = 0; i < 16; i++) h[i] = h2_as_u32(__floats2half2_rn(d[2 * i], d[2 * i + 1]));
-	const bool b0 = (lane & 1) != 0, b1 = (lane & 2) != 0;
-	uint32_t r[8];
-#pragma unroll
-	for (int i = 0; i < 8; i++) {
-		const uint32_t send = b0 ? h[i] : h[i + 8], keep = b0 ? h[i + 8] : h[i];
-		r[i] = hmin2_u32(keep, __shfl_xor_sync(0xffffffffu, send, 1));
-	}
-	uint32_t o[4];
-#pragma unroll
-	for (int i = 0; i < 4; i++) {
-		const uint32_t send = b1 ? r[i] : r[i + 4], keep = b1 ? r[i + 4] : r[i];
-		o[i] = hmin2_u32(keep, __shfl_xor_sync(0xffffffffu, send, 2)) & 0x7fff7fffu;
-	}
-	*colp = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 __global__ void __launch_bounds__(KNN_THREADS, 1)
@@ -385,7 +376,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUt
 		const int ew = warp - 2;
 		const int quarter = warp & 3;            // TMEM lanes [32*quarter, 32*quarter+32) are the only ones this warp may read
 		const int cq = ew >> 2;                  // columns [64*cq, 64*cq+64) of the 256-column tile
-		const int row = quarter * 32 + lane;     // A row inside the tile == TMEM lane
+		const int rq = lane >> 2, m = lane & 3;  // this thread: tile rows 32*quarter + rq + 8k (k = 0..3), column pairs 64*cq + 8j + 2m (+1), j = 0..7
 		const int etid = threadIdx.x - 64;       // 0..511
 		uint32_t tcount = 0;
 		UnitWalk w; w.init(pairs, n_pairs, u0);
@@ -394,34 +385,58 @@ k_knn_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUt
 		for (int u = u0; u < u1; u++, tcount++) {
 			const bool newb = (u == u0) || (w.qt == 0);
 			if (w.p != cur_p) { cur_p = w.p; s = pconst[cur_p].s; }
-			const float nA = __ldg(norms + w.pr.a_row0 + w.qt * BM + row);      // (used after the accumulator wait: the load has long landed)
+			const float* nAp = norms + w.pr.a_row0 + w.qt * BM + quarter * 32 + rq;      // (used after the accumulator wait: the loads have long landed)
+			const float nA0 = __ldg(nAp) * s, nA1 = __ldg(nAp + 8) * s, nA2 = __ldg(nAp + 16) * s, nA3 = __ldg(nAp + 24) * s;
 			if (newb) {      // |b~|^2 of the resident B tile (scaled) -> smem, one float per thread of the first 8 epilogue warps
 				asm volatile("bar.sync 1, 512;" ::: "memory");       // every epilogue thread is done with the previous tile's norms
 				if (etid < BN) sNorm[etid] = __ldg(norms + w.pr.b_row0 + w.tt * BN + etid) * s;
 				asm volatile("bar.sync 1, 512;" ::: "memory");
 			}
-			const float m2s = -2.0f * s;
+			unsigned long long m2s2;
+			{ const float m2s = -2.0f * s; asm("mov.b64 %0, {%1, %1};" : "=l"(m2s2) : "f"(m2s)); }
 			const uint32_t buf = tcount & 1, tphase = (tcount >> 1) & 1;
-			const uint32_t nrm_s = smem_u32(sNorm + cq * 64);
+			unsigned long long nb[8];      // (|b~|^2 of columns 8j + 2m, 8j + 2m + 1), j = 0..7
+			{
+				const uint32_t nrm_s = smem_u32(sNorm + cq * 64 + 2 * m);
+#pragma unroll
+				for (int j = 0; j < 8; j++) asm volatile("ld.shared.b64 %0, [%1];" : "=l"(nb[j]) : "r"(nrm_s + 32u * j));
+			}
 			const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + cq * 64;
+			// A->B matrix [B group][A position]: this thread's four rows are positions 4 rq .. 4 rq + 3 of their block of 32; its groups are 2m, 2m + 1 of each block of 32 columns
+			__half* rowp = G + w.pr.g_row + (size_t)(w.tt * (BN / GRP) + cq * 16 + 2 * m) * (size_t)w.pr.nA_pad + (size_t)(w.qt * BM + quarter * 32 + 4 * rq);
+			// B->A matrix [A group][B position]: row group rq of this quarter; its eight columns of a block of 32 are positions 8m .. 8m + 7
+			__half* colp = G + w.pr.g_col + (size_t)(w.qt * (BM / GRP) + quarter * 8 + rq) * (size_t)w.pr.nB_pad + (size_t)(w.tt * BN + cq * 64 + 8 * m);
 			const size_t rstride = (size_t)w.pr.nA_pad;
-			__half* rowp = G + w.pr.g_row + (size_t)((w.tt * BN + cq * 64) / GRP) * rstride + (size_t)(w.qt * BM + row);
-			uint4* colp = reinterpret_cast<uint4*>(G + w.pr.g_col + (size_t)(w.qt * (BM / GRP) + quarter * 8 + (lane >> 2)) * (size_t)w.pr.nB_pad
-			                                       + (size_t)(w.tt * BN + cq * 64 + 16 * (lane & 1) + 8 * ((lane >> 1) & 1)));
 			mbar_wait(tm_full + buf, tphase);
 			tc_fence_after();
-			const float nAs = nA * s;
-			// TMEM -> registers: the second chunk is in flight while the first is reduced
+			// TMEM -> registers: the second half (rows +16, +24) is in flight while the first is converted
 			uint32_t va[32], vb[32];
-			TMEM_LD32(taddr0, va);
+			uint32_t h0[8], h1[8], h2[8], h3[8];
+			TMEM_LD_16x256b_x8(taddr0, va);
 			asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-			TMEM_LD32(taddr0 + 32, vb);
-			epi_chunk(va, nrm_s, nAs, m2s, rowp, rstride, colp, lane);
+			TMEM_LD_16x256b_x8(taddr0 + (16u << 16), vb);
+			epi_rows(va, nb, nA0, nA1, m2s2, h0, h1);
 			asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 			tc_fence_before();
 			__syncwarp();
 			if (lane == 0) mbar_arrive(tm_empty + buf);      // the accumulator is in registers: the next unit's MMAs may overwrite it
-			epi_chunk(vb, nrm_s + 128u, nAs, m2s, rowp + 8 * rstride, rstride, colp + 4, lane);
+			epi_rows(vb, nb, nA2, nA3, m2s2, h2, h3);
+#pragma unroll
+			for (int jb = 0; jb < 2; jb++) {
+				// ---- B->A: minimum over the thread's four rows, per column pair; transposed into position order and stored as 16 bytes
+				uint32_t c[4];
+#pragma unroll
+				for (int jj = 0; jj < 4; jj++) { const int j = 4 * jb + jj; c[jj] = hmin2_u32(hmin2_u32(h0[j], h1[j]), hmin2_u32(h2[j], h3[j])); }
+				*reinterpret_cast<uint4*>(colp + 32 * jb) = make_uint4(__byte_perm(c[0], c[1], 0x5410), __byte_perm(c[2], c[3], 0x5410), __byte_perm(c[0], c[1], 0x7632), __byte_perm(c[2], c[3], 0x7632));
+				// ---- A->B: minimum over the four column pairs of this block of 32 columns, per row: (group 2m, group 2m + 1) x four rows
+				const uint32_t r0 = hmin2_u32(hmin2_u32(h0[4 * jb], h0[4 * jb + 1]), hmin2_u32(h0[4 * jb + 2], h0[4 * jb + 3]));
+				const uint32_t r1 = hmin2_u32(hmin2_u32(h1[4 * jb], h1[4 * jb + 1]), hmin2_u32(h1[4 * jb + 2], h1[4 * jb + 3]));
+				const uint32_t r2 = hmin2_u32(hmin2_u32(h2[4 * jb], h2[4 * jb + 1]), hmin2_u32(h2[4 * jb + 2], h2[4 * jb + 3]));
+				const uint32_t r3 = hmin2_u32(hmin2_u32(h3[4 * jb], h3[4 * jb + 1]), hmin2_u32(h3[4 * jb + 2], h3[4 * jb + 3]));
+				__half* rp = rowp + (size_t)(8 * jb) * rstride;
+				*reinterpret_cast<uint2*>(rp) = make_uint2(__byte_perm(r0, r1, 0x5410), __byte_perm(r2, r3, 0x5410));
+				*reinterpret_cast<uint2*>(rp + rstride) = make_uint2(__byte_perm(r0, r1, 0x7632), __byte_perm(r2, r3, 0x7632));
+			}
 			if (u + 1 < u1) w.next();
 		}
 	}
@@ -479,8 +494,10 @@ template <int K> __global__ void __launch_bounds__(256) k_knn_select(const SelJo
 	const SelJob jb = jobs[ji];
 	const int q0 = ((int)blockIdx.x - jb.blk0) * 64;
 	const bool live = jb.pconst >= 0;
-	const int qa = q0 + 2 * lane;                                   // my two queries: qa, qa + 1 (the matrices are padded to whole tiles: both loads stay inside)
-	const bool anyq = live && qa < jb.nq;
+	// Everything here runs in POSITION space (see knn_unpos): the matrices are stored by position, a group is four consecutive positions;
+	// real row numbers only appear where a row's data (error norm, bounds, outputs) is touched.
+	const int qa = q0 + 2 * lane;                                   // my two query positions: qa, qa + 1 (the matrices are padded to whole tiles: both loads stay inside)
+	const bool anyq = live && (knn_unpos(qa) < jb.nq || knn_unpos(qa + 1) < jb.nq);
 	const unsigned* Gq = reinterpret_cast<const unsigned*>(G + jb.g_off + qa);
 	const size_t gstride = (size_t)jb.q_stride >> 1;                // in 32-bit words
 	const int per = (jb.n_groups + 7) >> 3;
@@ -517,7 +534,7 @@ template <int K> __global__ void __launch_bounds__(256) k_knn_select(const SelJo
 		for (int j = 0; j < K; j++) if (j == kk - 1) hk2 = h2_as_u32(all[j]);
 #pragma unroll
 		for (int hq = 0; hq < 2; hq++) {
-			const int q = qa + hq;
+			const int q = knn_unpos(qa + hq);      // the real query row
 			const unsigned hk16 = hq ? (hk2 >> 16) : (hk2 & 0xffffu);
 			unsigned hmax = 0u;
 			if (live && q < jb.nq) {
@@ -555,22 +572,22 @@ template <int K> __global__ void __launch_bounds__(256) k_knn_select(const SelJo
 	// ---- members: the other direction's matrix holds, for (my 4-row group, member column), a minimum that includes my own entry
 	//      => a lower bound of the member's stored key; 8 bytes per group instead of four descriptor rows
 	for (int w2 = threadIdx.x; w2 < 64 * SEL_MAXG; w2 += 256) {
-		const int ql = w2 & 63, it = w2 >> 6, q = q0 + ql;
-		if (live && q < jb.nq && it < min(s_ng[ql], SEL_MAXG)) {
+		const int ql = w2 & 63, it = w2 >> 6, q = q0 + ql;      // q: query POSITION
+		if (live && it < min(s_ng[ql], SEL_MAXG)) {      // (queries beyond nq have hmax = 0 and therefore no groups)
 			const int g = s_grp[ql][it];
 			const unsigned hmax = s_hmax[ql];
 			const uint2 m = __ldg(reinterpret_cast<const uint2*>(G + jb.x_off + (size_t)(q >> 2) * jb.x_stride + (size_t)g * GRP));
 			const unsigned key4[4] = { m.x & 0xffffu, m.x >> 16, m.y & 0xffffu, m.y >> 16 };
 #pragma unroll
 			for (int j = 0; j < 4; j++) {
-				const int t = g * GRP + j;
+				const int t = knn_unpos(g * GRP + j);      // the member's real row
 				if (t < jb.nt && key4[j] <= hmax) { const int c = atomicAdd(&s_nc[ql], 1); if (c < SEL_MAXC) s_cand[ql][c] = t; }
 			}
 		}
 	}
 	__syncthreads();
 	for (int w2 = threadIdx.x; w2 < 64 * SEL_MAXC; w2 += 256) {
-		const int ql = w2 & 63, c = w2 >> 6, q = q0 + ql;
+		const int ql = w2 & 63, c = w2 >> 6, q = knn_unpos(q0 + ql);      // back to the real query row for the outputs
 		if (q < jb.nq) {
 			const int ng = s_ng[ql], nc = s_nc[ql];
 			const bool over = ng > SEL_MAXG || nc > SEL_MAXC;
@@ -862,7 +879,7 @@ static int knn_run(bt_ctx* ctx, int n_pairs, const PoolSetRef* A, const PoolSetR
 		}
 		for (int dir = 0; dir < 2; dir++) {
 			SelJob jb; memset(&jb, 0, sizeof jb);
-			jb.nq = dir == 0 ? nA : nB; jb.nt = dir == 0 ? nB : nA; jb.n_groups = (jb.nt + GRP - 1) / GRP;
+			jb.nq = dir == 0 ? nA : nB; jb.nt = dir == 0 ? nB : nA; jb.n_groups = (jb.nt + 31) / 32 * (32 / GRP);      // whole blocks of 32 positions: a block's valid rows are spread over all of its groups
 			jb.q_pool_row0 = (dir == 0 ? A[p].slot : B[p].slot) * m->slot_rows; jb.t_pool_row0 = (dir == 0 ? B[p].slot : A[p].slot) * m->slot_rows;
 			jb.pconst = live ? (int)pairs.size() - 1 : -1;
 			if (live) {
