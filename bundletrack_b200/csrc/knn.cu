@@ -483,7 +483,7 @@ __device__ __forceinline__ __half2 u32_as_h2(unsigned v) { return *reinterpret_c
 // and every min / max of the selection network serves both queries), 8 warps = 8 segments of the group axis.
 template <int K> __global__ void __launch_bounds__(256) k_knn_select(const SelJob* __restrict__ jobs, const int* __restrict__ blk_start, int n_jobs,
                                                                      const __half* __restrict__ G, const float* __restrict__ errn, const PairConst* __restrict__ pconst,
-                                                                     int k, int32_t* __restrict__ cand, int32_t* __restrict__ cand_cnt) {
+                                                                     int k, int32_t* __restrict__ cand, int32_t* __restrict__ cand_cnt, int* __restrict__ qjob) {
 	__shared__ unsigned s_top[8][K][32];
 	__shared__ unsigned s_hmax[64];
 	__shared__ int s_ng[64], s_nc[64];
@@ -510,6 +510,13 @@ template <int K> __global__ void __launch_bounds__(256) k_knn_select(const SelJo
 	for (int j = 0; j < K; j++) top[j] = inf2;
 	if (anyq) {
 		int g = g0;
+		for (; g + 8 <= g1; g += 8) {      // eight independent loads in flight per lane: the matrices come from L2 / DRAM and this pass is latency-bound
+			unsigned kq[8];
+#pragma unroll
+			for (int u = 0; u < 8; u++) kq[u] = __ldg(Gq + (size_t)(g + u) * gstride);
+#pragma unroll
+			for (int u = 0; u < 8; u++) kmin_insert2<K>(top, u32_as_h2(kq[u]));
+		}
 		for (; g + 4 <= g1; g += 4) {
 			const unsigned k0 = __ldg(Gq + (size_t)g * gstride), k1 = __ldg(Gq + (size_t)(g + 1) * gstride);
 			const unsigned k2 = __ldg(Gq + (size_t)(g + 2) * gstride), k3 = __ldg(Gq + (size_t)(g + 3) * gstride);
@@ -561,11 +568,18 @@ template <int K> __global__ void __launch_bounds__(256) k_knn_select(const SelJo
 	// ---- pass 2: groups that can still hold one of the k nearest (keys order like their bit patterns)
 	const unsigned hm0 = s_hmax[2 * lane], hm1 = s_hmax[2 * lane + 1];
 	if (anyq) {
-		for (int g = g0; g < g1; g++) {
-			const unsigned key2 = __ldg(Gq + (size_t)g * gstride);
-			const bool p0 = (key2 & 0xffffu) <= hm0 && hm0 != 0u, p1 = (key2 >> 16) <= hm1 && hm1 != 0u;
-			if (p0) { const int slot = atomicAdd(&s_ng[2 * lane], 1); if (slot < SEL_MAXG) s_grp[2 * lane][slot] = g; }
-			if (p1) { const int slot = atomicAdd(&s_ng[2 * lane + 1], 1); if (slot < SEL_MAXG) s_grp[2 * lane + 1][slot] = g; }
+		for (int gb = g0; gb < g1; gb += 8) {      // (second sweep over the same column: eight loads in flight again)
+			unsigned kq[8];
+#pragma unroll
+			for (int u = 0; u < 8; u++) kq[u] = __ldg(Gq + (size_t)min(gb + u, g1 - 1) * gstride);
+#pragma unroll
+			for (int u = 0; u < 8; u++) {
+				const int g = gb + u;
+				const unsigned key2 = kq[u];
+				const bool p0 = g < g1 && (key2 & 0xffffu) <= hm0 && hm0 != 0u, p1 = g < g1 && (key2 >> 16) <= hm1 && hm1 != 0u;
+				if (p0) { const int slot = atomicAdd(&s_ng[2 * lane], 1); if (slot < SEL_MAXG) s_grp[2 * lane][slot] = g; }
+				if (p1) { const int slot = atomicAdd(&s_ng[2 * lane + 1], 1); if (slot < SEL_MAXG) s_grp[2 * lane + 1][slot] = g; }
+			}
 		}
 	}
 	__syncthreads();
@@ -591,7 +605,7 @@ template <int K> __global__ void __launch_bounds__(256) k_knn_select(const SelJo
 		if (q < jb.nq) {
 			const int ng = s_ng[ql], nc = s_nc[ql];
 			const bool over = ng > SEL_MAXG || nc > SEL_MAXC;
-			if (c == 0) cand_cnt[jb.q_base + q] = over ? -1 : nc;
+			if (c == 0) { cand_cnt[jb.q_base + q] = over ? -1 : nc; qjob[jb.q_base + q] = ji; }
 			if (!over && c < nc) cand[(size_t)(jb.q_base + q) * SEL_MAXC + c] = s_cand[ql][c];
 		}
 	}
@@ -604,15 +618,17 @@ __device__ __forceinline__ bool dist_less(double da, int ia, double db, int ib) 
 }
 
 // one warp per query row: exact float64 distance of every candidate on the fp32 copies of the rows (two rows in flight), top k by
-// (distance, index)
-__global__ void __launch_bounds__(256) k_knn_rerank(const SelJob* __restrict__ jobs, const int* __restrict__ q_start, int n_jobs, int total_q,
+// (distance, index).  The kernel is paced by the float -> double conversions (XU pipe) and the FP64 pipe; a variant with eight lanes per
+// candidate and four candidates in flight (three shuffle steps instead of five) was measured SLOWER (0.30 vs 0.23 ms for 180 k rows): it
+// converts the query's slice four times as often and idles on the last round's unused candidate slots.
+__global__ void __launch_bounds__(256) k_knn_rerank(const SelJob* __restrict__ jobs, const int* __restrict__ qjob, int total_q,
                                                     const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt, const float* __restrict__ pool_f,
                                                     int k, KnnOut out, int* fallback_rows, int* fallback_count, int force_fallback) {
 	const int lane = threadIdx.x & 31;
 	const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (gw >= total_q) return;
-	const int ji = find_by_start(q_start, n_jobs, gw);
-	const SelJob jb = jobs[ji];
+	const SelJob jb = jobs[__ldg(qjob + gw)];      // (k_knn_select wrote the job of every query next to its candidate count: a binary search over the
+	                                               //  job table per warp cost 66 instructions and 10 % of this kernel's stall samples)
 	const int r = gw - jb.q_base;
 	const int kk = min(k, jb.nt);
 	const float INF = __int_as_float(0x7f800000);
@@ -785,7 +801,7 @@ struct MatcherState {
 	int slot_rows = 0;                      // rows per pool slot (max_feats padded to 256)
 	int n_transient = 0, n_persist = 0;     // transient slots [0, n_transient) serve bt_knn_match_pairs; persistent ones follow
 	std::vector<int> slot_n;                // persistent slots: number of rows stored, -1 = empty
-	DevBuf pool_h, pool_f, norms, errn, slot_meta, sets, pairs, pconst, G, jobs, blk_start, q_start, cand, cand_cnt, fb_rows, fb_count, fb_part_d, fb_part_i, fb_tickets;
+	DevBuf pool_h, pool_f, norms, errn, slot_meta, sets, pairs, pconst, G, jobs, blk_start, q_start, cand, cand_cnt, qjob, fb_rows, fb_count, fb_part_d, fb_part_i, fb_tickets;
 	PinnedBuf h_stage;
 	cudaEvent_t ev_up = nullptr;            // behind the upload of h_stage: the next call waits on it before rewriting the pinned block
 	PFN_encodeTiled encode = nullptr;
@@ -802,7 +818,7 @@ struct MatcherState {
 void matcher_destroy(bt_ctx* ctx) {
 	MatcherState* m = ctx->matcher;
 	if (!m) return;
-	DevBuf* bufs[] = { &m->pool_h, &m->pool_f, &m->norms, &m->errn, &m->slot_meta, &m->sets, &m->pairs, &m->pconst, &m->G, &m->jobs, &m->blk_start, &m->q_start, &m->cand, &m->cand_cnt,
+	DevBuf* bufs[] = { &m->pool_h, &m->pool_f, &m->norms, &m->errn, &m->slot_meta, &m->sets, &m->pairs, &m->pconst, &m->G, &m->jobs, &m->blk_start, &m->q_start, &m->cand, &m->cand_cnt, &m->qjob,
 	                   &m->fb_rows, &m->fb_count, &m->fb_part_d, &m->fb_part_i, &m->fb_tickets };
 	for (DevBuf* b : bufs) b->release();
 	m->h_stage.release();
@@ -908,19 +924,19 @@ static int knn_run(bt_ctx* ctx, int n_pairs, const PoolSetRef* A, const PoolSetR
 	BT_CUDA(cudaMemcpyAsync(m->q_start.p, h0 + b_pairs + b_jobs + b_int, b_int, cudaMemcpyHostToDevice, stream));
 	BT_CUDA(cudaEventRecord(m->ev_up, stream));
 	BT_CUDA(cudaMemsetAsync(m->fb_count.p, 0, 16, stream));
-	if (m->timing) BT_CUDA(cudaEventRecord(m->ev[1], stream));      // [ev0, ev1) = descriptor conversion + table upload
+	if (n_live > 0) k_knn_pairconst<<<(n_live + 127) / 128, 128, 0, stream>>>(m->pairs.as<KnnPair>(), n_live, m->slot_meta.as<int>(), m->pconst.as<PairConst>());
+	if (m->timing) BT_CUDA(cudaEventRecord(m->ev[1], stream));      // [ev0, ev1) = descriptor conversion + table upload + per-pair constants; [ev1, ev2) = k_knn_tc alone
 	// ---- kernels
 	if (n_live > 0) {
-		k_knn_pairconst<<<(n_live + 127) / 128, 128, 0, stream>>>(m->pairs.as<KnnPair>(), n_live, m->slot_meta.as<int>(), m->pconst.as<PairConst>());
 		const int grid = (int)std::min<long long>(units, ctx->sm_count);
 		k_knn_tc<<<grid, KNN_THREADS, SMEM_TOTAL, stream>>>(m->tmap_a, m->tmap_b, m->pairs.as<KnnPair>(), n_live, (int)units, m->norms.as<float>(), m->pconst.as<PairConst>(), m->G.as<__half>());
 	}
 	if (m->timing) BT_CUDA(cudaEventRecord(m->ev[2], stream));
 	KnnOut out; out.idx[0] = idxAB; out.idx[1] = idxBA; out.dist[0] = distAB; out.dist[1] = distBA;
 	if (q_total > 0) {
-		if (k <= 5) k_knn_select<5><<<blocks, 256, 0, stream>>>(m->jobs.as<SelJob>(), m->blk_start.as<int>(), (int)jobs.size(), m->G.as<__half>(), m->errn.as<float>(), m->pconst.as<PairConst>(), k, m->cand.as<int32_t>(), m->cand_cnt.as<int32_t>());
-		else k_knn_select<8><<<blocks, 256, 0, stream>>>(m->jobs.as<SelJob>(), m->blk_start.as<int>(), (int)jobs.size(), m->G.as<__half>(), m->errn.as<float>(), m->pconst.as<PairConst>(), k, m->cand.as<int32_t>(), m->cand_cnt.as<int32_t>());
-		k_knn_rerank<<<(q_total + 7) / 8, 256, 0, stream>>>(m->jobs.as<SelJob>(), m->q_start.as<int>(), (int)jobs.size(), q_total, m->cand.as<int32_t>(), m->cand_cnt.as<int32_t>(), m->pool_f.as<float>(),
+		if (k <= 5) k_knn_select<5><<<blocks, 256, 0, stream>>>(m->jobs.as<SelJob>(), m->blk_start.as<int>(), (int)jobs.size(), m->G.as<__half>(), m->errn.as<float>(), m->pconst.as<PairConst>(), k, m->cand.as<int32_t>(), m->cand_cnt.as<int32_t>(), m->qjob.as<int>());
+		else k_knn_select<8><<<blocks, 256, 0, stream>>>(m->jobs.as<SelJob>(), m->blk_start.as<int>(), (int)jobs.size(), m->G.as<__half>(), m->errn.as<float>(), m->pconst.as<PairConst>(), k, m->cand.as<int32_t>(), m->cand_cnt.as<int32_t>(), m->qjob.as<int>());
+		k_knn_rerank<<<(q_total + 7) / 8, 256, 0, stream>>>(m->jobs.as<SelJob>(), m->qjob.as<int>(), q_total, m->cand.as<int32_t>(), m->cand_cnt.as<int32_t>(), m->pool_f.as<float>(),
 		                                                 k, out, m->fb_rows.as<int>(), m->fb_count.as<int>(), m->force_fallback);
 		if (m->timing) BT_CUDA(cudaEventRecord(m->ev[3], stream));
 		k_knn_exact<<<ctx->sm_count * 2, 256, 0, stream>>>(m->jobs.as<SelJob>(), m->q_start.as<int>(), (int)jobs.size(), m->pool_f.as<float>(), m->fb_rows.as<int>(), m->fb_count.as<int>(), k, out,
@@ -970,6 +986,7 @@ extern "C" int bt_matcher_reserve(bt_ctx* ctx, int max_pairs, int max_feats, int
 	RES(blk_start, sizeof(int) * m->max_jobs); RES(q_start, sizeof(int) * m->max_jobs);
 	RES(cand, sizeof(int32_t) * SEL_MAXC * (size_t)m->max_q_total);
 	RES(cand_cnt, sizeof(int32_t) * (size_t)m->max_q_total);
+	RES(qjob, sizeof(int) * (size_t)m->max_q_total);
 	RES(fb_rows, sizeof(int) * (size_t)m->max_q_total);
 	RES(fb_count, 16);
 	RES(fb_part_d, sizeof(double) * (size_t)FB_SPLIT_ROWS * FB_SEG * 8); RES(fb_part_i, sizeof(int) * (size_t)FB_SPLIT_ROWS * FB_SEG * 8);
