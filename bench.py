@@ -611,7 +611,9 @@ def main():
         matcher = matcher_microbench(dev, stream)
         extras = frontend_microbench(opt, dev, stream)
         cfg3 = cfg3_microbench(dev, stream) if not args.skip_cfg3 else None
-        launches_per_step = 1 + int(stats["n_kernel_launches"])
+        # per step: the new frames' store (k_cache_count + k_cache_build below 2 x SM-count frames, else one k_frame_cache_store) + pose prep + k_solve
+        store_launches = 2 if len(new_slots) < 2 * torch.cuda.get_device_properties(dev).multi_processor_count else 1
+        launches_per_step = store_launches + int(stats["n_kernel_launches"])
         out = dict(base, value=value, ms_per_step=ms_step, gpu_launches=launches_per_step * args.steps * len(blk_ms),
                    e2e={"value": e2e_val, "unit": "windows/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": float(t_e2e.item()),
                         "api": "bt_frame_cache_store + bt_solve_windows_begin / bt_solve_windows_end (two batches in flight)",

@@ -10,6 +10,9 @@
 #include <algorithm>
 #include <limits>
 #include <vector>
+#include <string>
+#include <stdio.h>
+#include <string.h>
 #include "bt_common.cuh"
 
 namespace {
@@ -169,6 +172,72 @@ extern "C" int bt_rigid_transform(const float* pts1, const float* pts2, int n, f
 // (lf-net-release/run_server.py:171-177): part 0 = int32 (n, dim), part 1 = float32 n x 2 keypoints (x, y) in the 400 x 400 network input,
 // part 2 = float32 n x dim descriptors (row-major: exactly the matrix bt_knn_match_pairs takes, no repacking).  Keypoints go back to
 // image pixels through forward^-1, forward = scale(400/side) * translate(-umin, -vmin), side = max(roi height, roi width).
+extern "C" int bt_ba_gate(int n_edges_newframe, int min_fm_edges_newframe) {
+	return n_edges_newframe > min_fm_edges_newframe ? 1 : 0;      // `if (n_edges_newframe<=min_fm_edges_newframe) { NO_BA; return; }`, Bundler.cpp:343
+}
+
+// inverse of a 4x4 in float, by cofactors (what Eigen's Matrix4f::inverse() evaluates); row-major in and out
+static bool inverse4(const float* m, float* inv) {
+	float t[16];
+	t[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+	t[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+	t[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+	t[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+	t[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+	t[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+	t[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+	t[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+	t[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+	t[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+	t[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+	t[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+	t[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+	t[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+	t[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+	t[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+	const float det = m[0] * t[0] + m[1] * t[4] + m[2] * t[8] + m[3] * t[12];
+	if (!(det != 0.f)) return false;
+	const float id = 1.0f / det;
+	for (int i = 0; i < 16; i++) inv[i] = t[i] * id;
+	return true;
+}
+
+extern "C" int bt_pose_format(const float* cur_in_model, char* text, int cap) {
+	BT_REQUIRE(cur_in_model && text && cap > 0, BT_ERR_INVALID_ARG, "bt_pose_format: NULL argument");
+	float ob[16];
+	BT_REQUIRE(inverse4(cur_in_model, ob), BT_ERR_INVALID_ARG, "bt_pose_format: the pose is singular");
+	// Eigen's default IOFormat with the stream's precision: every coefficient printed like `os << std::setprecision(10) << float`
+	// (= %.10g), padded on the left to the widest one, coefficients separated by one blank, rows by a newline, `endl` after the matrix
+	char cell[16][40];
+	size_t width = 0;
+	for (int i = 0; i < 16; i++) { snprintf(cell[i], sizeof cell[i], "%.10g", (double)ob[i]); width = std::max(width, strlen(cell[i])); }
+	std::string out;
+	for (int r = 0; r < 4; r++) {
+		for (int c = 0; c < 4; c++) {
+			if (c) out += ' ';
+			out.append(width - strlen(cell[r * 4 + c]), ' ');
+			out += cell[r * 4 + c];
+		}
+		out += '\n';
+	}
+	BT_REQUIRE((int)out.size() + 1 <= cap, BT_ERR_CAPACITY, "bt_pose_format: %zu bytes needed, %d given", out.size() + 1, cap);
+	memcpy(text, out.c_str(), out.size() + 1);
+	return BT_OK;
+}
+
+extern "C" int bt_pose_write_txt(const char* path, const float* cur_in_model) {
+	BT_REQUIRE(path, BT_ERR_INVALID_ARG, "bt_pose_write_txt: NULL path");
+	char text[1024];
+	const int rc = bt_pose_format(cur_in_model, text, (int)sizeof text);
+	if (rc != BT_OK) return rc;
+	FILE* f = fopen(path, "w");
+	BT_REQUIRE(f != nullptr, BT_ERR_INVALID_ARG, "bt_pose_write_txt: cannot open %s", path);
+	const size_t n = strlen(text);
+	const bool ok = fwrite(text, 1, n, f) == n;
+	BT_REQUIRE(fclose(f) == 0 && ok, BT_ERR_INVALID_ARG, "bt_pose_write_txt: short write to %s", path);
+	return BT_OK;
+}
+
 extern "C" int bt_lfnet_parse_reply(const void* info, size_t info_bytes, const void* kpts, size_t kpts_bytes, size_t desc_bytes, const int* roi,
                                     float* kpts_out, int kpts_capacity, int* n_out, int* dim_out) {
 	BT_REQUIRE(info && roi && n_out && dim_out, BT_ERR_INVALID_ARG, "bt_lfnet_parse_reply: NULL argument");

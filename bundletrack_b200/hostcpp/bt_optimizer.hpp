@@ -84,6 +84,17 @@ public:
 		for (int f = 0; f < n_frames; f++)
 			for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) poses[f](r, c) = flat[16 * f + 4 * r + c];
 	}
+	// Bundler::optimizeGPU from the gate onwards (/root/reference/src/Bundler.cpp:343-358): `n_edges_newframe` = the number of emitted
+	// correspondences with the new frame on either side.  Returns false (the caller sets _newframe->_status = Frame::NO_BA) without
+	// touching the GPU when the new frame has too few edges, true after optimizeFrames has rewritten `poses`.
+	template <class EntryJT, class Uchar4T, class Float4T, class Mat4, class Alloc, class Mat3>
+	bool optimizeGPU(const std::vector<EntryJT>& global_corres, const std::vector<int>& n_match_per_pair, int n_edges_newframe, int min_fm_edges_newframe,
+	                 int n_frames, int H, int W, const std::vector<float*>& depths_gpu, const std::vector<Uchar4T*>& colors_gpu,
+	                 const std::vector<Float4T*>& normals_gpu, std::vector<Mat4, Alloc>& poses, const Mat3& K, void* stream = nullptr) {
+		if (!bt_ba_gate(n_edges_newframe, min_fm_edges_newframe)) return false;
+		optimizeFrames(global_corres, n_match_per_pair, n_frames, H, W, depths_gpu, colors_gpu, normals_gpu, poses, K, stream);
+		return true;
+	}
 	// Batched form: the windows of several tracked objects (or several frames' worth of work) in one call.  Every element of `windows`
 	// carries what one optimizeFrames call takes; poses[w] is in-out like above.
 	template <class EntryJT, class Float4T, class Mat4, class Alloc, class Mat3>
@@ -131,6 +142,15 @@ private:
 	BtSolverConfig cfg_;
 	bt_ctx* ctx_ = nullptr;
 };
+
+// Bundler::saveNewframeResult's pose record (/root/reference/src/Bundler.cpp:362-378): <pose_out_dir>/<id_str>.txt holds ob_in_cam =
+// cur_in_model^-1 printed with 10 significant digits the way Eigen prints a Matrix4f.  The caller creates the directory, as the reference does.
+template <class Mat4>
+inline void saveNewframePose(const std::string& path, const Mat4& cur_in_model) {
+	float flat[16];
+	for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) flat[4 * r + c] = cur_in_model(r, c);
+	if (bt_pose_write_txt(path.c_str(), flat) != BT_OK) throw std::runtime_error(std::string("bt_pose_write_txt: ") + bt_last_error());
+}
 
 // ransacMultiPairGPU with the reference's argument list (device float4 arrays per pair, host result vectors).  The device result
 // buffers and the library's scratch belong to the object: nothing is allocated per call (the reference allocates six arrays and a

@@ -95,3 +95,21 @@ class Tracks:
         a, b = ctypes.c_int(0), ctypes.c_int(0)
         _lib.check(self.lib.bt_tracks_stats(self.h, ctypes.byref(a), ctypes.byref(b)), "bt_tracks_stats")
         return a.value, b.value
+
+
+def ba_gate(n_edges_newframe: int, min_fm_edges_newframe: int = 10) -> bool:
+    """Bundler::optimizeGPU's gate (/root/reference/src/Bundler.cpp:343-347): False = Frame::NO_BA, the optimizer is not called."""
+    return bool(_lib.load().bt_ba_gate(ctypes.c_int(n_edges_newframe), ctypes.c_int(min_fm_edges_newframe)))
+
+
+def pose_text(cur_in_model) -> str:
+    """Bundler::saveNewframeResult's pose record (Bundler.cpp:362-378): ob_in_cam = inverse(cur_in_model), printed like Eigen prints it."""
+    p = np.ascontiguousarray(cur_in_model, np.float32)
+    buf = ctypes.create_string_buffer(1024)
+    _lib.check(_lib.load().bt_pose_format(_p(p), buf, ctypes.c_int(1024)), "bt_pose_format")
+    return buf.value.decode()
+
+
+def save_pose_txt(path: str, cur_in_model) -> None:
+    p = np.ascontiguousarray(cur_in_model, np.float32)
+    _lib.check(_lib.load().bt_pose_write_txt(path.encode(), _p(p)), "bt_pose_write_txt")

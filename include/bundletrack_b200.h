@@ -354,6 +354,19 @@ BT_API int bt_select_keyframes(const float* pose_new, const float* keyframe_pose
  * the fit degenerates, as in the reference. */
 BT_API int bt_rigid_transform(const float* pts1, const float* pts2, int n, float* pose_out);
 
+/* The gate in front of the optimizer in Bundler::optimizeGPU (/root/reference/src/Bundler.cpp:343-347): bundle adjustment runs only when
+ * the new frame takes part in MORE than min_fm_edges_newframe correspondences of the window; otherwise the frame's status becomes
+ * Frame::NO_BA and the poses stay as they are.  n_edges_newframe = number of EntryJ records with the new frame on either side
+ * (bt_match_cache_gather / FindCorres report it).  Returns 1 = run bt_solve_windows, 0 = NO_BA. */
+BT_API int bt_ba_gate(int n_edges_newframe, int min_fm_edges_newframe);
+/* Bundler::saveNewframeResult's pose record (/root/reference/src/Bundler.cpp:362-378): ob_in_cam = inverse(cur_in_model) as text, the 4 x 4
+ * matrix printed the way `ofstream << std::setprecision(10) << Eigen::Matrix4f` prints it (10 significant digits, columns right-aligned
+ * to the widest coefficient, one row per line).  bt_pose_format writes at most `cap` bytes incl. the terminating 0 into `text` and
+ * returns BT_ERR_CAPACITY when it does not fit (1024 is always enough); bt_pose_write_txt writes `path` (the caller creates
+ * <debug_dir>/poses/ as the reference does). */
+BT_API int bt_pose_format(const float* cur_in_model, char* text, int cap);
+BT_API int bt_pose_write_txt(const char* path, const float* cur_in_model);
+
 /* Lfnet::detectFeature's reply handling (/root/reference/src/FeatureManager.cpp:876-907; rot_deg = 0, the only value the tracker uses):
  * validates the three message parts of the LF-Net server's reply (int32 (n, dim) | float32 n x 2 keypoints in the 400 x 400 network
  * input | float32 n x dim descriptors) and maps the keypoints back to image pixels through the crop / pad-to-square / resize

@@ -44,7 +44,13 @@ int main(int argc, char** argv) {
 		BtSolverConfig cfg;      // the shipped config_nocs.yml values
 		OptimizerGpu opt(cfg, 0, N > 2 ? N : 2, C > 0 ? C : 1, H, W, 2);
 		std::vector<int> n_match_per_pair;
-		opt.optimizeFrames(corr, n_match_per_pair, N, H, W, depths, colors, normals, poses, K);
+		{   // Bundler::optimizeGPU's gate (Bundler.cpp:343): too few edges to the new frame -> NO_BA, the poses stay as they are
+			std::vector<Mat4> untouched = poses;
+			if (opt.optimizeGPU(corr, n_match_per_pair, 10, 10, N, H, W, depths, colors, normals, untouched, K)) return 4;
+			for (int f = 0; f < N; f++) for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) if (untouched[f](r, c) != poses[f](r, c)) return 5;
+		}
+		if (!opt.optimizeGPU(corr, n_match_per_pair, 11, 10, N, H, W, depths, colors, normals, poses, K)) return 6;      // = optimizeFrames behind the gate
+		saveNewframePose(std::string(argv[2]) + ".pose.txt", poses[N - 1]);
 		for (int f = 0; f < N; f++) for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) flat[16 * f + 4 * r + c] = poses[f](r, c);
 		wr(out, flat.data(), flat.size() * 4);
 		{   // the batched form: the same window twice in one call must reproduce the single call

@@ -97,6 +97,9 @@ def test_cpp_shim_runs_on_gpu_and_equals_ctypes_path(tmp_path, cuda_device):
     opt.close()
     assert np.array_equal(poses_cpp, ref)
     assert np.array_equal(poses_cpp_batch, ref_batch)
+    # saveNewframePose (Bundler::saveNewframeResult's pose record): ob_in_cam of the newest frame, as text
+    from bundletrack_b200 import policy
+    assert open(str(outp) + ".pose.txt").read() == policy.pose_text(ref[N - 1])
     assert synth.pose_errors(ref, w.poses_gt)[0] < synth.pose_errors(w.poses_init, w.poses_gt)[0]
     m = KnnMatcher(max_pairs=1, max_feats=1024)
     iAB, dAB, iBA, dBA = m.knn_match_pairs([(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev))])

@@ -151,3 +151,28 @@ def test_map_point_tracks_match_the_restatement():
     with pytest.raises(_lib.BtError):
         t.propagate(2, 1, np.zeros((0, 4)), capacity=0)           # more matches than the caller made room for
     t.close(); got.close()
+
+
+def test_ba_gate_and_pose_record(tmp_path):
+    """Bundler::optimizeGPU's NO_BA gate (Bundler.cpp:343) and saveNewframeResult's pose file (Bundler.cpp:362-378): ob_in_cam =
+    inverse(cur_in_model), 10 significant digits, columns right-aligned to the widest coefficient like Eigen's operator<<."""
+    from bundletrack_b200 import synth
+    assert not policy.ba_gate(10, 10) and policy.ba_gate(11, 10) and not policy.ba_gate(0, 0) and policy.ba_gate(1, 0)
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        T = synth.se3(synth.so3_exp(rng.normal(0, 0.8, 3)), rng.normal(0, 0.5, 3)).astype(np.float32)
+        txt = policy.pose_text(T)
+        lines = txt.split("\n")
+        assert len(lines) == 5 and lines[4] == "" and len({len(l) for l in lines[:4]}) == 1      # four rows of equal width, trailing newline
+        got = np.array([[float(v) for v in l.split()] for l in lines[:4]])
+        assert got.shape == (4, 4)
+        want = np.linalg.inv(T.astype(np.float64))
+        assert np.abs(got - want).max() <= 2e-6
+        # every coefficient carries the 10 significant digits of the float it was printed from
+        inv32 = np.array([[np.float32(v) for v in l.split()] for l in lines[:4]], np.float32)
+        assert np.array_equal(inv32, got.astype(np.float32))
+        p = tmp_path / "0001.txt"
+        policy.save_pose_txt(str(p), T)
+        assert p.read_text() == txt
+    with pytest.raises(Exception):
+        policy.pose_text(np.zeros((4, 4), np.float32))      # singular
