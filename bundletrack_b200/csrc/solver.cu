@@ -1499,7 +1499,7 @@ static StageLayout stage_layout(int n_windows, size_t F, size_t C, int max_frame
 struct SolverState {
 	bt_solver_limits lim{};
 	int npix_max = 0, max_pairs = 0, max_frames_total = 0, max_tiles = 0, max_groups = 0;
-	DevBuf blk_cnt, grp_sums, stage_dev, texel, src, nsrc, x, T, pose_out, tiles, scalars, partial, tiles_done, iter_done, pair_tile0, pair_ntile, dbgJ, dbgR, dbgC, prof;
+	DevBuf blk_cnt, grp_sums, stage_buf[2], texel, src, nsrc, x, T, pose_out, tiles, scalars, partial, tiles_done, iter_done, pair_tile0, pair_ntile, dbgJ, dbgR, dbgC, prof;
 	StageLayout layout{};
 	// frame cache (bt_frame_cache_*): quarter-res maps of keyframes, built once, referenced by bt_window::cache_slots
 	struct CacheMeta { bool valid = false; int H = 0, W = 0; float fx = 0, fy = 0, cx = 0, cy = 0, dmin = 0, dmax = 0; };
@@ -1531,21 +1531,23 @@ struct SolverState {
 	int attr_bytes = 0, occ = BT_SOLVE_MIN_CTAS, occ_smem = -1;
 	bool prep_launched = false, any_uncached = true;
 	cudaStream_t copy_stream = nullptr;
-	cudaEvent_t ev_prev = nullptr, ev_corr = nullptr, ev_h2d = nullptr;
+	cudaEvent_t ev_prev = nullptr, ev_corr = nullptr, ev_h2d = nullptr, ev_early = nullptr;
+	cudaEvent_t ev_stage_free[2] = { nullptr, nullptr };   // behind the k_solve that last read staging block 0 / 1
+	int stage_cur = 0;
 	cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
 };
 
 void solver_destroy(bt_ctx* ctx) {
 	SolverState* s = ctx->solver;
 	if (!s) return;
-	DevBuf* bufs[] = { &s->blk_cnt, &s->grp_sums, &s->c_texel, &s->c_src, &s->c_nsrc, &s->c_tables, &s->c_blk, &s->stage_dev, &s->texel, &s->src, &s->nsrc, &s->x, &s->T, &s->pose_out, &s->tiles, &s->scalars, &s->partial,
+	DevBuf* bufs[] = { &s->blk_cnt, &s->grp_sums, &s->c_texel, &s->c_src, &s->c_nsrc, &s->c_tables, &s->c_blk, &s->stage_buf[0], &s->stage_buf[1], &s->texel, &s->src, &s->nsrc, &s->x, &s->T, &s->pose_out, &s->tiles, &s->scalars, &s->partial,
 	                   &s->tiles_done, &s->iter_done, &s->pair_tile0, &s->pair_ntile, &s->dbgJ, &s->dbgR, &s->dbgC, &s->prof };
 	for (DevBuf* b : bufs) b->release();
 	s->h_stage.release(); s->h_poses.release(); s->h_pipe[0].release(); s->h_pipe[1].release();
 	for (auto& e : s->ev_pipe) if (e) cudaEventDestroy(e); s->c_htables[0].release(); s->c_htables[1].release();
 	for (auto& e : s->c_ev) if (e) cudaEventDestroy(e);
 	for (auto& e : s->ev) if (e) cudaEventDestroy(e);
-	for (cudaEvent_t e : { s->ev_prev, s->ev_corr, s->ev_h2d }) if (e) cudaEventDestroy(e);
+	for (cudaEvent_t e : { s->ev_prev, s->ev_corr, s->ev_h2d, s->ev_early, s->ev_stage_free[0], s->ev_stage_free[1] }) if (e) cudaEventDestroy(e);
 	if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
 	delete s;
 	ctx->solver = nullptr;
@@ -1570,7 +1572,7 @@ static int reserve_impl(bt_ctx* ctx, const bt_solver_limits* lim) {
 #define RES(buf, bytes) if ((rc = s->buf.alloc(bytes)) != BT_OK) return rc
 	{   // worst case over every window count <= max_windows (the table offsets grow with the count, so the maximum is at max_windows)
 		const StageLayout L = stage_layout(lim->max_windows, (size_t)F, (size_t)lim->max_corr * lim->max_windows, lim->max_frames, (size_t)s->max_groups, (size_t)s->max_pairs);
-		RES(stage_dev, L.total);
+		RES(stage_buf[0], L.total); RES(stage_buf[1], L.total);
 	}
 	RES(texel, sizeof(float4) * 2 * (size_t)s->npix_max * F);
 	RES(src, sizeof(float4) * 2 * (size_t)s->npix_max * F);
@@ -1671,7 +1673,7 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 	// ---- host staging: one pinned block mirrored by one device block
 	const size_t maxP = (size_t)s->max_pairs, maxG = (size_t)s->max_groups;
 	const StageLayout L = stage_layout(n_windows, F, C, s->lim.max_frames, maxG, maxP);
-	BT_REQUIRE(L.total <= s->stage_dev.bytes, BT_ERR_CAPACITY, "bt_solve_stage: staging block %zu > reserved %zu bytes", L.total, s->stage_dev.bytes);
+	BT_REQUIRE(L.total <= s->stage_buf[0].bytes, BT_ERR_CAPACITY, "bt_solve_stage: staging block %zu > reserved %zu bytes", L.total, s->stage_buf[0].bytes);
 	int rc = s->h_stage.alloc(L.total);
 	if (rc != BT_OK) return rc;
 	char* hb = s->h_stage.as<char>();
@@ -1755,10 +1757,23 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 		BT_CUDA(cudaEventCreateWithFlags(&s->ev_corr, cudaEventDisableTiming));
 		BT_CUDA(cudaEventCreateWithFlags(&s->ev_h2d, cudaEventDisableTiming));
 	}
-	// early tables, in stream order behind whatever the caller's stream still runs on the previous batch; then (fused call) the frame prep
-	BT_CUDA(cudaMemcpyAsync(s->stage_dev.p, hb, L.late, cudaMemcpyHostToDevice, stream));
-	BT_CUDA(cudaEventRecord(s->ev_prev, stream));
-	BT_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_prev, 0));
+	// Two device staging blocks, used alternately: every upload of this batch runs on the private copy stream and only waits for the
+	// k_solve that last read THIS block (two batches ago) - so with the streaming form the 2 MB of batch k+1 cross PCIe while batch k is
+	// still being solved.  (With one block the uploads queued behind the previous k_solve: ~50 us of every streaming step.)
+	s->stage_cur ^= 1;
+	DevBuf& stage_dev = s->stage_buf[s->stage_cur];
+	if (!s->ev_stage_free[s->stage_cur]) BT_CUDA(cudaEventCreateWithFlags(&s->ev_stage_free[s->stage_cur], cudaEventDisableTiming));
+	else BT_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_stage_free[s->stage_cur], 0));
+	{   // correspondence blocks produced on the device (bt_match_pairs on the caller's stream) are copied device -> device on the copy stream: order them
+		bool any_dev = false;
+		for (int w = 0; w < n_windows && !any_dev; w++) any_dev = windows[w].corr_dev != nullptr;
+		if (any_dev) { BT_CUDA(cudaEventRecord(s->ev_prev, stream)); BT_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_prev, 0)); }
+	}
+	// early tables first; the caller's stream (frame prep in the fused call) waits for them only
+	BT_CUDA(cudaMemcpyAsync(stage_dev.p, hb, L.late, cudaMemcpyHostToDevice, s->copy_stream));
+	if (!s->ev_early) BT_CUDA(cudaEventCreateWithFlags(&s->ev_early, cudaEventDisableTiming));
+	BT_CUDA(cudaEventRecord(s->ev_early, s->copy_stream));
+	BT_CUDA(cudaStreamWaitEvent(stream, s->ev_early, 0));
 	s->host_us[0] = us_since(t_h0);
 	if (early_prep) { if ((rc = launch_prep(ctx, stream)) != BT_OK) return rc; }
 	s->host_us[1] = us_since(t_h0) - s->host_us[0];
@@ -1787,9 +1802,9 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 			hgs[g_off + w + ng] = n_valid;
 			if (n_valid) {
 				if (c_off > sent) {     // flush what the host path has staged so far: the pinned block has a hole where this window's entries would be
-					BT_CUDA(cudaMemcpyAsync(s->stage_dev.as<char>() + L.corr + sent * sizeof(bt_entryj), hcorr + sent, (c_off - sent) * sizeof(bt_entryj), cudaMemcpyHostToDevice, s->copy_stream));
+					BT_CUDA(cudaMemcpyAsync(stage_dev.as<char>() + L.corr + sent * sizeof(bt_entryj), hcorr + sent, (c_off - sent) * sizeof(bt_entryj), cudaMemcpyHostToDevice, s->copy_stream));
 				}
-				BT_CUDA(cudaMemcpyAsync(s->stage_dev.as<char>() + L.corr + c_off * sizeof(bt_entryj), bw.corr_dev + bw.block_off[0], (size_t)n_valid * sizeof(bt_entryj),
+				BT_CUDA(cudaMemcpyAsync(stage_dev.as<char>() + L.corr + c_off * sizeof(bt_entryj), bw.corr_dev + bw.block_off[0], (size_t)n_valid * sizeof(bt_entryj),
 				                        cudaMemcpyDeviceToDevice, s->copy_stream));
 				sent = c_off + n_valid;
 			}
@@ -1839,11 +1854,11 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 				const bool pinned_src = cudaPointerGetAttributes(&pa, bw.corr) == cudaSuccess && pa.type == cudaMemoryTypeHost;
 				if (pinned_src) {
 					if (c_off > sent) {      // flush what was staged so far: the staging block has a hole where this window's entries would be
-						BT_CUDA(cudaMemcpyAsync(s->stage_dev.as<char>() + L.corr + sent * sizeof(bt_entryj), hcorr + sent, (c_off - sent) * sizeof(bt_entryj), cudaMemcpyHostToDevice, s->copy_stream));
+						BT_CUDA(cudaMemcpyAsync(stage_dev.as<char>() + L.corr + sent * sizeof(bt_entryj), hcorr + sent, (c_off - sent) * sizeof(bt_entryj), cudaMemcpyHostToDevice, s->copy_stream));
 					}
 					if (run_n && run_src + run_n == bw.corr && run_dst + run_n == c_off) run_n += (size_t)n_valid;      // extends the pending run
 					else {
-						if (run_n) BT_CUDA(cudaMemcpyAsync(s->stage_dev.as<char>() + L.corr + run_dst * sizeof(bt_entryj), run_src, run_n * sizeof(bt_entryj), cudaMemcpyHostToDevice, s->copy_stream));
+						if (run_n) BT_CUDA(cudaMemcpyAsync(stage_dev.as<char>() + L.corr + run_dst * sizeof(bt_entryj), run_src, run_n * sizeof(bt_entryj), cudaMemcpyHostToDevice, s->copy_stream));
 						run_src = bw.corr; run_dst = c_off; run_n = (size_t)n_valid;
 					}
 					sent = c_off + n_valid;
@@ -1914,16 +1929,16 @@ static int stage_impl(bt_ctx* ctx, int n_windows, const bt_window* windows, cons
 		c_off += n_valid; g_off += ng; p_off += np;
 		// upload what has accumulated once it is worth a copy (>= 256 KB), and whatever is left after the last window
 		if ((c_off - sent) * sizeof(bt_entryj) >= 256 * 1024 || (w + 1 == n_windows && c_off > sent)) {
-			BT_CUDA(cudaMemcpyAsync(s->stage_dev.as<char>() + L.corr + sent * sizeof(bt_entryj), hcorr + sent, (c_off - sent) * sizeof(bt_entryj), cudaMemcpyHostToDevice, s->copy_stream));
+			BT_CUDA(cudaMemcpyAsync(stage_dev.as<char>() + L.corr + sent * sizeof(bt_entryj), hcorr + sent, (c_off - sent) * sizeof(bt_entryj), cudaMemcpyHostToDevice, s->copy_stream));
 			sent = c_off;
 		}
 	}
-	if (run_n) BT_CUDA(cudaMemcpyAsync(s->stage_dev.as<char>() + L.corr + run_dst * sizeof(bt_entryj), run_src, run_n * sizeof(bt_entryj), cudaMemcpyHostToDevice, s->copy_stream));
+	if (run_n) BT_CUDA(cudaMemcpyAsync(stage_dev.as<char>() + L.corr + run_dst * sizeof(bt_entryj), run_src, run_n * sizeof(bt_entryj), cudaMemcpyHostToDevice, s->copy_stream));
 	s->grp_in_smem = smem_need <= kTailSmemMax;
 	if (!s->grp_in_smem) smem_need = smem_lean;
 	BT_REQUIRE(smem_need <= kTailSmemMax, BT_ERR_CAPACITY, "bt_solve_stage: window needs %zu bytes of shared memory (> %d KB)", smem_need, (int)(kTailSmemMax / 1024));
 	s->smem_bytes = (int)smem_need;
-	BT_CUDA(cudaMemcpyAsync(s->stage_dev.as<char>() + L.late, hb + L.late, L.corr - L.late, cudaMemcpyHostToDevice, s->copy_stream));      // group tables, CSR, WinSparse
+	BT_CUDA(cudaMemcpyAsync(stage_dev.as<char>() + L.late, hb + L.late, L.corr - L.late, cudaMemcpyHostToDevice, s->copy_stream));      // group tables, CSR, WinSparse
 	BT_CUDA(cudaEventRecord(s->ev_corr, s->copy_stream));
 	BT_CUDA(cudaEventRecord(s->ev_h2d, s->copy_stream));
 	BT_CUDA(cudaStreamWaitEvent(stream, s->ev_corr, 0));     // everything later on the caller's stream sees the correspondences
@@ -1961,7 +1976,7 @@ static SolveArgs make_args(bt_ctx* ctx) {
 	SolverState* s = ctx->solver;
 	SolveArgs a;
 	memset(&a, 0, sizeof a);
-	char* sd = s->stage_dev.as<char>();
+	char* sd = s->stage_buf[s->stage_cur].as<char>();
 	const StageLayout& L = s->layout;
 	a.wins = (WinDesc*)(sd + L.wins); a.wsp = (const WinSparse*)(sd + L.wsp); a.n_windows = s->n_windows;
 	a.depth_ptr = (const float**)(sd + L.dp); a.normal_ptr = (const float4**)(sd + L.np); a.frame_win = (int*)(sd + L.fw);
@@ -2025,6 +2040,7 @@ extern "C" int bt_solve_run(bt_ctx* ctx, void* stream_) {
 	const int grid = ctx->sm_count * occ;
 	k_solve<256, BT_SOLVE_MIN_CTAS><<<grid, 256, s->smem_bytes, stream>>>(a);
 	BT_CUDA(cudaGetLastError());
+	if (s->ev_stage_free[s->stage_cur]) BT_CUDA(cudaEventRecord(s->ev_stage_free[s->stage_cur], stream));      // this batch's staging block may be overwritten after this point
 	if (s->timing) BT_CUDA(cudaEventRecord(s->ev[3], stream));
 	s->launches = s->any_uncached ? 3 : 2;
 	return BT_OK;

@@ -107,6 +107,14 @@ class SolveWindow:
         return self.poses.shape[0]
 
 
+class _PreparedBatch:
+    """bt_window array + pose block of a batch (OptimizerGpu.prepare_batch)."""
+    __slots__ = ("arr", "poses", "keep", "off")
+
+    def __init__(self, arr, poses, keep, off):
+        self.arr, self.poses, self.keep, self.off = arr, poses, keep, off
+
+
 class OptimizerGpu:
     def __init__(self, yml=None, device: int = 0, max_windows: int = 1, max_frames: int = 15, max_corr: int = 65536,
                  H: int = 480, W: int = 640, stream: int = 0):
@@ -145,6 +153,48 @@ class OptimizerGpu:
         _lib.check(self.lib.bt_frame_cache_store(self.ctx, ctypes.c_int(n), sl, dp, nq, ctypes.c_int(H), ctypes.c_int(W), ctypes.c_float(fx), ctypes.c_float(fy),
                                                  ctypes.c_float(cx), ctypes.c_float(cy), ctypes.c_float(self.params.depth_min), ctypes.c_float(self.params.depth_max),
                                                  self.stream), "bt_frame_cache_store")
+
+    def prepare_store(self, slots: Sequence[int], depths_gpu: Sequence, normals_gpu: Sequence, H: int, W: int, K):
+        """The argument block of one bt_frame_cache_store call, marshalled ONCE (a C / C++ caller hands the library plain arrays; from Python
+        the per-frame pointer extraction costs more than the library call itself).  Pass the result to store_prepared()."""
+        n = len(slots)
+        K = np.asarray(K, np.float64)
+        fx, fy, cx, cy = (K[0, 0], K[1, 1], K[0, 2], K[1, 2]) if K.ndim == 2 else K
+        sl = (ctypes.c_int32 * n)(*[int(v) for v in slots])
+        dp = (ctypes.c_void_p * n)(*[_ptr(d) for d in depths_gpu])
+        nq = (ctypes.c_void_p * n)(*[_ptr(d) for d in normals_gpu])
+        args = (self.ctx, ctypes.c_int(n), sl, dp, nq, ctypes.c_int(H), ctypes.c_int(W), ctypes.c_float(fx), ctypes.c_float(fy), ctypes.c_float(cx), ctypes.c_float(cy),
+                ctypes.c_float(self.params.depth_min), ctypes.c_float(self.params.depth_max), self.stream)
+        return args, (depths_gpu, normals_gpu)      # (the tensors are kept alive with the block)
+
+    def store_prepared(self, prepared):
+        _lib.check(self.lib.bt_frame_cache_store(*prepared[0]), "bt_frame_cache_store")
+
+    def prepare_batch(self, windows: List[SolveWindow]):
+        """The bt_window array + the flat pose block of a batch, marshalled once; begin_prepared() / solve_prepared() then cost one library
+        call.  `batch.poses` ([sum n_frames, 16] float32) is the input pose block: rewrite it in place between calls if the poses change."""
+        arr, poses, keep = self._marshal(windows)
+        off = np.cumsum([0] + [w.n_frames for w in windows])
+        return _PreparedBatch(arr, np.ascontiguousarray(poses, np.float32), keep, off)
+
+    def begin_prepared(self, batch):
+        _lib.check(self.lib.bt_solve_windows_begin(self.ctx, ctypes.c_int(len(batch.keep)), batch.arr, ctypes.byref(self.params),
+                                                   batch.poses.ctypes.data_as(ctypes.c_void_p), self.stream), "bt_solve_windows_begin")
+
+    def end_prepared(self, batch, out: np.ndarray = None) -> np.ndarray:
+        """Poses of the oldest batch in flight as one [sum n_frames, 4, 4] array (batch.off gives the windows' first frames)."""
+        if out is None:
+            out = np.empty((batch.poses.shape[0], 4, 4), np.float32)
+        _lib.check(self.lib.bt_solve_windows_end(self.ctx, out.ctypes.data_as(ctypes.c_void_p)), "bt_solve_windows_end")
+        return out
+
+    def solve_prepared(self, batch, out: np.ndarray = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((batch.poses.shape[0], 4, 4), np.float32)
+        np.copyto(out.reshape(-1, 16), batch.poses)
+        _lib.check(self.lib.bt_solve_windows(self.ctx, ctypes.c_int(len(batch.keep)), batch.arr, ctypes.byref(self.params),
+                                             out.ctypes.data_as(ctypes.c_void_p), self.stream), "bt_solve_windows")
+        return out
 
     # ---- reference-shaped single-window call (LossGPU.h:50) -------------------------------------------------
     def optimizeFrames(self, global_corres, n_match_per_pair, n_frames, H, W, depths_gpu, colors_gpu, normals_gpu, poses, K,

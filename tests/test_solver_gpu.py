@@ -347,6 +347,38 @@ def test_streaming_begin_end_equals_blocking_call(cuda_device):
     o.close()
 
 
+def test_prepared_argument_blocks_equal_the_convenience_calls(cuda_device):
+    """prepare_batch / begin_prepared / end_prepared / solve_prepared and prepare_store / store_prepared hand the library the same
+    bt_window array, pose block and frame table as the per-call marshalling: bit-identical poses, also with several steps in flight
+    (each step re-uses the same argument blocks while the other device staging block is still being read by the previous k_solve)."""
+    from bundletrack_b200.optimizer import OptimizerGpu, SolveWindow
+    o = OptimizerGpu(None, max_windows=3, max_frames=6, max_corr=2000)
+    ws = [synth.make_window(120 + k, n_frames=4 + (k % 3), n_corr=500 + 100 * k) for k in range(3)]
+    ups = [_upload(w, cuda_device) for w in ws]
+    nF = sum(w.n_frames for w in ws)
+    o.reserve_frame_cache(nF, ws[0].H, ws[0].W)
+    slots, f0 = [], 0
+    for w in ws:
+        slots.append(list(range(f0, f0 + w.n_frames))); f0 += w.n_frames
+    flat = [s_ for sl in slots for s_ in sl]
+    st = o.prepare_store(flat, [d for u in ups for d in u[0]], [n for u in ups for n in u[1]], ws[0].H, ws[0].W, ws[0].K)
+    o.store_prepared(st)
+    wins = [SolveWindow(w.corr, w.H, w.W, None, None, w.poses_init, w.K, cache_slots=slots[i]) for i, w in enumerate(ws)]
+    want = np.concatenate(o.optimizeWindows(wins), 0)
+    b = o.prepare_batch(wins)
+    assert np.array_equal(o.solve_prepared(b), want)
+    outs = []
+    o.begin_prepared(b)
+    for _ in range(5):      # steady state of the streaming loop: store, begin k+1, end k
+        o.store_prepared(st)
+        o.begin_prepared(b)
+        outs.append(o.end_prepared(b).copy())
+    outs.append(o.end_prepared(b).copy())
+    for got in outs:
+        assert np.array_equal(got, want)
+    o.close()
+
+
 def test_cfg3_whole_pool_window_n30(cuda_device):
     """BASELINE configs[2] with max_BA_frames overridden to the whole 30-keyframe pool: 435 dense pairs, 3000 correspondences,
     YCBInEOAT-style occlusion; a 174 x 174 system (the groups' moment sums stay in global memory: the tail's shared memory would not
