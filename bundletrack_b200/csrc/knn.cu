@@ -35,6 +35,7 @@
 #include <cuda_fp16.h>
 #include <map>
 #include <math.h>
+#include <stdlib.h>
 #include "bt_common.cuh"
 
 namespace bt {
@@ -55,6 +56,14 @@ static constexpr uint32_t SMEM_A = STAGES * SA_BYTES; // 80 KB
 static constexpr uint32_t SMEM_NORM = BN * 4;         // 1 KB
 static constexpr uint32_t SMEM_BAR = 256;
 static constexpr uint32_t SMEM_TOTAL = SMEM_B + SMEM_A + SMEM_NORM + SMEM_BAR + 1024;   // + alignment slack
+// CTA-pair form (cta_group::2, M = 256): a CTA keeps HALF of the B tile (128 rows, 64 KB) and streams its own 128 A rows through a deeper ring
+static constexpr int STAGES_P = 5;
+static constexpr uint32_t SBH_BYTES = (BN / 2) * BK * 2;                 // 16 KB per K-chunk of the B half tile
+static constexpr uint32_t SMEM_BH = KCH * SBH_BYTES;                     // 64 KB: one B half tile
+static constexpr uint32_t SMEM_B_P = 2 * SMEM_BH;                        // 128 KB: DOUBLE-BUFFERED - the next B tile loads while the current one is used (its own producer warp)
+static constexpr uint32_t SMEM_A_P = STAGES_P * SA_BYTES;                // 80 KB
+static constexpr uint32_t SMEM_TOTAL_P = SMEM_B_P + SMEM_A_P + SMEM_NORM + SMEM_BAR + 1024;
+static constexpr int KNN_THREADS_P = KNN_THREADS + 32;                   // + the B-tile producer warp
 static constexpr int SEL_MAXG = 16;         // groups / candidates kept per query; more => exact fallback
 static constexpr int SEL_MAXC = 16;
 
@@ -99,6 +108,35 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
 	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
 	             "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
 	             : "memory");
+}
+// ---- CTA-pair (cta_group::2) variants: both CTAs of a pair issue their TMA loads against the LEADER's (rank 0) full barrier, the leader's
+//      MMA thread commits to the same barrier offset in BOTH CTAs (multicast), the peer's epilogue arrives on the leader's barrier remotely
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+	asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+	             "l"(tmap), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)      // peer bit cleared: the transaction bytes land on CTA 0's barrier
+	             : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+	asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((unsigned short)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "setp.ne.b32 p, %4, 0;\n"
+	    "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+	    "}\n" ::"r"(d_tmem),
+	    "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+	    : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_rank0(uint64_t* bar) {      // arrive on the barrier at this offset in the cluster's CTA 0
+	uint32_t remote;
+	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(0u));
+	asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");      // (default .release.cta: with .release.cluster the arrive queued behind the previous unit's global stores - 26 % of the kernel's stall samples)
+}
+__device__ __forceinline__ void cluster_sync_all() {
+	asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+	asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -281,42 +319,66 @@ __device__ __forceinline__ void epi_rows(const uint32_t (&v)[32], const unsigned
 	}
 }
 
-__global__ void __launch_bounds__(KNN_THREADS, 1)
+// developer aid: cycles the MMA-issuing thread of every CTA spent waiting, by cause (read with bt_knn_debug_prof)
+__device__ long long g_knn_prof[160][6];
+
+// PAIR = false: one CTA per (128 A rows x 256 B rows) unit.  PAIR = true: a CLUSTER OF TWO CTAs (one TPC) per (256 x 256) unit -
+// tcgen05.mma.cta_group::2, M = 256: CTA r holds A rows [128 r, 128 r + 128) of the unit and HALF of the B tile; the leader (rank 0)
+// issues every MMA, each SM's tensor core accumulates its own 128 rows x 256 columns in its own TMEM, the B operand is read from shared
+// memory once per pair instead of once per SM, and the freed 64 KB hold a SECOND B buffer filled by its own producer warp (no bubble at
+// a tile switch).  Measured on B200 (45 pairs x 2000^2): correct on the first run, but NOT faster - 0.083-0.088 ms vs 0.081 ms.  The MMA
+// thread's own clock (bt_knn_debug_prof) shows why: per unit it waits ~100 cycles for the epilogue, ~110-250 for B and ~320 for A tiles in
+// BOTH forms, and issues for ~2500 - the pass is paced by the tensor pipe at the clock the chip sustains under this load (~1.5 GHz: the
+// kernel's 125 k cycles take 81 us), not by shared-memory bandwidth.  Kept behind BT_KNN_CTA_PAIRS=1 (tested), not the default.
+template <bool PAIR> __global__ void __launch_bounds__(PAIR ? KNN_THREADS_P : KNN_THREADS, 1)
 k_knn_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const KnnPair* __restrict__ pairs, int n_pairs, int total_units,
          const float* __restrict__ norms, const PairConst* __restrict__ pconst, __half* __restrict__ G) {
+	constexpr int NST = PAIR ? STAGES_P : STAGES;
+	constexpr uint32_t B_CHUNK = PAIR ? SBH_BYTES : SB_BYTES;
+	constexpr uint32_t B_BYTES = PAIR ? SMEM_B_P : SMEM_B, A_BYTES = PAIR ? SMEM_A_P : SMEM_A;
+	constexpr int UM = PAIR ? 2 * BM : BM;      // A rows per unit
 	extern __shared__ uint8_t smem_raw[];
 	uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024-B alignment
 	uint8_t* sB = smem;
-	uint8_t* sA = smem + SMEM_B;
-	float* sNorm = reinterpret_cast<float*>(smem + SMEM_B + SMEM_A);
-	uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_B + SMEM_A + SMEM_NORM);
+	uint8_t* sA = smem + B_BYTES;
+	float* sNorm = reinterpret_cast<float*>(smem + B_BYTES + A_BYTES);
+	uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_BYTES + A_BYTES + SMEM_NORM);
 	uint64_t* b_full = bars + 0;               // [KCH]  resident B tile, per K-chunk
 	uint64_t* b_empty = bars + KCH;            // [KCH]
-	uint64_t* full = bars + 2 * KCH;           // [STAGES]
-	uint64_t* empty = full + STAGES;           // [STAGES]
-	uint64_t* tm_full = empty + STAGES;        // [2]
+	uint64_t* full = bars + 2 * KCH;           // [NST]
+	uint64_t* empty = full + NST;              // [NST]
+	uint64_t* tm_full = empty + NST;           // [2]
 	uint64_t* tm_empty = tm_full + 2;          // [2]
 	uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tm_empty + 2);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	uint32_t cr = 0;      // rank of this CTA in its pair
+	if constexpr (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cr));
 	if (warp == 0 && lane == 0) {
 		asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
 		asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
 		for (int s = 0; s < KCH; s++) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
-		for (int s = 0; s < STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-		for (int b = 0; b < 2; b++) { mbar_init(tm_full + b, 1); mbar_init(tm_empty + b, EPI_WARPS); }
+		for (int s = 0; s < NST; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+		for (int b = 0; b < 2; b++) { mbar_init(tm_full + b, 1); mbar_init(tm_empty + b, PAIR ? 2 * EPI_WARPS : EPI_WARPS); }
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
+	if constexpr (PAIR) cluster_sync_all();      // the peer's barriers exist before anything can arrive on them
 	if (warp == 1) {   // TMEM: all 512 columns (two 256-column accumulators); this kernel runs 1 CTA / SM
-		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
-		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+		if constexpr (PAIR) {
+			asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
+			asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+		} else {
+			asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
+			asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+		}
 	}
 	tc_fence_before();
 	__syncthreads();
 	tc_fence_after();
 	const uint32_t tmem_base = *tmem_ptr_smem;
-	// this CTA's contiguous slice of the unit list (balanced to +-1 unit)
-	const int u0 = (int)(((long long)blockIdx.x * total_units) / gridDim.x), u1 = (int)(((long long)(blockIdx.x + 1) * total_units) / gridDim.x);
+	// this CTA's (pair's) contiguous slice of the unit list (balanced to +-1 unit)
+	const int wid_ = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, nw_ = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+	const int u0 = (int)(((long long)wid_ * total_units) / nw_), u1 = (int)(((long long)(wid_ + 1) * total_units) / nw_);
 
 	if (warp == 0) {
 		// ================================================= TMA producer
@@ -326,15 +388,22 @@ k_knn_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUt
 			for (int u = u0; u < u1; u++) {
 				const bool newb = (u == u0) || (w.qt == 0);
 				for (int kc = 0; kc < KCH; kc++) {
-					if (newb) {      // the previous B tile's last MMAs of this K-chunk have retired: reload the chunk while the others still run
-						mbar_wait(b_empty + kc, bphase ^ 1);
-						mbar_expect_tx(b_full + kc, SB_BYTES);
-						tma_load_2d(sB + kc * SB_BYTES, &tmap_b, b_full + kc, kc * BK, w.pr.b_row0 + w.tt * BN);
-					}
+					if constexpr (!PAIR) {
+						if (newb) {      // the previous B tile's last MMAs of this K-chunk have retired: reload the chunk while the others still run
+							mbar_wait(b_empty + kc, bphase ^ 1);
+							mbar_expect_tx(b_full + kc, SB_BYTES);
+							tma_load_2d(sB + kc * SB_BYTES, &tmap_b, b_full + kc, kc * BK, w.pr.b_row0 + w.tt * BN);
+						}
+					}      // (pair: the B tiles have their own producer warp and two buffers - this thread never blocks behind a tile switch)
 					mbar_wait(empty + stage, sphase ^ 1);
-					mbar_expect_tx(full + stage, SA_BYTES);
-					tma_load_2d(sA + stage * SA_BYTES, &tmap_a, full + stage, kc * BK, w.pr.a_row0 + w.qt * BM);
-					if (++stage == STAGES) { stage = 0; sphase ^= 1; }
+					if constexpr (PAIR) {
+						if (cr == 0) mbar_expect_tx(full + stage, 2 * SA_BYTES);
+						tma_load_2d_pair(sA + stage * SA_BYTES, &tmap_a, full + stage, kc * BK, w.pr.a_row0 + w.qt * UM + (int)cr * BM);
+					} else {
+						mbar_expect_tx(full + stage, SA_BYTES);
+						tma_load_2d(sA + stage * SA_BYTES, &tmap_a, full + stage, kc * BK, w.pr.a_row0 + w.qt * BM);
+					}
+					if (++stage == NST) { stage = 0; sphase ^= 1; }
 				}
 				if (newb) bphase ^= 1;
 				if (u + 1 < u1) w.next();
@@ -342,33 +411,64 @@ k_knn_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUt
 		}
 	} else if (warp == 1) {
 		// ================================================= MMA issuer (one thread)
-		if (lane == 0 && u0 < u1) {
-			constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
-			uint32_t stage = 0, sphase = 0, bphase = 0, tcount = 0;
+		if (lane == 0 && u0 < u1 && cr == 0) {      // (pair: the leader issues for both SMs)
+			constexpr uint32_t idesc = umma_idesc_f16(UM, BN);
+			uint32_t stage = 0, sphase = 0, bphase = 0, tcount = 0, btile = 0;
 			UnitWalk w; w.init(pairs, n_pairs, u0);
+			long long t_tm = 0, t_b = 0, t_a = 0; const long long t_begin = clock64();
 			for (int u = u0; u < u1; u++, tcount++) {
 				const bool newb = (u == u0) || (w.qt == 0);
 				const bool lastb = (u + 1 == u1) || (w.qt == w.pr.n_qt - 1);
 				const uint32_t buf = tcount & 1, tphase = (tcount >> 1) & 1;
+				long long t0 = clock64();
 				mbar_wait(tm_empty + buf, tphase ^ 1);      // epilogue drained this accumulator
+				t_tm += clock64() - t0;
 				tc_fence_after();
 				const uint32_t d_tmem = tmem_base + buf * BN;
+				if constexpr (PAIR) { if (newb) { t0 = clock64(); mbar_wait(b_full + (btile & 1), (btile >> 1) & 1); t_b += clock64() - t0; } }      // the whole half tile (both CTAs') has landed
 				for (int kc = 0; kc < KCH; kc++) {
-					if (newb) mbar_wait(b_full + kc, bphase);
+					t0 = clock64();
+					if constexpr (!PAIR) { if (newb) mbar_wait(b_full + kc, bphase); }
+					long long t1 = clock64();
 					mbar_wait(full + stage, sphase);
+					t_b += t1 - t0; t_a += clock64() - t1;
 					tc_fence_after();
-					const uint32_t a_base = smem_u32(sA + stage * SA_BYTES), b_base = smem_u32(sB + kc * SB_BYTES);
+					const uint32_t a_base = smem_u32(sA + stage * SA_BYTES), b_base = smem_u32(sB + (PAIR ? (btile & 1) * SMEM_BH : 0u) + kc * B_CHUNK);
 #pragma unroll
 					for (int k = 0; k < BK / 16; k++) {      // UMMA K = 16 halves = 32 bytes inside the 128-byte swizzle row
-						tc_mma_f16(d_tmem, umma_desc_k128(a_base + k * 32), umma_desc_k128(b_base + k * 32), idesc, (uint32_t)((kc | k) != 0));
+						if constexpr (PAIR) tc_mma_f16_pair(d_tmem, umma_desc_k128(a_base + k * 32), umma_desc_k128(b_base + k * 32), idesc, (uint32_t)((kc | k) != 0));
+						else tc_mma_f16(d_tmem, umma_desc_k128(a_base + k * 32), umma_desc_k128(b_base + k * 32), idesc, (uint32_t)((kc | k) != 0));
 					}
-					tc_commit(empty + stage);                // frees the A stage when these MMAs retire
-					if (lastb) tc_commit(b_empty + kc);      // ... and this K-chunk of the B tile after its last use
-					if (++stage == STAGES) { stage = 0; sphase ^= 1; }
+					if constexpr (PAIR) { tc_commit_pair(empty + stage); if (lastb && kc == KCH - 1) tc_commit_pair(b_empty + (btile & 1)); }      // (the same barrier in both CTAs; the B buffer is free after the tile's last MMA)
+					else { tc_commit(empty + stage);                // frees the A stage when these MMAs retire
+					       if (lastb) tc_commit(b_empty + kc); }    // ... and this K-chunk of the B tile after its last use
+					if (++stage == NST) { stage = 0; sphase ^= 1; }
 				}
-				tc_commit(tm_full + buf);                    // accumulator complete -> epilogue
+				if constexpr (PAIR) tc_commit_pair(tm_full + buf); else tc_commit(tm_full + buf);      // accumulator complete -> epilogue
 				if (newb) bphase ^= 1;
+				if (lastb) btile++;
 				if (u + 1 < u1) w.next();
+			}
+			if (blockIdx.x < 160) { long long* o = g_knn_prof[blockIdx.x]; o[0] = t_tm; o[1] = t_b; o[2] = t_a; o[3] = clock64() - t_begin; o[4] = u1 - u0; o[5] = 0; }
+		}
+	} else if (warp == 2 + EPI_WARPS) {
+		// ================================================= (pair only) B-tile producer: the next tile's half loads into the other buffer while the current one is in use
+		if constexpr (PAIR) {
+			if (lane == 0 && u0 < u1) {
+				uint32_t btile = 0;
+				UnitWalk w; w.init(pairs, n_pairs, u0);
+				for (int u = u0; u < u1; u++) {
+					const bool newb = (u == u0) || (w.qt == 0);
+					if (newb) {
+						const uint32_t bb = btile & 1, ph = (btile >> 1) & 1;
+						mbar_wait(b_empty + bb, ph ^ 1);      // the tile that used this buffer two tiles ago has retired
+						if (cr == 0) mbar_expect_tx(b_full + bb, 2 * SMEM_BH);      // both CTAs' halves land on the leader's barrier
+						for (int kc = 0; kc < KCH; kc++)
+							tma_load_2d_pair(sB + bb * SMEM_BH + kc * SBH_BYTES, &tmap_a, b_full + bb, kc * BK, w.pr.b_row0 + w.tt * BN + (int)cr * (BN / 2));
+						btile++;
+					}
+					if (u + 1 < u1) w.next();
+				}
 			}
 		}
 	} else if (u0 < u1) {
@@ -385,7 +485,8 @@ k_knn_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUt
 		for (int u = u0; u < u1; u++, tcount++) {
 			const bool newb = (u == u0) || (w.qt == 0);
 			if (w.p != cur_p) { cur_p = w.p; s = pconst[cur_p].s; }
-			const float* nAp = norms + w.pr.a_row0 + w.qt * BM + quarter * 32 + rq;      // (used after the accumulator wait: the loads have long landed)
+			const int qrow0 = w.qt * UM + (int)cr * BM;      // first A row (within the pair's set) of this CTA's 128-row tile
+			const float* nAp = norms + w.pr.a_row0 + qrow0 + quarter * 32 + rq;      // (used after the accumulator wait: the loads have long landed)
 			const float nA0 = __ldg(nAp) * s, nA1 = __ldg(nAp + 8) * s, nA2 = __ldg(nAp + 16) * s, nA3 = __ldg(nAp + 24) * s;
 			if (newb) {      // |b~|^2 of the resident B tile (scaled) -> smem, one float per thread of the first 8 epilogue warps
 				asm volatile("bar.sync 1, 512;" ::: "memory");       // every epilogue thread is done with the previous tile's norms
@@ -403,9 +504,9 @@ k_knn_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUt
 			}
 			const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + cq * 64;
 			// A->B matrix [B group][A position]: this thread's four rows are positions 4 rq .. 4 rq + 3 of their block of 32; its groups are 2m, 2m + 1 of each block of 32 columns
-			__half* rowp = G + w.pr.g_row + (size_t)(w.tt * (BN / GRP) + cq * 16 + 2 * m) * (size_t)w.pr.nA_pad + (size_t)(w.qt * BM + quarter * 32 + 4 * rq);
+			__half* rowp = G + w.pr.g_row + (size_t)(w.tt * (BN / GRP) + cq * 16 + 2 * m) * (size_t)w.pr.nA_pad + (size_t)(qrow0 + quarter * 32 + 4 * rq);
 			// B->A matrix [A group][B position]: row group rq of this quarter; its eight columns of a block of 32 are positions 8m .. 8m + 7
-			__half* colp = G + w.pr.g_col + (size_t)(w.qt * (BM / GRP) + quarter * 8 + rq) * (size_t)w.pr.nB_pad + (size_t)(w.tt * BN + cq * 64 + 8 * m);
+			__half* colp = G + w.pr.g_col + (size_t)(qrow0 / GRP + quarter * 8 + rq) * (size_t)w.pr.nB_pad + (size_t)(w.tt * BN + cq * 64 + 8 * m);
 			const size_t rstride = (size_t)w.pr.nA_pad;
 			mbar_wait(tm_full + buf, tphase);
 			tc_fence_after();
@@ -419,7 +520,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUt
 			asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 			tc_fence_before();
 			__syncwarp();
-			if (lane == 0) mbar_arrive(tm_empty + buf);      // the accumulator is in registers: the next unit's MMAs may overwrite it
+			if (lane == 0) { if constexpr (PAIR) mbar_arrive_rank0(tm_empty + buf); else mbar_arrive(tm_empty + buf); }      // the accumulator is in registers: the next unit's MMAs may overwrite it
 			epi_rows(vb, nb, nA2, nA3, m2s2, h2, h3);
 #pragma unroll
 			for (int jb = 0; jb < 2; jb++) {
@@ -442,9 +543,11 @@ k_knn_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUt
 	}
 	tc_fence_before();
 	__syncthreads();
+	if constexpr (PAIR) cluster_sync_all();      // neither CTA's shared memory / tensor memory goes away while the other still uses it
 	if (warp == 1) {
 		tc_fence_after();
-		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+		if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+		else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 	}
 }
 
@@ -812,6 +915,7 @@ struct MatcherState {
 	int last_units = 0, last_rows = 0;
 	cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
 	bool timing = false;
+	bool cta_pairs = false;     // BT_KNN_CTA_PAIRS=1: tensor pass on clusters of two CTAs (cta_group::2, M = 256).  Measured on B200: no faster than one CTA per tile (0.083-0.088 vs 0.081 ms for 45 pairs x 2000^2) - see the kernel's header - so it is not the default
 	int force_fallback = 0;     // test knob: every n-th query row is sent to the exact fallback regardless of its candidates
 };
 
@@ -874,6 +978,7 @@ static int launch_prep(bt_ctx* ctx, const std::vector<PrepSet>& sets, char* hb, 
 static int knn_run(bt_ctx* ctx, int n_pairs, const PoolSetRef* A, const PoolSetRef* B, int k, int32_t* idxAB, float* distAB, int32_t* idxBA, float* distBA,
                    char* hb, size_t hoff, cudaStream_t stream) {
 	MatcherState* m = ctx->matcher;
+	const int UM = m->cta_pairs ? 2 * BM : BM;
 	std::vector<KnnPair> pairs;
 	std::vector<SelJob> jobs;
 	std::vector<int> blk_start, q_start;
@@ -886,8 +991,8 @@ static int knn_run(bt_ctx* ctx, int n_pairs, const PoolSetRef* A, const PoolSetR
 		KnnPair pr; memset(&pr, 0, sizeof pr);
 		if (live) {
 			pr.a_row0 = A[p].slot * m->slot_rows; pr.b_row0 = B[p].slot * m->slot_rows; pr.nA = nA; pr.nB = nB;
-			pr.n_qt = (nA + BM - 1) / BM; pr.n_tt = (nB + BN - 1) / BN; pr.unit0 = (int)units;
-			pr.nA_pad = pr.n_qt * BM; pr.nB_pad = pr.n_tt * BN; pr.setA = A[p].slot; pr.setB = B[p].slot;
+			pr.n_qt = (nA + UM - 1) / UM; pr.n_tt = (nB + BN - 1) / BN; pr.unit0 = (int)units;      // a unit = UM A rows x 256 B rows (UM = 256 with CTA pairs)
+			pr.nA_pad = pr.n_qt * UM; pr.nB_pad = pr.n_tt * BN; pr.setA = A[p].slot; pr.setB = B[p].slot;
 			pr.g_row = g_off; g_off += (long long)(pr.nB_pad / GRP) * pr.nA_pad;
 			pr.g_col = g_off; g_off += (long long)(pr.nA_pad / GRP) * pr.nB_pad;
 			units += (long long)pr.n_qt * pr.n_tt;
@@ -928,8 +1033,19 @@ static int knn_run(bt_ctx* ctx, int n_pairs, const PoolSetRef* A, const PoolSetR
 	if (m->timing) BT_CUDA(cudaEventRecord(m->ev[1], stream));      // [ev0, ev1) = descriptor conversion + table upload + per-pair constants; [ev1, ev2) = k_knn_tc alone
 	// ---- kernels
 	if (n_live > 0) {
-		const int grid = (int)std::min<long long>(units, ctx->sm_count);
-		k_knn_tc<<<grid, KNN_THREADS, SMEM_TOTAL, stream>>>(m->tmap_a, m->tmap_b, m->pairs.as<KnnPair>(), n_live, (int)units, m->norms.as<float>(), m->pconst.as<PairConst>(), m->G.as<__half>());
+		if (m->cta_pairs) {      // clusters of two CTAs (one TPC each): cta_group::2 MMAs, M = 256
+			cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+			const int n_cl = (int)std::min<long long>(units, ctx->sm_count / 2);
+			cfg.gridDim = dim3(2 * n_cl); cfg.blockDim = dim3(KNN_THREADS_P); cfg.dynamicSmemBytes = SMEM_TOTAL_P; cfg.stream = stream;
+			cudaLaunchAttribute at[1];
+			at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+			cfg.attrs = at; cfg.numAttrs = 1;
+			BT_CUDA(cudaLaunchKernelEx(&cfg, k_knn_tc<true>, m->tmap_a, m->tmap_b, (const KnnPair*)m->pairs.as<KnnPair>(), n_live, (int)units, (const float*)m->norms.as<float>(),
+			                           (const PairConst*)m->pconst.as<PairConst>(), m->G.as<__half>()));
+		} else {
+			const int grid = (int)std::min<long long>(units, ctx->sm_count);
+			k_knn_tc<false><<<grid, KNN_THREADS, SMEM_TOTAL, stream>>>(m->tmap_a, m->tmap_b, m->pairs.as<KnnPair>(), n_live, (int)units, m->norms.as<float>(), m->pconst.as<PairConst>(), m->G.as<__half>());
+		}
 	}
 	if (m->timing) BT_CUDA(cudaEventRecord(m->ev[2], stream));
 	KnnOut out; out.idx[0] = idxAB; out.idx[1] = idxBA; out.dist[0] = distAB; out.dist[1] = distBA;
@@ -972,7 +1088,8 @@ extern "C" int bt_matcher_reserve(bt_ctx* ctx, int max_pairs, int max_feats, int
 	m->n_transient = std::min(2 * max_pairs, 128);       // distinct descriptor sets one bt_knn_match_pairs call may name (all pairs of K frames: K sets)
 	int rc;
 	if ((rc = pool_alloc(m)) != BT_OK) return rc;
-	const int pad_a = (max_feats + BM - 1) / BM * BM;
+	{ const char* e = getenv("BT_KNN_CTA_PAIRS"); m->cta_pairs = (e && atoi(e) != 0); }
+	const int pad_a = (max_feats + 2 * BM - 1) / (2 * BM) * (2 * BM);      // A sets are padded to whole 256-row units of the CTA-pair kernel
 	m->g_halves_cap = (size_t)max_pairs * ((size_t)(slot_rows / GRP) * pad_a + (size_t)(pad_a / GRP) * slot_rows);
 	m->max_jobs = 2 * max_pairs;
 	m->max_q_total = 2 * max_pairs * max_feats;
@@ -995,7 +1112,8 @@ extern "C" int bt_matcher_reserve(bt_ctx* ctx, int max_pairs, int max_feats, int
 #undef RES
 	if ((rc = m->h_stage.alloc(sizeof(PrepSet) * 2 * max_pairs + sizeof(KnnPair) * ((size_t)max_pairs + 1) + (sizeof(SelJob) + 2 * sizeof(int)) * m->max_jobs + 4096)) != BT_OK) return rc;
 	if (!m->ev_up) BT_CUDA(cudaEventCreateWithFlags(&m->ev_up, cudaEventDisableTiming));
-	BT_CUDA(cudaFuncSetAttribute(k_knn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
+	BT_CUDA(cudaFuncSetAttribute(k_knn_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
+	BT_CUDA(cudaFuncSetAttribute(k_knn_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL_P));
 	return BT_OK;
 }
 
@@ -1057,6 +1175,9 @@ extern "C" int bt_knn_match_slots(bt_ctx* ctx, int n_pairs, const int32_t* slotA
 	return knn_run(ctx, n_pairs, A.data(), B.data(), k, idxAB, distAB, idxBA, distBA, m->h_stage.as<char>(), 0, stream);
 }
 
+extern "C" BT_API int bt_knn_debug_prof(long long* out960) {      // developer aid, not part of the public header
+	return cudaMemcpyFromSymbol(out960, g_knn_prof, sizeof(long long) * 160 * 6) == cudaSuccess ? BT_OK : BT_ERR_CUDA;
+}
 extern "C" int bt_knn_debug_force_fallback(bt_ctx* ctx, int every_nth) {
 	BT_REQUIRE(ctx && ctx->matcher, BT_ERR_INVALID_ARG, "bt_knn_debug_force_fallback: call bt_matcher_reserve first");
 	ctx->matcher->force_fallback = every_nth > 0 ? every_nth : 0;
