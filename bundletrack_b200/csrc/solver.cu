@@ -50,6 +50,8 @@ namespace bt {
 static constexpr int kTileVals = 28;          // 21 (sym 6x6) + 6 (rhs) + 1 (#correspondences found)
 static constexpr int kGrpVals = 44;           // sparse moment sums per pair group
 static constexpr int kMaxFrames = 32;
+static constexpr int kSparseTiles = 2;        // sparse tiles per window and GN iteration: each takes a contiguous share of the window's (i,j) groups (45 groups = 23 + 22: one round of
+                                              // 32 eight-lane teams each instead of two; measured as the longest tile of a lone window when it was one tile)
 static constexpr size_t kTailSmemMax = 224 * 1024;   // dynamic shared memory a tail may use (227 KB per CTA minus k_solve's static arrays)
 // (a 128-thread CTA variant of k_solve was measured on B200: SLOWER, 0.55 vs 0.46 ms for 32 windows - dropped)
 static constexpr float kEps = 0.000001f;      // FLOAT_EPSILON, /root/reference/src/cuda/SolverUtil.h:10
@@ -611,16 +613,20 @@ __device__ void plan_body(const SolveArgs& a, WinDesc* wins_rw) {
 		__shared__ int s_total;
 		const WinDesc wl0 = a.wins[a.n_windows - 1];
 		const int n_pairs_all = wl0.pair_off + wl0.n_pairs;
+		// (a lone window's plan is on its critical path: the pairs' source counts - two dependent global loads - are read once, not per attempt)
+		const bool one_each = n_pairs_all <= 1024;
+		const int n_mine = (one_each && tid < n_pairs_all) ? a.nsrc[a.pair_src_slot[tid]] : 0;
 		for (int attempt = 0; attempt < 4; attempt++) {
 			if (tid == 0) s_total = 0;
 			__syncthreads();
 			int mine = 0;
-			for (int q = tid; q < n_pairs_all; q += 1024) { int per; mine += chunks_for(a.nsrc[a.pair_src_slot[q]], chunk, per); }
+			if (one_each) { int per; mine = chunks_for(n_mine, chunk, per); }
+			else for (int q = tid; q < n_pairs_all; q += 1024) { int per; mine += chunks_for(a.nsrc[a.pair_src_slot[q]], chunk, per); }
 #pragma unroll
 			for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
 			if ((tid & 31) == 0 && mine) atomicAdd(&s_total, mine);
 			__syncthreads();
-			const int total = s_total + a.n_windows;      // + one sparse tile per window
+			const int total = s_total + kSparseTiles * a.n_windows;      // + the sparse tiles of every window
 			__syncthreads();
 			if (total <= a.grid_ctas || total > 2 * a.grid_ctas) break;
 			chunk = (int)(((long long)chunk * total / a.grid_ctas + 63) / 32 * 32);     // ~(total/grid) x larger, rounded up to warps
@@ -652,7 +658,7 @@ __device__ void plan_body(const SolveArgs& a, WinDesc* wins_rw) {
 		PROF_T(1);
 		// (2) exclusive scan of the per-window tile counts: the dense tiles plus ONE sparse tile (the window's moment sums), first in line
 		int cnt = 0;
-		if (tid < nw) { cnt = s_cnt[tid] + 1; a.tiles_done[base + tid] = 0; a.iter_done[base + tid] = 0; }
+		if (tid < nw) { cnt = s_cnt[tid] + kSparseTiles; a.tiles_done[base + tid] = 0; a.iter_done[base + tid] = 0; }
 		{   // inclusive scan over the 1024 per-window counts: warp shuffles + one pass over the 32 warp totals
 			__shared__ int s_wtot[32];
 			int incl = cnt;
@@ -690,10 +696,13 @@ __device__ void plan_body(const SolveArgs& a, WinDesc* wins_rw) {
 				int incl = v;
 #pragma unroll
 				for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-				if (p < np) a.pair_tile0[poff + p] = 1 + carry + incl - v;      // slot 0 of the window is its sparse tile
+				if (p < np) a.pair_tile0[poff + p] = kSparseTiles + carry + incl - v;      // the first slots of the window are its sparse tiles
 				carry += __shfl_sync(0xffffffffu, incl, 31);
 			}
-			if (lane == 0 && fits) { Tile tl; tl.win = w; tl.pair = -2; tl.start = 0; tl.count = 0; tl.tgt_slot = tl.src_slot = 0; tl.n_tiles_win = wins_rw[w].n_tiles; tl.pad = 0; tl.src = tl.tex = nullptr; a.tiles[s_cnt[wl]] = tl; }
+			if (lane < kSparseTiles && fits) {      // start / count of a sparse tile = its share: part `start` of `count`
+				Tile tl; tl.win = w; tl.pair = -2; tl.start = lane; tl.count = kSparseTiles; tl.tgt_slot = tl.src_slot = 0; tl.n_tiles_win = wins_rw[w].n_tiles;
+				tl.pad = 0; tl.src = tl.tex = nullptr; a.tiles[s_cnt[wl] + lane] = tl;
+			}
 		}
 		__syncthreads();
 		PROF_T(3);
@@ -884,17 +893,18 @@ __device__ __forceinline__ void unpack_sym(int e, int& r, int& c) {
 // Sparse moment sums of one window for the CURRENT poses: 8 lanes per (i,j) group of correspondences, loads one iteration
 // ahead; 44 sums per group go to a.grp_sums.  This is the window's SPARSE tile: first in the window's slice of the queue, it runs
 // on whichever CTA claims it while the dense tiles are in flight, so the window's tail does not wait for it.
-template <int NT> __device__ void sparse_sums(const SolveArgs& a, int w) {
+template <int NT> __device__ void sparse_sums(const SolveArgs& a, int w, int part, int nparts) {
 	const WinDesc wd0 = a.wins[w];
 	const WinSparse ws = a.wsp[w];
 	const int G = ws.n_groups, tid = threadIdx.x;
 	const int sub = tid >> 3, sl = tid & 7, nsub = NT >> 3;
-	for (int g0 = 0; g0 < G; g0 += nsub) {
+	const int g_lo = (int)(((long long)G * part) / nparts), g_hi = (int)(((long long)G * (part + 1)) / nparts);      // this tile's share of the groups
+	for (int g0 = g_lo; g0 < g_hi; g0 += nsub) {
 		const int g = g0 + sub;
 		float m[kGrpVals];
 #pragma unroll
 		for (int k = 0; k < kGrpVals; k++) m[k] = 0.f;
-		if (g < G) {
+		if (g < g_hi) {
 			const int c0 = a.grp_start[ws.grp_off + w + g], c1 = a.grp_start[ws.grp_off + w + g + 1];
 			const float* Ti = a.T + (size_t)(wd0.frame_off + a.grp_i[ws.grp_off + g]) * 12; const float* Tj = a.T + (size_t)(wd0.frame_off + a.grp_j[ws.grp_off + g]) * 12;
 			const float t00 = __ldcg(Ti + 0), t01 = __ldcg(Ti + 1), t02 = __ldcg(Ti + 2), t03 = __ldcg(Ti + 3), t10 = __ldcg(Ti + 4), t11 = __ldcg(Ti + 5), t12 = __ldcg(Ti + 6), t13 = __ldcg(Ti + 7),
@@ -935,7 +945,7 @@ template <int NT> __device__ void sparse_sums(const SolveArgs& a, int w) {
 		for (int k = 0; k < kGrpVals; k++) {
 			float v = m[k];
 			v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 1);
-			if (g < G && sl == 0) __stcg(a.grp_sums + (size_t)(ws.grp_off + g) * kGrpVals + k, v);
+			if (g < g_hi && sl == 0) __stcg(a.grp_sums + (size_t)(ws.grp_off + g) * kGrpVals + k, v);
 		}
 	}
 }
@@ -1364,7 +1374,7 @@ template <int NT, int MINB> __global__ void __launch_bounds__(NT, MINB) k_solve(
 		PROF_T(1);
 		if (tl.pair == -2) {     // the window's sparse tile: moment sums of all its (i,j) groups for the current poses (CTA-uniform branch)
 			PROF_T(2);
-			sparse_sums<NT>(a, tl.win);
+			sparse_sums<NT>(a, tl.win, tl.start, tl.count);
 			PROF_T(3);
 			int itn = 0, idxn = 0;      // thread 0: the record of the tile claimed above (in flight across the barrier and the ticket)
 			if (tid == 0 && nxt < all) { itn = nxt / total; idxn = nxt - itn * total; tile_fetch_async(&s_tl[cur ^ 1], a.tiles + idxn); }
@@ -1578,7 +1588,7 @@ static int reserve_impl(bt_ctx* ctx, const bt_solver_limits* lim) {
 	s->max_pairs = lim->max_frames * (lim->max_frames - 1);   // both directions allowed in custom lists
 	s->max_groups = lim->max_frames * lim->max_frames;
 	const int min_chunk = 256;   // worst case: every pixel valid at the smallest chunk the scheduler ever picks
-	s->max_tiles = lim->max_windows * (lim->max_frames * (lim->max_frames - 1) / 2) * ((s->npix_max + min_chunk - 1) / min_chunk + 1) + lim->max_windows;
+	s->max_tiles = lim->max_windows * (lim->max_frames * (lim->max_frames - 1) / 2) * ((s->npix_max + min_chunk - 1) / min_chunk + 1) + kSparseTiles * lim->max_windows;
 	int rc;
 #define RES(buf, bytes) if ((rc = s->buf.alloc(bytes)) != BT_OK) return rc
 	{   // worst case over every window count <= max_windows (the table offsets grow with the count, so the maximum is at max_windows)
