@@ -145,6 +145,39 @@ def test_batch_equals_single_and_is_deterministic(opt, cuda_device):
         assert r <= TOL and t <= TOL, (k, r, t)
 
 
+def test_queue_and_static_schedules_agree(cuda_device):
+    """k_solve hands tiles out from a queue when one GN iteration has more tiles than the grid has CTAs, and assigns them statically
+    (CTA c = tile c of every iteration) when it fits: a 12-window batch (queue) must give each window the poses it gets alone (static),
+    up to summation order (the tile size differs), and both must sit on the oracle."""
+    from bundletrack_b200.optimizer import OptimizerGpu, SolveWindow
+    import torch
+    o = OptimizerGpu(None, max_windows=12, max_frames=10, max_corr=2000)
+    scenes = [synth.make_window(300 + k, n_frames=10, n_corr=1500) for k in range(3)]
+    ups = [_upload(w, cuda_device) for w in scenes]
+    rng = np.random.default_rng(5)
+    wins, inits = [], []
+    for k in range(12):
+        sc, (d, n) = scenes[k % 3], ups[k % 3]
+        poses = sc.poses_gt.copy()
+        for f in range(1, sc.n_frames):
+            poses[f] = sc.poses_gt[f] @ synth.se3(synth.so3_exp(rng.normal(0, np.deg2rad(1.0), 3)), rng.normal(0, 0.003, 3))
+        inits.append(poses.astype(np.float32))
+        wins.append(SolveWindow(sc.corr, sc.H, sc.W, d, n, inits[-1], sc.K))
+    batch = o.optimizeWindows(wins)
+    n_sm = torch.cuda.get_device_properties(cuda_device).multi_processor_count
+    assert o.stats()["n_tiles_total"] > 2 * n_sm          # more tiles per iteration than resident CTAs: the queue
+    for k in (0, 5, 11):
+        alone = o.optimizeWindows([wins[k]])[0]
+        assert o.stats()["n_tiles_total"] <= 2 * n_sm      # one wave: static assignment
+        r, t = synth.pose_errors(batch[k], alone)
+        assert r <= 3e-5 and t <= 3e-5, (k, r, t)      # (another tile size = another summation order: a gated pixel may flip, ~1e-5 each)
+        ref = oracle.solve_window(scenes[k % 3].depth, scenes[k % 3].normal, scenes[k % 3].K, scenes[k % 3].corr, inits[k])
+        r, t = synth.pose_errors(batch[k], ref)
+        assert r <= TOL and t <= TOL, (k, r, t)
+    assert np.array_equal(np.concatenate(o.optimizeWindows(wins), 0), np.concatenate(batch, 0))      # the queue order does not change a bit
+    o.close()
+
+
 def test_edge_cases(opt, cuda_device):
     from bundletrack_b200.optimizer import SolveWindow
     from bundletrack_b200 import _lib
