@@ -120,32 +120,55 @@ static constexpr int kEvalCheck = 128;   // points between two looks at the best
 //    is <= thresh (computed on the host): same truth value for every float, no square root;
 //  * a trial stops as soon as it can no longer reach the best count any trial of this pair has finished with so far
 //    (count + points left < best): it cannot win and it cannot tie, so the winner (max count, then lowest trial) is unchanged.
+// packed f32x2 arithmetic (sm_100): two points per instruction, each lane an ordinary IEEE operation
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) { unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) { unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) { unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) { unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+// One thread per trial, the pair's points broadcast from shared memory; TWO points per instruction (the kernel is issue-bound: 2000
+// trials x ~2-3 k candidate points x 45 pairs).  Every lane performs exactly the operations, in exactly the order, of the scalar
+// expression `pb - (P[0]*pa.x + P[1]*pa.y + P[2]*pa.z + P[3])` as nvcc contracts it (mul y, fma x, fma z, add t; squares: mul dy, fma dx, fma
+// dz), so the inlier counts are bit-identical to the scalar version that was pinned against the reference's ransacMultiPairGPU.
 __global__ void __launch_bounds__(256) k_ransac_eval(const RansacPair* __restrict__ pairs, int n_trials, const float* __restrict__ poses, const int* __restrict__ good,
                                                       float d2_max, unsigned long long* __restrict__ best) {
-	__shared__ float4 sA[kEvalPts];
-	__shared__ float4 sB[kEvalPts];
+	__shared__ float4 sP[3][kEvalPts / 2];      // per PAIR of points: (ax, ax', ay, ay') | (az, az', bx, bx') | (by, by', bz, bz')
 	const int pair = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
 	const RansacPair pr = pairs[pair];
 	const bool live = t < n_trials && good[(size_t)pair * n_trials + t] != 0;
-	float P[12];
-	if (live) { const float* Pg = poses + ((size_t)pair * n_trials + t) * 12; for (int k = 0; k < 12; k++) P[k] = Pg[k]; }
-	else for (int k = 0; k < 12; k++) P[k] = 0.f;
+	unsigned long long P2[12];
+	{
+		const float* Pg = poses + ((size_t)pair * n_trials + t) * 12;
+		for (int k = 0; k < 12; k++) { const float v = live ? Pg[k] : 0.f; P2[k] = pk2(v, v); }
+	}
 	int count = 0;
 	bool running = live;
 	for (int base = 0; base < pr.n; base += kEvalPts) {
 		const int m = min(kEvalPts, pr.n - base);
 		__syncthreads();
-		for (int k = threadIdx.x; k < m; k += blockDim.x) { sA[k] = __ldg(pr.A + base + k); sB[k] = __ldg(pr.B + base + k); }
+		for (int k = threadIdx.x; k < ((m + 1) & ~1); k += blockDim.x) {
+			float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = make_float4(3e38f, 3e38f, 3e38f, 0.f);      // padding point of an odd tail: never an inlier (its squared distance overflows)
+			if (k < m) { a4 = __ldg(pr.A + base + k); b4 = __ldg(pr.B + base + k); }
+			const int j = k >> 1, h = k & 1;
+			float* p0 = reinterpret_cast<float*>(&sP[0][j]); float* p1 = reinterpret_cast<float*>(&sP[1][j]); float* p2 = reinterpret_cast<float*>(&sP[2][j]);
+			p0[h] = a4.x; p0[2 + h] = a4.y; p1[h] = a4.z; p1[2 + h] = b4.x; p2[h] = b4.y; p2[2 + h] = b4.z;
+		}
 		__syncthreads();
 		for (int k0 = 0; k0 < m && running; k0 += kEvalCheck) {
 			const int k1 = min(m, k0 + kEvalCheck);
 #pragma unroll 4
-			for (int k = k0; k < k1; k++) {
-				const float4 pa = sA[k], pb = sB[k];
-				const float dx = pb.x - (P[0] * pa.x + P[1] * pa.y + P[2] * pa.z + P[3]);
-				const float dy = pb.y - (P[4] * pa.x + P[5] * pa.y + P[6] * pa.z + P[7]);
-				const float dz = pb.z - (P[8] * pa.x + P[9] * pa.y + P[10] * pa.z + P[11]);
-				count += (dx * dx + dy * dy + dz * dz <= d2_max) ? 1 : 0;
+			for (int j = k0 >> 1; j < (k1 + 1) >> 1; j++) {
+				const float4 u = sP[0][j], v = sP[1][j], w = sP[2][j];
+				const unsigned long long ax = pk2(u.x, u.y), ay = pk2(u.z, u.w), az = pk2(v.x, v.y), bx = pk2(v.z, v.w), by = pk2(w.x, w.y), bz = pk2(w.z, w.w);
+				const unsigned long long dx = sub2(bx, add2(fma2(P2[2], az, fma2(P2[0], ax, mul2(P2[1], ay))), P2[3]));
+				const unsigned long long dy = sub2(by, add2(fma2(P2[6], az, fma2(P2[4], ax, mul2(P2[5], ay))), P2[7]));
+				const unsigned long long dz = sub2(bz, add2(fma2(P2[10], az, fma2(P2[8], ax, mul2(P2[9], ay))), P2[11]));
+				const unsigned long long d2 = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+				float d2a, d2b;
+				asm("mov.b64 {%0, %1}, %2;" : "=f"(d2a), "=f"(d2b) : "l"(d2));
+				count += (d2a <= d2_max) ? 1 : 0;
+				count += (d2b <= d2_max) ? 1 : 0;
 			}
 			// best[pair] only ever holds counts of trials that have seen ALL points
 			const int best_cnt = (int)(__ldcg(best + pair) >> 32);
