@@ -12,14 +12,15 @@
 //                  valid source pixels (the object mask leaves ~10 % of the image valid), + se(3) of the input pose.
 //                  Each block's offset in the ordered list = the counts of the blocks before it.
 //   (plan)         the LAST CTA of k_prep_frames to finish: per-window tile counts -> exclusive scan -> flat tile list.
-//   k_solve        persistent, dynamically scheduled: tiles are (GN iteration, window, pair, pixel chunk); a tile
-//                  evaluates point-to-plane residuals/Jacobians for its chunk and reduces a 6x6 system in the TARGET
-//                  camera frame; every window also has one SPARSE tile per iteration (the moment sums of its
-//                  correspondences: they only need the poses, so they run next to the dense tiles); the CTA that retires
-//                  a window's last tile of an iteration runs that window's "tail":
-//                  assembles the (6(N-1))^2 normal equations in shared memory (dense blocks + explicit sparse
-//                  blocks from per-pair moment sums), runs the PCG steps, updates the poses and releases the
-//                  window's next iteration.  Tiles of iteration k+1 wait on a per-window flag, so all GN iterations
+//   k_solve        persistent: tiles are (GN iteration, window, pair, pixel chunk), handed out by a queue (the next tile's 48-byte
+//                  record is fetched one tile ahead) or - when one iteration's tiles fit the grid - assigned statically (CTA c =
+//                  tile c of every iteration).  A tile evaluates point-to-plane residuals/Jacobians for its chunk and reduces a 6x6
+//                  system in the TARGET camera frame; every window also has two SPARSE tiles per iteration (the moment sums of half
+//                  of its correspondence groups each: they only need the poses, so they run next to the dense tiles); the CTA that
+//                  retires a window's last tile of an iteration runs that window's "tail": table loads as asynchronous copies next
+//                  to the per-pair sums, assembly of the (6(N-1))^2 normal equations in shared memory (dense blocks + explicit
+//                  sparse blocks from per-pair moment sums), the PCG steps with one thread per unknown, the pose update, and the
+//                  release of the window's next iteration.  Tiles of iteration k+1 wait on a per-window flag, so all GN iterations
 //                  of all windows flow through ONE launch with no host round trip.
 //
 // Maths restated from the reference (see oracle/solver_oracle.c for the statement-by-statement CPU version):
