@@ -623,6 +623,22 @@ def main():
         tm1 = opt.timing_ms()
         single = {"e2e_ms": single_ms, "kernel_ms": {"prep": tm1["prep"], "solve": tm1["solve"]},
                   "note": "bt_solve_windows on ONE 10-keyframe x 2000-correspondence window, host buffers in/out, all maps rebuilt in the call (the reference's call)"}
+        # the same window the way a tracker presents it: the new frame's maps stored once (bt_frame_cache_store), its 9 keyframes already in the cache
+        try:
+            one_c = [cwins[0]]
+            st1 = opt.prepare_store(new_slots[:1], new_d[:1], new_n[:1], wins[0].H, wins[0].W, wins[0].K)
+            for _ in range(5):
+                opt.store_prepared(st1); opt.optimizeWindows(one_c)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(50):
+                opt.store_prepared(st1); opt.optimizeWindows(one_c)
+            torch.cuda.synchronize()
+            tmc = opt.timing_ms()
+            single["keyframes_cached"] = {"e2e_ms": (time.perf_counter() - t0) / 50 * 1e3, "kernel_ms": {"prep": tmc["prep"], "solve": tmc["solve"]},
+                                          "note": "bt_frame_cache_store of the ONE new frame + bt_solve_windows with cache slots (9 keyframes reused), host buffers in/out"}
+        except Exception as e:
+            single["keyframes_cached"] = {"error": repr(e)}
         # (before the matcher / cfg3 blocks allocate gigabytes: the reference's per-call cudaMalloc/cudaFree pattern slows down with the memory the process holds)
         cb = cpu_baseline(host, args.cpu_windows, check_against=out_poses[0], single_window=(wins[0], single_ms))
         matcher = matcher_microbench(dev, stream)
